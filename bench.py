@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- grid-point updates/s of the fused shallow-water step on B200.
+
+One "step" = one pass of the hot path (numpy.py:496-549 of the reference: CFL dt,
+Lax-Wendroff update, boundary conditions, CFL maxima of the new state) over the whole grid.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--grid MxN] [--mode fast|strict] [--diffusion]
+
+Default workload (N = 1): the configuration BASELINE.json's targets are quoted on --
+Rossby-Haurwitz wave on the 16384 x 8192 fp64 grid, diffusion off, CFL 0.5 -- whose state
+(3.2 GB read + 3.2 GB written per step) is far larger than the 126 MB L2, so no L2 flush is
+needed between timed steps.  Prints ONE JSON line (see the task contract): `value` is
+whole-job updates/s with the state resident in HBM; `e2e` is the same metric through the
+public host API with HOST buffers (H2D of the initial state and D2H of the result inside the
+timed region); `roofline` is the step kernel's achieved algorithmic HBM bandwidth (48 B per
+update) against MEASURED_PEAKS.json; `cpu_baseline` is the oracle port of the reference loop
+body timed on this box's host cores on a bounded latitude-band sample.
+
+`--impl reference` times the reference's CPU implementation of the path.  The reference is
+pure Python/numpy and cannot travel to the GPU box, so this arm runs the oracle port
+(oracle/sw_oracle.c, OpenMP over all host cores) on the same workload definition, each
+step a bounded sample.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_UPDATE_F64 = 48.0  # read h,u,v + write h,u,v
+METRIC = "grid-point updates/sec (fp64)"
+UNIT = "updates/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", default="16384x8192")
+    ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
+    ap.add_argument("--diffusion", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.02):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+            "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference loop body on a bounded sample
+# --------------------------------------------------------------------------------------
+def cpu_reference_run(M, N_sample, diffusion, steps, warmup):
+    """Time `steps` loop bodies (numpy.py:503-549) of the oracle port on an M x N_sample
+    latitude-band grid (same longitudes as the workload, fewer latitudes)."""
+    from oracle import sw_oracle as so
+
+    og = so.OracleGrid(M, N_sample)
+    h, u, v, f = so.initial_conditions(0, og)
+    h, u, v = (np.ascontiguousarray(x) for x in (h, u, v))
+    stp = so.Stepper(og, f, None, diffusion)
+    t = 0.0
+    for _ in range(warmup):
+        _, t = stp.step(h, u, v, 0.5, t, 1e12)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, t = stp.step(h, u, v, 0.5, t, 1e12)
+    el = time.perf_counter() - t0
+    pts = (M + 1) * (og.N - 2)
+    return {"value": pts * steps / el, "seconds": el, "pts_per_step": pts, "threads": so.num_threads(),
+            "N_sample": og.N, "steps": steps}
+
+
+def cpu_sample_rows(M):
+    # ~4 M points per sampled step keeps each step well under a second on a multi-core host
+    return int(max(8, min(512, (4_000_000 // (M + 1)) // 2 * 2)))
+
+
+def run_reference_arm(args, M, N):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ns = cpu_sample_rows(M)
+    r = cpu_reference_run(M, ns, args.diffusion, max(1, args.steps), max(1, args.warmup))
+    sample = (f"oracle port (oracle/sw_oracle.c, OpenMP) of numpy.py:503-549 on a {M}x{r['N_sample']} latitude band "
+              f"of the {M}x{N} workload, {r['steps']} steps")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Rossby-Haurwitz {M}x{N} fp64, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
+                   "reference_kind": "the reference is pure Python/numpy and cannot run on the GPU box; "
+                                     "this arm is its C port (oracle), pinned bit-exact to the reference"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args, M, N):
+    import torch
+
+    from sw_solver_b200.grid import CartesianGrid, LatLonGrid
+    from sw_solver_b200.ic import ICType, coriolis_latitude, get_initial_conditions
+    from sw_solver_b200.solver import Stepper
+
+    if args.gpus != 1:
+        raise SystemExit("multi-GPU bench path: see bench_multi (not in this build)")
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    h, u, v, _ = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+    f = coriolis_latitude(ll)
+    pts = (M + 1) * (ll.N - 2)
+    state_bytes = 3 * (M + 3) * ll.N * 8
+
+    # pinned host copies of the initial state for the end-to-end leg
+    host = [torch.from_numpy(q).pin_memory() for q in (h, u, v)]
+    del h, u, v
+
+    st = Stepper(ll, cg, host[0], host[1], host[2], f, None, courant=0.5, final_time=1e12,
+                 use_diffusion=args.diffusion, mode=args.mode, device=dev)
+    st.cfl_init()
+    st.enqueue(args.warmup)
+    torch.cuda.synchronize(dev)
+    launches0 = st.launch_count
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clk:
+        torch.cuda.synchronize(dev)
+        ev0.record()
+        st.enqueue(args.steps)
+        ev1.record()
+        torch.cuda.synchronize(dev)
+    ms = ev0.elapsed_time(ev1)
+    launches = st.launch_count - launches0
+    s = st.status()
+    assert s.steps == args.warmup + args.steps and not s.done and s.error == 0, (s.steps, s.done, s.error)
+    hcur = st.state()[0]
+    assert bool(torch.isfinite(hcur).all()), "non-finite state after the timed region"
+    value = pts * args.steps / (ms * 1e-3)
+    st.close()
+    del st
+
+    # --- end to end through the public host API, HOST buffers in and out -----------------
+    e2e = None
+    if not args.no_e2e:
+        out = [torch.empty_like(q).pin_memory() for q in host]
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        st2 = Stepper(ll, cg, host[0], host[1], host[2], f, None, courant=0.5, final_time=1e12,
+                      use_diffusion=args.diffusion, mode=args.mode, device=dev)   # H2D of h, u, v
+        st2.enqueue(args.steps)
+        cur = st2.status().current                                                  # blocks until done
+        for k in range(3):
+            out[k].copy_(st2.buf[cur, k], non_blocking=True)                        # D2H of h, u, v
+        torch.cuda.synchronize(dev)
+        el = time.perf_counter() - t0
+        st2.close()
+        e2e = {"value": pts * args.steps / el, "unit": UNIT,
+               "h2d_bytes_per_step": state_bytes / args.steps, "d2h_bytes_per_step": state_bytes / args.steps,
+               "call": f"Stepper(host h,u,v) + enqueue({args.steps}) + D2H of h,u,v; {state_bytes} B each way per call",
+               "seconds": el}
+
+    peak, peak_src = measured_peak_gbs()
+    kernel_ms = ms / args.steps
+    achieved = BYTES_PER_UPDATE_F64 * pts / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "swb::step_kernel", "kernel_ms": kernel_ms,
+                "bytes_per_launch": BYTES_PER_UPDATE_F64 * pts, "peak_source": peak_src}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        try:
+            roofline["traffic"] = json.load(open(prof)).get(f"{M}x{ll.N}:{args.mode}")
+        except Exception:
+            pass
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        ns = cpu_sample_rows(M)
+        probe = cpu_reference_run(M, ns, args.diffusion, 1, 1)
+        nsteps = int(max(2, min(200, 12.0 / max(probe["seconds"], 1e-3))))
+        r = cpu_reference_run(M, ns, args.diffusion, nsteps, 1)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+               "sample": f"oracle port of numpy.py:503-549 (C, OpenMP) on a {M}x{r['N_sample']} latitude band of the "
+                         f"workload, {nsteps} steps, {r['seconds']:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"Rossby-Haurwitz {M}x{ll.N} fp64, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
+                   "mode": args.mode, "l2": "state (6.4 GB touched per step) is larger than L2; no flush needed",
+                   "pts_per_step": pts},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    M, N = (int(x) for x in args.grid.lower().split("x"))
+    if args.impl == "reference":
+        run_reference_arm(args, M, N)
+    else:
+        run_ours(args, M, N)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""Builds libswb200.so (the sm_100a kernels + C ABI) in-tree with nvcc.
+
+``python -m sw_solver_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles
+without a GPU; the resulting shared object travels to the GPU box with the repo snapshot.
+"""
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libswb200.so")
+SOURCES = [os.path.join(CSRC, "swb200.cu")]
+HEADERS = [os.path.join(CSRC, "swb_kernels.cuh"), os.path.join(ROOT, "include", "swb200.h")]
+
+
+def nvcc_path() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(cand):
+        raise RuntimeError("nvcc not found: libswb200.so cannot be built (there is no CPU fallback)")
+    return cand
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [
+        nvcc_path(),
+        "-gencode", "arch=compute_100a,code=sm_100a",
+        "-O3", "-std=c++17", "-lineinfo",
+        "-Xcompiler", "-fPIC", "-shared",
+        "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+        "-o", LIB,
+    ] + SOURCES
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,112 @@
+"""Initial conditions (Williamson test cases 6 and 2) on a ``LatLonGrid``.
+
+Same entry points as the reference's ``src/sw_solver/ic.py`` (``ICType`` 12-19,
+``get_initial_conditions`` 22-159) and bit-identical values, but evaluated from the
+grid's 1-D vectors: all transcendental work happens on O(M + N) points and only the final
+products / sums are broadcast to (M+3, N).  ``separable_rossby_haurwitz`` exposes that
+factorisation so that large grids can be assembled directly on the GPU.
+"""
+
+import enum
+import math
+from typing import Dict
+
+import numpy as np
+
+from .grid import LatLonGrid
+from .utils import EARTH_CONSTANTS
+
+
+class ICType(enum.IntEnum):
+    """Initial condition types (reference ic.py:12-19)."""
+
+    RossbyHaurwitzWave = 0
+    """Test case 6 by Williamson."""
+
+    ZonalGeostrophicFlow = 1
+    """Test case 2 by Williamson."""
+
+
+def coriolis_latitude(latlon_grid: LatLonGrid) -> np.ndarray:
+    """f = 2 omega sin(theta) as a latitude vector (reference ic.py:46)."""
+    return 2.0 * EARTH_CONSTANTS.omega * np.sin(latlon_grid.theta1d)
+
+
+def separable_rossby_haurwitz(latlon_grid: LatLonGrid) -> Dict[str, np.ndarray]:
+    """Latitude / longitude factors of the Rossby-Haurwitz wave (reference ic.py:53-107).
+
+    With them (all products formed left to right exactly as the reference forms them):
+
+        h[i, j] = h0 + ((hA[j] + hB[j] * cosR[i]) + hC[j] * cos2R[i]) / g
+        u[i, j] = uA[j] + uB[j] * cosR[i]
+        v[i, j] = vB[j] * sinR[i]
+    """
+    a, om, g = EARTH_CONSTANTS.a, EARTH_CONSTANTS.omega, EARTH_CONSTANTS.g
+    th, ph = latlon_grid.theta1d, latlon_grid.phi1d
+    w = 7.848e-6
+    K = 7.848e-6
+    h0 = 8e3
+    R = 4.0
+    ct, st = np.cos(th), np.sin(th)
+    A = 0.5 * w * (2.0 * om + w) * (ct ** 2.0) + 0.25 * (K ** 2.0) * (ct ** (2.0 * R)) * (
+        (R + 1.0) * (ct ** 2.0) + (2.0 * (R ** 2.0) - R - 2.0) - 2.0 * (R ** 2.0) * (ct ** (-2.0))
+    )
+    B = (
+        (2.0 * (om + w) * K)
+        / ((R + 1.0) * (R + 2.0))
+        * (ct ** R)
+        * (((R ** 2.0) + 2.0 * R + 2.0) - ((R + 1.0) ** 2.0) * (ct ** 2.0))
+    )
+    C = 0.25 * (K ** 2.0) * (ct ** (2.0 * R)) * ((R + 1.0) * (ct ** 2.0) - (R + 2.0))
+    a2 = a ** 2.0
+    return {
+        "h0": np.float64(h0),
+        "g": np.float64(g),
+        "hA": a2 * A,
+        "hB": a2 * B,
+        "hC": a2 * C,
+        "cosR": np.cos(R * ph),
+        "cos2R": np.cos(2.0 * R * ph),
+        "sinR": np.sin(R * ph),
+        "uA": a * w * ct,
+        "uB": a * K * (ct ** (R - 1.0)) * (R * (st ** 2.0) - (ct ** 2.0)),
+        "vB": -a * K * R * (ct ** (R - 1.0)) * st,
+    }
+
+
+def get_initial_conditions(ic_type: ICType, latlon_grid: LatLonGrid):
+    """Return ``h, u, v, f`` on the full ghosted (M+3, N) grid (reference ic.py:22-159).
+
+    ``h, u, v`` are freshly allocated C-contiguous float64 arrays.  For the
+    Rossby-Haurwitz wave ``f`` depends on latitude only and is returned as a 2-D view of
+    that vector (a real array on small grids).
+    """
+    g = EARTH_CONSTANTS.g
+    shape = latlon_grid.shape
+    f_lat = coriolis_latitude(latlon_grid)
+
+    if ic_type == ICType.RossbyHaurwitzWave:
+        s = separable_rossby_haurwitz(latlon_grid)
+        cR, c2R, sR = s["cosR"][:, None], s["cos2R"][:, None], s["sinR"][:, None]
+        h = s["h0"] + (s["hA"][None, :] + s["hB"][None, :] * cR + s["hC"][None, :] * c2R) / g
+        u = s["uA"][None, :] + s["uB"][None, :] * cR
+        v = s["vB"][None, :] * sR
+        f = np.broadcast_to(f_lat[None, :], shape)
+        if latlon_grid._real:
+            f = np.array(f)
+    elif ic_type == ICType.ZonalGeostrophicFlow:
+        a, om = EARTH_CONSTANTS.a, EARTH_CONSTANTS.omega
+        alpha = math.pi / 2
+        u0 = 2.0 * math.pi * a / (12.0 * 24.0 * 3600.0)
+        h0 = 2.94e4 / g
+        th, ph = latlon_grid.theta1d[None, :], latlon_grid.phi1d[:, None]
+        # ic.py:126-133: the rotated Coriolis parameter is genuinely 2-D
+        rot = -np.cos(ph) * np.cos(th) * np.sin(alpha) + np.sin(th) * np.cos(alpha)
+        f = 2.0 * om * rot
+        h = h0 - (a * om * u0 + 0.5 * (u0 ** 2.0)) * (rot ** 2.0) / g
+        u = u0 * (np.cos(th) * np.cos(alpha) + np.cos(ph) * np.sin(th) * np.sin(alpha))
+        v = np.array(np.broadcast_to(-u0 * np.sin(ph) * np.sin(alpha), shape))
+    else:
+        raise ValueError(f"Unknown ICType: {ic_type}")
+
+    return np.ascontiguousarray(h), np.ascontiguousarray(u), np.ascontiguousarray(v), f

@@ -1,0 +1,525 @@
+"""B200 solver: the reference's ``sw_solver.numpy`` entry points on sm_100a kernels.
+
+Same names, positional signatures and error behaviour as ``src/sw_solver/numpy.py``:
+
+* ``solve``                 numpy.py:409-575 -- the time loop runs on the GPU (one fused
+  kernel per step, dt / time / step count device-resident, no per-step host sync);
+* ``lax_wendroff_update``   numpy.py:136-356;
+* ``DiffusionCoefficients`` numpy.py:12-63, ``compute_diffusion`` 359-382,
+  ``compute_laplacian`` 66-133, ``_apply_bcs`` 385-406;
+* ``Stepper``               (new) the device-resident loop body for callers that drive
+  their own loop or already hold the state on the GPU.
+
+Python only prepares 1-D tables and moves pointers; all arithmetic of the path happens in
+``libswb200.so`` (hand-written CUDA, see csrc/), reached through the C ABI in
+include/swb200.h.  PyTorch allocates device memory and provides streams.  There is no CPU
+fallback: without a CUDA device every entry point raises.
+"""
+
+import ctypes
+import math
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MODES, SwbConfig, SwbError, SwbStatus, SwbTables, check
+from .grid import CartesianGrid, LatLonGrid
+from .ic import ICType, coriolis_latitude, get_initial_conditions
+from .utils import EARTH_CONSTANTS, FloatArray2D, FloatT
+
+#: arithmetic mode used when a caller does not choose: "fast" (FMA contraction, shared
+#: reciprocals; <= 1e-12 from numpy) or "strict" (bit-identical to numpy, slower)
+DEFAULT_MODE = "fast"
+
+
+# --------------------------------------------------------------------------------------
+# host-side helpers (pure numpy / python; covered by CPU tests)
+# --------------------------------------------------------------------------------------
+def band_layout(N: int, world: int, halo: int) -> List[Dict[str, int]]:
+    """Split the updated latitude rows 1..N-2 into ``world`` contiguous bands.
+
+    Each band holds ``halo`` extra rows beyond each updated edge (the pole bands hold the
+    single copy row 0 / N-1 instead).  Returns, per rank, the fields of ``swb_config``:
+    j_first, j_last (inclusive, global), j_begin, n_local.
+    """
+    rows = N - 2
+    if world < 1 or rows < world:
+        raise ValueError(f"cannot split {rows} latitude rows into {world} bands")
+    out = []
+    base, extra = divmod(rows, world)
+    j = 1
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        j_first, j_last = j, j + n - 1
+        j_begin = max(0, j_first - halo)
+        j_end = min(N, j_last + 1 + halo)
+        out.append({"rank": r, "j_first": j_first, "j_last": j_last, "j_begin": j_begin, "n_local": j_end - j_begin})
+        j += n
+    return out
+
+
+def _pad_to(vec: np.ndarray, n: int, lead: int = 0) -> np.ndarray:
+    """Place ``vec`` at offset ``lead`` of a length-n vector, repeating the end values."""
+    out = np.empty(n, dtype=np.float64)
+    out[lead:lead + len(vec)] = vec
+    out[:lead] = vec[0]
+    out[lead + len(vec):] = vec[-1]
+    return out
+
+
+def diffusion_weights_lat(cart_grid: CartesianGrid) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """The latitude set Ay, By, Cy of numpy.py:50-63 as length-N vectors (edge rows
+    duplicated exactly as the reference pads them)."""
+    d0, d1 = cart_grid.dy1d[:-1], cart_grid.dy1d[1:]
+    Ay = (d1 - d0) / (d1 * d0)
+    By = d0 / (d1 * (d1 + d0))
+    Cy = -d1 / (d0 * (d1 + d0))
+    N = cart_grid.N
+    return _pad_to(Ay, N, 1), _pad_to(By, N, 1), _pad_to(Cy, N, 1)
+
+
+def latitude_tables(latlon_grid: LatLonGrid, cart_grid: CartesianGrid, f_lat: Optional[np.ndarray],
+                    use_diffusion: bool, j_begin: int = 0, n_local: Optional[int] = None) -> Dict[str, np.ndarray]:
+    """The 1-D tables ``swb_set_tables`` takes, sliced to a band (include/swb200.h)."""
+    N = latlon_grid.N
+    n_local = N if n_local is None else n_local
+    sl = slice(j_begin, j_begin + n_local)
+    full = {
+        "c": latlon_grid.c1d,
+        "tg": latlon_grid.tg1d,
+        "ac": cart_grid.ac1d,
+        "tgMidy": _pad_to(latlon_grid.tgMidy1d, N),
+        "cMidy": _pad_to(latlon_grid.cMidy1d, N),
+        "dy": _pad_to(cart_grid.dy1d, N),
+        "dy1": _pad_to(cart_grid.dy11d, N),
+        "dyc": _pad_to(cart_grid.dyc1d, N, 1),
+        "dy1c": _pad_to(cart_grid.dy1c1d, N, 1),
+    }
+    if f_lat is not None:
+        full["f_lat"] = np.asarray(f_lat, dtype=np.float64)
+    if use_diffusion:
+        full["Ay"], full["By"], full["Cy"] = diffusion_weights_lat(cart_grid)
+    out = {k: np.ascontiguousarray(v[sl], dtype=np.float64) for k, v in full.items()}
+    out["phi"] = np.ascontiguousarray(latlon_grid.phi1d, dtype=np.float64)
+    return out
+
+
+def _latitude_only(f) -> Optional[np.ndarray]:
+    """Return f as a latitude vector if it does not depend on longitude, else None."""
+    if isinstance(f, torch.Tensor):
+        f = f.detach().cpu().numpy()
+    f = np.asarray(f)
+    if f.ndim == 1:
+        return np.ascontiguousarray(f, dtype=np.float64)
+    if f.strides[0] == 0 or bool((f == f[0:1]).all()):
+        return np.ascontiguousarray(f[0], dtype=np.float64)
+    return None
+
+
+def _require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("sw_solver_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("sw_solver_b200 runs on CUDA devices only")
+    return torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+
+
+def _stream(device) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+# --------------------------------------------------------------------------------------
+# the device-resident loop body
+# --------------------------------------------------------------------------------------
+class Stepper:
+    """Device-resident state + the fused step kernel for one grid (or latitude band).
+
+    ``h, u, v`` (and a 2-D ``f`` / ``hs`` when given) are (M+3, N) arrays in the
+    reference layout -- numpy arrays are uploaded, CUDA tensors are copied on the device.
+    After construction ``enqueue(n)`` runs n iterations of numpy.py:496-549 without
+    involving the host; ``status()`` synchronises and reports time / step count.
+    """
+
+    def __init__(self, latlon_grid: LatLonGrid, cart_grid: CartesianGrid, h, u, v, f, hs=None, *,
+                 courant: float, final_time: float, use_diffusion: bool = True, mode: Optional[str] = None,
+                 device=None, log_capacity: int = 0):
+        mode = DEFAULT_MODE if mode is None else mode
+        if mode not in MODES:
+            raise ValueError(f"mode must be one of {sorted(MODES)}, got {mode!r}")
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.latlon_grid, self.cart_grid = latlon_grid, cart_grid
+        self.M, self.N = latlon_grid.M, latlon_grid.N
+        self.mode = mode
+        self.use_diffusion = bool(use_diffusion)
+        M, N = self.M, self.N
+        shape = (M + 3, N)
+
+        f_lat = _latitude_only(f)
+        self._f2d = None if f_lat is not None else self._to_device(f, shape)
+        self._hs = None
+        if hs is not None:
+            hs_t = self._to_device(hs, shape)
+            if bool((hs_t != 0).any()):  # flat topography only subtracts an exact zero
+                self._hs = hs_t
+
+        # two buffer sets {h,u,v}; set 0 receives the initial state
+        self.buf = torch.empty((2, 3) + shape, dtype=torch.float64, device=self.device)
+        for k, q in enumerate((h, u, v)):
+            self.buf[0, k].copy_(self._as_tensor(q, shape), non_blocking=False)
+        self.buf[1].zero_()
+
+        cfg = SwbConfig()
+        cfg.struct_bytes = ctypes.sizeof(SwbConfig)
+        cfg.M, cfg.N = M, N
+        cfg.j_begin, cfg.n_local, cfg.j_first, cfg.j_last, cfg.pitch = 0, N, 1, N - 2, N
+        cfg.dtype, cfg.mode = _lib.SWB_F64, MODES[mode]
+        cfg.use_diffusion = int(self.use_diffusion)
+        cfg.f_is_2d = int(self._f2d is not None)
+        cfg.has_hs = int(self._hs is not None)
+        cfg.device = self.device.index
+        cfg.log_capacity = int(log_capacity)
+        cfg.rank, cfg.world = 0, 1
+        cfg.courant, cfg.final_time = float(courant), float(final_time)
+        cfg.dxmin, cfg.dymin = float(cart_grid.dxmin), float(cart_grid.dymin)
+        cfg.g, cfg.a, cfg.nu = EARTH_CONSTANTS.g, EARTH_CONSTANTS.a, EARTH_CONSTANTS.nu
+        cfg.dphi = float(latlon_grid.dphi)
+        self.cfg = cfg
+        self._ctx = ctypes.c_void_p()
+        check(self.lib.swb_create(ctypes.byref(self._ctx), ctypes.byref(cfg)))
+
+        tabs = latitude_tables(latlon_grid, cart_grid, f_lat, self.use_diffusion)
+        ct = SwbTables()
+        for name in _lib.TABLE_FIELDS:
+            arr = tabs.get(name)
+            setattr(ct, name, arr.ctypes.data_as(_lib._dp) if arr is not None else None)
+        check(self.lib.swb_set_tables(self._ctx, ctypes.byref(ct)))
+
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        check(self.lib.swb_bind_state(self._ctx, *(ptr(self.buf[s, k]) for s in (0, 1) for k in range(3)),
+                                      ptr(self._f2d), ptr(self._hs)))
+        self._cfl_ready = False
+
+    # -- plumbing ------------------------------------------------------------------
+    def _as_tensor(self, q, shape) -> torch.Tensor:
+        if isinstance(q, torch.Tensor):
+            t = q
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64))
+        if tuple(t.shape) != tuple(shape) or t.dtype != torch.float64:
+            raise ValueError(f"expected a float64 array of shape {shape}, got {tuple(t.shape)} {t.dtype}")
+        return t
+
+    def _to_device(self, q, shape) -> torch.Tensor:
+        return self._as_tensor(q, shape).to(self.device).contiguous()
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            torch.cuda.synchronize(self.device)
+            self.lib.swb_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the path ------------------------------------------------------------------
+    def cfl_init(self):
+        """numpy.py:503-521 on the full initial state; time and step count restart at 0."""
+        check(self.lib.swb_cfl_init(self._ctx, _stream(self.device)))
+        self._cfl_ready = True
+
+    def enqueue(self, n: int):
+        """Enqueue n loop iterations (numpy.py:496-549).  Returns immediately."""
+        if not self._cfl_ready:
+            self.cfl_init()
+        check(self.lib.swb_enqueue_steps(self._ctx, int(n), _stream(self.device)))
+
+    def step_fixed_dt(self, dt: float):
+        """One update with a caller-given dt, buffer set 0 -> set 1 (numpy.py:136-356, 541-549)."""
+        check(self.lib.swb_step_fixed_dt(self._ctx, float(dt), _stream(self.device)))
+
+    def status_async(self, pinned: Optional[torch.Tensor] = None):
+        """Enqueue a status snapshot into ``pinned`` (uint8, >= sizeof(swb_status))."""
+        dst = ctypes.c_void_p(pinned.data_ptr()) if pinned is not None else None
+        check(self.lib.swb_status_async(self._ctx, dst, _stream(self.device)))
+
+    def status(self) -> SwbStatus:
+        st = SwbStatus()
+        check(self.lib.swb_get_status(self._ctx, ctypes.byref(st), _stream(self.device)))
+        return st
+
+    def state(self, current: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Device views (M+3, N) of the current h, u, v (synchronises unless ``current`` is given)."""
+        cur = self.status().current if current is None else current
+        return self.buf[cur, 0], self.buf[cur, 1], self.buf[cur, 2]
+
+    def to_numpy(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        return tuple(q.cpu().numpy() for q in self.state())
+
+    def max_speed(self) -> float:
+        """max sqrt(u^2+v^2) over the full current state (numpy.py:553-554)."""
+        out = ctypes.c_double()
+        check(self.lib.swb_max_speed(self._ctx, ctypes.byref(out), _stream(self.device)))
+        return out.value
+
+    def read_log(self, count: int) -> Tuple[np.ndarray, np.ndarray]:
+        dts, ts = np.empty(count), np.empty(count)
+        check(self.lib.swb_read_log(self._ctx, dts.ctypes.data_as(_lib._dp), ts.ctypes.data_as(_lib._dp),
+                                    int(count), _stream(self.device)))
+        return dts, ts
+
+    def laplacian(self, q) -> torch.Tensor:
+        """(D_x D_x + D_y D_y) q at the interior cells (numpy.py:359-382), as (M+1, N-2)."""
+        shape = (self.M + 3, self.N)
+        qd = self._to_device(q, shape)
+        out = torch.zeros(shape, dtype=torch.float64, device=self.device)
+        check(self.lib.swb_laplacian(self._ctx, ctypes.c_void_p(qd.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                     _stream(self.device)))
+        return out[1:-1, 1:-1]
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.swb_launch_count(self._ctx))
+
+
+# --------------------------------------------------------------------------------------
+# operator-level drop-ins (numpy.py:12-63, 66-133, 136-356, 359-406)
+# --------------------------------------------------------------------------------------
+class DiffusionCoefficients:
+    """Diffusion weight container with the reference's attributes Ax..Cy (numpy.py:12-63).
+
+    The kernels need only the latitude vectors (``Ay1d`` ...) -- the longitude set is
+    rebuilt in registers from ``x = ac_j * phi_i`` -- so the 2-D arrays are materialised
+    on first access only.
+    """
+
+    def __init__(self, cart_grid: CartesianGrid):
+        self.cart_grid = cart_grid
+        self.Ay1d, self.By1d, self.Cy1d = diffusion_weights_lat(cart_grid)
+        self._x = None
+
+    def _xset(self):
+        if self._x is None:
+            dx = self.cart_grid.dx
+            d0, d1 = dx[:-1, 1:-1], dx[1:, 1:-1]
+            wrap = lambda w: np.concatenate((w[-2:-1, :], w, w[1:2, :]), axis=0)  # noqa: E731  numpy.py:35
+            self._x = (wrap((d1 - d0) / (d1 * d0)), wrap(d0 / (d1 * (d1 + d0))), wrap(-d1 / (d0 * (d1 + d0))))
+        return self._x
+
+    Ax = property(lambda self: self._xset()[0])
+    Bx = property(lambda self: self._xset()[1])
+    Cx = property(lambda self: self._xset()[2])
+
+    def _yview(self, v):
+        return np.broadcast_to(v[None, :], (self.cart_grid.M + 1, self.cart_grid.N))
+
+    Ay = property(lambda self: self._yview(self.Ay1d))
+    By = property(lambda self: self._yview(self.By1d))
+    Cy = property(lambda self: self._yview(self.Cy1d))
+
+
+def _grids_of(cart_grid: CartesianGrid) -> LatLonGrid:
+    return LatLonGrid(cart_grid.M, cart_grid.N)
+
+
+def _match(result: torch.Tensor, like):
+    """Return device results in the kind of array the caller passed in."""
+    if isinstance(like, torch.Tensor):
+        return result.clone() if like.is_cuda else result.cpu()
+    return result.cpu().numpy()
+
+
+def lax_wendroff_update(latlon_grid: LatLonGrid, cart_grid: CartesianGrid, dt: FloatT, f: FloatArray2D,
+                        hs: FloatArray2D, h: FloatArray2D, u: FloatArray2D, v: FloatArray2D, *,
+                        mode: Optional[str] = "strict", device=None):
+    """One Lax-Wendroff update (numpy.py:136-356) on the GPU.
+
+    Takes (M+3, N) arrays (numpy or torch), returns ``hnew, unew, vnew`` of shape
+    (M+1, N-2) in the same kind of array; inputs are not modified
+    (reference tests/numpy_test.py:33-80).  Defaults to the bit-exact arithmetic mode.
+    """
+    st = Stepper(latlon_grid, cart_grid, h, u, v, f, hs, courant=0.0, final_time=0.0, use_diffusion=False,
+                 mode=mode, device=device)
+    try:
+        st.step_fixed_dt(dt)
+        out = tuple(_match(st.buf[1, k, 1:-1, 1:-1], h) for k in range(3))
+        torch.cuda.synchronize(st.device)
+    finally:
+        st.close()
+    return out
+
+
+def compute_diffusion(quantity: FloatArray2D, diffusion: DiffusionCoefficients, *, device=None):
+    """Laplacian of a (M+3, N) quantity at the interior cells, shape (M+1, N-2)
+    (numpy.py:359-382: periodic extension in longitude, duplicated rows in latitude)."""
+    cart = diffusion.cart_grid
+    ll = _grids_of(cart)
+    zeros = np.zeros((cart.M + 3, cart.N))
+    st = Stepper(ll, cart, zeros, zeros, zeros, np.zeros(cart.N), None, courant=0.0, final_time=0.0,
+                 use_diffusion=True, mode="strict", device=device)
+    try:
+        out = _match(st.laplacian(quantity), quantity)
+        torch.cuda.synchronize(st.device)
+    finally:
+        st.close()
+    return out
+
+
+def compute_laplacian(coeff: DiffusionCoefficients, q: FloatArray2D, *, device=None):
+    """Laplacian of an already-extended (M+5, N+2) array (numpy.py:66-133).
+
+    The kernel applies the reference's extension (numpy.py:376-381) itself, so the
+    argument must be such an extension; anything else is rejected rather than silently
+    computed differently.
+    """
+    qa = q.detach().cpu().numpy() if isinstance(q, torch.Tensor) else np.asarray(q)
+    core = qa[1:-1, 1:-1]
+    ext = np.concatenate((core[-4:-3, :], core, core[3:4, :]), axis=0)
+    ext = np.concatenate((ext[:, 0:1], ext, ext[:, -1:]), axis=1)
+    if ext.shape != qa.shape or not np.array_equal(ext, qa, equal_nan=True):
+        raise NotImplementedError("compute_laplacian expects the extension built by compute_diffusion")
+    return compute_diffusion(q[1:-1, 1:-1], coeff, device=device)
+
+
+def _apply_bcs(q, qnew):
+    """Boundary conditions (numpy.py:385-406): periodic wrap in longitude, zero-gradient
+    copy at the pole rows; ``q`` is modified in place and returned.  Inside ``solve`` this
+    is fused into the step kernel; this stand-alone form serves callers of the operator API
+    (numpy arrays or torch tensors on any device)."""
+    cat = torch.cat if isinstance(q, torch.Tensor) else np.concatenate
+    q[:, 1:-1] = cat((qnew[-2:-1, :], qnew, qnew[1:2, :]), 0)
+    q[:, 0] = q[:, 1]
+    q[:, -1] = q[:, -2]
+    return q
+
+
+# --------------------------------------------------------------------------------------
+# the driver
+# --------------------------------------------------------------------------------------
+_STATUS_BYTES = ctypes.sizeof(SwbStatus)
+
+
+def _read_status(pinned: torch.Tensor) -> SwbStatus:
+    return SwbStatus.from_buffer_copy(pinned.numpy().tobytes()[:_STATUS_BYTES])
+
+
+def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, courant: float,
+          use_diffusion: bool = True, save_data: Optional[Dict[str, Any]] = None, print_interval: int = -1, *,
+          mode: Optional[str] = None, device=None, batch_steps: int = 512
+          ) -> Tuple[FloatArray2D, FloatArray2D, FloatArray2D]:
+    """Drop-in for ``sw_solver.numpy.solve`` (numpy.py:409-575) on a B200.
+
+    Same positional parameters, same ``save_data`` contract (keys h, u, v, t, phi, theta
+    when ``save_data["interval"] > 0``; first snapshot is the initial state), same error
+    order (grid ValueError, negative ``sim_days`` ValueError, non-``ICType`` TypeError).
+    Returns the full ghosted (M+3, N) float64 arrays h, u, v as numpy arrays.
+
+    Backend-only keywords: ``mode`` ("fast" | "strict"), ``device``, ``batch_steps`` (how
+    many steps are enqueued between two non-blocking termination checks).
+    """
+    save_data = save_data if save_data is not None else {}
+
+    latlon_grid = LatLonGrid(num_lon_pts, num_lat_pts)
+    cart_grid = CartesianGrid(latlon_grid)
+
+    if sim_days < 0.0:
+        raise ValueError(f"Final time {sim_days} must be non-negative.")
+    final_time = 24 * 3600 * sim_days
+
+    if not isinstance(ic_type, ICType):
+        raise TypeError(
+            f"Invalid problem IC: {ic_type}. See code documentation for implemented initial conditions."
+        )
+    dev = _require_cuda(device)
+
+    h, u, v, f = get_initial_conditions(ic_type, latlon_grid)
+    if ic_type == ICType.RossbyHaurwitzWave:
+        f = coriolis_latitude(latlon_grid)
+
+    save_interval = int(save_data.get("interval", 0))
+    st = Stepper(latlon_grid, cart_grid, h, u, v, f, None, courant=courant, final_time=final_time,
+                 use_diffusion=use_diffusion, mode=mode, device=dev)
+    try:
+        st.cfl_init()
+        snaps: List[torch.Tensor] = []   # pinned (3, M+1, N) host copies, one per save point
+        snap_status: List[torch.Tensor] = []
+        if save_interval > 0:
+            first = torch.empty((3, latlon_grid.M + 1, latlon_grid.N), dtype=torch.float64).pin_memory()
+            first.copy_(st.buf[0, :, 1:-1, :], non_blocking=True)
+            snaps.append(first)
+
+        def stops():
+            """Step counts at which the host must do something, in increasing order."""
+            n = 0
+            while True:
+                nxt = n + max(1, int(batch_steps))
+                for iv in (save_interval, print_interval):
+                    if iv > 0:
+                        nxt = min(nxt, (n // iv + 1) * iv)
+                yield nxt
+                n = nxt
+
+        ring: List[Tuple[int, torch.Tensor, torch.cuda.Event]] = []
+        enq = 0
+        finished: Optional[SwbStatus] = None
+        for target in stops():
+            st.enqueue(target - enq)
+            enq = target
+            if print_interval > 0 and enq % print_interval == 0:
+                s = st.status()
+                if s.steps == enq:  # the loop was still running at this step
+                    print(
+                        f"Time = {s.time / 3600.0:6.2f} hours (max {int(final_time / 3600.0)}); "
+                        f"max(|u|) = {st.max_speed():16.16f}"
+                    )
+            if save_interval > 0 and enq % save_interval == 0:
+                # valid only if all `enq` steps ran, in which case the parity is known
+                snap = torch.empty((3, latlon_grid.M + 1, latlon_grid.N), dtype=torch.float64).pin_memory()
+                snap.copy_(st.buf[enq & 1, :, 1:-1, :], non_blocking=True)
+                snaps.append(snap)
+                pin = torch.zeros(_STATUS_BYTES, dtype=torch.uint8).pin_memory()
+                st.status_async(pin)
+                snap_status.append(pin)
+            pin = torch.zeros(_STATUS_BYTES, dtype=torch.uint8).pin_memory()
+            st.status_async(pin)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            ring.append((enq, pin, ev))
+            # look at the batch before the one just enqueued: keeps one batch in flight
+            if len(ring) >= 2:
+                _, pin0, ev0 = ring.pop(0)
+                ev0.synchronize()
+                s0 = _read_status(pin0)
+                if s0.done:
+                    finished = s0
+                    break
+        final = st.status()
+        if final.error:
+            raise SwbError(final.error, "device-side error flag raised during the time loop")
+        hh, uu, vv = st.to_numpy()
+
+        if save_interval > 0:
+            torch.cuda.synchronize(dev)
+            keep = [snaps[0]]
+            tsave = [0.0]
+            for k, pin in enumerate(snap_status):
+                s = _read_status(pin)
+                if s.steps == (k + 1) * save_interval:  # numpy.py:559: taken while the loop ran
+                    keep.append(snaps[k + 1])
+                    tsave.append(s.time)
+            for idx, name in enumerate(("h", "u", "v")):
+                save_data[name] = np.stack([s[idx].numpy() for s in keep], axis=2)
+            save_data["t"] = np.asarray(tsave)
+            save_data["phi"] = latlon_grid.phi
+            save_data["theta"] = latlon_grid.theta
+    finally:
+        st.close()
+    return hh, uu, vv

@@ -1,0 +1,285 @@
+"""GPU parity tests: the CUDA path (through the C ABI in include/swb200.h, bound by
+sw_solver_b200) against
+
+* the reference-generated golden fixtures in tests/golden (bit-for-bit in STRICT mode),
+* the reference's own known-answer files data/swes-numpy-ref-10-*.npy,
+* the CPU oracle (oracle/) on seeded inputs at sizes it finishes in seconds.
+
+Tolerances: STRICT is bit-exact (integer comparison of the float64 patterns); FAST must
+stay within 1e-12 normwise (max|diff| / max|ref| per field) -- BASELINE.json's north-star
+tolerance -- and in practice stays below 1e-13 on these runs, which the tests also pin.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import sw_solver_b200 as swb
+from sw_solver_b200.grid import CartesianGrid, LatLonGrid
+from sw_solver_b200.ic import ICType, get_initial_conditions
+from sw_solver_b200.solver import DiffusionCoefficients, Stepper, compute_diffusion, lax_wendroff_update, solve
+from oracle import sw_oracle as so
+from conftest import load_golden, normwise
+
+pytestmark = pytest.mark.gpu
+
+TOL_FAST = 1e-12  # north-star tolerance (fp64)
+
+
+def _bits(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+def _worst(a, b):
+    with np.errstate(all="ignore"):
+        return np.nanmax(np.abs(np.asarray(a) - np.asarray(b)))
+
+
+def _one_step_gpu(M, N, dt, f, hs, h, u, v, diff, mode):
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    st = Stepper(ll, cg, h, u, v, f, hs, courant=0.5, final_time=1.0, use_diffusion=diff, mode=mode)
+    st.step_fixed_dt(dt)
+    torch.cuda.synchronize()
+    full = [st.buf[1, k].cpu().numpy() for k in range(3)]
+    st.close()
+    return full
+
+
+def _case_inputs(g, tag):
+    size, kind, d = tag.split("/")
+    M, N = (int(x) for x in size.split("x"))
+    ll = LatLonGrid(M, N)
+    if kind.startswith("ic"):
+        h, u, v, f = get_initial_conditions(ICType(int(kind[2:])), ll)
+        hs, dt = np.zeros(ll.shape), 1.25
+    else:
+        h, u, v, f, hs = (g[f"{tag}/{k}"] for k in ("h", "u", "v", "f", "hs"))
+        dt = 40.0
+    return M, N, dt, f, hs, h, u, v, d == "d1"
+
+
+def test_single_step_strict_is_bit_exact(golden_single_step):
+    """Every single-step fixture (reference-generated): both ICs, +-diffusion, rough random
+    states, negative depths, non-flat topography, 2-D Coriolis."""
+    g = golden_single_step
+    for tag in map(str, g["cases"]):
+        M, N, dt, f, hs, h, u, v, diff = _case_inputs(g, tag)
+        before = [np.array(x, copy=True) for x in (h, u, v, f, hs)]
+        full = _one_step_gpu(M, N, dt, f, hs, h, u, v, diff, "strict")
+        for name, arr in zip(("hnew", "unew", "vnew"), full):
+            assert _bits(arr[1:-1, 1:-1], g[f"{tag}/{name}"]), (tag, name, _worst(arr[1:-1, 1:-1], g[f"{tag}/{name}"]))
+            # boundary conditions (numpy.py:402-404) written by the same kernel
+            exp = so.apply_bcs(np.zeros((M + 3, N + N % 2)), g[f"{tag}/{name}"])
+            assert _bits(arr, exp), (tag, name, "bcs")
+        for x0, x1 in zip(before, (h, u, v, f, hs)):  # purity (reference tests/numpy_test.py:33-80)
+            assert _bits(x0, x1)
+
+
+def test_single_step_fast_within_tolerance(golden_single_step):
+    g = golden_single_step
+    worst = 0.0
+    for tag in map(str, g["cases"]):
+        if "randneg" in tag:
+            continue  # inf/nan patterns of non-physical negative depths: strict-only contract
+        M, N, dt, f, hs, h, u, v, diff = _case_inputs(g, tag)
+        full = _one_step_gpu(M, N, dt, f, hs, h, u, v, diff, "fast")
+        for name, arr in zip(("hnew", "unew", "vnew"), full):
+            err = normwise(arr[1:-1, 1:-1], g[f"{tag}/{name}"])
+            worst = max(worst, err)
+            assert err < 1e-13, (tag, name, err)
+    print("fast single-step worst normwise error", worst)
+
+
+def test_operator_api_matches_reference_shapes_and_values(golden_single_step):
+    """lax_wendroff_update / compute_diffusion called as the reference's tests call them
+    (tests/numpy_test.py:53-77, tests/gt4py_test.py:52-54)."""
+    g = golden_single_step
+    for M, N in ((4, 4), (5, 6)):
+        for ic in ICType:
+            ll = LatLonGrid(M, N)
+            cg = CartesianGrid(ll)
+            h, u, v, f = get_initial_conditions(ic, ll)
+            hs = np.zeros(ll.shape, float)
+            dt = 1.25
+            hn, un, vn = lax_wendroff_update(ll, cg, dt, f, hs, h, u, v)
+            tag = f"{M}x{N}/ic{int(ic)}/d0"
+            assert _bits(hn, g[f"{tag}/hnew"]) and _bits(un, g[f"{tag}/unew"]) and _bits(vn, g[f"{tag}/vnew"])
+            dc = DiffusionCoefficients(cg)
+            hn = hn + dt * swb.utils.EARTH_CONSTANTS.nu * compute_diffusion(h, dc)
+            un = un + dt * swb.utils.EARTH_CONSTANTS.nu * compute_diffusion(u, dc)
+            vn = vn + dt * swb.utils.EARTH_CONSTANTS.nu * compute_diffusion(v, dc)
+            tag = f"{M}x{N}/ic{int(ic)}/d1"
+            assert _bits(hn, g[f"{tag}/hnew"]) and _bits(un, g[f"{tag}/unew"]) and _bits(vn, g[f"{tag}/vnew"])
+    # torch tensors in -> torch tensors out
+    ht = torch.from_numpy(h).cuda()
+    out = lax_wendroff_update(ll, cg, dt, f, hs, ht, torch.from_numpy(u).cuda(), torch.from_numpy(v).cuda())
+    assert all(isinstance(o, torch.Tensor) and o.is_cuda and o.shape == (M + 1, N - 2) for o in out)
+
+
+def test_multi_step_driver_strict_is_bit_exact(golden_multi_step):
+    """Full `solve` runs saved every step: t, phi, theta, h, u, v and the returned state."""
+    g = golden_multi_step
+    for k, (M, N, ic, T, cfl, diff) in enumerate(g["runs"]):
+        sd = {"interval": 1}
+        h, u, v = solve(int(M), int(N), ICType(int(ic)), float(T), float(cfl), bool(diff), save_data=sd, mode="strict")
+        for name in ("t", "phi", "theta", "h", "u", "v"):
+            assert _bits(sd[name], g[f"run{k}/{name}"]), (k, name, _worst(sd[name], g[f"run{k}/{name}"]))
+        for name, arr in zip(("h_final", "u_final", "v_final"), (h, u, v)):
+            assert _bits(arr, g[f"run{k}/{name}"]), (k, name)
+
+
+def test_multi_step_driver_fast(golden_multi_step):
+    g = golden_multi_step
+    for k, (M, N, ic, T, cfl, diff) in enumerate(g["runs"]):
+        sd = {"interval": 1}
+        solve(int(M), int(N), ICType(int(ic)), float(T), float(cfl), bool(diff), save_data=sd, mode="fast")
+        assert sd["t"].shape == g[f"run{k}/t"].shape
+        assert normwise(sd["t"], g[f"run{k}/t"]) < 1e-13
+        for name in ("h", "u", "v"):
+            assert normwise(sd[name], g[f"run{k}/{name}"]) < TOL_FAST, (k, name)
+
+
+@pytest.mark.parametrize("mode", ["strict", "fast"])
+def test_reference_known_answer_files(golden_ref10, mode):
+    """The reference's regression test (tests/numpy_test.py:9-30) run through our `solve`."""
+    sd = {"interval": 392}
+    solve(10, 10, ICType.RossbyHaurwitzWave, 2, 0.5, True, save_data=sd, mode=mode)
+    for name in ("h", "u", "v", "t", "phi", "theta"):
+        assert sd[name].shape == golden_ref10[name].shape, name
+        assert np.allclose(sd[name], golden_ref10[name]), name  # the reference's own criterion
+    for name in ("h", "u", "v"):
+        assert normwise(sd[name], golden_ref10[name]) < TOL_FAST, name
+    live = load_golden("ref_live_10.npz")  # the reference re-run under today's numpy
+    if mode == "strict":
+        for name in ("h", "u", "v", "t"):
+            assert _bits(sd[name], live[name]), name
+    else:
+        for name in ("h", "u", "v", "t"):
+            assert normwise(sd[name], live[name]) < TOL_FAST, name
+
+
+@pytest.mark.parametrize("M,N,ic,diff,nsteps", [
+    (360, 180, 0, False, 100),   # BASELINE configs[1]
+    (360, 180, 1, True, 40),
+    (1440, 720, 0, True, 20),    # BASELINE configs[2]
+    (333, 97, 0, False, 25),     # ragged: odd N -> 98, widths not multiples of the 30-lane strips
+    (2, 4, 0, True, 5),          # smallest legal grid
+])
+def test_against_oracle_multi_step(M, N, ic, diff, nsteps):
+    og = so.OracleGrid(M, N)
+    h, u, v, f = so.initial_conditions(ic, og)
+    h, u, v = (np.ascontiguousarray(x) for x in (h, u, v))
+    stp = so.Stepper(og, f, None, diff)
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    final_time = 1.0e9
+    gpu = {m: Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=final_time, use_diffusion=diff, mode=m,
+                      log_capacity=nsteps) for m in ("strict", "fast")}
+    t, dts = 0.0, []
+    for _ in range(nsteps):
+        dt, t = stp.step(h, u, v, 0.5, t, final_time)
+        dts.append(dt)
+    for m, st in gpu.items():
+        st.enqueue(nsteps)
+        s = st.status()
+        assert s.steps == nsteps and not s.done
+        hg, ug, vg = st.to_numpy()
+        gdts, gts = st.read_log(nsteps)
+        if m == "strict":
+            assert _bits(gdts, np.asarray(dts)) and s.time == t
+            assert _bits(hg, h) and _bits(ug, u) and _bits(vg, v), (_worst(hg, h), _worst(ug, u), _worst(vg, v))
+        else:
+            assert normwise(gdts, np.asarray(dts)) < 1e-13
+            for name, a, b in (("h", hg, h), ("u", ug, u), ("v", vg, v)):
+                assert normwise(a, b) < TOL_FAST, (name, normwise(a, b))
+        st.close()
+
+
+def test_seeded_rough_state_multi_step():
+    """Seeded non-smooth fields: h = 8000 + 500 U(-1,1), u, v = 50 N(0,1)."""
+    M, N = 96, 64
+    rng = np.random.default_rng(0)
+    og = so.OracleGrid(M, N)
+    shape = og.shape
+    h = 8000.0 + 500.0 * rng.uniform(-1, 1, shape)
+    u = 50.0 * rng.standard_normal(shape)
+    v = 50.0 * rng.standard_normal(shape)
+    f = 1e-4 * rng.uniform(-1, 1, shape)  # genuinely 2-D Coriolis
+    ll, cg = LatLonGrid(M, N), None
+    cg = CartesianGrid(ll)
+    for diff in (False, True):
+        hh, uu, vv = h.copy(), u.copy(), v.copy()
+        stp = so.Stepper(og, f, None, diff)
+        st = Stepper(ll, cg, h, u, v, f, None, courant=0.3, final_time=1e9, use_diffusion=diff, mode="strict")
+        t = 0.0
+        for _ in range(6):
+            _, t = stp.step(hh, uu, vv, 0.3, t, 1e9)
+        st.enqueue(6)
+        hg, ug, vg = st.to_numpy()
+        assert _bits(hg, hh) and _bits(ug, uu) and _bits(vg, vv)
+        st.close()
+
+
+def test_driver_semantics_match_reference():
+    with pytest.raises(ValueError):
+        solve(1, 10, ICType.RossbyHaurwitzWave, 1, 0.5)
+    with pytest.raises(ValueError):
+        solve(10, 10, ICType.RossbyHaurwitzWave, -1.0, 0.5)
+    with pytest.raises(TypeError):
+        solve(10, 10, 0, 1, 0.5)
+    # sim_days == 0 returns the untouched initial state (numpy.py:496)
+    h, u, v = solve(6, 6, ICType.RossbyHaurwitzWave, 0.0, 0.5)
+    h0, u0, v0, _ = get_initial_conditions(ICType.RossbyHaurwitzWave, LatLonGrid(6, 6))
+    assert _bits(h, h0) and _bits(u, u0) and _bits(v, v0)
+    # save_data without a positive interval stays untouched (numpy.py:486)
+    sd = {}
+    solve(6, 6, ICType.RossbyHaurwitzWave, 0.01, 0.5, save_data=sd)
+    assert sd == {}
+    # snapshots only at multiples of the interval; the final state need not be saved
+    sd, ref = {"interval": 7}, {"interval": 7}
+    solve(12, 10, ICType.ZonalGeostrophicFlow, 0.05, 0.5, False, save_data=sd, mode="strict")
+    so.solve(12, 10, 1, 0.05, 0.5, False, save_data=ref)
+    assert _bits(sd["t"], ref["t"]) and _bits(sd["h"], ref["h"]) and _bits(sd["v"], ref["v"])
+
+
+def test_print_interval_output(capsys):
+    solve(10, 10, ICType.RossbyHaurwitzWave, 0.02, 0.5, True, print_interval=3, mode="strict")
+    ours = capsys.readouterr().out
+    so.solve(10, 10, 0, 0.02, 0.5, True, print_interval=3)
+    theirs = capsys.readouterr().out
+    assert ours == theirs and ours.count("max(|u|)") >= 1
+
+
+def test_steps_past_final_time_are_noops():
+    ll = LatLonGrid(10, 10)
+    cg = CartesianGrid(ll)
+    h, u, v, f = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+    st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=3600.0, use_diffusion=True, mode="strict")
+    st.enqueue(500)
+    s1 = st.status()
+    a = [q.copy() for q in st.to_numpy()]
+    st.enqueue(7)
+    s2 = st.status()
+    b = st.to_numpy()
+    assert s1.done and s2.done and s1.steps == s2.steps and s1.time == s2.time == 3600.0
+    assert all(_bits(x, y) for x, y in zip(a, b))
+    ref = {}
+    hr, ur, vr = so.solve(10, 10, 0, 3600.0 / 86400.0, 0.5, True, save_data=ref)
+    assert s1.steps == len(ref["_dts"]) and _bits(a[0], hr) and _bits(a[1], ur) and _bits(a[2], vr)
+    st.close()
+
+
+def test_nan_state_stops_like_the_reference():
+    """numpy's max/minimum propagate NaN: dt = nan, time = nan, loop exits (numpy.py:496-532)."""
+    ll = LatLonGrid(8, 8)
+    cg = CartesianGrid(ll)
+    h, u, v, f = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+    u = u.copy()
+    u[4, 3] = np.nan
+    st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=1e6, use_diffusion=False, mode="strict")
+    st.enqueue(5)
+    s = st.status()
+    assert s.steps == 1 and s.done and np.isnan(s.time)
+    st.close()
