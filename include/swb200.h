@@ -13,7 +13,10 @@
  *  - no C++ types or exceptions cross this boundary; all pointers are plain;
  *  - state arrays are DEVICE pointers in the reference's own layout: C-contiguous
  *    [i = longitude 0..M+2][j = latitude], latitude contiguous, `pitch` elements between
- *    consecutive longitudes (pitch == n_local for a dense array);
+ *    consecutive longitudes and `lead_pad` unused elements before local latitude 0
+ *    (pitch == n_local, lead_pad == 0 for the reference's dense array; the TMA kernel
+ *    needs an even pitch, 16-byte aligned bases and an EVEN first updated column, i.e.
+ *    lead_pad == 1 on one GPU -- bulk tensor boxes must start on 16-byte boundaries);
  *  - table pointers passed to swb_set_tables are HOST pointers (copied);
  *  - `stream` is a cudaStream_t passed as void*; calls only enqueue work unless stated;
  *  - the caller (PyTorch on the Python side) owns every state buffer and keeps it alive
@@ -68,7 +71,7 @@ typedef struct swb_config {
     int32_t log_capacity; /* steps of (dt, time) history kept on the device (0 = none)*/
     int32_t rank;         /* latitude-band index (0 on one GPU)                       */
     int32_t world;        /* number of latitude bands / GPUs (1 on one GPU)           */
-    int32_t reserved;
+    int32_t lead_pad;     /* padding columns before local row 0 in every state array  */
     double courant;       /* CFL number (numpy.py:413)                                */
     double final_time;    /* seconds (numpy.py:470-472)                               */
     double dxmin, dymin;  /* CartesianGrid.dxmin / dymin (grid.py:46-47)              */

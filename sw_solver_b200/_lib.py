@@ -28,7 +28,7 @@ class SwbError(RuntimeError):
 class SwbConfig(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "struct_bytes", "M", "N", "j_begin", "n_local", "j_first", "j_last", "pitch", "dtype", "mode",
-        "use_diffusion", "f_is_2d", "has_hs", "device", "log_capacity", "rank", "world", "reserved",
+        "use_diffusion", "f_is_2d", "has_hs", "device", "log_capacity", "rank", "world", "lead_pad",
     )] + [(n, c_double) for n in (
         "courant", "final_time", "dxmin", "dymin", "g", "a", "nu", "dphi",
     )]

@@ -7,6 +7,7 @@
 #include "swb_kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -53,6 +54,9 @@ struct swb_ctx {
     int launch = 0;                  // index of the next step launch
     int64_t launches = 0;
     int sm_count = 148;
+    bool use_tma = false;
+    int tma_variant = 0;  // index into kTmaVariants
+    TmaMaps maps;
 };
 
 namespace {
@@ -84,15 +88,82 @@ void pick_d(const Params &p, dim3 g, cudaStream_t st, bool diff, bool f2d, bool 
     else pick_f<S, false>(p, g, st, f2d, hs);
 }
 
+// TMA pipeline shapes built into the library: {rows per box R, stages S}
+struct TmaVariant { int R, S; };
+constexpr TmaVariant kTmaVariants[] = {{2, 4}, {4, 3}, {4, 4}, {2, 6}, {8, 3}};
+constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
+
+template <bool STRICT, int R, int S>
+cudaError_t launch_tma_rs(const Params &p, const TmaMaps &m, dim3 grid, cudaStream_t st)
+{
+    using LY = TmaLayout<R, S>;
+    static bool configured = false;  // per instantiation; contexts of one process share devices' function attributes
+    auto fn = step_kernel_tma<STRICT, R, S>;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::kBlockBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    fn<<<grid, kWarpsPerBlock * 32, LY::kBlockBytes, st>>>(p, m);
+    return cudaSuccess;
+}
+
+template <bool STRICT>
+cudaError_t launch_tma(int variant, const Params &p, const TmaMaps &m, dim3 grid, cudaStream_t st)
+{
+    switch (variant) {
+        case 0: return launch_tma_rs<STRICT, 2, 4>(p, m, grid, st);
+        case 1: return launch_tma_rs<STRICT, 4, 3>(p, m, grid, st);
+        case 2: return launch_tma_rs<STRICT, 4, 4>(p, m, grid, st);
+        case 3: return launch_tma_rs<STRICT, 2, 6>(p, m, grid, st);
+        default: return launch_tma_rs<STRICT, 8, 3>(p, m, grid, st);
+    }
+}
+
 int launch_one(swb_ctx *c, cudaStream_t st)
 {
     const swb_config &cfg = c->cfg;
     const Params &p = c->prm;
     dim3 grid((unsigned)((p.nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)((p.M + 1 + p.chunk - 1) / p.chunk));
-    if (cfg.mode == SWB_STRICT) pick_d<true>(p, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs);
-    else pick_d<false>(p, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs);
+    if (c->use_tma) {
+        CK(cfg.mode == SWB_STRICT ? launch_tma<true>(c->tma_variant, p, c->maps, grid, st)
+                                  : launch_tma<false>(c->tma_variant, p, c->maps, grid, st));
+    } else if (cfg.mode == SWB_STRICT) {
+        pick_d<true>(p, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs);
+    } else {
+        pick_d<false>(p, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs);
+    }
     c->launches++;
     CK(cudaGetLastError());
+    return 0;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D fp64 tensor map over a (rows x cols) window of a state array with `pitch` elements per row
+int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_cols, uint32_t box_rows)
+{
+    static encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn) return fail(SWB_E_NODEVICE, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (encode_tiled_fn)fn;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {pitch * sizeof(double)};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d (base %p, pitch %llu)", (int)r, base, (unsigned long long)pitch);
+        return fail(SWB_E_INVALID, buf);
+    }
     return 0;
 }
 
@@ -121,7 +192,8 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     if (cfg->M < 2 || cfg->N < 2 || (cfg->N & 1)) return fail(SWB_E_INVALID, "swb_create: need M >= 2 and an even N >= 2");
     if (cfg->dtype != SWB_F64) return fail(SWB_E_INVALID, "swb_create: only SWB_F64 is built in this version");
     if (cfg->mode != SWB_STRICT && cfg->mode != SWB_FAST) return fail(SWB_E_INVALID, "swb_create: bad mode");
-    if (cfg->n_local < 3 || cfg->pitch < cfg->n_local) return fail(SWB_E_INVALID, "swb_create: bad n_local / pitch");
+    if (cfg->lead_pad < 0 || cfg->lead_pad > 8) return fail(SWB_E_INVALID, "swb_create: bad lead_pad");
+    if (cfg->n_local < 3 || cfg->pitch < cfg->lead_pad + cfg->n_local) return fail(SWB_E_INVALID, "swb_create: bad n_local / pitch");
     if (cfg->j_begin < 0 || cfg->j_begin + cfg->n_local > cfg->N) return fail(SWB_E_INVALID, "swb_create: band outside the grid");
     if (cfg->j_first < 1 || cfg->j_last > cfg->N - 2 || cfg->j_first > cfg->j_last) return fail(SWB_E_INVALID, "swb_create: bad j_first / j_last");
     if (cfg->j_first - 1 < cfg->j_begin || cfg->j_last + 1 >= cfg->j_begin + cfg->n_local)
@@ -141,8 +213,9 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     if (!c) return fail(SWB_E_INVALID, "swb_create: out of host memory");
     c->cfg = *cfg;
     c->sm_count = prop.multiProcessorCount;
-    const size_t nloc = (size_t)cfg->n_local;
-    CK(cudaMalloc(&c->d_phi, sizeof(double) * (size_t)(cfg->M + 3)));
+    const size_t nloc = (size_t)(cfg->lead_pad + cfg->n_local);
+    CK(cudaMalloc(&c->d_phi, sizeof(double) * (size_t)(cfg->M + 3 + 16)));  // padded: the last tile of a march may peek past M+2
+    CK(cudaMemset(c->d_phi, 0, sizeof(double) * (size_t)(cfg->M + 3 + 16)));
     CK(cudaMalloc(&c->d_tab, sizeof(double) * (size_t)T_COUNT * nloc));
     CK(cudaMemset(c->d_tab, 0, sizeof(double) * (size_t)T_COUNT * nloc));
     CK(cudaMalloc(&c->d_ctrl, sizeof(Ctrl) * 3));
@@ -163,14 +236,20 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     p.log = c->d_log;
     p.log_cap = cfg->log_capacity;
     p.M = cfg->M;
-    p.nloc = cfg->n_local;
+    p.ncols = cfg->lead_pad + cfg->n_local;
+    p.jl_lo = cfg->lead_pad;
+    p.jl_hi = p.ncols - 1;
     p.pitch = cfg->pitch;
-    p.jl_first = cfg->j_first - cfg->j_begin;
-    p.jl_last = cfg->j_last - cfg->j_begin;
+    p.jl_first = cfg->j_first - cfg->j_begin + cfg->lead_pad;
+    p.jl_last = cfg->j_last - cfg->j_begin + cfg->lead_pad;
     p.pole_s = (cfg->j_begin == 0);
     p.pole_n = (cfg->j_begin + cfg->n_local == cfg->N);
     p.nstrips = (p.jl_last - p.jl_first + 1 + kCellsPerWarp - 1) / kCellsPerWarp;
     p.chunk = pick_chunk(p.M, p.nstrips, c->sm_count);
+    if (const char *ch = getenv("SWB_CHUNK")) {  // tuning knob: a power of two >= 8
+        const int v = atoi(ch);
+        if (v >= 8 && (v & (v - 1)) == 0) p.chunk = v;
+    }
     p.courant = cfg->courant;
     p.final_time = cfg->final_time;
     p.dxmin = cfg->dxmin;
@@ -205,11 +284,14 @@ int swb_set_tables(swb_ctx *c, const swb_tables *t)
     if (!c->cfg.f_is_2d && !t->f_lat) return fail(SWB_E_INVALID, "swb_set_tables: f_lat required when f_is_2d == 0");
     if (c->cfg.use_diffusion && (!t->Ay || !t->By || !t->Cy)) return fail(SWB_E_INVALID, "swb_set_tables: Ay/By/Cy required with diffusion");
     CK(cudaSetDevice(c->cfg.device));
-    const size_t nloc = (size_t)c->cfg.n_local;
-    std::vector<double> host((size_t)T_COUNT * nloc, 0.0);
+    const size_t nloc = (size_t)c->cfg.n_local, pad = (size_t)c->cfg.lead_pad, ncols = nloc + pad;
+    std::vector<double> host((size_t)T_COUNT * ncols, 0.0);
     const double *src[T_COUNT] = {t->c, t->tg, t->ac, t->f_lat, t->tgMidy, t->cMidy, t->dy, t->dy1, t->dyc, t->dy1c, t->Ay, t->By, t->Cy};
     for (int k = 0; k < T_COUNT; ++k)
-        if (src[k]) memcpy(&host[(size_t)k * nloc], src[k], sizeof(double) * nloc);
+        if (src[k]) {
+            for (size_t j = 0; j < pad; ++j) host[(size_t)k * ncols + j] = src[k][0];  // padding columns replay row 0
+            memcpy(&host[(size_t)k * ncols + pad], src[k], sizeof(double) * nloc);
+        }
     CK(cudaMemcpy(c->d_tab, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_phi, t->phi, sizeof(double) * (size_t)(c->cfg.M + 3), cudaMemcpyHostToDevice));
     c->tables_set = true;
@@ -228,6 +310,31 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     p.hs = (const double *)hs;
     c->state_bound = true;
     c->cfl_ready = false;
+
+    // The TMA pipeline serves the plain variant (flat topography, latitude-only Coriolis,
+    // no diffusion); SWB_KERNEL=ldg forces the direct-load kernel, SWB_TMA_VARIANT picks a
+    // pipeline shape.
+    const char *force = getenv("SWB_KERNEL");
+    const bool plain = !c->cfg.use_diffusion && !c->cfg.f_is_2d && !c->cfg.has_hs;
+    bool aligned = (p.pitch % 2 == 0) && (p.jl_first % 2 == 0) && (p.jl_first >= 2);  // TMA boxes start on 16-byte columns
+    for (int s = 0; s < 2 && aligned; ++s)
+        for (int k = 0; k < 3; ++k) aligned = aligned && (((uintptr_t)p.buf[s][k]) % 16 == 0);
+    c->use_tma = plain && aligned && !(force && strcmp(force, "ldg") == 0);
+    if (force && strcmp(force, "tma") == 0 && !c->use_tma) return fail(SWB_E_INVALID, "SWB_KERNEL=tma but this configuration cannot use the TMA kernel");
+    if (c->use_tma) {
+        const char *v = getenv("SWB_TMA_VARIANT");
+        c->tma_variant = v ? atoi(v) : 0;
+        if (c->tma_variant < 0 || c->tma_variant >= kNumTmaVariants) return fail(SWB_E_INVALID, "bad SWB_TMA_VARIANT");
+        const TmaVariant tv = kTmaVariants[c->tma_variant];
+        CK(cudaSetDevice(c->cfg.device));
+        for (int s = 0; s < 2; ++s)
+            for (int k = 0; k < 3; ++k) {
+                int rc = make_map(&c->maps.in[s][k], p.buf[s][k], (uint64_t)p.ncols, (uint64_t)(p.M + 3), (uint64_t)p.pitch, 34, (uint32_t)tv.R);
+                if (rc) return rc;
+                rc = make_map(&c->maps.out[s][k], p.buf[s][k], (uint64_t)(p.jl_last + 1), (uint64_t)(p.M + 2), (uint64_t)p.pitch, 30, (uint32_t)tv.R);
+                if (rc) return rc;
+            }
+    }
     return 0;
 }
 
@@ -241,7 +348,7 @@ int swb_cfl_init(swb_ctx *c, void *stream)
     CK(cudaMemsetAsync(c->d_ctrl, 0, sizeof(Ctrl) * 3, st));
     // every local row this band owns or mirrors takes part at step 1 (ghosts hold real
     // initial values); rows that are another band's interior are scanned by that band.
-    const int jl0 = p.pole_s ? 0 : p.jl_first, jl1 = p.pole_n ? p.nloc : p.jl_last + 1;
+    const int jl0 = p.pole_s ? p.jl_lo : p.jl_first, jl1 = p.pole_n ? p.jl_hi + 1 : p.jl_last + 1;
     const int blocks = c->sm_count * 8;
     cfl_init_kernel<<<blocks, 256, 0, st>>>(p.buf[0][0], p.buf[0][1], p.buf[0][2], p.M + 3, jl0, jl1, p.pitch, p.g, c->d_ctrl);
     c->launches++;
@@ -331,7 +438,7 @@ int swb_max_speed(swb_ctx *c, double *out_host, void *stream)
     const Params &p = c->prm;
     const int cur = s.current;
     CK(cudaMemsetAsync(c->d_scratch, 0, sizeof(unsigned long long), st));
-    const int jl0 = p.pole_s ? 0 : p.jl_first, jl1 = p.pole_n ? p.nloc : p.jl_last + 1;
+    const int jl0 = p.pole_s ? p.jl_lo : p.jl_first, jl1 = p.pole_n ? p.jl_hi + 1 : p.jl_last + 1;
     max_speed_kernel<<<c->sm_count * 8, 256, 0, st>>>(p.buf[cur][1], p.buf[cur][2], p.M + 3, jl0, jl1, p.pitch, c->d_scratch);
     c->launches++;
     CK(cudaGetLastError());

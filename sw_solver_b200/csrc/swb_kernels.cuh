@@ -16,6 +16,7 @@
 // face is computed exactly once per warp.  All metric terms are per-lane registers
 // derived from 1-D latitude tables; nothing 2-D but h, u, v is read from HBM.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -48,13 +49,14 @@ struct Params {
     const double *f2d;  // (M+3, pitch) or null
     const double *hs;   // (M+3, pitch) or null
     const double *phi;  // M+3
-    const double *tab;  // T_COUNT x nloc
+    const double *tab;  // T_COUNT x ncols
     Ctrl *ctrl;         // 3 slots
     double *log;        // 2 x log_cap: dt then time, or null
     int log_cap;
-    int M, nloc, pitch;
+    int M, ncols, pitch;    // ncols = lead_pad + n_local: local columns [jl_lo, jl_hi] are real
+    int jl_lo, jl_hi;
     int jl_first, jl_last;  // local latitude rows updated by this context (inclusive)
-    int pole_s, pole_n;     // local row 0 / nloc-1 is the global copy row 0 / N-1
+    int pole_s, pole_n;     // local row jl_lo / jl_hi is the global copy row 0 / N-1
     int chunk;              // longitudes marched by one warp
     int nstrips;            // warps needed along latitude
     int launch;             // launch index L
@@ -90,8 +92,9 @@ __device__ __forceinline__ double fast_rcp(double x)
 __device__ __forceinline__ unsigned long long nonneg_bits(double v)
 {
     // |v| as an unsigned integer: monotone for finite values and +inf, and every NaN maps
-    // above +inf, so an integer max reproduces numpy's NaN-propagating max.
-    return (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffULL;
+    // above +inf, so an integer max reproduces numpy's NaN-propagating max.  (Integer
+    // pipe only: the FP64 pipe is the scarce resource of this kernel.)
+    return ((unsigned long long)(unsigned)(__double2hiint(v) & 0x7fffffff) << 32) | (unsigned)__double2loint(v);
 }
 
 __device__ __forceinline__ double shfl_down1(double x) { return __shfl_down_sync(0xffffffffu, x, 1); }
@@ -286,190 +289,178 @@ __device__ __forceinline__ double laplacian_at(const double *__restrict__ q, con
 }
 
 // ------------------------------------------------------------------------------------
-// the fused step kernel
+// step prologue: dt from the device-resident CFL maxima (numpy.py:524-532)
 // ------------------------------------------------------------------------------------
-template <bool STRICT, bool DIFF, bool F2D, bool HS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const __grid_constant__ Params p)
+// Executed by thread 0 of every block (every block needs dt); block (0,0) also advances
+// the loop state.  Returns through shared memory: dt and flags (bit 0 active, bit 1 parity).
+__device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int *s_flags)
 {
-    using O = Op<STRICT>;
-    __shared__ double s_dt;
-    __shared__ int s_flags;  // bit 0: active, bit 1: parity of the current buffer set
-
     Ctrl *const cur_slot = p.ctrl + (p.launch % 3);
     Ctrl *const new_slot = p.ctrl + ((p.launch + 1) % 3);
-
-    if (threadIdx.x == 0) {
-        if (p.fixed) {
-            s_dt = p.fixed_dt;
-            s_flags = 1;
+    if (p.fixed) {
+        *s_dt = p.fixed_dt;
+        *s_flags = 1;
+        return;
+    }
+    const double time = cur_slot->time;
+    const long long nsteps = cur_slot->nsteps;
+    const unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
+    const double tx = __ddiv_rn(p.dxmin, __longlong_as_double((long long)exb));
+    const double ty = __ddiv_rn(p.dymin, __longlong_as_double((long long)eyb));
+    const double dtmax = (tx != tx) ? tx : ((ty != ty) ? ty : (tx < ty ? tx : ty));  // np.minimum propagates NaN
+    double dt = __dmul_rn(p.courant, dtmax);
+    const bool active = time < p.final_time;  // numpy.py:496 (false for NaN)
+    double tnew = time;
+    if (active) {
+        if (__dadd_rn(time, dt) > p.final_time) {
+            dt = __dsub_rn(p.final_time, time);
+            tnew = p.final_time;
         } else {
-            // numpy.py:524-532 (np.minimum propagates NaN)
-            const double time = cur_slot->time;
-            const long long nsteps = cur_slot->nsteps;
-            const unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
-            const double tx = __ddiv_rn(p.dxmin, __longlong_as_double((long long)exb));
-            const double ty = __ddiv_rn(p.dymin, __longlong_as_double((long long)eyb));
-            const double dtmax = (tx != tx) ? tx : ((ty != ty) ? ty : (tx < ty ? tx : ty));
-            double dt = __dmul_rn(p.courant, dtmax);
-            const bool active = time < p.final_time;  // numpy.py:496 (false for NaN)
-            double tnew = time;
-            if (active) {
-                if (__dadd_rn(time, dt) > p.final_time) {
-                    dt = __dsub_rn(p.final_time, time);
-                    tnew = p.final_time;
-                } else {
-                    tnew = __dadd_rn(time, dt);
-                }
-            }
-            s_dt = dt;
-            s_flags = (active ? 1 : 0) | (int)((nsteps & 1) << 1);
-            if (blockIdx.x == 0 && blockIdx.y == 0) {
-                Ctrl *const clr_slot = p.ctrl + ((p.launch + 2) % 3);
-                clr_slot->ex_bits = 0ULL;
-                clr_slot->ey_bits = 0ULL;
-                new_slot->time = tnew;
-                new_slot->nsteps = nsteps + (active ? 1 : 0);
-                new_slot->current = (int)((nsteps + (active ? 1 : 0)) & 1);
-                new_slot->last_dt = active ? dt : cur_slot->last_dt;
-                new_slot->done = !(tnew < p.final_time);
-                new_slot->error = cur_slot->error;
-                if (!active) {  // nothing will be accumulated: carry the maxima forward
-                    new_slot->ex_bits = exb;
-                    new_slot->ey_bits = eyb;
-                } else if (p.log != nullptr && nsteps < (long long)p.log_cap) {
-                    p.log[nsteps] = dt;
-                    p.log[(size_t)p.log_cap + nsteps] = tnew;
-                }
-            }
+            tnew = __dadd_rn(time, dt);
         }
     }
-    __syncthreads();
-    const int flags = s_flags;
-    if (!(flags & 1)) return;
-    const double dt = s_dt;
-    const int par = (flags >> 1) & 1;
+    *s_dt = dt;
+    *s_flags = (active ? 1 : 0) | (int)((nsteps & 1) << 1);
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        Ctrl *const clr_slot = p.ctrl + ((p.launch + 2) % 3);
+        clr_slot->ex_bits = 0ULL;
+        clr_slot->ey_bits = 0ULL;
+        new_slot->time = tnew;
+        new_slot->nsteps = nsteps + (active ? 1 : 0);
+        new_slot->current = (int)((nsteps + (active ? 1 : 0)) & 1);
+        new_slot->last_dt = active ? dt : cur_slot->last_dt;
+        new_slot->done = !(tnew < p.final_time);
+        new_slot->error = cur_slot->error;
+        if (!active) {  // nothing will be accumulated: carry the maxima forward
+            new_slot->ex_bits = exb;
+            new_slot->ey_bits = eyb;
+        } else if (p.log != nullptr && nsteps < (long long)p.log_cap) {
+            p.log[nsteps] = dt;
+            p.log[(size_t)p.log_cap + nsteps] = tnew;
+        }
+    }
+}
 
-    const double *__restrict__ H = p.buf[par][0];
-    const double *__restrict__ U = p.buf[par][1];
-    const double *__restrict__ V = p.buf[par][2];
-    double *__restrict__ Hn = p.buf[par ^ 1][0];
-    double *__restrict__ Un = p.buf[par ^ 1][1];
-    double *__restrict__ Vn = p.buf[par ^ 1][2];
-
-    const int lane = threadIdx.x & 31;
-    const int strip = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (strip >= p.nstrips) return;
-
-    const int M = p.M;
-    const size_t P = (size_t)p.pitch;
-    const int jl_raw = p.jl_first - 1 + kCellsPerWarp * strip + lane;
-    const int jl = min(jl_raw, p.nloc - 1);  // lanes past the array replay the last row
-    const bool upd = (lane >= 1) && (lane <= kCellsPerWarp) && (jl_raw <= p.jl_last);
-
-    const int ia = 1 + blockIdx.y * p.chunk;        // first longitude updated
-    const int ib = min(ia + p.chunk, M + 2);        // one past the last
-
-    // ---- per-lane constants ------------------------------------------------------------
-    const double *tab = p.tab + jl;
-    const size_t TS = (size_t)p.nloc;
-    const double c_j = tab[T_C * TS];
-    const double tg_j = tab[T_TG * TS];
-    const double ac_j = tab[T_AC * TS];
-    const double f_j = F2D ? 0.0 : tab[T_F * TS];
-    const double f_jp = F2D ? 0.0 : p.tab[T_F * TS + min(jl + 1, p.nloc - 1)];
-    const double cm_j = tab[T_CMIDY * TS];
-    const double hdt = O::mul(0.5, dt);
-    const double hgCell = O::mul(0.5, p.g);  // numpy.py:203, 255: 0.5*g
-
-    // STRICT: the reference's coefficients; FAST: pre-scaled variants (see x_face / y_face)
-    double hgK, raK;          // hg (or g/4), a
-    double kx, fKx;           // x-face Coriolis/metric factors
-    double ky, fKy;           // y-face
+// ------------------------------------------------------------------------------------
+// one lane of the march: per-latitude constants + the per-row work
+// ------------------------------------------------------------------------------------
+template <bool STRICT, bool DIFF, bool F2D, bool HS>
+struct Lane {
+    using O = Op<STRICT>;
+    int jl;                   // local latitude row of this lane (clamped into the array)
+    double dt, hdt, hgCell, dnu;
+    double c_j, ac_j;
+    double hgK, raK;          // hg (FAST: g/4), a (FAST: 1/a)
+    double kx, fKx;           // x-face Coriolis / metric factors
+    double ky, fKy, cm_j;     // y-face
     double cy1f, cyf;         // y-face flux coefficients
-    double cxu = 0.0, cy1u, cyu;  // update coefficients (cxu: FAST only; strict is per (i,j))
-    double kc, fD;            // update Coriolis/metric
-    double cdx_fast = 0.0;
-    if (STRICT) {
-        hgK = O::mul(0.5, p.g);
-        raK = p.a;
-        kx = tg_j;  // tgMidx == tan(theta_j): 0.5*(theta+theta) is exact (grid.py:107)
-        fKx = f_j;  // 0.5*(f+f) is exact
-        ky = tab[T_TGMIDY * TS];
-        fKy = O::mul(0.5, O::add(f_jp, f_j));
-        cy1f = O::div(hdt, tab[T_DY1 * TS]);
-        cyf = O::div(hdt, tab[T_DY * TS]);
-        cy1u = O::div(dt, tab[T_DY1C * TS]);
-        cyu = O::div(dt, tab[T_DYC * TS]);
-        kc = tg_j;
-        fD = f_j;
-    } else {
-        const double ra = 1.0 / p.a;
-        const double dxa = ac_j * p.dphi;  // analytic dx_j (the reference's differs by roundoff only)
-        hgK = 0.25 * p.g;
-        raK = ra;
-        kx = hdt * 0.5 * tg_j * ra;
-        fKx = hdt * f_j;
-        ky = hdt * 0.5 * tab[T_TGMIDY * TS] * ra;
-        fKy = hdt * 0.5 * (f_jp + f_j);
-        cdx_fast = dt / dxa;
-        cy1f = dt / tab[T_DY1 * TS];
-        cyf = dt / tab[T_DY * TS];
-        cxu = 0.5 * dt / dxa;
-        cy1u = 0.5 * dt / tab[T_DY1C * TS];
-        cyu = 0.5 * dt / tab[T_DYC * TS];
-        kc = dt * 0.25 * 0.5 * 0.25 * tg_j * ra;  // (dt*0.25) * 0.5[doubled sums] * 0.25 * tg/a
-        fD = dt * 0.25 * 0.5 * f_j;
-    }
-    const double dy1s = HS ? O::add(p.tab[T_DY1 * TS + max(jl - 1, 0)], tab[T_DY1 * TS]) : 0.0;
-
+    double cxu, cy1u, cyu;    // update coefficients (cxu: FAST only; STRICT forms dt/dxc per cell)
+    double kc, fD;            // update Coriolis / metric
+    double cdx_fast;
+    double dy1s;              // HS: dy1[j-1] + dy1[j]
+    double x_m, x_c;          // STRICT: x[i-1, j], x[i, j]
     LapCtx L;
-    if (DIFF) {
-        const int jm = max(jl - 1, 0), jp = min(jl + 1, p.nloc - 1);
-        L.Aym = p.tab[T_AY * TS + jm]; L.Bym = p.tab[T_BY * TS + jm]; L.Cym = p.tab[T_CY * TS + jm];
-        L.Ay0 = tab[T_AY * TS]; L.By0 = tab[T_BY * TS]; L.Cy0 = tab[T_CY * TS];
-        L.Ayp = p.tab[T_AY * TS + jp]; L.Byp = p.tab[T_BY * TS + jp]; L.Cyp = p.tab[T_CY * TS + jp];
-        // numpy.py:379-381: one duplicated latitude each side (only at the pole rows;
-        // a band interior has real halo rows there)
-        L.jm1 = max(jl - 1, 0);
-        L.jp1 = min(jl + 1, p.nloc - 1);
-        L.jm2 = max(jl - 2, 0);
-        L.jp2 = min(jl + 2, p.nloc - 1);
-        if (!STRICT) {
-            L.w[0] = L.Cy0 * L.Cym;
-            L.w[1] = L.Ay0 * L.Cy0 + L.Cy0 * L.Aym;
-            L.w[2] = L.Ay0 * L.Ay0 + L.By0 * L.Cyp + L.Cy0 * L.Bym;
-            L.w[3] = L.Ay0 * L.By0 + L.By0 * L.Ayp;
-            L.w[4] = L.By0 * L.Byp;
-            const double dxa = ac_j * p.dphi;
-            L.bx2 = 0.25 / (dxa * dxa);
+    unsigned long long mx, my;  // running CFL maxima (bit patterns)
+
+    __device__ __forceinline__ void init(const Params &p, int jl_, double dt_)
+    {
+        jl = jl_;
+        dt = dt_;
+        mx = my = 0ULL;
+        const double *tab = p.tab + jl;
+        const size_t TS = (size_t)p.ncols;
+        c_j = tab[T_C * TS];
+        const double tg_j = tab[T_TG * TS];
+        ac_j = tab[T_AC * TS];
+        const double f_j = F2D ? 0.0 : tab[T_F * TS];
+        const double f_jp = F2D ? 0.0 : p.tab[T_F * TS + min(jl + 1, p.jl_hi)];
+        cm_j = tab[T_CMIDY * TS];
+        hdt = O::mul(0.5, dt);
+        hgCell = O::mul(0.5, p.g);  // numpy.py:203, 255: 0.5*g
+        dnu = O::mul(dt, p.nu);
+        cxu = 0.0;
+        cdx_fast = 0.0;
+        x_m = x_c = 0.0;
+        if (STRICT) {
+            hgK = O::mul(0.5, p.g);
+            raK = p.a;
+            kx = tg_j;  // tgMidx == tan(theta_j): 0.5*(theta+theta) is exact (grid.py:107)
+            fKx = f_j;  // 0.5*(f+f) is exact
+            ky = tab[T_TGMIDY * TS];
+            fKy = O::mul(0.5, O::add(f_jp, f_j));
+            cy1f = O::div(hdt, tab[T_DY1 * TS]);
+            cyf = O::div(hdt, tab[T_DY * TS]);
+            cy1u = O::div(dt, tab[T_DY1C * TS]);
+            cyu = O::div(dt, tab[T_DYC * TS]);
+            kc = tg_j;
+            fD = f_j;
+        } else {
+            const double ra = 1.0 / p.a;
+            const double dxa = ac_j * p.dphi;  // analytic dx_j (the reference's differs by roundoff only)
+            hgK = 0.25 * p.g;
+            raK = ra;
+            kx = hdt * 0.5 * tg_j * ra;
+            fKx = hdt * f_j;
+            ky = hdt * 0.5 * tab[T_TGMIDY * TS] * ra;
+            fKy = hdt * 0.5 * (f_jp + f_j);
+            cdx_fast = dt / dxa;
+            cy1f = dt / tab[T_DY1 * TS];
+            cyf = dt / tab[T_DY * TS];
+            cxu = 0.5 * dt / dxa;
+            cy1u = 0.5 * dt / tab[T_DY1C * TS];
+            cyu = 0.5 * dt / tab[T_DYC * TS];
+            kc = dt * 0.25 * 0.5 * 0.25 * tg_j * ra;  // (dt*0.25) * 0.5[doubled sums] * 0.25 * tg/a
+            fD = dt * 0.25 * 0.5 * f_j;
+        }
+        dy1s = HS ? O::add(p.tab[T_DY1 * TS + max(jl - 1, p.jl_lo)], tab[T_DY1 * TS]) : 1.0;
+        if (DIFF) {
+            const int jm = max(jl - 1, p.jl_lo), jp = min(jl + 1, p.jl_hi);
+            L.Aym = p.tab[T_AY * TS + jm]; L.Bym = p.tab[T_BY * TS + jm]; L.Cym = p.tab[T_CY * TS + jm];
+            L.Ay0 = tab[T_AY * TS]; L.By0 = tab[T_BY * TS]; L.Cy0 = tab[T_CY * TS];
+            L.Ayp = p.tab[T_AY * TS + jp]; L.Byp = p.tab[T_BY * TS + jp]; L.Cyp = p.tab[T_CY * TS + jp];
+            // numpy.py:379-381: one duplicated latitude each side (only at the pole rows;
+            // a band interior has real halo rows there)
+            L.jm1 = jm;
+            L.jp1 = jp;
+            L.jm2 = max(jl - 2, p.jl_lo);
+            L.jp2 = min(jl + 2, p.jl_hi);
+            if (!STRICT) {
+                L.w[0] = L.Cy0 * L.Cym;
+                L.w[1] = L.Ay0 * L.Cy0 + L.Cy0 * L.Aym;
+                L.w[2] = L.Ay0 * L.Ay0 + L.By0 * L.Cyp + L.Cy0 * L.Bym;
+                L.w[3] = L.Ay0 * L.By0 + L.By0 * L.Ayp;
+                L.w[4] = L.By0 * L.Byp;
+                const double dxa = ac_j * p.dphi;
+                L.bx2 = 0.25 / (dxa * dxa);
+            }
         }
     }
-    const double dnu = O::mul(dt, p.nu);
 
-    // ---- march ------------------------------------------------------------------------
-    auto load_cell = [&](int i) {
-        const size_t k = (size_t)i * P + jl;
-        return make_cell<STRICT>(H[k], U[k], V[k], c_j, hgCell, F2D ? p.f2d[k] : 0.0);
-    };
-
-    Cell prev = load_cell(ia - 1);
-    Cell cur = load_cell(ia);
-    double x_m = 0.0, x_c = 0.0;  // STRICT: x[i-1, j], x[i, j]
-    Face x0;
-    if (STRICT) {
-        x_m = O::mul(ac_j, p.phi[ia - 1]);
-        x_c = O::mul(ac_j, p.phi[ia]);
-        const double cdx = O::div(hdt, O::sub(x_c, x_m));
-        x0 = x_face<true>(prev, cur, cdx, kx, F2D ? O::mul(0.5, O::add(cur.f, prev.f)) : fKx, hdt, hgK, raK);
-    } else {
-        x0 = x_face<false>(prev, cur, cdx_fast, kx, F2D ? hdt * 0.5 * (cur.f + prev.f) : fKx, hdt, hgK, raK);
+    __device__ __forceinline__ Cell cell(double h, double u, double v, double f) const
+    {
+        return make_cell<STRICT>(h, u, v, c_j, hgCell, f);
     }
 
-    unsigned long long mx = 0ULL, my = 0ULL;  // running CFL maxima (bit patterns)
+    // face (ia-1 | ia) that starts a march
+    __device__ __forceinline__ Face first_face(const Params &p, const Cell &prev, const Cell &cur, int ia)
+    {
+        if (STRICT) {
+            x_m = O::mul(ac_j, p.phi[ia - 1]);
+            x_c = O::mul(ac_j, p.phi[ia]);
+            const double cdx = O::div(hdt, O::sub(x_c, x_m));
+            return x_face<true>(prev, cur, cdx, kx, F2D ? O::mul(0.5, O::add(cur.f, prev.f)) : fKx, hdt, hgK, raK);
+        }
+        return x_face<false>(prev, cur, cdx_fast, kx, F2D ? hdt * 0.5 * (cur.f + prev.f) : fKx, hdt, hgK, raK);
+    }
 
-    for (int i = ia; i < ib; ++i) {
-        const Cell nxt = load_cell(i + 1);
-
+    // Update cell (i, j) given its own products `cur`, the next longitude `nxt` and the
+    // left face `x0`; returns the right face (the next iteration's left face).
+    // numpy.py:193-354 (+541-544 with DIFF).  `count` says whether this lane's result is a
+    // real cell (takes part in the CFL maxima).
+    __device__ __forceinline__ Face advance(const Params &p, const double *__restrict__ H, const double *__restrict__ U,
+                                            const double *__restrict__ V, const Cell &cur, const Cell &nxt,
+                                            const Face &x0, int i, bool count, double &hn, double &un, double &vn)
+    {
         // x-face (i | i+1)
         Face x1;
         double dx0 = 0.0, dx1 = 0.0;
@@ -504,8 +495,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const __grid_
         y0.hvc = shfl_up1(y1.hvc);
         y0.hM = HS ? shfl_up1(y1.hM) : 0.0;
 
-        // ---- full-step update of cell (i, j): numpy.py:275-354 ---------------------
-        double hn, un, vn;
+        // full-step update of cell (i, j): numpy.py:275-354
+        const size_t P = (size_t)p.pitch;
         if (STRICT) {
             const double cx = O::div(dt, O::mul(0.5, O::add(dx0, dx1)));
             hn = O::sub(O::sub(cur.h, O::mul(cx, O::sub(x1.huM, x0.huM))), O::mul(cy1u, O::sub(y1.hvc, y0.hvc)));
@@ -525,7 +516,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const __grid_
                 const double gq = O::mul(O::mul(O::mul(dt, p.g), 0.25), hsum);
                 const size_t k = (size_t)i * P + jl;
                 const double dhx = O::sub(p.hs[k + P], p.hs[k - P]);
-                const double dhy = O::sub(p.hs[(size_t)i * P + min(jl + 1, p.nloc - 1)], p.hs[(size_t)i * P + max(jl - 1, 0)]);
+                const double dhy = O::sub(p.hs[(size_t)i * P + min(jl + 1, p.jl_hi)], p.hs[(size_t)i * P + max(jl - 1, p.jl_lo)]);
                 hun = O::sub(hun, O::div(O::mul(gq, dhx), O::add(dx0, dx1)));
                 hvn = O::sub(hvn, O::div(O::mul(gq, dhy), dy1s));
             }
@@ -545,7 +536,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const __grid_
                 const double gq = dt * p.g * 0.125 * hsum;
                 const size_t k = (size_t)i * P + jl;
                 const double dhx = p.hs[k + P] - p.hs[k - P];
-                const double dhy = p.hs[(size_t)i * P + min(jl + 1, p.nloc - 1)] - p.hs[(size_t)i * P + max(jl - 1, 0)];
+                const double dhy = p.hs[(size_t)i * P + min(jl + 1, p.jl_hi)] - p.hs[(size_t)i * P + max(jl - 1, p.jl_lo)];
                 hun -= gq * dhx / (2.0 * ac_j * p.dphi);
                 hvn -= gq * dhy / dy1s;
             }
@@ -567,21 +558,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const __grid_
                 vn = fma(dnu, lv, vn);
             }
         }
-
-        if (upd) {
-            // numpy.py:402-404: periodic longitude wrap and zero-gradient pole rows are
-            // extra copies of the freshly computed value.
-            const bool south = p.pole_s && (jl == 1);
-            const bool north = p.pole_n && (jl == p.nloc - 2);
-            auto put = [&](int row) {
-                const size_t k = (size_t)row * P + jl;
-                Hn[k] = hn; Un[k] = un; Vn[k] = vn;
-                if (south) { Hn[k - 1] = hn; Un[k - 1] = un; Vn[k - 1] = vn; }
-                if (north) { Hn[k + 1] = hn; Un[k + 1] = un; Vn[k + 1] = vn; }
-            };
-            put(i);
-            if (i == M) put(0);
-            if (i == 2) put(M + 2);
+        if (count) {
             // CFL maxima of the new state: max(|q-c|, |q|, |q+c|) == |q| + c for c >= 0
             const double cs = STRICT ? __dsqrt_rn(O::mul(p.g, fabs(hn))) : sqrt(p.g * fabs(hn));
             const unsigned long long bx = nonneg_bits(O::add(fabs(un), cs));
@@ -589,12 +566,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const __grid_
             mx = bx > mx ? bx : mx;
             my = by > my ? by : my;
         }
-
-        x0 = x1;
-        cur = nxt;
+        return x1;
     }
 
-    if (!p.fixed) {
+    // warp-reduce the running maxima and publish them (one atomic pair per warp)
+    __device__ __forceinline__ void publish(const Params &p, int lane)
+    {
+        if (p.fixed) return;
+        Ctrl *const new_slot = p.ctrl + ((p.launch + 1) % 3);
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
             const unsigned long long ox = __shfl_xor_sync(0xffffffffu, mx, s);
@@ -607,6 +586,251 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const __grid_
             atomicMax(&new_slot->ey_bits, my);
         }
     }
+};
+
+// Extra copies of a freshly computed cell: periodic wrap in longitude and zero-gradient
+// pole rows (numpy.py:402-404).  `main` says whether (i, jl) itself is still to be written.
+__device__ __forceinline__ void put_cell(const Params &p, double *__restrict__ Hn, double *__restrict__ Un,
+                                         double *__restrict__ Vn, int i, int jl, double hn, double un, double vn, bool main)
+{
+    const size_t P = (size_t)p.pitch;
+    const bool south = p.pole_s && (jl == p.jl_lo + 1);
+    const bool north = p.pole_n && (jl == p.jl_hi - 1);
+    auto put = [&](int row, bool centre) {
+        const size_t k = (size_t)row * P + jl;
+        if (centre) { Hn[k] = hn; Un[k] = un; Vn[k] = vn; }
+        if (south) { Hn[k - 1] = hn; Un[k - 1] = un; Vn[k - 1] = vn; }
+        if (north) { Hn[k + 1] = hn; Un[k + 1] = un; Vn[k + 1] = vn; }
+    };
+    if (main || south || north) put(i, main);
+    if (i == p.M) put(0, true);
+    if (i == 2) put(p.M + 2, true);
+}
+
+// ------------------------------------------------------------------------------------
+// the fused step kernel, direct-load form (all variants)
+// ------------------------------------------------------------------------------------
+template <bool STRICT, bool DIFF, bool F2D, bool HS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const __grid_constant__ Params p)
+{
+    __shared__ double s_dt;
+    __shared__ int s_flags;
+    if (threadIdx.x == 0) step_prologue(p, &s_dt, &s_flags);
+    __syncthreads();
+    const int flags = s_flags;
+    if (!(flags & 1)) return;
+    const int par = (flags >> 1) & 1;
+
+    const double *__restrict__ H = p.buf[par][0];
+    const double *__restrict__ U = p.buf[par][1];
+    const double *__restrict__ V = p.buf[par][2];
+    double *__restrict__ Hn = p.buf[par ^ 1][0];
+    double *__restrict__ Un = p.buf[par ^ 1][1];
+    double *__restrict__ Vn = p.buf[par ^ 1][2];
+
+    const int lane = threadIdx.x & 31;
+    const int strip = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (strip >= p.nstrips) return;
+
+    const size_t P = (size_t)p.pitch;
+    const int jl_raw = p.jl_first - 1 + kCellsPerWarp * strip + lane;
+    const int jl = min(jl_raw, p.jl_hi);  // lanes past the array replay the last row
+    const bool upd = (lane >= 1) && (lane <= kCellsPerWarp) && (jl_raw <= p.jl_last);
+    const int ia = 1 + blockIdx.y * p.chunk;     // first longitude updated
+    const int ib = min(ia + p.chunk, p.M + 2);   // one past the last
+
+    Lane<STRICT, DIFF, F2D, HS> ln;
+    ln.init(p, jl, s_dt);
+    auto load_cell = [&](int i) {
+        const size_t k = (size_t)i * P + jl;
+        return ln.cell(H[k], U[k], V[k], F2D ? p.f2d[k] : 0.0);
+    };
+    Cell cur;
+    Face x0;
+    {
+        const Cell prev = load_cell(ia - 1);
+        cur = load_cell(ia);
+        x0 = ln.first_face(p, prev, cur, ia);
+    }
+    for (int i = ia; i < ib; ++i) {
+        const Cell nxt = load_cell(i + 1);
+        double hn, un, vn;
+        x0 = ln.advance(p, H, U, V, cur, nxt, x0, i, upd, hn, un, vn);
+        if (upd) put_cell(p, Hn, Un, Vn, i, jl, hn, un, vn, true);
+        cur = nxt;
+    }
+    ln.publish(p, lane);
+}
+
+// ------------------------------------------------------------------------------------
+// the fused step kernel, TMA form (flat topography, latitude-only Coriolis, no diffusion)
+// ------------------------------------------------------------------------------------
+// Every warp runs its own asynchronous pipeline: lane 0 issues cp.async.bulk.tensor loads
+// of {34 latitudes x R longitudes} boxes of h, u, v into a ring of S shared-memory stages
+// (completion on one mbarrier per stage) and bulk tensor stores of the {30 x R} result
+// boxes; lanes read / write shared memory only.  Loads of the rows far ahead of the march
+// are in flight while the FP64 pipe works, without costing registers.
+struct TmaMaps {
+    CUtensorMap in[2][3];   // box {34, R} over (ncols, M+3)
+    CUtensorMap out[2][3];  // box {30, R} over (jl_last+1, M+2): clips garbage rows / halo columns
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"((unsigned long long)map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+
+template <int R, int S>
+struct TmaLayout {
+    static constexpr int kInCols = 34;  // lane 0's column is odd; boxes must start on 16-byte (even) columns
+    static constexpr int kInTile = ((R * kInCols * 8 + 127) / 128) * 128;  // one field, one stage
+    static constexpr int kOutTile = ((R * 30 * 8 + 127) / 128) * 128;
+    static constexpr int kIn = S * 3 * kInTile;
+    static constexpr int kOut = 2 * 3 * kOutTile;
+    static constexpr int kBars = 128;
+    static constexpr int kWarpBytes = kIn + kOut + kBars;
+    static constexpr int kBlockBytes = kWarpsPerBlock * kWarpBytes;
+};
+
+template <bool STRICT, int R, int S>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, STRICT ? 3 : 4) step_kernel_tma(const __grid_constant__ Params p,
+                                                                       const __grid_constant__ TmaMaps tm)
+{
+    using LY = TmaLayout<R, S>;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ double s_dt;
+    __shared__ int s_flags;
+    if (threadIdx.x == 0) step_prologue(p, &s_dt, &s_flags);
+    __syncthreads();
+    const int flags = s_flags;
+    if (!(flags & 1)) return;
+    const int par = (flags >> 1) & 1;
+
+    const double *__restrict__ H = p.buf[par][0];
+    const double *__restrict__ U = p.buf[par][1];
+    const double *__restrict__ V = p.buf[par][2];
+    double *__restrict__ Hn = p.buf[par ^ 1][0];
+    double *__restrict__ Un = p.buf[par ^ 1][1];
+    double *__restrict__ Vn = p.buf[par ^ 1][2];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * kWarpsPerBlock + warp;
+    if (strip >= p.nstrips) return;
+
+    const size_t P = (size_t)p.pitch;
+    const int c0 = p.jl_first - 1 + kCellsPerWarp * strip;  // latitude held by lane 0
+    const int jl_raw = c0 + lane;
+    const int jl = min(jl_raw, p.jl_hi);
+    const bool upd = (lane >= 1) && (lane <= kCellsPerWarp) && (jl_raw <= p.jl_last);
+    const int ia = 1 + blockIdx.y * p.chunk;
+    const int ib = min(ia + p.chunk, p.M + 2);
+    const int ntiles = (ib - ia + R - 1) / R;
+
+    unsigned char *wbase = smem_raw + (size_t)warp * LY::kWarpBytes;
+    const double *in_s = reinterpret_cast<const double *>(wbase);
+    double *out_s = reinterpret_cast<double *>(wbase + LY::kIn);
+    const uint32_t in_a = smem_u32(wbase), out_a = in_a + LY::kIn, bar_a = out_a + LY::kOut;
+
+    const CUtensorMap *min_ = tm.in[par];
+    const CUtensorMap *mout = tm.out[par ^ 1];
+
+    if (lane == 0) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) mbar_init(bar_a + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    auto issue_load = [&](int t) {  // lane 0 only: rows ia+1+tR .. of h, u, v into stage t % S
+        const int s = t % S;
+        const uint32_t bar = bar_a + 8 * s;
+        mbar_expect_tx(bar, 3 * R * LY::kInCols * 8);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tma_load_2d(in_a + (s * 3 + k) * LY::kInTile, &min_[k], c0 - 1, ia + 1 + t * R, bar);
+    };
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < S - 1; ++t)
+            if (t < ntiles) issue_load(t);
+    }
+
+    Lane<STRICT, false, false, false> ln;
+    ln.init(p, jl, s_dt);
+    Cell cur;
+    Face x0;
+    {
+        const size_t k0 = (size_t)(ia - 1) * P + jl, k1 = k0 + P;
+        const Cell prev = ln.cell(H[k0], U[k0], V[k0], 0.0);
+        cur = ln.cell(H[k1], U[k1], V[k1], 0.0);
+        x0 = ln.first_face(p, prev, cur, ia);
+    }
+    const bool edge = p.pole_s && (jl == p.jl_lo + 1) || p.pole_n && (jl == p.jl_hi - 1);
+
+    for (int t = 0; t < ntiles; ++t) {
+        const int s = t % S;
+        mbar_wait(bar_a + 8 * s, (uint32_t)((t / S) & 1));
+        const int ob = t & 1;
+        if (t >= 2) {  // the store that last read out buffer `ob` must have drained it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+        }
+        const double *ti = in_s + (size_t)s * 3 * (LY::kInTile / 8) + lane + 1;
+        double *to = out_s + (size_t)ob * 3 * (LY::kOutTile / 8) + (lane - 1);
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const int i = ia + t * R + rr;
+            const Cell nxt = ln.cell(ti[rr * LY::kInCols], ti[LY::kInTile / 8 + rr * LY::kInCols], ti[2 * (LY::kInTile / 8) + rr * LY::kInCols], 0.0);
+            double hn, un, vn;
+            const bool live = upd && (i < ib);
+            x0 = ln.advance(p, H, U, V, cur, nxt, x0, i, live, hn, un, vn);
+            if (lane >= 1 && lane <= kCellsPerWarp) {
+                to[rr * 30] = hn;
+                to[LY::kOutTile / 8 + rr * 30] = un;
+                to[2 * (LY::kOutTile / 8) + rr * 30] = vn;
+            }
+            if (live && (edge || i == p.M || i == 2)) put_cell(p, Hn, Un, Vn, i, jl, hn, un, vn, false);
+            cur = nxt;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) tma_store_2d(&mout[k], out_a + (ob * 3 + k) * LY::kOutTile, c0 + 1, ia + t * R);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (t + S - 1 < ntiles) issue_load(t + S - 1);
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    ln.publish(p, lane);
 }
 
 // ------------------------------------------------------------------------------------
@@ -673,13 +897,13 @@ __global__ void __launch_bounds__(128) laplacian_kernel(const double *__restrict
     const int jl = p.jl_first + blockIdx.x * blockDim.x + threadIdx.x;
     const int i = 1 + blockIdx.y;
     if (jl > p.jl_last || i > p.M + 1) return;
-    const size_t TS = (size_t)p.nloc;
+    const size_t TS = (size_t)p.ncols;
     LapCtx L;
-    const int jm = max(jl - 1, 0), jp = min(jl + 1, p.nloc - 1);
+    const int jm = max(jl - 1, p.jl_lo), jp = min(jl + 1, p.jl_hi);
     L.Aym = p.tab[T_AY * TS + jm]; L.Bym = p.tab[T_BY * TS + jm]; L.Cym = p.tab[T_CY * TS + jm];
     L.Ay0 = p.tab[T_AY * TS + jl]; L.By0 = p.tab[T_BY * TS + jl]; L.Cy0 = p.tab[T_CY * TS + jl];
     L.Ayp = p.tab[T_AY * TS + jp]; L.Byp = p.tab[T_BY * TS + jp]; L.Cyp = p.tab[T_CY * TS + jp];
-    L.jm1 = jm; L.jp1 = jp; L.jm2 = max(jl - 2, 0); L.jp2 = min(jl + 2, p.nloc - 1);
+    L.jm1 = jm; L.jp1 = jp; L.jm2 = max(jl - 2, p.jl_lo); L.jp2 = min(jl + 2, p.jl_hi);
     out[(size_t)i * p.pitch + jl] = laplacian_at<true>(q, p, L, p.tab[T_AC * TS + jl], i, jl);
 }
 

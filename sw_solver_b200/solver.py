@@ -160,24 +160,32 @@ class Stepper:
         M, N = self.M, self.N
         shape = (M + 3, N)
 
+        # Device layout: the reference's (M+3, N) arrays with `lead_pad` unused columns in front
+        # and an even pitch, so that the first updated latitude sits on a 16-byte boundary
+        # (TMA boxes must start there; include/swb200.h).
+        self.lead_pad = 1
+        self.pitch = (self.lead_pad + N + 1) // 2 * 2
+        self._cols = slice(self.lead_pad, self.lead_pad + N)
+
         f_lat = _latitude_only(f)
-        self._f2d = None if f_lat is not None else self._to_device(f, shape)
+        self._f2d = None if f_lat is not None else self._padded(f)
         self._hs = None
         if hs is not None:
-            hs_t = self._to_device(hs, shape)
+            hs_t = self._padded(hs)
             if bool((hs_t != 0).any()):  # flat topography only subtracts an exact zero
                 self._hs = hs_t
 
         # two buffer sets {h,u,v}; set 0 receives the initial state
-        self.buf = torch.empty((2, 3) + shape, dtype=torch.float64, device=self.device)
+        self._raw = torch.zeros((2, 3, M + 3, self.pitch), dtype=torch.float64, device=self.device)
+        self.buf = self._raw[..., self._cols]  # (2, 3, M+3, N) view in the reference layout
         for k, q in enumerate((h, u, v)):
             self.buf[0, k].copy_(self._as_tensor(q, shape), non_blocking=False)
-        self.buf[1].zero_()
 
         cfg = SwbConfig()
         cfg.struct_bytes = ctypes.sizeof(SwbConfig)
         cfg.M, cfg.N = M, N
-        cfg.j_begin, cfg.n_local, cfg.j_first, cfg.j_last, cfg.pitch = 0, N, 1, N - 2, N
+        cfg.j_begin, cfg.n_local, cfg.j_first, cfg.j_last, cfg.pitch = 0, N, 1, N - 2, self.pitch
+        cfg.lead_pad = self.lead_pad
         cfg.dtype, cfg.mode = _lib.SWB_F64, MODES[mode]
         cfg.use_diffusion = int(self.use_diffusion)
         cfg.f_is_2d = int(self._f2d is not None)
@@ -201,7 +209,7 @@ class Stepper:
         check(self.lib.swb_set_tables(self._ctx, ctypes.byref(ct)))
 
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
-        check(self.lib.swb_bind_state(self._ctx, *(ptr(self.buf[s, k]) for s in (0, 1) for k in range(3)),
+        check(self.lib.swb_bind_state(self._ctx, *(ptr(self._raw[s, k]) for s in (0, 1) for k in range(3)),
                                       ptr(self._f2d), ptr(self._hs)))
         self._cfl_ready = False
 
@@ -215,8 +223,11 @@ class Stepper:
             raise ValueError(f"expected a float64 array of shape {shape}, got {tuple(t.shape)} {t.dtype}")
         return t
 
-    def _to_device(self, q, shape) -> torch.Tensor:
-        return self._as_tensor(q, shape).to(self.device).contiguous()
+    def _padded(self, q) -> torch.Tensor:
+        """Copy an (M+3, N) array into a fresh device array in the padded layout."""
+        out = torch.zeros((self.M + 3, self.pitch), dtype=torch.float64, device=self.device)
+        out[:, self._cols].copy_(self._as_tensor(q, (self.M + 3, self.N)))
+        return out
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
@@ -278,12 +289,11 @@ class Stepper:
 
     def laplacian(self, q) -> torch.Tensor:
         """(D_x D_x + D_y D_y) q at the interior cells (numpy.py:359-382), as (M+1, N-2)."""
-        shape = (self.M + 3, self.N)
-        qd = self._to_device(q, shape)
-        out = torch.zeros(shape, dtype=torch.float64, device=self.device)
+        qd = self._padded(q)
+        out = torch.zeros_like(qd)
         check(self.lib.swb_laplacian(self._ctx, ctypes.c_void_p(qd.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                      _stream(self.device)))
-        return out[1:-1, 1:-1]
+        return out[1:-1, self.lead_pad + 1:self.lead_pad + self.N - 1]
 
     @property
     def launch_count(self) -> int:
