@@ -323,7 +323,7 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     if (force && strcmp(force, "tma") == 0 && !c->use_tma) return fail(SWB_E_INVALID, "SWB_KERNEL=tma but this configuration cannot use the TMA kernel");
     if (c->use_tma) {
         const char *v = getenv("SWB_TMA_VARIANT");
-        c->tma_variant = v ? atoi(v) : 0;
+        c->tma_variant = v ? atoi(v) : 1;
         if (c->tma_variant < 0 || c->tma_variant >= kNumTmaVariants) return fail(SWB_E_INVALID, "bad SWB_TMA_VARIANT");
         const TmaVariant tv = kTmaVariants[c->tma_variant];
         CK(cudaSetDevice(c->cfg.device));

@@ -89,6 +89,21 @@ __device__ __forceinline__ double fast_rcp(double x)
     return fma(r, e, r);
 }
 
+// sqrt(x) for positive finite x from the hardware seed (MUFU.RSQ64H) and a coupled Newton
+// iteration + one residual correction; no special-case branch (FAST mode only).
+__device__ __forceinline__ double fast_sqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double s = x * y;
+    double hy = 0.5 * y;
+    const double e = fma(-s, hy, 0.5);
+    s = fma(s, e, s);
+    hy = fma(hy, e, hy);
+    const double d = fma(-s, s, x);
+    return fma(d, hy, s);
+}
+
 __device__ __forceinline__ unsigned long long nonneg_bits(double v)
 {
     // |v| as an unsigned integer: monotone for finite values and +inf, and every NaN maps
@@ -144,7 +159,7 @@ struct Face {
 // 287-291, 321.
 //   STRICT: cdx = hdt/dx[i,j];  kt = tan(theta_j) (tgMidx);  fK = 0.5*(f_b+f_a)
 //   FAST:   cdx = dt/dx_j;      kt = hdt*0.5*tan/a;          fK = hdt*f
-template <bool STRICT>
+template <bool STRICT, bool GUARD = true>
 __device__ __forceinline__ Face x_face(const Cell &a, const Cell &b, double cdx, double kt, double fK,
                                        double hdt, double hg, double ra)
 {
@@ -172,7 +187,7 @@ __device__ __forceinline__ Face x_face(const Cell &a, const Cell &b, double cdx,
         const double r = fast_rcp(F.hM);
         F.q = F.huM * r;
         const double pres = (hg * F.hM) * F.hM;               // hg here is g/4: 2*(g/2)*hM^2
-        const bool pos = __double2hiint(F.hM) > 0 || (__double2hiint(F.hM) == 0 && __double2loint(F.hM) != 0);
+        const bool pos = !GUARD || __double2hiint(F.hM) > 0 || (__double2hiint(F.hM) == 0 && __double2loint(F.hM) != 0);
         F.F1 = pos ? fma(F.huM, F.q, pres) : pres;            // 2 UxMid
         F.F2 = pos ? F.hvM * F.q : 0.0;                       // 2 VxMid
     }
@@ -185,7 +200,7 @@ __device__ __forceinline__ Face x_face(const Cell &a, const Cell &b, double cdx,
 // 292, 322-323.
 //   STRICT: c1 = hdt/dy1_j, c2 = hdt/dy_j, kt = tgMidy_j, fK = 0.5*(f_b+f_a)
 //   FAST:   c1 = dt/dy1_j,  c2 = dt/dy_j,  kt = hdt*0.5*tgMidy/a, fK = hdt*0.5*(f_b+f_a)
-template <bool STRICT>
+template <bool STRICT, bool GUARD = true>
 __device__ __forceinline__ Face y_face(const Cell &a, const Cell &b, double c1, double c2, double kt, double fK,
                                        double cm, double hdt, double hg, double ra)
 {
@@ -215,7 +230,7 @@ __device__ __forceinline__ Face y_face(const Cell &a, const Cell &b, double c1, 
         const double r = fast_rcp(F.hM);
         F.q = F.huM * r;
         F.hvc = F.hvM * cm;
-        const bool pos = __double2hiint(F.hM) > 0 || (__double2hiint(F.hM) == 0 && __double2loint(F.hM) != 0);
+        const bool pos = !GUARD || __double2hiint(F.hM) > 0 || (__double2hiint(F.hM) == 0 && __double2loint(F.hM) != 0);
         F.F1 = pos ? F.hvc * F.q : 0.0;            // 2 UyMid
         F.F2 = pos ? F.hvc * (F.hvM * r) : 0.0;    // 2 Vy1Mid
         F.F3 = (hg * F.hM) * F.hM;                 // 2 Vy2Mid (hg = g/4)
@@ -569,10 +584,52 @@ struct Lane {
         return x1;
     }
 
+    // Branch-free form of `advance` for the hot configuration (FAST arithmetic, latitude-only
+    // Coriolis, flat topography, no diffusion).  Assumes positive layer depths: the
+    // reference's `hMid > 0` selects (numpy.py:287-292, 321-322) always take their first
+    // branch there, so they are not evaluated.  The CFL maxima are accumulated for every lane
+    // and row; lanes / rows that are not real cells are masked when published.
+    __device__ __forceinline__ Face advance_fast(const Cell &cur, const Cell &nxt, const Face &x0, double g,
+                                                 double &hn, double &un, double &vn)
+    {
+        static_assert(!STRICT && !DIFF && !F2D && !HS, "advance_fast serves the plain FAST variant");
+        const Face x1 = x_face<false, false>(cur, nxt, cdx_fast, kx, fKx, hdt, hgK, raK);
+        Cell up;
+        up.h = shfl_down1(cur.h);   up.u = shfl_down1(cur.u);
+        up.hu = shfl_down1(cur.hu); up.hv = shfl_down1(cur.hv);
+        up.hw = shfl_down1(cur.hw); up.Uy = shfl_down1(cur.Uy);
+        up.Vy1 = shfl_down1(cur.Vy1); up.pr = shfl_down1(cur.pr);
+        const Face y1 = y_face<false, false>(cur, up, cy1f, cyf, ky, fKy, cm_j, hdt, hgK, raK);
+        Face y0;
+        y0.huM = shfl_up1(y1.huM); y0.hvM = shfl_up1(y1.hvM); y0.q = shfl_up1(y1.q);
+        y0.F1 = shfl_up1(y1.F1);   y0.F2 = shfl_up1(y1.F2);   y0.F3 = shfl_up1(y1.F3);
+        y0.hvc = shfl_up1(y1.hvc);
+
+        hn = fma(-cy1u, y1.hvc - y0.hvc, fma(-cxu, x1.huM - x0.huM, cur.h));
+        const double qs = (x0.q + x1.q) + (y0.q + y1.q);
+        const double D = fma(qs, kc, fD);  // 0.5 * dt * Fc * 0.25
+        const double shv = (x0.hvM + x1.hvM) + (y0.hvM + y1.hvM);
+        const double shu = (x0.huM + x1.huM) + (y0.huM + y1.huM);
+        const double hun = fma(D, shv, fma(-cy1u, y1.F1 - y0.F1, fma(-cxu, x1.F1 - x0.F1, cur.hu)));
+        const double hvn = fma(-D, shu, fma(-cyu, y1.F3 - y0.F3, fma(-cy1u, y1.F2 - y0.F2, fma(-cxu, x1.F2 - x0.F2, cur.hv))));
+        const double r = fast_rcp(hn);
+        un = hun * r;
+        vn = hvn * r;
+        // |q| + sqrt(g |h|) is non-negative (or NaN, which compares above everything as an
+        // unsigned pattern whatever its sign bit): no masking needed before the integer max
+        const double cs = fast_sqrt(g * fabs(hn));
+        const unsigned long long bx = (unsigned long long)__double_as_longlong(fabs(un) + cs);
+        const unsigned long long by = (unsigned long long)__double_as_longlong(fabs(vn) + cs);
+        mx = bx > mx ? bx : mx;
+        my = by > my ? by : my;
+        return x1;
+    }
+
     // warp-reduce the running maxima and publish them (one atomic pair per warp)
-    __device__ __forceinline__ void publish(const Params &p, int lane)
+    __device__ __forceinline__ void publish(const Params &p, int lane, bool valid_lane = true)
     {
         if (p.fixed) return;
+        if (!valid_lane) mx = my = 0ULL;
         Ctrl *const new_slot = p.ctrl + ((p.launch + 1) % 3);
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
@@ -794,6 +851,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, STRICT ? 3 : 4) step_kern
         x0 = ln.first_face(p, prev, cur, ia);
     }
     const bool edge = p.pole_s && (jl == p.jl_lo + 1) || p.pole_n && (jl == p.jl_hi - 1);
+    const bool cell_lane = (lane >= 1) && (lane <= kCellsPerWarp);
+    const bool warp_has_edge = __any_sync(0xffffffffu, edge && upd);
+    constexpr int kOutF = LY::kOutTile / 8;  // doubles per output field tile
 
     for (int t = 0; t < ntiles; ++t) {
         const int s = t % S;
@@ -804,33 +864,67 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, STRICT ? 3 : 4) step_kern
             __syncwarp();
         }
         const double *ti = in_s + (size_t)s * 3 * (LY::kInTile / 8) + lane + 1;
-        double *to = out_s + (size_t)ob * 3 * (LY::kOutTile / 8) + (lane - 1);
+        double *to = out_s + (size_t)ob * 3 * kOutF + (lane - 1);
+        const int i0 = ia + t * R;
+        const bool full = (i0 + R <= ib);  // warp-uniform
+        bool done_fast = false;
+        if constexpr (!STRICT) {
+          if (full) {
+            done_fast = true;
+            // hot path: R rows in one branch-free basic block
 #pragma unroll
-        for (int rr = 0; rr < R; ++rr) {
-            const int i = ia + t * R + rr;
-            const Cell nxt = ln.cell(ti[rr * LY::kInCols], ti[LY::kInTile / 8 + rr * LY::kInCols], ti[2 * (LY::kInTile / 8) + rr * LY::kInCols], 0.0);
-            double hn, un, vn;
-            const bool live = upd && (i < ib);
-            x0 = ln.advance(p, H, U, V, cur, nxt, x0, i, live, hn, un, vn);
-            if (lane >= 1 && lane <= kCellsPerWarp) {
-                to[rr * 30] = hn;
-                to[LY::kOutTile / 8 + rr * 30] = un;
-                to[2 * (LY::kOutTile / 8) + rr * 30] = vn;
+            for (int rr = 0; rr < R; ++rr) {
+                const Cell nxt = ln.cell(ti[rr * LY::kInCols], ti[LY::kInTile / 8 + rr * LY::kInCols],
+                                         ti[2 * (LY::kInTile / 8) + rr * LY::kInCols], 0.0);
+                double hn, un, vn;
+                x0 = ln.advance_fast(cur, nxt, x0, p.g, hn, un, vn);
+                if (cell_lane) {
+                    to[rr * 30] = hn;
+                    to[kOutF + rr * 30] = un;
+                    to[2 * kOutF + rr * 30] = vn;
+                }
+                cur = nxt;
             }
-            if (live && (edge || i == p.M || i == 2)) put_cell(p, Hn, Un, Vn, i, jl, hn, un, vn, false);
-            cur = nxt;
+          }
+        }
+        if (!done_fast) {
+#pragma unroll 1
+            for (int rr = 0; rr < R; ++rr) {
+                const int i = i0 + rr;
+                const Cell nxt = ln.cell(ti[rr * LY::kInCols], ti[LY::kInTile / 8 + rr * LY::kInCols],
+                                         ti[2 * (LY::kInTile / 8) + rr * LY::kInCols], 0.0);
+                double hn, un, vn;
+                const bool live = upd && (i < ib);
+                x0 = ln.advance(p, H, U, V, cur, nxt, x0, i, live, hn, un, vn);
+                if (cell_lane) {
+                    to[rr * 30] = hn;
+                    to[kOutF + rr * 30] = un;
+                    to[2 * kOutF + rr * 30] = vn;
+                }
+                cur = nxt;
+            }
+        }
+        // periodic-wrap rows and pole copies (numpy.py:402-404): rare, read back from the tile
+        const bool wrap_tile = (i0 <= p.M && p.M < i0 + R) || (i0 <= 2 && 2 < i0 + R);
+        if (warp_has_edge || wrap_tile) {
+#pragma unroll 1
+            for (int rr = 0; rr < R; ++rr) {
+                const int i = i0 + rr;
+                if (upd && i < ib && (edge || i == p.M || i == 2))
+                    put_cell(p, Hn, Un, Vn, i, jl, to[rr * 30], to[kOutF + rr * 30], to[2 * kOutF + rr * 30], false);
+            }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) tma_store_2d(&mout[k], out_a + (ob * 3 + k) * LY::kOutTile, c0 + 1, ia + t * R);
+            for (int k = 0; k < 3; ++k) tma_store_2d(&mout[k], out_a + (ob * 3 + k) * LY::kOutTile, c0 + 1, i0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             if (t + S - 1 < ntiles) issue_load(t + S - 1);
         }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    ln.publish(p, lane);
+    ln.publish(p, lane, upd);
 }
 
 // ------------------------------------------------------------------------------------
