@@ -237,8 +237,9 @@ def run_ours(args, M, N):
                       use_diffusion=args.diffusion, mode=args.mode, device=dev)   # H2D of h, u, v
         st2.enqueue(args.steps)
         cur = st2.status().current                                                  # blocks until done
+        snap = st2.snapshot(cur)                                                   # K4: back to the reference layout
         for k in range(3):
-            out[k].copy_(st2.buf[cur, k], non_blocking=True)                        # D2H of h, u, v
+            out[k].copy_(snap[k], non_blocking=True)                                # D2H of h, u, v
         torch.cuda.synchronize(dev)
         el = time.perf_counter() - t0
         st2.close()

@@ -11,12 +11,12 @@
  *  - every function returns 0 on success, a positive cudaError_t or a negative SWB_E_*
  *    code on failure; swb_last_error() returns a message for the calling thread;
  *  - no C++ types or exceptions cross this boundary; all pointers are plain;
- *  - state arrays are DEVICE pointers in the reference's own layout: C-contiguous
- *    [i = longitude 0..M+2][j = latitude], latitude contiguous, `pitch` elements between
- *    consecutive longitudes and `lead_pad` unused elements before local latitude 0
- *    (pitch == n_local, lead_pad == 0 for the reference's dense array; the TMA kernel
- *    needs an even pitch, 16-byte aligned bases and an EVEN first updated column, i.e.
- *    lead_pad == 1 on one GPU -- bulk tensor boxes must start on 16-byte boundaries);
+ *  - state arrays are DEVICE pointers in the library's LATITUDE-MAJOR layout: C-contiguous
+ *    [jl = local latitude 0..n_local-1][i = longitude 0..M+2], longitude contiguous,
+ *    `pitch` elements between consecutive latitudes (the transpose of the reference's
+ *    (M+3, N) array; swb_import_state / swb_export_state convert on the device).  pitch
+ *    must be at least swb_required_pitch(M) -- the kernels read whole 64-column strips --
+ *    and even, bases 16-byte aligned; the padding columns are never written;
  *  - table pointers passed to swb_set_tables are HOST pointers (copied);
  *  - `stream` is a cudaStream_t passed as void*; calls only enqueue work unless stated;
  *  - the caller (PyTorch on the Python side) owns every state buffer and keeps it alive
@@ -33,14 +33,18 @@
 extern "C" {
 #endif
 
-#define SWB_ABI_VERSION 1
+#define SWB_ABI_VERSION 2
 
 enum {
     SWB_E_INVALID = -1,  /* bad argument / configuration                    */
     SWB_E_STATE = -2,    /* call sequence error (e.g. state not bound)      */
     SWB_E_NODEVICE = -3, /* no CUDA device / wrong architecture             */
     SWB_E_TIMEOUT = -4,  /* a peer never signalled (multi-GPU)              */
-    SWB_E_NONFINITE = -5 /* reserved                                        */
+    SWB_E_NONFINITE = -5,/* reserved                                        */
+    SWB_E_DEPTH = -6     /* SWB_FAST met a non-positive half-step layer depth: its
+                            results are not the reference's there (which switches
+                            formulas, numpy.py:287-292, 321-322); rerun with
+                            SWB_FAST_GUARDED or SWB_STRICT                  */
 };
 
 enum { SWB_F64 = 0, SWB_F32 = 1 };
@@ -48,8 +52,10 @@ enum { SWB_F64 = 0, SWB_F32 = 1 };
 /* Arithmetic mode.  STRICT evaluates every expression in the reference's operation order
  * with IEEE add/mul/div/sqrt and no FMA contraction: results are bit-identical to numpy.
  * FAST computes each face once with FMA contraction and shared reciprocals: results
- * agree with numpy to <= 1e-12 (normwise) over benchmark-length runs. */
-enum { SWB_STRICT = 0, SWB_FAST = 1 };
+ * agree with numpy to <= 1e-12 (normwise) over benchmark-length runs.  FAST assumes the
+ * half-step layer depths stay positive (every physical run) and raises SWB_E_DEPTH in
+ * swb_status.error otherwise; FAST_GUARDED evaluates the reference's `hMid > 0` selects. */
+enum { SWB_STRICT = 0, SWB_FAST = 1, SWB_FAST_GUARDED = 2 };
 
 typedef struct swb_ctx swb_ctx;
 
@@ -61,7 +67,7 @@ typedef struct swb_config {
     int32_t n_local;      /* latitude rows held locally, halo/ghost rows included     */
     int32_t j_first;      /* first global latitude row this context UPDATES (>= 1)    */
     int32_t j_last;       /* last global latitude row this context updates (<= N-2)   */
-    int32_t pitch;        /* elements between consecutive longitudes in state arrays  */
+    int32_t pitch;        /* elements between consecutive latitudes in state arrays   */
     int32_t dtype;        /* SWB_F64 | SWB_F32                                        */
     int32_t mode;         /* SWB_STRICT | SWB_FAST                                    */
     int32_t use_diffusion;/* numpy.py:541-544                                         */
@@ -71,7 +77,8 @@ typedef struct swb_config {
     int32_t log_capacity; /* steps of (dt, time) history kept on the device (0 = none)*/
     int32_t rank;         /* latitude-band index (0 on one GPU)                       */
     int32_t world;        /* number of latitude bands / GPUs (1 on one GPU)           */
-    int32_t lead_pad;     /* padding columns before local row 0 in every state array  */
+    int32_t halo;         /* rows exchanged with each neighbour band (1; 2 with
+                             diffusion); ignored when world == 1                      */
     double courant;       /* CFL number (numpy.py:413)                                */
     double final_time;    /* seconds (numpy.py:470-472)                               */
     double dxmin, dymin;  /* CartesianGrid.dxmin / dymin (grid.py:46-47)              */
@@ -122,10 +129,21 @@ int swb_destroy(swb_ctx *ctx);
 
 int swb_set_tables(swb_ctx *ctx, const swb_tables *tabs);
 
+/* Smallest legal `pitch` for a grid with M longitudes (a multiple of 16 elements). */
+int swb_required_pitch(int M);
+
 /* Bind the two buffer sets the path ping-pongs between (set 0 holds the initial state),
- * plus the optional 2-D Coriolis array and topography (device pointers or NULL). */
+ * plus the optional 2-D Coriolis array and topography (device pointers or NULL), all
+ * (n_local, pitch) arrays in the latitude-major device layout. */
 int swb_bind_state(swb_ctx *ctx, void *h0, void *u0, void *v0, void *h1, void *u1, void *v1,
                    const void *f2d, const void *hs);
+
+/* Layout conversion on the device (numpy.py:488-492, 559-563 snapshots; the IC upload):
+ * `ref` is a window of an array in the reference's layout -- element (i, jl) at
+ * ref[i*ref_pitch + jl], i = 0..M+2, jl = 0..n_local-1 -- and `dev` an (n_local, pitch)
+ * array in the device layout.  Both are device pointers. */
+int swb_to_device_layout(swb_ctx *ctx, const void *ref, int ref_pitch, void *dev, void *stream);
+int swb_from_device_layout(swb_ctx *ctx, const void *dev, void *ref, int ref_pitch, void *stream);
 
 /* numpy.py:503-521 on the FULL ghosted initial state (ghost cells hold genuine initial
  * values at step 1); resets time and step count to zero. */
@@ -142,8 +160,8 @@ int swb_enqueue_steps(swb_ctx *ctx, int n, void *stream);
  * 359-382 `compute_diffusion`, 385-406 `_apply_bcs`.  Does not touch time bookkeeping. */
 int swb_step_fixed_dt(swb_ctx *ctx, double dt, void *stream);
 
-/* Laplacian of one field (numpy.py:359-382 `compute_diffusion`): q is an (M+3, n_local)
- * device array, out receives (M+3, n_local) with the interior filled. */
+/* Laplacian of one field (numpy.py:359-382 `compute_diffusion`): q is an (n_local, pitch)
+ * device array, out receives the same shape with the interior filled. */
 int swb_laplacian(swb_ctx *ctx, const void *q, void *out, void *stream);
 
 /* max sqrt(u^2+v^2) over the full current state (numpy.py:553-554); result (double)
@@ -180,8 +198,12 @@ int swb_ipc_close(void *base);
 int swb_exchange_block(swb_ctx *ctx, void **dptr, uint64_t *bytes);
 
 /* Give the context its peers: for every band r, the (peer-mapped) address of its exchange
- * block; for the south (rank-1) and north (rank+1) neighbours the addresses of their two
- * buffer sets (h0,u0,v0,h1,u1,v1), their j_begin and pitch.  Absent neighbours: NULL. */
+ * block (this context's own included); for the south (rank-1) and north (rank+1)
+ * neighbours the addresses of their two buffer sets (h0,u0,v0,h1,u1,v1), their j_begin
+ * and pitch.  Absent neighbours: NULL.  From then on every step stores the rows a
+ * neighbour reads as halo straight into the neighbour's arrays (peer stores over NVLink)
+ * and deposits this band's CFL maxima in every exchange block; the next step's prologue
+ * waits for all bands' maxima -- no host call, no NCCL on the step path. */
 int swb_link_peers(swb_ctx *ctx, void *const *exchange_blocks,
                    void *const south_bufs[6], int south_j_begin, int south_pitch,
                    void *const north_bufs[6], int north_j_begin, int north_pitch);

@@ -12,8 +12,9 @@ c_int32, c_int64, c_double, c_void_p = ctypes.c_int32, ctypes.c_int64, ctypes.c_
 _dp = ctypes.POINTER(ctypes.c_double)
 
 SWB_F64, SWB_F32 = 0, 1
-SWB_STRICT, SWB_FAST = 0, 1
-MODES = {"strict": SWB_STRICT, "fast": SWB_FAST}
+SWB_STRICT, SWB_FAST, SWB_FAST_GUARDED = 0, 1, 2
+MODES = {"strict": SWB_STRICT, "fast": SWB_FAST, "fast_guarded": SWB_FAST_GUARDED}
+SWB_E_TIMEOUT, SWB_E_DEPTH = -4, -6
 IPC_HANDLE_BYTES = 64
 
 
@@ -28,7 +29,7 @@ class SwbError(RuntimeError):
 class SwbConfig(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "struct_bytes", "M", "N", "j_begin", "n_local", "j_first", "j_last", "pitch", "dtype", "mode",
-        "use_diffusion", "f_is_2d", "has_hs", "device", "log_capacity", "rank", "world", "lead_pad",
+        "use_diffusion", "f_is_2d", "has_hs", "device", "log_capacity", "rank", "world", "halo",
     )] + [(n, c_double) for n in (
         "courant", "final_time", "dxmin", "dymin", "g", "a", "nu", "dphi",
     )]
@@ -54,7 +55,10 @@ SYMBOLS = {
     "swb_create": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(SwbConfig)]),
     "swb_destroy": (ctypes.c_int, [c_void_p]),
     "swb_set_tables": (ctypes.c_int, [c_void_p, ctypes.POINTER(SwbTables)]),
+    "swb_required_pitch": (ctypes.c_int, [ctypes.c_int]),
     "swb_bind_state": (ctypes.c_int, [c_void_p] + [c_void_p] * 8),
+    "swb_to_device_layout": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, c_void_p, c_void_p]),
+    "swb_from_device_layout": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, c_void_p]),
     "swb_cfl_init": (ctypes.c_int, [c_void_p, c_void_p]),
     "swb_enqueue_steps": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p]),
     "swb_step_fixed_dt": (ctypes.c_int, [c_void_p, c_double, c_void_p]),
@@ -97,7 +101,7 @@ def load():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError here means header and library disagree
             fn.restype, fn.argtypes = res, args
-        if L.swb_abi_version() != 1:
+        if L.swb_abi_version() != 2:
             raise ImportError("libswb200.so ABI version mismatch")
         _lib = L
     return _lib

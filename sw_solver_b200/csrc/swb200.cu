@@ -41,17 +41,30 @@ int cuda_fail(cudaError_t e, const char *where)
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
+int nstrips_of(int M) { return (M + 1 + kStripValid - 1) / kStripValid; }
+
+int required_pitch(int M)
+{
+    // the last strip reads 64 columns (+2 for the topography differences); round to 128 bytes
+    const int need = kStripValid * (nstrips_of(M) - 1) + kStripCols + 2;
+    return (need + 15) / 16 * 16;
+}
+
 }  // namespace
 
 struct swb_ctx {
     swb_config cfg;
     Params prm;
-    bool tables_set = false, state_bound = false, cfl_ready = false;
+    bool tables_set = false, state_bound = false, cfl_ready = false, linked = false;
     double *d_phi = nullptr, *d_tab = nullptr, *d_log = nullptr;
     Ctrl *d_ctrl = nullptr;
+    int *d_err = nullptr;
+    unsigned int *d_done = nullptr;
+    XBlock *d_xblock = nullptr;
     unsigned long long *d_scratch = nullptr;
     swb_status *h_status = nullptr;  // pinned mirror
-    int launch = 0;                  // index of the next step launch
+    int launch = 0;                  // index of the next step launch (mod-3 cycle)
+    unsigned long long seq = 1;      // stamp of the next step launch (multi-GPU)
     int64_t launches = 0;
     int sm_count = 148;
     bool use_tma = false;
@@ -61,62 +74,68 @@ struct swb_ctx {
 
 namespace {
 
-typedef void (*step_fn)(const Params);
-
-template <bool S, bool D, bool F, bool H>
-void launch_step(const Params &p, dim3 grid, cudaStream_t st)
-{
-    step_kernel<S, D, F, H><<<grid, kWarpsPerBlock * 32, 0, st>>>(p);
-}
-
-template <bool S, bool D, bool F>
-void pick_h(const Params &p, dim3 g, cudaStream_t st, bool hs)
-{
-    if (hs) launch_step<S, D, F, true>(p, g, st);
-    else launch_step<S, D, F, false>(p, g, st);
-}
-template <bool S, bool D>
-void pick_f(const Params &p, dim3 g, cudaStream_t st, bool f2d, bool hs)
-{
-    if (f2d) pick_h<S, D, true>(p, g, st, hs);
-    else pick_h<S, D, false>(p, g, st, hs);
-}
-template <bool S>
-void pick_d(const Params &p, dim3 g, cudaStream_t st, bool diff, bool f2d, bool hs)
-{
-    if (diff) pick_f<S, true>(p, g, st, f2d, hs);
-    else pick_f<S, false>(p, g, st, f2d, hs);
-}
-
-// TMA pipeline shapes built into the library: {rows per box R, stages S}
-struct TmaVariant { int R, S; };
-constexpr TmaVariant kTmaVariants[] = {{2, 4}, {4, 3}, {4, 4}, {2, 6}, {8, 3}};
+// TMA ring shapes built into the library: {latitudes per box R, stages S}
+struct TmaVariant { int R, S, minb; };
+constexpr TmaVariant kTmaVariants[] = {{2, 4, 3}, {4, 2, 3}, {2, 3, 3}, {4, 3, 2}, {2, 4, 2}, {4, 4, 2}};
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
+constexpr int kDefaultTmaVariant = 5;  // R = 4, S = 4, two blocks per SM: no spills (1.26 ms/step at 16384 x 8192)
 
-template <bool STRICT, int R, int S>
-cudaError_t launch_tma_rs(const Params &p, const TmaMaps &m, dim3 grid, cudaStream_t st)
+template <bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB>
+cudaError_t launch_inst(const swb_ctx *c, dim3 grid, cudaStream_t st)
 {
     using LY = TmaLayout<R, S>;
-    static bool configured = false;  // per instantiation; contexts of one process share devices' function attributes
-    auto fn = step_kernel_tma<STRICT, R, S>;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, LY::kBlockBytes);
+    const int smem = rec_bytes(c->prm.chunk, DIFF) + (TMA ? kWarpsPerBlock * LY::kWarpBytes : 0);
+    static int configured[64] = {0};  // per instantiation and device: largest size opted in so far
+    auto fn = march_kernel<STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, MINB>;
+    const int dev = c->cfg.device & 63;
+    if (configured[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = smem;
     }
-    fn<<<grid, kWarpsPerBlock * 32, LY::kBlockBytes, st>>>(p, m);
+    fn<<<grid, kWarpsPerBlock * 32, smem, st>>>(c->prm, c->maps);
     return cudaSuccess;
 }
 
-template <bool STRICT>
-cudaError_t launch_tma(int variant, const Params &p, const TmaMaps &m, dim3 grid, cudaStream_t st)
+// mode: SWB_STRICT, SWB_FAST, SWB_FAST_GUARDED
+template <bool DIFF, bool F2D, bool HS>
+cudaError_t launch_ldg_m(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
-    switch (variant) {
-        case 0: return launch_tma_rs<STRICT, 2, 4>(p, m, grid, st);
-        case 1: return launch_tma_rs<STRICT, 4, 3>(p, m, grid, st);
-        case 2: return launch_tma_rs<STRICT, 4, 4>(p, m, grid, st);
-        case 3: return launch_tma_rs<STRICT, 2, 6>(p, m, grid, st);
-        default: return launch_tma_rs<STRICT, 8, 3>(p, m, grid, st);
+    if (mode == SWB_STRICT) return launch_inst<true, DIFF, F2D, HS, false, 1, 1, true, 2>(c, g, st);
+    if (mode == SWB_FAST) return launch_inst<false, DIFF, F2D, HS, false, 1, 1, false, 2>(c, g, st);
+    return launch_inst<false, DIFF, F2D, HS, false, 1, 1, true, 2>(c, g, st);
+}
+template <bool DIFF, bool F2D>
+cudaError_t launch_ldg_h(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool hs)
+{
+    return hs ? launch_ldg_m<DIFF, F2D, true>(c, mode, g, st) : launch_ldg_m<DIFF, F2D, false>(c, mode, g, st);
+}
+template <bool DIFF>
+cudaError_t launch_ldg_f(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool f2d, bool hs)
+{
+    return f2d ? launch_ldg_h<DIFF, true>(c, mode, g, st, hs) : launch_ldg_h<DIFF, false>(c, mode, g, st, hs);
+}
+cudaError_t launch_ldg(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool diff, bool f2d, bool hs)
+{
+    return diff ? launch_ldg_f<true>(c, mode, g, st, f2d, hs) : launch_ldg_f<false>(c, mode, g, st, f2d, hs);
+}
+
+template <int R, int S, int MINB>
+cudaError_t launch_tma_rs(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
+{
+    if (mode == SWB_STRICT) return launch_inst<true, false, false, false, true, R, S, true, 2>(c, g, st);
+    if (mode == SWB_FAST) return launch_inst<false, false, false, false, true, R, S, false, MINB>(c, g, st);
+    return launch_inst<false, false, false, false, true, R, S, true, MINB>(c, g, st);
+}
+cudaError_t launch_tma(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
+{
+    switch (c->tma_variant) {
+        case 0: return launch_tma_rs<2, 4, 3>(c, mode, g, st);
+        case 1: return launch_tma_rs<4, 2, 3>(c, mode, g, st);
+        case 2: return launch_tma_rs<2, 3, 3>(c, mode, g, st);
+        case 3: return launch_tma_rs<4, 3, 2>(c, mode, g, st);
+        case 4: return launch_tma_rs<2, 4, 2>(c, mode, g, st);
+        default: return launch_tma_rs<4, 4, 2>(c, mode, g, st);
     }
 }
 
@@ -124,17 +143,17 @@ int launch_one(swb_ctx *c, cudaStream_t st)
 {
     const swb_config &cfg = c->cfg;
     const Params &p = c->prm;
-    dim3 grid((unsigned)((p.nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)((p.M + 1 + p.chunk - 1) / p.chunk));
-    if (c->use_tma) {
-        CK(cfg.mode == SWB_STRICT ? launch_tma<true>(c->tma_variant, p, c->maps, grid, st)
-                                  : launch_tma<false>(c->tma_variant, p, c->maps, grid, st));
-    } else if (cfg.mode == SWB_STRICT) {
-        pick_d<true>(p, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs);
-    } else {
-        pick_d<false>(p, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs);
-    }
+    const int rows = p.jl_last - p.jl_first + 1;
+    dim3 grid((unsigned)((p.nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)((rows + p.chunk - 1) / p.chunk));
+    if (c->use_tma) CK(launch_tma(c, cfg.mode, grid, st));
+    else CK(launch_ldg(c, cfg.mode, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs));
     c->launches++;
     CK(cudaGetLastError());
+    if (c->linked && !p.fixed) {
+        publish_kernel<<<1, 32, 0, st>>>(p);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -167,13 +186,14 @@ int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_
     return 0;
 }
 
-// marching length: long enough to amortise the one-row start-up, short enough to fill
-// the machine with several waves of warps.
-int pick_chunk(int M, int nstrips, int sm_count)
+// marching length: long enough to amortise the two-row start-up, short enough to fill
+// the machine with several waves of blocks.
+int pick_chunk(int rows, int nstrips, int sm_count)
 {
-    const long long want_warps = (long long)sm_count * 64;  // >= 4 waves of 16 warps/SM
-    int chunk = 128;
-    while (chunk > 8 && (long long)nstrips * ((M + 1 + chunk - 1) / chunk) < want_warps) chunk >>= 1;
+    const long long want_blocks = (long long)sm_count * 3 * 4;  // >= 4 waves at 3 blocks/SM
+    const int gx = (nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    int chunk = 64;  // with the default ring, two blocks of 64-row records + rings fit one SM
+    while (chunk > 4 && (long long)gx * ((rows + chunk - 1) / chunk) < want_blocks) chunk >>= 1;
     return chunk;
 }
 
@@ -183,6 +203,7 @@ extern "C" {
 
 int swb_abi_version(void) { return SWB_ABI_VERSION; }
 const char *swb_last_error(void) { return g_err.c_str(); }
+int swb_required_pitch(int M) { return M >= 2 ? required_pitch(M) : SWB_E_INVALID; }
 
 int swb_create(swb_ctx **out, const swb_config *cfg)
 {
@@ -191,14 +212,22 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     if (cfg->struct_bytes != (int32_t)sizeof(swb_config)) return fail(SWB_E_INVALID, "swb_create: swb_config size mismatch (ABI)");
     if (cfg->M < 2 || cfg->N < 2 || (cfg->N & 1)) return fail(SWB_E_INVALID, "swb_create: need M >= 2 and an even N >= 2");
     if (cfg->dtype != SWB_F64) return fail(SWB_E_INVALID, "swb_create: only SWB_F64 is built in this version");
-    if (cfg->mode != SWB_STRICT && cfg->mode != SWB_FAST) return fail(SWB_E_INVALID, "swb_create: bad mode");
-    if (cfg->lead_pad < 0 || cfg->lead_pad > 8) return fail(SWB_E_INVALID, "swb_create: bad lead_pad");
-    if (cfg->n_local < 3 || cfg->pitch < cfg->lead_pad + cfg->n_local) return fail(SWB_E_INVALID, "swb_create: bad n_local / pitch");
+    if (cfg->mode != SWB_STRICT && cfg->mode != SWB_FAST && cfg->mode != SWB_FAST_GUARDED) return fail(SWB_E_INVALID, "swb_create: bad mode");
+    if (cfg->n_local < 3) return fail(SWB_E_INVALID, "swb_create: a band needs at least three latitude rows");
+    if (cfg->pitch < required_pitch(cfg->M) || (cfg->pitch & 1)) return fail(SWB_E_INVALID, "swb_create: pitch must be even and >= swb_required_pitch(M)");
     if (cfg->j_begin < 0 || cfg->j_begin + cfg->n_local > cfg->N) return fail(SWB_E_INVALID, "swb_create: band outside the grid");
     if (cfg->j_first < 1 || cfg->j_last > cfg->N - 2 || cfg->j_first > cfg->j_last) return fail(SWB_E_INVALID, "swb_create: bad j_first / j_last");
     if (cfg->j_first - 1 < cfg->j_begin || cfg->j_last + 1 >= cfg->j_begin + cfg->n_local)
         return fail(SWB_E_INVALID, "swb_create: the band must hold one row beyond each updated edge");
     if (cfg->world < 1 || cfg->world > kMaxRanks || cfg->rank < 0 || cfg->rank >= cfg->world) return fail(SWB_E_INVALID, "swb_create: bad rank / world");
+    if (cfg->world > 1) {
+        const int need = cfg->use_diffusion ? 2 : 1;
+        if (cfg->halo < need || cfg->halo > 2) return fail(SWB_E_INVALID, "swb_create: halo must be 1 (2 with diffusion)");
+        if ((cfg->j_begin > 0 && cfg->j_first - cfg->halo < cfg->j_begin) ||
+            (cfg->j_begin + cfg->n_local < cfg->N && cfg->j_last + cfg->halo >= cfg->j_begin + cfg->n_local))
+            return fail(SWB_E_INVALID, "swb_create: the band does not hold `halo` rows beyond its interior edges");
+        if (cfg->j_last - cfg->j_first + 1 < cfg->halo) return fail(SWB_E_INVALID, "swb_create: band narrower than the halo");
+    }
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -213,13 +242,20 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     if (!c) return fail(SWB_E_INVALID, "swb_create: out of host memory");
     c->cfg = *cfg;
     c->sm_count = prop.multiProcessorCount;
-    const size_t nloc = (size_t)(cfg->lead_pad + cfg->n_local);
-    CK(cudaMalloc(&c->d_phi, sizeof(double) * (size_t)(cfg->M + 3 + 16)));  // padded: the last tile of a march may peek past M+2
-    CK(cudaMemset(c->d_phi, 0, sizeof(double) * (size_t)(cfg->M + 3 + 16)));
+    const size_t nloc = (size_t)cfg->n_local;
+    const size_t nphi = (size_t)cfg->pitch + 8;  // lanes of the last strip look past M+2
+    CK(cudaMalloc(&c->d_phi, sizeof(double) * nphi));
+    CK(cudaMemset(c->d_phi, 0, sizeof(double) * nphi));
     CK(cudaMalloc(&c->d_tab, sizeof(double) * (size_t)T_COUNT * nloc));
     CK(cudaMemset(c->d_tab, 0, sizeof(double) * (size_t)T_COUNT * nloc));
     CK(cudaMalloc(&c->d_ctrl, sizeof(Ctrl) * 3));
     CK(cudaMemset(c->d_ctrl, 0, sizeof(Ctrl) * 3));
+    CK(cudaMalloc(&c->d_err, sizeof(int)));
+    CK(cudaMemset(c->d_err, 0, sizeof(int)));
+    CK(cudaMalloc(&c->d_done, sizeof(unsigned int) * 4));
+    CK(cudaMemset(c->d_done, 0, sizeof(unsigned int) * 4));
+    CK(cudaMalloc(&c->d_xblock, sizeof(XBlock)));
+    CK(cudaMemset(c->d_xblock, 0, sizeof(XBlock)));
     CK(cudaMalloc(&c->d_scratch, sizeof(unsigned long long) * 4));
     if (cfg->log_capacity > 0) {
         CK(cudaMalloc(&c->d_log, sizeof(double) * 2 * (size_t)cfg->log_capacity));
@@ -233,22 +269,22 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     p.phi = c->d_phi;
     p.tab = c->d_tab;
     p.ctrl = c->d_ctrl;
+    p.err = c->d_err;
+    p.done_ctr = c->d_done;
     p.log = c->d_log;
     p.log_cap = cfg->log_capacity;
     p.M = cfg->M;
-    p.ncols = cfg->lead_pad + cfg->n_local;
-    p.jl_lo = cfg->lead_pad;
-    p.jl_hi = p.ncols - 1;
+    p.nrows = cfg->n_local;
     p.pitch = cfg->pitch;
-    p.jl_first = cfg->j_first - cfg->j_begin + cfg->lead_pad;
-    p.jl_last = cfg->j_last - cfg->j_begin + cfg->lead_pad;
+    p.jl_first = cfg->j_first - cfg->j_begin;
+    p.jl_last = cfg->j_last - cfg->j_begin;
     p.pole_s = (cfg->j_begin == 0);
     p.pole_n = (cfg->j_begin + cfg->n_local == cfg->N);
-    p.nstrips = (p.jl_last - p.jl_first + 1 + kCellsPerWarp - 1) / kCellsPerWarp;
-    p.chunk = pick_chunk(p.M, p.nstrips, c->sm_count);
-    if (const char *ch = getenv("SWB_CHUNK")) {  // tuning knob: a power of two >= 8
+    p.nstrips = nstrips_of(p.M);
+    p.chunk = pick_chunk(p.jl_last - p.jl_first + 1, p.nstrips, c->sm_count);
+    if (const char *ch = getenv("SWB_CHUNK")) {  // tuning knob: a power of two in [4, 128]
         const int v = atoi(ch);
-        if (v >= 8 && (v & (v - 1)) == 0) p.chunk = v;
+        if (v >= 4 && v <= kMaxChunk && (v & (v - 1)) == 0) p.chunk = v;
     }
     p.courant = cfg->courant;
     p.final_time = cfg->final_time;
@@ -258,6 +294,11 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     p.a = cfg->a;
     p.nu = cfg->nu;
     p.dphi = cfg->dphi;
+    p.rank = cfg->rank;
+    p.world = 1;  // becomes cfg->world once the peers are linked
+    p.halo = cfg->halo;
+    p.xlocal = c->d_xblock;
+    p.spin_limit = 20000000000LL;  // ~10 s of SM clock ticks
     *out = c;
     return 0;
 }
@@ -269,6 +310,9 @@ int swb_destroy(swb_ctx *c)
     cudaFree(c->d_phi);
     cudaFree(c->d_tab);
     cudaFree(c->d_ctrl);
+    cudaFree(c->d_err);
+    cudaFree(c->d_done);
+    cudaFree(c->d_xblock);
     cudaFree(c->d_scratch);
     cudaFree(c->d_log);
     cudaFreeHost(c->h_status);
@@ -284,14 +328,11 @@ int swb_set_tables(swb_ctx *c, const swb_tables *t)
     if (!c->cfg.f_is_2d && !t->f_lat) return fail(SWB_E_INVALID, "swb_set_tables: f_lat required when f_is_2d == 0");
     if (c->cfg.use_diffusion && (!t->Ay || !t->By || !t->Cy)) return fail(SWB_E_INVALID, "swb_set_tables: Ay/By/Cy required with diffusion");
     CK(cudaSetDevice(c->cfg.device));
-    const size_t nloc = (size_t)c->cfg.n_local, pad = (size_t)c->cfg.lead_pad, ncols = nloc + pad;
-    std::vector<double> host((size_t)T_COUNT * ncols, 0.0);
+    const size_t nloc = (size_t)c->cfg.n_local;
+    std::vector<double> host((size_t)T_COUNT * nloc, 0.0);
     const double *src[T_COUNT] = {t->c, t->tg, t->ac, t->f_lat, t->tgMidy, t->cMidy, t->dy, t->dy1, t->dyc, t->dy1c, t->Ay, t->By, t->Cy};
     for (int k = 0; k < T_COUNT; ++k)
-        if (src[k]) {
-            for (size_t j = 0; j < pad; ++j) host[(size_t)k * ncols + j] = src[k][0];  // padding columns replay row 0
-            memcpy(&host[(size_t)k * ncols + pad], src[k], sizeof(double) * nloc);
-        }
+        if (src[k]) memcpy(&host[(size_t)k * nloc], src[k], sizeof(double) * nloc);
     CK(cudaMemcpy(c->d_tab, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_phi, t->phi, sizeof(double) * (size_t)(c->cfg.M + 3), cudaMemcpyHostToDevice));
     c->tables_set = true;
@@ -304,6 +345,9 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     if (c->cfg.f_is_2d && !f2d) return fail(SWB_E_INVALID, "swb_bind_state: f_is_2d set but no f array");
     if (c->cfg.has_hs && !hs) return fail(SWB_E_INVALID, "swb_bind_state: has_hs set but no hs array");
     Params &p = c->prm;
+    void *all[8] = {h0, u0, v0, h1, u1, v1, const_cast<void *>(f2d), const_cast<void *>(hs)};
+    for (void *q : all)
+        if (q && ((uintptr_t)q % 16) != 0) return fail(SWB_E_INVALID, "swb_bind_state: arrays must be 16-byte aligned");
     p.buf[0][0] = (double *)h0; p.buf[0][1] = (double *)u0; p.buf[0][2] = (double *)v0;
     p.buf[1][0] = (double *)h1; p.buf[1][1] = (double *)u1; p.buf[1][2] = (double *)v1;
     p.f2d = (const double *)f2d;
@@ -311,30 +355,52 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     c->state_bound = true;
     c->cfl_ready = false;
 
-    // The TMA pipeline serves the plain variant (flat topography, latitude-only Coriolis,
-    // no diffusion); SWB_KERNEL=ldg forces the direct-load kernel, SWB_TMA_VARIANT picks a
-    // pipeline shape.
+    // The TMA ring serves the plain variant (flat topography, latitude-only Coriolis, no
+    // diffusion); SWB_KERNEL=ldg forces the direct-load kernel, SWB_TMA_VARIANT picks a
+    // ring shape.
     const char *force = getenv("SWB_KERNEL");
     const bool plain = !c->cfg.use_diffusion && !c->cfg.f_is_2d && !c->cfg.has_hs;
-    bool aligned = (p.pitch % 2 == 0) && (p.jl_first % 2 == 0) && (p.jl_first >= 2);  // TMA boxes start on 16-byte columns
-    for (int s = 0; s < 2 && aligned; ++s)
-        for (int k = 0; k < 3; ++k) aligned = aligned && (((uintptr_t)p.buf[s][k]) % 16 == 0);
-    c->use_tma = plain && aligned && !(force && strcmp(force, "ldg") == 0);
+    c->use_tma = plain && !(force && strcmp(force, "ldg") == 0);
     if (force && strcmp(force, "tma") == 0 && !c->use_tma) return fail(SWB_E_INVALID, "SWB_KERNEL=tma but this configuration cannot use the TMA kernel");
     if (c->use_tma) {
         const char *v = getenv("SWB_TMA_VARIANT");
-        c->tma_variant = v ? atoi(v) : 1;
+        c->tma_variant = v ? atoi(v) : kDefaultTmaVariant;
         if (c->tma_variant < 0 || c->tma_variant >= kNumTmaVariants) return fail(SWB_E_INVALID, "bad SWB_TMA_VARIANT");
         const TmaVariant tv = kTmaVariants[c->tma_variant];
         CK(cudaSetDevice(c->cfg.device));
         for (int s = 0; s < 2; ++s)
             for (int k = 0; k < 3; ++k) {
-                int rc = make_map(&c->maps.in[s][k], p.buf[s][k], (uint64_t)p.ncols, (uint64_t)(p.M + 3), (uint64_t)p.pitch, 34, (uint32_t)tv.R);
-                if (rc) return rc;
-                rc = make_map(&c->maps.out[s][k], p.buf[s][k], (uint64_t)(p.jl_last + 1), (uint64_t)(p.M + 2), (uint64_t)p.pitch, 30, (uint32_t)tv.R);
+                int rc = make_map(&c->maps.in[s][k], p.buf[s][k], (uint64_t)(p.M + 3), (uint64_t)p.nrows, (uint64_t)p.pitch, kStripCols,
+                                  (uint32_t)tv.R);
                 if (rc) return rc;
             }
     }
+    return 0;
+}
+
+int swb_to_device_layout(swb_ctx *c, const void *ref, int ref_pitch, void *dev, void *stream)
+{
+    if (!c || !ref || !dev) return fail(SWB_E_INVALID, "swb_to_device_layout: null argument");
+    if (ref_pitch < c->cfg.n_local) return fail(SWB_E_INVALID, "swb_to_device_layout: ref_pitch < n_local");
+    CK(cudaSetDevice(c->cfg.device));
+    const int rows = c->cfg.n_local, cols = c->cfg.M + 3;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)ref, ref_pitch, (double *)dev, c->cfg.pitch, rows, cols);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int swb_from_device_layout(swb_ctx *c, const void *dev, void *ref, int ref_pitch, void *stream)
+{
+    if (!c || !ref || !dev) return fail(SWB_E_INVALID, "swb_from_device_layout: null argument");
+    if (ref_pitch < c->cfg.n_local) return fail(SWB_E_INVALID, "swb_from_device_layout: ref_pitch < n_local");
+    CK(cudaSetDevice(c->cfg.device));
+    const int rows = c->cfg.M + 3, cols = c->cfg.n_local;
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+    transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)dev, c->cfg.pitch, (double *)ref, ref_pitch, rows, cols);
+    c->launches++;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -342,18 +408,27 @@ int swb_cfl_init(swb_ctx *c, void *stream)
 {
     if (!c) return fail(SWB_E_INVALID, "swb_cfl_init: null context");
     if (!c->state_bound) return fail(SWB_E_STATE, "swb_cfl_init: no state bound");
+    if (c->cfg.world > 1 && !c->linked) return fail(SWB_E_STATE, "swb_cfl_init: call swb_link_peers first (world > 1)");
     CK(cudaSetDevice(c->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
-    const Params &p = c->prm;
+    Params &p = c->prm;
     CK(cudaMemsetAsync(c->d_ctrl, 0, sizeof(Ctrl) * 3, st));
+    CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), st));
     // every local row this band owns or mirrors takes part at step 1 (ghosts hold real
     // initial values); rows that are another band's interior are scanned by that band.
-    const int jl0 = p.pole_s ? p.jl_lo : p.jl_first, jl1 = p.pole_n ? p.jl_hi + 1 : p.jl_last + 1;
+    const int jl0 = p.pole_s ? 0 : p.jl_first, jl1 = p.pole_n ? p.nrows : p.jl_last + 1;
     const int blocks = c->sm_count * 8;
     cfl_init_kernel<<<blocks, 256, 0, st>>>(p.buf[0][0], p.buf[0][1], p.buf[0][2], p.M + 3, jl0, jl1, p.pitch, p.g, c->d_ctrl);
     c->launches++;
     CK(cudaGetLastError());
     c->launch = 0;
+    if (c->linked) {  // deposit the maxima of slot 0 with the first step's stamp
+        p.launch = 2;
+        p.stamp = c->seq - 1;
+        publish_kernel<<<1, 32, 0, st>>>(p);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
     c->cfl_ready = true;
     return 0;
 }
@@ -368,9 +443,11 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
     c->prm.fixed = 0;
     for (int k = 0; k < n; ++k) {
         c->prm.launch = c->launch;
+        c->prm.stamp = c->seq;
         int rc = launch_one(c, st);
         if (rc) return rc;
         c->launch = (c->launch + 1) % 3000000;  // stays a multiple-of-3 cycle
+        c->seq++;
     }
     return 0;
 }
@@ -394,7 +471,7 @@ int swb_laplacian(swb_ctx *c, const void *q, void *out, void *stream)
     if (!c->tables_set || !c->cfg.use_diffusion) return fail(SWB_E_STATE, "swb_laplacian: needs tables with diffusion weights");
     CK(cudaSetDevice(c->cfg.device));
     const Params &p = c->prm;
-    dim3 grid((unsigned)((p.jl_last - p.jl_first + 1 + 127) / 128), (unsigned)(p.M + 1));
+    dim3 grid((unsigned)((p.M + 1 + 127) / 128), (unsigned)(p.jl_last - p.jl_first + 1));
     laplacian_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const double *)q, (double *)out, p);
     c->launches++;
     CK(cudaGetLastError());
@@ -406,8 +483,9 @@ int swb_status_async(swb_ctx *c, swb_status *host_out, void *stream)
     if (!c) return fail(SWB_E_INVALID, "swb_status_async: null context");
     static_assert(sizeof(Ctrl) == sizeof(swb_status), "Ctrl mirrors swb_status");
     CK(cudaSetDevice(c->cfg.device));
-    void *dst = host_out ? (void *)host_out : (void *)c->h_status;
+    swb_status *dst = host_out ? host_out : c->h_status;
     CK(cudaMemcpyAsync(dst, c->d_ctrl + (c->launch % 3), sizeof(Ctrl), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(&dst->error, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     return 0;
 }
 
@@ -438,7 +516,7 @@ int swb_max_speed(swb_ctx *c, double *out_host, void *stream)
     const Params &p = c->prm;
     const int cur = s.current;
     CK(cudaMemsetAsync(c->d_scratch, 0, sizeof(unsigned long long), st));
-    const int jl0 = p.pole_s ? p.jl_lo : p.jl_first, jl1 = p.pole_n ? p.jl_hi + 1 : p.jl_last + 1;
+    const int jl0 = p.pole_s ? 0 : p.jl_first, jl1 = p.pole_n ? p.nrows : p.jl_last + 1;
     max_speed_kernel<<<c->sm_count * 8, 256, 0, st>>>(p.buf[cur][1], p.buf[cur][2], p.M + 3, jl0, jl1, p.pitch, c->d_scratch);
     c->launches++;
     CK(cudaGetLastError());
@@ -506,11 +584,43 @@ int swb_ipc_close(void *base)
     return 0;
 }
 
-int swb_exchange_block(swb_ctx *, void **, uint64_t *) { return fail(SWB_E_STATE, "swb_exchange_block: multi-GPU linking not built yet"); }
-
-int swb_link_peers(swb_ctx *, void *const *, void *const[6], int, int, void *const[6], int, int)
+int swb_exchange_block(swb_ctx *c, void **dptr, uint64_t *bytes)
 {
-    return fail(SWB_E_STATE, "swb_link_peers: multi-GPU linking not built yet");
+    if (!c || !dptr || !bytes) return fail(SWB_E_INVALID, "swb_exchange_block: null argument");
+    *dptr = c->d_xblock;
+    *bytes = sizeof(XBlock);
+    return 0;
+}
+
+int swb_link_peers(swb_ctx *c, void *const *exchange_blocks, void *const south_bufs[6], int south_j_begin, int south_pitch,
+                   void *const north_bufs[6], int north_j_begin, int north_pitch)
+{
+    if (!c || !exchange_blocks) return fail(SWB_E_INVALID, "swb_link_peers: null argument");
+    const swb_config &cfg = c->cfg;
+    if (cfg.world < 2) return fail(SWB_E_STATE, "swb_link_peers: the context was created with world == 1");
+    const bool has_s = cfg.rank > 0, has_n = cfg.rank < cfg.world - 1;
+    if ((has_s && !south_bufs) || (has_n && !north_bufs)) return fail(SWB_E_INVALID, "swb_link_peers: a neighbour's buffers are missing");
+    Params &p = c->prm;
+    for (int r = 0; r < cfg.world; ++r) {
+        if (!exchange_blocks[r]) return fail(SWB_E_INVALID, "swb_link_peers: null exchange block");
+        p.xpeer[r] = (XBlock *)exchange_blocks[r];
+    }
+    for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < 3; ++k) {
+            p.south[s][k] = has_s ? (double *)south_bufs[s * 3 + k] : nullptr;
+            p.north[s][k] = has_n ? (double *)north_bufs[s * 3 + k] : nullptr;
+            if ((has_s && !p.south[s][k]) || (has_n && !p.north[s][k])) return fail(SWB_E_INVALID, "swb_link_peers: null neighbour buffer");
+        }
+    // our first updated row (global j_first) is the south neighbour's first halo row above
+    // its interior; our last updated row is the north neighbour's last halo row below it
+    p.south_row = cfg.j_first - south_j_begin;
+    p.south_pitch = south_pitch;
+    p.north_row = cfg.j_last - north_j_begin;
+    p.north_pitch = north_pitch;
+    p.world = cfg.world;
+    c->linked = true;
+    c->cfl_ready = false;
+    return 0;
 }
 
 }  // extern "C"

@@ -1,6 +1,6 @@
 // swb_kernels.cuh -- device code of libswb200.so (sm_100a).
 //
-// The hot path is ONE kernel per time step (`step_kernel`) that replaces the body of the
+// The hot path is ONE kernel per time step (`march_kernel`) that replaces the body of the
 // loop at src/sw_solver/numpy.py:496-549 of the reference:
 //   * prologue: dt from the device-resident CFL maxima + final-time clamp (numpy.py:524-532)
 //   * Lax-Wendroff half-step face values and full-step update      (numpy.py:185-354)
@@ -8,26 +8,58 @@
 //   * boundary conditions written in place of the ghost cells        (numpy.py:402-404)
 //   * epilogue: CFL maxima of the NEW state for the next step        (numpy.py:503-521)
 //
-// Data layout (HBM): the reference's own -- state[i][j], i = longitude 0..M+2,
-// j = latitude (contiguous).  A warp covers 32 consecutive latitudes and MARCHES along
-// longitude: the x-face (i | i+1) computed at one iteration is the left face of the next
-// one and stays in registers; y-face inputs/results travel between neighbouring lanes by
-// warp shuffles.  Lanes 1..30 update cells (warps overlap by two latitudes), so every
-// face is computed exactly once per warp.  All metric terms are per-lane registers
-// derived from 1-D latitude tables; nothing 2-D but h, u, v is read from HBM.
+// Data layout (HBM): LATITUDE-MAJOR, state[jl][i] with i = longitude 0..M+2 contiguous and
+// `pitch` elements between consecutive latitudes (the transpose of the reference's array;
+// swb_import_state / swb_export_state convert).  A latitude band's halo rows are therefore
+// contiguous, and every metric term (a function of latitude only) is uniform across a warp.
+//
+// Work decomposition: a warp owns a strip of 64 consecutive longitudes -- two cells per
+// lane -- and MARCHES along latitude.  The y-face (j | j+1) computed at one iteration is
+// the lower face of the next one and stays in registers; of the two x-faces a lane
+// computes, one lies between its own two cells and the other is shared with the next
+// lane through warp shuffles.  Columns 1..62 of a strip are updated (strips overlap by
+// two columns), so every face is computed once per warp.  Per-row metric/Coriolis/dt
+// factors are built once per block in shared memory and broadcast; nothing 2-D but
+// h, u, v is read from HBM.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace swb {
 
 constexpr int kWarpsPerBlock = 4;
-constexpr int kCellsPerWarp = 30;  // lanes 1..30 update cells
+constexpr int kStripCols = 64;   // longitudes held by a warp (2 per lane)
+constexpr int kStripValid = 62;  // longitudes updated by a warp (columns 1..62 of the strip)
+constexpr int kMaxChunk = 128;   // latitudes marched by one warp, at most
+constexpr int kRowRec = 16;      // doubles per row record
+constexpr int kRowDiff = 8;      // doubles per diffusion row record
 constexpr int kMaxRanks = 8;
 
-// row indices of the packed latitude table (each row n_local long)
+// row indices of the packed latitude table (each row `nrows` long, indexed by local latitude)
 enum Tab { T_C = 0, T_TG, T_AC, T_F, T_TGMIDY, T_CMIDY, T_DY, T_DY1, T_DYC, T_DY1C, T_AY, T_BY, T_CY, T_COUNT };
+
+// slots of a row record (shared memory, one record per latitude of the block's chunk)
+enum Rec {
+    RC_C = 0,   // cos(theta_j)
+    RC_AC,      // a cos(theta_j)
+    RC_KX,      // x-face metric factor   STRICT: tan(theta_j)      FAST: hdt*0.5*tan/a
+    RC_FKX,     // x-face Coriolis        STRICT: f_j               FAST: hdt*f_j
+    RC_CDX,     // FAST: dt/dx_j
+    RC_CXU,     // FAST: 0.5*dt/dx_j
+    RC_KY,      // y-face (j|j+1) metric  STRICT: tgMidy_j          FAST: hdt*0.5*tgMidy/a
+    RC_FKY,     // y-face Coriolis        STRICT: 0.5*(f_j+f_j+1)   FAST: hdt*0.5*(f_j+f_j+1)
+    RC_CM,      // cMidy_j
+    RC_CY1F,    // STRICT: hdt/dy1_j      FAST: dt/dy1_j
+    RC_CYF,     // STRICT: hdt/dy_j       FAST: dt/dy_j
+    RC_CY1U,    // STRICT: dt/dy1c_j      FAST: 0.5*dt/dy1c_j
+    RC_CYU,     // STRICT: dt/dyc_j       FAST: 0.5*dt/dyc_j
+    RC_KC,      // update metric factor   STRICT: tan(theta_j)      FAST: dt/64*tan/a
+    RC_FD,      // update Coriolis        STRICT: f_j               FAST: dt/8*f_j
+    RC_DY1S     // dy1_{j-1} + dy1_j (topography term)
+};
 
 // Device-resident loop state (numpy.py:494-496, 500, 524-532).  Three slots rotate with
 // the launch index L: kernel L reads slot L%3, writes time/steps and accumulates the new
@@ -44,25 +76,48 @@ struct Ctrl {  // same layout as swb_status (include/swb200.h): mirrored to the 
     int reserved;
 };
 
+// Multi-GPU exchange block (one per context, peers write into it): per launch slot and per
+// rank the CFL maxima of that rank's band plus an arrival stamp.
+struct XSlot {
+    unsigned long long ex_bits, ey_bits;
+    unsigned long long stamp;  // launch index + 1 of the step that produced the maxima
+    unsigned long long pad;
+};
+struct XBlock {
+    XSlot slot[3][kMaxRanks];
+};
+
 struct Params {
     double *buf[2][3];  // two buffer sets {h,u,v}; set (nsteps & 1) holds the current state
-    const double *f2d;  // (M+3, pitch) or null
-    const double *hs;   // (M+3, pitch) or null
-    const double *phi;  // M+3
-    const double *tab;  // T_COUNT x ncols
+    const double *f2d;  // (nrows, pitch) or null
+    const double *hs;   // (nrows, pitch) or null
+    const double *phi;  // M+3 (+ padding)
+    const double *tab;  // T_COUNT x nrows
     Ctrl *ctrl;         // 3 slots
+    int *err;           // sticky device-side error word (0 or a negative SWB_E_*)
+    unsigned int *done_ctr;  // 3 counters: blocks of launch L that finished (multi-GPU epilogue)
     double *log;        // 2 x log_cap: dt then time, or null
     int log_cap;
-    int M, ncols, pitch;    // ncols = lead_pad + n_local: local columns [jl_lo, jl_hi] are real
-    int jl_lo, jl_hi;
+    int M, nrows, pitch;    // nrows = local latitudes (halo / pole rows included)
     int jl_first, jl_last;  // local latitude rows updated by this context (inclusive)
-    int pole_s, pole_n;     // local row jl_lo / jl_hi is the global copy row 0 / N-1
-    int chunk;              // longitudes marched by one warp
-    int nstrips;            // warps needed along latitude
-    int launch;             // launch index L
+    int pole_s, pole_n;     // local row 0 / nrows-1 is the global copy row 0 / N-1
+    int chunk;              // latitudes marched by one warp
+    int nstrips;            // warps needed along longitude
+    int launch;             // launch index L (mod 3 cycle)
     int fixed;              // 1: use fixed_dt, buffers 0 -> 1, no bookkeeping
     double fixed_dt;
     double courant, final_time, dxmin, dymin, g, a, nu, dphi;
+    // multi-GPU (world > 1): peers' exchange blocks and neighbour halo rows
+    int rank, world;
+    unsigned long long stamp;       // launch sequence number (monotone, never wraps in practice)
+    XBlock *xlocal;                 // this context's exchange block
+    XBlock *xpeer[kMaxRanks];       // every rank's exchange block as mapped here (self included)
+    double *south[2][3];            // south neighbour's buffer sets (peer mapped) or null
+    double *north[2][3];
+    int south_row, north_row;       // row index, in the neighbour's arrays, of the halo row we fill
+    int south_pitch, north_pitch;
+    int halo;                       // rows exchanged per side (1, or 2 with diffusion)
+    long long spin_limit;           // clock64 ticks to wait for peers before flagging SWB_E_TIMEOUT
 };
 
 // ------------------------------------------------------------------------------------
@@ -112,6 +167,8 @@ __device__ __forceinline__ unsigned long long nonneg_bits(double v)
     return ((unsigned long long)(unsigned)(__double2hiint(v) & 0x7fffffff) << 32) | (unsigned)__double2loint(v);
 }
 
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+
 __device__ __forceinline__ double shfl_down1(double x) { return __shfl_down_sync(0xffffffffu, x, 1); }
 __device__ __forceinline__ double shfl_up1(double x) { return __shfl_up_sync(0xffffffffu, x, 1); }
 
@@ -119,7 +176,7 @@ __device__ __forceinline__ double shfl_up1(double x) { return __shfl_up_sync(0xf
 // per-cell products (numpy.py:185-188, 203, 220, 237, 254-255)
 // ------------------------------------------------------------------------------------
 struct Cell {
-    double h, u, v;
+    double h, u;
     double hu, hv;   // h*u, h*v
     double Ux, Vx;   // hu*u + (hg*h)*h ; hu*v
     double hw;       // h*(v*c)          ("hv1")
@@ -133,7 +190,7 @@ __device__ __forceinline__ Cell make_cell(double h, double u, double v, double c
 {
     using O = Op<STRICT>;
     Cell q;
-    q.h = h; q.u = u; q.v = v; q.f = f;
+    q.h = h; q.u = u; q.f = f;
     q.hu = O::mul(h, u);
     q.hv = O::mul(h, v);
     q.pr = O::mul(O::mul(hg, h), h);
@@ -155,11 +212,17 @@ struct Face {
     double hvc;         // y only: hvMidy * cMidy
 };
 
+// hM > 0 on the integer pipe (false for -0, +0 and negative values; NaN is not an issue:
+// a NaN state stops the loop through the CFL maxima)
+__device__ __forceinline__ bool positive(double x) { return __double_as_longlong(x) > 0; }
+
 // x-face between (i, j) = `a` and (i+1, j) = `b`.  numpy.py:193-195, 203-217, 237-251,
 // 287-291, 321.
 //   STRICT: cdx = hdt/dx[i,j];  kt = tan(theta_j) (tgMidx);  fK = 0.5*(f_b+f_a)
 //   FAST:   cdx = dt/dx_j;      kt = hdt*0.5*tan/a;          fK = hdt*f
-template <bool STRICT, bool GUARD = true>
+// GUARD evaluates the reference's `hMid > 0` selects; without it they are assumed true
+// (positive layer depth) and the caller watches the sign of hM instead.
+template <bool STRICT, bool GUARD>
 __device__ __forceinline__ Face x_face(const Cell &a, const Cell &b, double cdx, double kt, double fK,
                                        double hdt, double hg, double ra)
 {
@@ -187,9 +250,9 @@ __device__ __forceinline__ Face x_face(const Cell &a, const Cell &b, double cdx,
         const double r = fast_rcp(F.hM);
         F.q = F.huM * r;
         const double pres = (hg * F.hM) * F.hM;               // hg here is g/4: 2*(g/2)*hM^2
-        const bool pos = !GUARD || __double2hiint(F.hM) > 0 || (__double2hiint(F.hM) == 0 && __double2loint(F.hM) != 0);
-        F.F1 = pos ? fma(F.huM, F.q, pres) : pres;            // 2 UxMid
-        F.F2 = pos ? F.hvM * F.q : 0.0;                       // 2 VxMid
+        const double qg = (!GUARD || positive(F.hM)) ? F.q : 0.0;
+        F.F1 = fma(F.huM, qg, pres);                          // 2 UxMid
+        F.F2 = F.hvM * qg;                                    // 2 VxMid
     }
     F.F3 = 0.0;
     F.hvc = 0.0;
@@ -200,7 +263,7 @@ __device__ __forceinline__ Face x_face(const Cell &a, const Cell &b, double cdx,
 // 292, 322-323.
 //   STRICT: c1 = hdt/dy1_j, c2 = hdt/dy_j, kt = tgMidy_j, fK = 0.5*(f_b+f_a)
 //   FAST:   c1 = dt/dy1_j,  c2 = dt/dy_j,  kt = hdt*0.5*tgMidy/a, fK = hdt*0.5*(f_b+f_a)
-template <bool STRICT, bool GUARD = true>
+template <bool STRICT, bool GUARD>
 __device__ __forceinline__ Face y_face(const Cell &a, const Cell &b, double c1, double c2, double kt, double fK,
                                        double cm, double hdt, double hg, double ra)
 {
@@ -230,12 +293,64 @@ __device__ __forceinline__ Face y_face(const Cell &a, const Cell &b, double c1, 
         const double r = fast_rcp(F.hM);
         F.q = F.huM * r;
         F.hvc = F.hvM * cm;
-        const bool pos = !GUARD || __double2hiint(F.hM) > 0 || (__double2hiint(F.hM) == 0 && __double2loint(F.hM) != 0);
-        F.F1 = pos ? F.hvc * F.q : 0.0;            // 2 UyMid
-        F.F2 = pos ? F.hvc * (F.hvM * r) : 0.0;    // 2 Vy1Mid
+        const double t = F.hvM * r;
+        const bool pos = !GUARD || positive(F.hM);
+        F.F1 = F.hvc * (pos ? F.q : 0.0);          // 2 UyMid
+        F.F2 = F.hvc * (pos ? t : 0.0);            // 2 Vy1Mid
         F.F3 = (hg * F.hM) * F.hM;                 // 2 Vy2Mid (hg = g/4)
     }
     return F;
+}
+
+// Full-step update of one cell from its four faces (numpy.py:275-354).
+//   STRICT: cx = dt/dxc[i,j], cy1u = dt/dy1c_j, cyu = dt/dyc_j, kc = tan(theta_j), fc = f
+//   FAST:   cx = 0.5*dt/dx_j, cy1u, cyu halved, kc = dt/64*tan/a, fc = dt/8*f
+// hsx = hs[i+1,j]-hs[i-1,j], hsy = hs[i,j+1]-hs[i,j-1], dxs = dx[i-1,j]+dx[i,j], dy1s = dy1_{j-1}+dy1_j.
+template <bool STRICT, bool HS>
+__device__ __forceinline__ void update_cell(const Cell &cur, const Face &x0, const Face &x1, const Face &y0, const Face &y1,
+                                            double cx, double cy1u, double cyu, double kc, double fc, double dt, double g,
+                                            double ra, double hsx, double hsy, double dxs, double dy1s, double &hn,
+                                            double &un, double &vn)
+{
+    using O = Op<STRICT>;
+    if (STRICT) {
+        hn = O::sub(O::sub(cur.h, O::mul(cx, O::sub(x1.huM, x0.huM))), O::mul(cy1u, O::sub(y1.hvc, y0.hvc)));
+        const double qs = O::add(O::add(O::add(x0.q, x1.q), y0.q), y1.q);
+        const double Fc = O::add(fc, O::div(O::mul(O::mul(0.25, qs), kc), ra));
+        const double D = O::mul(O::mul(dt, Fc), 0.25);
+        const double shv = O::add(O::add(O::add(x0.hvM, x1.hvM), y0.hvM), y1.hvM);
+        const double shu = O::add(O::add(O::add(x0.huM, x1.huM), y0.huM), y1.huM);
+        double hun = O::add(O::sub(O::sub(cur.hu, O::mul(cx, O::sub(x1.F1, x0.F1))), O::mul(cy1u, O::sub(y1.F1, y0.F1))),
+                            O::mul(D, shv));
+        double hvn = O::sub(O::sub(O::sub(O::sub(cur.hv, O::mul(cx, O::sub(x1.F2, x0.F2))), O::mul(cy1u, O::sub(y1.F2, y0.F2))),
+                                   O::mul(cyu, O::sub(y1.F3, y0.F3))),
+                            O::mul(D, shu));
+        if (HS) {  // numpy.py:310-317, 342-349
+            const double hsum = O::add(O::add(O::add(x0.hM, x1.hM), y0.hM), y1.hM);
+            const double gq = O::mul(O::mul(O::mul(dt, g), 0.25), hsum);
+            hun = O::sub(hun, O::div(O::mul(gq, hsx), dxs));
+            hvn = O::sub(hvn, O::div(O::mul(gq, hsy), dy1s));
+        }
+        un = O::div(hun, hn);
+        vn = O::div(hvn, hn);
+    } else {
+        hn = fma(-cy1u, y1.hvc - y0.hvc, fma(-cx, x1.huM - x0.huM, cur.h));
+        const double qs = (x0.q + x1.q) + (y0.q + y1.q);
+        const double D = fma(qs, kc, fc);  // 0.5 * dt * Fc * 0.25
+        const double shv = (x0.hvM + x1.hvM) + (y0.hvM + y1.hvM);
+        const double shu = (x0.huM + x1.huM) + (y0.huM + y1.huM);
+        double hun = fma(D, shv, fma(-cy1u, y1.F1 - y0.F1, fma(-cx, x1.F1 - x0.F1, cur.hu)));
+        double hvn = fma(-D, shu, fma(-cyu, y1.F3 - y0.F3, fma(-cy1u, y1.F2 - y0.F2, fma(-cx, x1.F2 - x0.F2, cur.hv))));
+        if (HS) {
+            const double hsum = (x0.hM + x1.hM) + (y0.hM + y1.hM);  // doubled
+            const double gq = dt * g * 0.125 * hsum;
+            hun -= gq * hsx / dxs;
+            hvn -= gq * hsy / dy1s;
+        }
+        const double r = fast_rcp(hn);
+        un = hun * r;
+        vn = hvn * r;
+    }
 }
 
 // 3-point first-derivative weights on spacings d0 (minus side), d1 (plus side):
@@ -248,59 +363,79 @@ __device__ __forceinline__ void weights_strict(double d0, double d1, double &A, 
     C = O::div(-d1, O::mul(d0, O::add(d1, d0)));
 }
 
-__device__ __forceinline__ double second_diff_strict(double Am, double Bm, double Cm, double A0, double B0, double C0,
-                                                     double Ap, double Bp, double Cp, double qmm, double qm, double q0,
-                                                     double qp, double qpp)
+struct W3 {  // weights of three consecutive points (minus, centre, plus)
+    double A[3], B[3], C[3];
+};
+
+__device__ __forceinline__ double second_diff_strict(const W3 &w, double qmm, double qm, double q0, double qp, double qpp)
 {
     using O = Op<true>;
     // numpy.py:87-105: A*(A q + B q+ + C q-) + B*(A+ q+ + B+ q++ + C+ q) + C*(A- q- + B- q + C- q--)
-    const double t0 = O::mul(A0, O::add(O::add(O::mul(A0, q0), O::mul(B0, qp)), O::mul(C0, qm)));
-    const double t1 = O::mul(B0, O::add(O::add(O::mul(Ap, qp), O::mul(Bp, qpp)), O::mul(Cp, q0)));
-    const double t2 = O::mul(C0, O::add(O::add(O::mul(Am, qm), O::mul(Bm, q0)), O::mul(Cm, qmm)));
+    const double t0 = O::mul(w.A[1], O::add(O::add(O::mul(w.A[1], q0), O::mul(w.B[1], qp)), O::mul(w.C[1], qm)));
+    const double t1 = O::mul(w.B[1], O::add(O::add(O::mul(w.A[2], qp), O::mul(w.B[2], qpp)), O::mul(w.C[2], q0)));
+    const double t2 = O::mul(w.C[1], O::add(O::add(O::mul(w.A[0], qm), O::mul(w.B[0], q0)), O::mul(w.C[0], qmm)));
     return O::add(O::add(t0, t1), t2);
 }
 
-// Everything a lane needs to evaluate the Laplacian (numpy.py:66-133 on the extension of
-// numpy.py:376-381) at its latitude.
-struct LapCtx {
-    // y weights of rows j-1, j, j+1 (strict) or the five combined weights (fast)
-    double Aym, Bym, Cym, Ay0, By0, Cy0, Ayp, Byp, Cyp;
-    double w[5];
-    double bx2;             // fast: 1 / (2 dx_j)^2
-    int jm2, jm1, jp1, jp2;  // clamped neighbour columns (local indices)
-};
-
-template <bool STRICT>
-__device__ __forceinline__ double laplacian_at(const double *__restrict__ q, const Params &p, const LapCtx &L,
-                                               double ac, int i, int jl)
+// longitude weights of columns i-1, i, i+1 (numpy.py:32-45; column 0 uses column M's,
+// column M+2 uses column 2's), rebuilt from x = ac_j * phi_i
+__device__ __forceinline__ W3 x_weights_strict(const double *__restrict__ phi, double ac, int i, int M)
 {
-    const int M = p.M;
-    const size_t P = (size_t)p.pitch;
+    using O = Op<true>;
+    W3 w;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        int k = i - 1 + s;
+        k = (k == 0) ? M : ((k == M + 2) ? 2 : k);
+        const double xm = O::mul(ac, phi[k - 1]), x0 = O::mul(ac, phi[k]), xp = O::mul(ac, phi[k + 1]);
+        weights_strict(O::sub(x0, xm), O::sub(xp, x0), w.A[s], w.B[s], w.C[s]);
+    }
+    return w;
+}
+
+// latitude weights of rows j-1, j, j+1 (numpy.py:50-63), clamped to the local array
+__device__ __forceinline__ W3 y_weights(const double *__restrict__ tab, int nrows, int jl)
+{
+    W3 w;
+    const int jm = max(jl - 1, 0), jp = min(jl + 1, nrows - 1);
+    const int idx[3] = {jm, jl, jp};
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+        w.A[s] = tab[(size_t)T_AY * nrows + idx[s]];
+        w.B[s] = tab[(size_t)T_BY * nrows + idx[s]];
+        w.C[s] = tab[(size_t)T_CY * nrows + idx[s]];
+    }
+    return w;
+}
+
+// the five stencil values of q along each axis around (jl, i), with the reference's
+// extension (numpy.py:376-381): periodic in longitude, duplicated rows in latitude
+struct Star {
+    double q0, xm, xp, xmm, xpp, ym, yp, ymm, ypp;
+};
+__device__ __forceinline__ Star load_star(const double *__restrict__ q, int pitch, int nrows, int M, int jl, int i)
+{
+    const size_t P = (size_t)pitch;
     const int im2 = (i - 2 < 0) ? M - 1 : i - 2;  // numpy.py:376-378
     const int ip2 = (i + 2 > M + 2) ? 3 : i + 2;
-    const double q0 = q[(size_t)i * P + jl];
-    const double qxm = q[(size_t)(i - 1) * P + jl], qxp = q[(size_t)(i + 1) * P + jl];
-    const double qxmm = q[(size_t)im2 * P + jl], qxpp = q[(size_t)ip2 * P + jl];
-    const double qym = q[(size_t)i * P + L.jm1], qyp = q[(size_t)i * P + L.jp1];
-    const double qymm = q[(size_t)i * P + L.jm2], qypp = q[(size_t)i * P + L.jp2];
-    if (STRICT) {
-        using O = Op<true>;
-        double A[3], B[3], C[3];
-#pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            int k = i - 1 + s;
-            k = (k == 0) ? M : ((k == M + 2) ? 2 : k);  // numpy.py:35, 40, 45
-            const double xm = O::mul(ac, p.phi[k - 1]), x0 = O::mul(ac, p.phi[k]), xp = O::mul(ac, p.phi[k + 1]);
-            weights_strict(O::sub(x0, xm), O::sub(xp, x0), A[s], B[s], C[s]);
-        }
-        const double qxx = second_diff_strict(A[0], B[0], C[0], A[1], B[1], C[1], A[2], B[2], C[2], qxmm, qxm, q0, qxp, qxpp);
-        const double qyy = second_diff_strict(L.Aym, L.Bym, L.Cym, L.Ay0, L.By0, L.Cy0, L.Ayp, L.Byp, L.Cyp, qymm, qym, q0, qyp, qypp);
-        return O::add(qxx, qyy);
-    } else {
-        const double qxx = L.bx2 * fma(-2.0, q0, qxpp + qxmm);
-        const double qyy = fma(L.w[0], qymm, fma(L.w[1], qym, fma(L.w[2], q0, fma(L.w[3], qyp, L.w[4] * qypp))));
-        return qxx + qyy;
-    }
+    const int jm1 = max(jl - 1, 0), jp1 = min(jl + 1, nrows - 1);
+    const int jm2 = max(jl - 2, 0), jp2 = min(jl + 2, nrows - 1);
+    Star s;
+    const double *row = q + (size_t)jl * P;
+    s.q0 = row[i];
+    s.xm = row[i - 1]; s.xp = row[i + 1];
+    s.xmm = row[im2];  s.xpp = row[ip2];
+    s.ym = q[(size_t)jm1 * P + i]; s.yp = q[(size_t)jp1 * P + i];
+    s.ymm = q[(size_t)jm2 * P + i]; s.ypp = q[(size_t)jp2 * P + i];
+    return s;
+}
+
+// FAST diffusion row record: w[0..4] combined latitude weights, [5] = 1/(2 dx_j)^2, [6] = dt*nu
+__device__ __forceinline__ double laplacian_fast(const Star &s, const double *__restrict__ rd)
+{
+    const double qxx = rd[5] * fma(-2.0, s.q0, s.xpp + s.xmm);
+    const double qyy = fma(rd[0], s.ymm, fma(rd[1], s.ym, fma(rd[2], s.q0, fma(rd[3], s.yp, rd[4] * s.ypp))));
+    return qxx + qyy;
 }
 
 // ------------------------------------------------------------------------------------
@@ -308,6 +443,9 @@ __device__ __forceinline__ double laplacian_at(const double *__restrict__ q, con
 // ------------------------------------------------------------------------------------
 // Executed by thread 0 of every block (every block needs dt); block (0,0) also advances
 // the loop state.  Returns through shared memory: dt and flags (bit 0 active, bit 1 parity).
+// With several latitude bands (world > 1) the maxima of every band's previous step are
+// read from this context's exchange block, where the peers deposited them; their arrival
+// also tells that the neighbours' halo rows are in place.
 __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int *s_flags)
 {
     Ctrl *const cur_slot = p.ctrl + (p.launch % 3);
@@ -319,7 +457,24 @@ __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int
     }
     const double time = cur_slot->time;
     const long long nsteps = cur_slot->nsteps;
-    const unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
+    unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
+    if (p.world > 1) {
+        const volatile XSlot *xs = p.xlocal->slot[p.launch % 3];
+        const long long t0 = clock64();
+        exb = eyb = 0ULL;
+        for (int r = 0; r < p.world; ++r) {
+            while (xs[r].stamp != p.stamp) {
+                if (clock64() - t0 > p.spin_limit) {
+                    atomicMin(p.err, -4);  // SWB_E_TIMEOUT
+                    break;
+                }
+                __nanosleep(64);
+            }
+            __threadfence_system();
+            exb = umax64(exb, xs[r].ex_bits);
+            eyb = umax64(eyb, xs[r].ey_bits);
+        }
+    }
     const double tx = __ddiv_rn(p.dxmin, __longlong_as_double((long long)exb));
     const double ty = __ddiv_rn(p.dymin, __longlong_as_double((long long)eyb));
     const double dtmax = (tx != tx) ? tx : ((ty != ty) ? ty : (tx < ty ? tx : ty));  // np.minimum propagates NaN
@@ -345,7 +500,11 @@ __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int
         new_slot->current = (int)((nsteps + (active ? 1 : 0)) & 1);
         new_slot->last_dt = active ? dt : cur_slot->last_dt;
         new_slot->done = !(tnew < p.final_time);
-        new_slot->error = cur_slot->error;
+        new_slot->error = 0;
+        if (p.world > 1) {  // what this launch consumed, for the status mirror
+            cur_slot->ex_bits = exb;
+            cur_slot->ey_bits = eyb;
+        }
         if (!active) {  // nothing will be accumulated: carry the maxima forward
             new_slot->ex_bits = exb;
             new_slot->ey_bits = eyb;
@@ -356,380 +515,77 @@ __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int
     }
 }
 
-// ------------------------------------------------------------------------------------
-// one lane of the march: per-latitude constants + the per-row work
-// ------------------------------------------------------------------------------------
-template <bool STRICT, bool DIFF, bool F2D, bool HS>
-struct Lane {
+// Row record of local latitude jl (clamped into the array) for time step dt.
+template <bool STRICT>
+__device__ __forceinline__ void build_row_record(const Params &p, int jl, double dt, double *__restrict__ rec)
+{
     using O = Op<STRICT>;
-    int jl;                   // local latitude row of this lane (clamped into the array)
-    double dt, hdt, hgCell, dnu;
-    double c_j, ac_j;
-    double hgK, raK;          // hg (FAST: g/4), a (FAST: 1/a)
-    double kx, fKx;           // x-face Coriolis / metric factors
-    double ky, fKy, cm_j;     // y-face
-    double cy1f, cyf;         // y-face flux coefficients
-    double cxu, cy1u, cyu;    // update coefficients (cxu: FAST only; STRICT forms dt/dxc per cell)
-    double kc, fD;            // update Coriolis / metric
-    double cdx_fast;
-    double dy1s;              // HS: dy1[j-1] + dy1[j]
-    double x_m, x_c;          // STRICT: x[i-1, j], x[i, j]
-    LapCtx L;
-    unsigned long long mx, my;  // running CFL maxima (bit patterns)
-
-    __device__ __forceinline__ void init(const Params &p, int jl_, double dt_)
-    {
-        jl = jl_;
-        dt = dt_;
-        mx = my = 0ULL;
-        const double *tab = p.tab + jl;
-        const size_t TS = (size_t)p.ncols;
-        c_j = tab[T_C * TS];
-        const double tg_j = tab[T_TG * TS];
-        ac_j = tab[T_AC * TS];
-        const double f_j = F2D ? 0.0 : tab[T_F * TS];
-        const double f_jp = F2D ? 0.0 : p.tab[T_F * TS + min(jl + 1, p.jl_hi)];
-        cm_j = tab[T_CMIDY * TS];
-        hdt = O::mul(0.5, dt);
-        hgCell = O::mul(0.5, p.g);  // numpy.py:203, 255: 0.5*g
-        dnu = O::mul(dt, p.nu);
-        cxu = 0.0;
-        cdx_fast = 0.0;
-        x_m = x_c = 0.0;
-        if (STRICT) {
-            hgK = O::mul(0.5, p.g);
-            raK = p.a;
-            kx = tg_j;  // tgMidx == tan(theta_j): 0.5*(theta+theta) is exact (grid.py:107)
-            fKx = f_j;  // 0.5*(f+f) is exact
-            ky = tab[T_TGMIDY * TS];
-            fKy = O::mul(0.5, O::add(f_jp, f_j));
-            cy1f = O::div(hdt, tab[T_DY1 * TS]);
-            cyf = O::div(hdt, tab[T_DY * TS]);
-            cy1u = O::div(dt, tab[T_DY1C * TS]);
-            cyu = O::div(dt, tab[T_DYC * TS]);
-            kc = tg_j;
-            fD = f_j;
-        } else {
-            const double ra = 1.0 / p.a;
-            const double dxa = ac_j * p.dphi;  // analytic dx_j (the reference's differs by roundoff only)
-            hgK = 0.25 * p.g;
-            raK = ra;
-            kx = hdt * 0.5 * tg_j * ra;
-            fKx = hdt * f_j;
-            ky = hdt * 0.5 * tab[T_TGMIDY * TS] * ra;
-            fKy = hdt * 0.5 * (f_jp + f_j);
-            cdx_fast = dt / dxa;
-            cy1f = dt / tab[T_DY1 * TS];
-            cyf = dt / tab[T_DY * TS];
-            cxu = 0.5 * dt / dxa;
-            cy1u = 0.5 * dt / tab[T_DY1C * TS];
-            cyu = 0.5 * dt / tab[T_DYC * TS];
-            kc = dt * 0.25 * 0.5 * 0.25 * tg_j * ra;  // (dt*0.25) * 0.5[doubled sums] * 0.25 * tg/a
-            fD = dt * 0.25 * 0.5 * f_j;
-        }
-        dy1s = HS ? O::add(p.tab[T_DY1 * TS + max(jl - 1, p.jl_lo)], tab[T_DY1 * TS]) : 1.0;
-        if (DIFF) {
-            const int jm = max(jl - 1, p.jl_lo), jp = min(jl + 1, p.jl_hi);
-            L.Aym = p.tab[T_AY * TS + jm]; L.Bym = p.tab[T_BY * TS + jm]; L.Cym = p.tab[T_CY * TS + jm];
-            L.Ay0 = tab[T_AY * TS]; L.By0 = tab[T_BY * TS]; L.Cy0 = tab[T_CY * TS];
-            L.Ayp = p.tab[T_AY * TS + jp]; L.Byp = p.tab[T_BY * TS + jp]; L.Cyp = p.tab[T_CY * TS + jp];
-            // numpy.py:379-381: one duplicated latitude each side (only at the pole rows;
-            // a band interior has real halo rows there)
-            L.jm1 = jm;
-            L.jp1 = jp;
-            L.jm2 = max(jl - 2, p.jl_lo);
-            L.jp2 = min(jl + 2, p.jl_hi);
-            if (!STRICT) {
-                L.w[0] = L.Cy0 * L.Cym;
-                L.w[1] = L.Ay0 * L.Cy0 + L.Cy0 * L.Aym;
-                L.w[2] = L.Ay0 * L.Ay0 + L.By0 * L.Cyp + L.Cy0 * L.Bym;
-                L.w[3] = L.Ay0 * L.By0 + L.By0 * L.Ayp;
-                L.w[4] = L.By0 * L.Byp;
-                const double dxa = ac_j * p.dphi;
-                L.bx2 = 0.25 / (dxa * dxa);
-            }
-        }
+    const int nr = p.nrows;
+    const int j = min(max(jl, 0), nr - 1), jp = min(j + 1, nr - 1), jm = max(j - 1, 0);
+    const double *tab = p.tab;
+    const double c = tab[(size_t)T_C * nr + j], tg = tab[(size_t)T_TG * nr + j], ac = tab[(size_t)T_AC * nr + j];
+    const double f_j = tab[(size_t)T_F * nr + j], f_jp = tab[(size_t)T_F * nr + jp];
+    const double tgm = tab[(size_t)T_TGMIDY * nr + j], cm = tab[(size_t)T_CMIDY * nr + j];
+    const double dy = tab[(size_t)T_DY * nr + j], dy1 = tab[(size_t)T_DY1 * nr + j];
+    const double dyc = tab[(size_t)T_DYC * nr + j], dy1c = tab[(size_t)T_DY1C * nr + j];
+    const double hdt = O::mul(0.5, dt);
+    rec[RC_C] = c;
+    rec[RC_AC] = ac;
+    rec[RC_CM] = cm;
+    rec[RC_DY1S] = O::add(tab[(size_t)T_DY1 * nr + jm], dy1);
+    if (STRICT) {
+        rec[RC_KX] = tg;   // tgMidx == tan(theta_j): 0.5*(theta+theta) is exact (grid.py:107)
+        rec[RC_FKX] = f_j; // 0.5*(f+f) is exact
+        rec[RC_CDX] = 0.0;
+        rec[RC_CXU] = 0.0;
+        rec[RC_KY] = tgm;
+        rec[RC_FKY] = O::mul(0.5, O::add(f_jp, f_j));
+        rec[RC_CY1F] = O::div(hdt, dy1);
+        rec[RC_CYF] = O::div(hdt, dy);
+        rec[RC_CY1U] = O::div(dt, dy1c);
+        rec[RC_CYU] = O::div(dt, dyc);
+        rec[RC_KC] = tg;
+        rec[RC_FD] = f_j;
+    } else {
+        const double ra = 1.0 / p.a;
+        const double dxa = ac * p.dphi;  // analytic dx_j (the reference's differs by roundoff only)
+        rec[RC_KX] = hdt * 0.5 * tg * ra;
+        rec[RC_FKX] = hdt * f_j;
+        rec[RC_CDX] = dt / dxa;
+        rec[RC_CXU] = 0.5 * dt / dxa;
+        rec[RC_KY] = hdt * 0.5 * tgm * ra;
+        rec[RC_FKY] = hdt * 0.5 * (f_jp + f_j);
+        rec[RC_CY1F] = dt / dy1;
+        rec[RC_CYF] = dt / dy;
+        rec[RC_CY1U] = 0.5 * dt / dy1c;
+        rec[RC_CYU] = 0.5 * dt / dyc;
+        rec[RC_KC] = dt * 0.25 * 0.5 * 0.25 * tg * ra;  // (dt*0.25) * 0.5[doubled sums] * 0.25 * tg/a
+        rec[RC_FD] = dt * 0.25 * 0.5 * f_j;
     }
+}
 
-    __device__ __forceinline__ Cell cell(double h, double u, double v, double f) const
-    {
-        return make_cell<STRICT>(h, u, v, c_j, hgCell, f);
-    }
-
-    // face (ia-1 | ia) that starts a march
-    __device__ __forceinline__ Face first_face(const Params &p, const Cell &prev, const Cell &cur, int ia)
-    {
-        if (STRICT) {
-            x_m = O::mul(ac_j, p.phi[ia - 1]);
-            x_c = O::mul(ac_j, p.phi[ia]);
-            const double cdx = O::div(hdt, O::sub(x_c, x_m));
-            return x_face<true>(prev, cur, cdx, kx, F2D ? O::mul(0.5, O::add(cur.f, prev.f)) : fKx, hdt, hgK, raK);
-        }
-        return x_face<false>(prev, cur, cdx_fast, kx, F2D ? hdt * 0.5 * (cur.f + prev.f) : fKx, hdt, hgK, raK);
-    }
-
-    // Update cell (i, j) given its own products `cur`, the next longitude `nxt` and the
-    // left face `x0`; returns the right face (the next iteration's left face).
-    // numpy.py:193-354 (+541-544 with DIFF).  `count` says whether this lane's result is a
-    // real cell (takes part in the CFL maxima).
-    __device__ __forceinline__ Face advance(const Params &p, const double *__restrict__ H, const double *__restrict__ U,
-                                            const double *__restrict__ V, const Cell &cur, const Cell &nxt,
-                                            const Face &x0, int i, bool count, double &hn, double &un, double &vn)
-    {
-        // x-face (i | i+1)
-        Face x1;
-        double dx0 = 0.0, dx1 = 0.0;
-        if (STRICT) {
-            const double x_p = O::mul(ac_j, p.phi[i + 1]);
-            dx0 = O::sub(x_c, x_m);
-            dx1 = O::sub(x_p, x_c);
-            x_m = x_c;
-            x_c = x_p;
-            x1 = x_face<true>(cur, nxt, O::div(hdt, dx1), kx, F2D ? O::mul(0.5, O::add(nxt.f, cur.f)) : fKx, hdt, hgK, raK);
-        } else {
-            x1 = x_face<false>(cur, nxt, cdx_fast, kx, F2D ? hdt * 0.5 * (nxt.f + cur.f) : fKx, hdt, hgK, raK);
-        }
-
-        // y-face (j | j+1): the northern cell comes from lane+1
-        Cell up;
-        up.h = shfl_down1(cur.h);   up.u = shfl_down1(cur.u);
-        up.hu = shfl_down1(cur.hu); up.hv = shfl_down1(cur.hv);
-        up.hw = shfl_down1(cur.hw); up.Uy = shfl_down1(cur.Uy);
-        up.Vy1 = shfl_down1(cur.Vy1); up.pr = shfl_down1(cur.pr);
-        double fy = fKy;
-        if (F2D) {
-            const double fup = shfl_down1(cur.f);
-            fy = STRICT ? O::mul(0.5, O::add(fup, cur.f)) : hdt * 0.5 * (fup + cur.f);
-        }
-        const Face y1 = y_face<STRICT>(cur, up, cy1f, cyf, ky, fy, cm_j, hdt, hgK, raK);
-
-        // y-face (j-1 | j) was computed by lane-1
-        Face y0;
-        y0.huM = shfl_up1(y1.huM); y0.hvM = shfl_up1(y1.hvM); y0.q = shfl_up1(y1.q);
-        y0.F1 = shfl_up1(y1.F1);   y0.F2 = shfl_up1(y1.F2);   y0.F3 = shfl_up1(y1.F3);
-        y0.hvc = shfl_up1(y1.hvc);
-        y0.hM = HS ? shfl_up1(y1.hM) : 0.0;
-
-        // full-step update of cell (i, j): numpy.py:275-354
-        const size_t P = (size_t)p.pitch;
-        if (STRICT) {
-            const double cx = O::div(dt, O::mul(0.5, O::add(dx0, dx1)));
-            hn = O::sub(O::sub(cur.h, O::mul(cx, O::sub(x1.huM, x0.huM))), O::mul(cy1u, O::sub(y1.hvc, y0.hvc)));
-            const double qs = O::add(O::add(O::add(x0.q, x1.q), y0.q), y1.q);
-            const double fc = F2D ? cur.f : fD;
-            const double Fc = O::add(fc, O::div(O::mul(O::mul(0.25, qs), kc), raK));
-            const double D = O::mul(O::mul(dt, Fc), 0.25);
-            const double shv = O::add(O::add(O::add(x0.hvM, x1.hvM), y0.hvM), y1.hvM);
-            const double shu = O::add(O::add(O::add(x0.huM, x1.huM), y0.huM), y1.huM);
-            double hun = O::add(O::sub(O::sub(cur.hu, O::mul(cx, O::sub(x1.F1, x0.F1))), O::mul(cy1u, O::sub(y1.F1, y0.F1))),
-                                O::mul(D, shv));
-            double hvn = O::sub(O::sub(O::sub(O::sub(cur.hv, O::mul(cx, O::sub(x1.F2, x0.F2))), O::mul(cy1u, O::sub(y1.F2, y0.F2))),
-                                       O::mul(cyu, O::sub(y1.F3, y0.F3))),
-                                O::mul(D, shu));
-            if (HS) {  // numpy.py:310-317, 342-349
-                const double hsum = O::add(O::add(O::add(x0.hM, x1.hM), y0.hM), y1.hM);
-                const double gq = O::mul(O::mul(O::mul(dt, p.g), 0.25), hsum);
-                const size_t k = (size_t)i * P + jl;
-                const double dhx = O::sub(p.hs[k + P], p.hs[k - P]);
-                const double dhy = O::sub(p.hs[(size_t)i * P + min(jl + 1, p.jl_hi)], p.hs[(size_t)i * P + max(jl - 1, p.jl_lo)]);
-                hun = O::sub(hun, O::div(O::mul(gq, dhx), O::add(dx0, dx1)));
-                hvn = O::sub(hvn, O::div(O::mul(gq, dhy), dy1s));
-            }
-            un = O::div(hun, hn);
-            vn = O::div(hvn, hn);
-        } else {
-            hn = fma(-cy1u, y1.hvc - y0.hvc, fma(-cxu, x1.huM - x0.huM, cur.h));
-            const double qs = (x0.q + x1.q) + (y0.q + y1.q);
-            const double D = F2D ? fma(qs, kc, dt * 0.125 * cur.f) : fma(qs, kc, fD);  // 0.5 * dt * Fc * 0.25
-            const double shv = (x0.hvM + x1.hvM) + (y0.hvM + y1.hvM);
-            const double shu = (x0.huM + x1.huM) + (y0.huM + y1.huM);
-            double hun = fma(D, shv, fma(-cy1u, y1.F1 - y0.F1, fma(-cxu, x1.F1 - x0.F1, cur.hu)));
-            double hvn = fma(-D, shu,
-                             fma(-cyu, y1.F3 - y0.F3, fma(-cy1u, y1.F2 - y0.F2, fma(-cxu, x1.F2 - x0.F2, cur.hv))));
-            if (HS) {
-                const double hsum = (x0.hM + x1.hM) + (y0.hM + y1.hM);  // doubled
-                const double gq = dt * p.g * 0.125 * hsum;
-                const size_t k = (size_t)i * P + jl;
-                const double dhx = p.hs[k + P] - p.hs[k - P];
-                const double dhy = p.hs[(size_t)i * P + min(jl + 1, p.jl_hi)] - p.hs[(size_t)i * P + max(jl - 1, p.jl_lo)];
-                hun -= gq * dhx / (2.0 * ac_j * p.dphi);
-                hvn -= gq * dhy / dy1s;
-            }
-            const double r = fast_rcp(hn);
-            un = hun * r;
-            vn = hvn * r;
-        }
-        if (DIFF) {  // numpy.py:541-544: old fields; u, v (not hu, hv)
-            const double lh = laplacian_at<STRICT>(H, p, L, ac_j, i, jl);
-            const double lu = laplacian_at<STRICT>(U, p, L, ac_j, i, jl);
-            const double lv = laplacian_at<STRICT>(V, p, L, ac_j, i, jl);
-            if (STRICT) {
-                hn = O::add(hn, O::mul(dnu, lh));
-                un = O::add(un, O::mul(dnu, lu));
-                vn = O::add(vn, O::mul(dnu, lv));
-            } else {
-                hn = fma(dnu, lh, hn);
-                un = fma(dnu, lu, un);
-                vn = fma(dnu, lv, vn);
-            }
-        }
-        if (count) {
-            // CFL maxima of the new state: max(|q-c|, |q|, |q+c|) == |q| + c for c >= 0
-            const double cs = STRICT ? __dsqrt_rn(O::mul(p.g, fabs(hn))) : sqrt(p.g * fabs(hn));
-            const unsigned long long bx = nonneg_bits(O::add(fabs(un), cs));
-            const unsigned long long by = nonneg_bits(O::add(fabs(vn), cs));
-            mx = bx > mx ? bx : mx;
-            my = by > my ? by : my;
-        }
-        return x1;
-    }
-
-    // Branch-free form of `advance` for the hot configuration (FAST arithmetic, latitude-only
-    // Coriolis, flat topography, no diffusion).  Assumes positive layer depths: the
-    // reference's `hMid > 0` selects (numpy.py:287-292, 321-322) always take their first
-    // branch there, so they are not evaluated.  The CFL maxima are accumulated for every lane
-    // and row; lanes / rows that are not real cells are masked when published.
-    __device__ __forceinline__ Face advance_fast(const Cell &cur, const Cell &nxt, const Face &x0, double g,
-                                                 double &hn, double &un, double &vn)
-    {
-        static_assert(!STRICT && !DIFF && !F2D && !HS, "advance_fast serves the plain FAST variant");
-        const Face x1 = x_face<false, false>(cur, nxt, cdx_fast, kx, fKx, hdt, hgK, raK);
-        Cell up;
-        up.h = shfl_down1(cur.h);   up.u = shfl_down1(cur.u);
-        up.hu = shfl_down1(cur.hu); up.hv = shfl_down1(cur.hv);
-        up.hw = shfl_down1(cur.hw); up.Uy = shfl_down1(cur.Uy);
-        up.Vy1 = shfl_down1(cur.Vy1); up.pr = shfl_down1(cur.pr);
-        const Face y1 = y_face<false, false>(cur, up, cy1f, cyf, ky, fKy, cm_j, hdt, hgK, raK);
-        Face y0;
-        y0.huM = shfl_up1(y1.huM); y0.hvM = shfl_up1(y1.hvM); y0.q = shfl_up1(y1.q);
-        y0.F1 = shfl_up1(y1.F1);   y0.F2 = shfl_up1(y1.F2);   y0.F3 = shfl_up1(y1.F3);
-        y0.hvc = shfl_up1(y1.hvc);
-
-        hn = fma(-cy1u, y1.hvc - y0.hvc, fma(-cxu, x1.huM - x0.huM, cur.h));
-        const double qs = (x0.q + x1.q) + (y0.q + y1.q);
-        const double D = fma(qs, kc, fD);  // 0.5 * dt * Fc * 0.25
-        const double shv = (x0.hvM + x1.hvM) + (y0.hvM + y1.hvM);
-        const double shu = (x0.huM + x1.huM) + (y0.huM + y1.huM);
-        const double hun = fma(D, shv, fma(-cy1u, y1.F1 - y0.F1, fma(-cxu, x1.F1 - x0.F1, cur.hu)));
-        const double hvn = fma(-D, shu, fma(-cyu, y1.F3 - y0.F3, fma(-cy1u, y1.F2 - y0.F2, fma(-cxu, x1.F2 - x0.F2, cur.hv))));
-        const double r = fast_rcp(hn);
-        un = hun * r;
-        vn = hvn * r;
-        // |q| + sqrt(g |h|) is non-negative (or NaN, which compares above everything as an
-        // unsigned pattern whatever its sign bit): no masking needed before the integer max
-        const double cs = fast_sqrt(g * fabs(hn));
-        const unsigned long long bx = (unsigned long long)__double_as_longlong(fabs(un) + cs);
-        const unsigned long long by = (unsigned long long)__double_as_longlong(fabs(vn) + cs);
-        mx = bx > mx ? bx : mx;
-        my = by > my ? by : my;
-        return x1;
-    }
-
-    // warp-reduce the running maxima and publish them (one atomic pair per warp)
-    __device__ __forceinline__ void publish(const Params &p, int lane, bool valid_lane = true)
-    {
-        if (p.fixed) return;
-        if (!valid_lane) mx = my = 0ULL;
-        Ctrl *const new_slot = p.ctrl + ((p.launch + 1) % 3);
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            const unsigned long long ox = __shfl_xor_sync(0xffffffffu, mx, s);
-            const unsigned long long oy = __shfl_xor_sync(0xffffffffu, my, s);
-            mx = ox > mx ? ox : mx;
-            my = oy > my ? oy : my;
-        }
-        if (lane == 0) {
-            atomicMax(&new_slot->ex_bits, mx);
-            atomicMax(&new_slot->ey_bits, my);
-        }
-    }
-};
-
-// Extra copies of a freshly computed cell: periodic wrap in longitude and zero-gradient
-// pole rows (numpy.py:402-404).  `main` says whether (i, jl) itself is still to be written.
-__device__ __forceinline__ void put_cell(const Params &p, double *__restrict__ Hn, double *__restrict__ Un,
-                                         double *__restrict__ Vn, int i, int jl, double hn, double un, double vn, bool main)
+// FAST diffusion record of local latitude jl
+__device__ __forceinline__ void build_diff_record(const Params &p, int jl, double dt, double *__restrict__ rd)
 {
-    const size_t P = (size_t)p.pitch;
-    const bool south = p.pole_s && (jl == p.jl_lo + 1);
-    const bool north = p.pole_n && (jl == p.jl_hi - 1);
-    auto put = [&](int row, bool centre) {
-        const size_t k = (size_t)row * P + jl;
-        if (centre) { Hn[k] = hn; Un[k] = un; Vn[k] = vn; }
-        if (south) { Hn[k - 1] = hn; Un[k - 1] = un; Vn[k - 1] = vn; }
-        if (north) { Hn[k + 1] = hn; Un[k + 1] = un; Vn[k + 1] = vn; }
-    };
-    if (main || south || north) put(i, main);
-    if (i == p.M) put(0, true);
-    if (i == 2) put(p.M + 2, true);
+    const int nr = p.nrows;
+    const int j = min(max(jl, 0), nr - 1);
+    const W3 w = y_weights(p.tab, nr, j);
+    rd[0] = w.C[1] * w.C[0];
+    rd[1] = w.A[1] * w.C[1] + w.C[1] * w.A[0];
+    rd[2] = w.A[1] * w.A[1] + w.B[1] * w.C[2] + w.C[1] * w.B[0];
+    rd[3] = w.A[1] * w.B[1] + w.B[1] * w.A[2];
+    rd[4] = w.B[1] * w.B[2];
+    const double dxa = p.tab[(size_t)T_AC * nr + j] * p.dphi;
+    rd[5] = 0.25 / (dxa * dxa);
+    rd[6] = dt * p.nu;
+    rd[7] = 0.0;
 }
 
 // ------------------------------------------------------------------------------------
-// the fused step kernel, direct-load form (all variants)
+// TMA plumbing
 // ------------------------------------------------------------------------------------
-template <bool STRICT, bool DIFF, bool F2D, bool HS>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) step_kernel(const __grid_constant__ Params p)
-{
-    __shared__ double s_dt;
-    __shared__ int s_flags;
-    if (threadIdx.x == 0) step_prologue(p, &s_dt, &s_flags);
-    __syncthreads();
-    const int flags = s_flags;
-    if (!(flags & 1)) return;
-    const int par = (flags >> 1) & 1;
-
-    const double *__restrict__ H = p.buf[par][0];
-    const double *__restrict__ U = p.buf[par][1];
-    const double *__restrict__ V = p.buf[par][2];
-    double *__restrict__ Hn = p.buf[par ^ 1][0];
-    double *__restrict__ Un = p.buf[par ^ 1][1];
-    double *__restrict__ Vn = p.buf[par ^ 1][2];
-
-    const int lane = threadIdx.x & 31;
-    const int strip = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    if (strip >= p.nstrips) return;
-
-    const size_t P = (size_t)p.pitch;
-    const int jl_raw = p.jl_first - 1 + kCellsPerWarp * strip + lane;
-    const int jl = min(jl_raw, p.jl_hi);  // lanes past the array replay the last row
-    const bool upd = (lane >= 1) && (lane <= kCellsPerWarp) && (jl_raw <= p.jl_last);
-    const int ia = 1 + blockIdx.y * p.chunk;     // first longitude updated
-    const int ib = min(ia + p.chunk, p.M + 2);   // one past the last
-
-    Lane<STRICT, DIFF, F2D, HS> ln;
-    ln.init(p, jl, s_dt);
-    auto load_cell = [&](int i) {
-        const size_t k = (size_t)i * P + jl;
-        return ln.cell(H[k], U[k], V[k], F2D ? p.f2d[k] : 0.0);
-    };
-    Cell cur;
-    Face x0;
-    {
-        const Cell prev = load_cell(ia - 1);
-        cur = load_cell(ia);
-        x0 = ln.first_face(p, prev, cur, ia);
-    }
-    for (int i = ia; i < ib; ++i) {
-        const Cell nxt = load_cell(i + 1);
-        double hn, un, vn;
-        x0 = ln.advance(p, H, U, V, cur, nxt, x0, i, upd, hn, un, vn);
-        if (upd) put_cell(p, Hn, Un, Vn, i, jl, hn, un, vn, true);
-        cur = nxt;
-    }
-    ln.publish(p, lane);
-}
-
-// ------------------------------------------------------------------------------------
-// the fused step kernel, TMA form (flat topography, latitude-only Coriolis, no diffusion)
-// ------------------------------------------------------------------------------------
-// Every warp runs its own asynchronous pipeline: lane 0 issues cp.async.bulk.tensor loads
-// of {34 latitudes x R longitudes} boxes of h, u, v into a ring of S shared-memory stages
-// (completion on one mbarrier per stage) and bulk tensor stores of the {30 x R} result
-// boxes; lanes read / write shared memory only.  Loads of the rows far ahead of the march
-// are in flight while the FP64 pipe works, without costing registers.
 struct TmaMaps {
-    CUtensorMap in[2][3];   // box {34, R} over (ncols, M+3)
-    CUtensorMap out[2][3];  // box {30, R} over (jl_last+1, M+2): clips garbage rows / halo columns
+    CUtensorMap in[2][3];  // box {64, R} over (M+3, nrows) of each buffer set's h, u, v
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
@@ -759,29 +615,54 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1)
-{
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"((unsigned long long)map), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
 
 template <int R, int S>
 struct TmaLayout {
-    static constexpr int kInCols = 34;  // lane 0's column is odd; boxes must start on 16-byte (even) columns
-    static constexpr int kInTile = ((R * kInCols * 8 + 127) / 128) * 128;  // one field, one stage
-    static constexpr int kOutTile = ((R * 30 * 8 + 127) / 128) * 128;
-    static constexpr int kIn = S * 3 * kInTile;
-    static constexpr int kOut = 2 * 3 * kOutTile;
+    static constexpr int kField = R * kStripCols * 8;  // one field, one stage
+    static constexpr int kStage = 3 * kField;
+    static constexpr int kRing = S * kStage;
     static constexpr int kBars = 128;
-    static constexpr int kWarpBytes = kIn + kOut + kBars;
-    static constexpr int kBlockBytes = kWarpsPerBlock * kWarpBytes;
+    static constexpr int kWarpBytes = kRing + kBars;
 };
 
-template <bool STRICT, int R, int S>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, STRICT ? 3 : 4) step_kernel_tma(const __grid_constant__ Params p,
-                                                                       const __grid_constant__ TmaMaps tm)
+// bytes of row records in front of the per-warp rings (multiple of 1024)
+__host__ __device__ constexpr int rec_bytes(int chunk, bool diff)
 {
+    return (((chunk + 2) * (kRowRec + (diff ? kRowDiff : 0)) * 8) + 1023) / 1024 * 1024;
+}
+
+__device__ __forceinline__ double2 ldg2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+
+// Store a lane's pair of values without branching: both (one 16-byte store), or only the
+// first / only the second (the strip's edge lanes and the right end of the grid).
+__device__ __forceinline__ void st_pair(double *addr, double a, double b, int both, int only_a, int only_b)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pb, pa, pc;\n\t"
+        "setp.ne.s32 pb, %3, 0;\n\t"
+        "setp.ne.s32 pa, %4, 0;\n\t"
+        "setp.ne.s32 pc, %5, 0;\n\t"
+        "@pb st.global.v2.f64 [%0], {%1, %2};\n\t"
+        "@pa st.global.f64 [%0], %1;\n\t"
+        "@pc st.global.f64 [%0+8], %2;\n\t"
+        "}" ::"l"(addr), "d"(a), "d"(b), "r"(both), "r"(only_a), "r"(only_b) : "memory");
+}
+
+// ------------------------------------------------------------------------------------
+// the fused step kernel
+// ------------------------------------------------------------------------------------
+// Template axes: arithmetic (STRICT / FAST), diffusion, 2-D Coriolis array, topography,
+// TMA ring (R latitudes per box, S stages) or direct loads, and whether FAST evaluates the
+// reference's hMid > 0 selects (GUARD) or assumes them true and raises SWB_E_DEPTH when a
+// half-step depth turns out non-positive.
+template <bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
+march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
+{
+    using O = Op<STRICT>;
     using LY = TmaLayout<R, S>;
+    constexpr bool kGuard = STRICT || GUARD;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ double s_dt;
     __shared__ int s_flags;
@@ -790,6 +671,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, STRICT ? 3 : 4) step_kern
     const int flags = s_flags;
     if (!(flags & 1)) return;
     const int par = (flags >> 1) & 1;
+    const double dt = s_dt;
 
     const double *__restrict__ H = p.buf[par][0];
     const double *__restrict__ U = p.buf[par][1];
@@ -801,161 +683,372 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, STRICT ? 3 : 4) step_kern
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int strip = blockIdx.x * kWarpsPerBlock + warp;
-    if (strip >= p.nstrips) return;
-
+    const bool warp_on = strip < p.nstrips;
+    const int ja = p.jl_first + blockIdx.y * p.chunk;  // first latitude updated
+    const int jb = min(ja + p.chunk, p.jl_last + 1);   // one past the last
+    const int c0 = kStripValid * strip;
     const size_t P = (size_t)p.pitch;
-    const int c0 = p.jl_first - 1 + kCellsPerWarp * strip;  // latitude held by lane 0
-    const int jl_raw = c0 + lane;
-    const int jl = min(jl_raw, p.jl_hi);
-    const bool upd = (lane >= 1) && (lane <= kCellsPerWarp) && (jl_raw <= p.jl_last);
-    const int ia = 1 + blockIdx.y * p.chunk;
-    const int ib = min(ia + p.chunk, p.M + 2);
-    const int ntiles = (ib - ia + R - 1) / R;
 
-    unsigned char *wbase = smem_raw + (size_t)warp * LY::kWarpBytes;
-    const double *in_s = reinterpret_cast<const double *>(wbase);
-    double *out_s = reinterpret_cast<double *>(wbase + LY::kIn);
-    const uint32_t in_a = smem_u32(wbase), out_a = in_a + LY::kIn, bar_a = out_a + LY::kOut;
-
-    const CUtensorMap *min_ = tm.in[par];
-    const CUtensorMap *mout = tm.out[par ^ 1];
-
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) mbar_init(bar_a + 8 * s, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-
-    auto issue_load = [&](int t) {  // lane 0 only: rows ia+1+tR .. of h, u, v into stage t % S
+    // ---- TMA ring: start the first loads before anything else ----------------------
+    const int recb = rec_bytes(p.chunk, DIFF);
+    unsigned char *wbase = smem_raw + recb + (size_t)warp * LY::kWarpBytes;
+    const uint32_t ring_a = smem_u32(wbase), bar_a = ring_a + LY::kRing;
+    const CUtensorMap *maps = tm.in[par];
+    const int ntiles = (jb - ja + R - 1) / R;
+    auto issue_load = [&](int t) {  // lane 0 only: latitudes ja+1+tR .. of h, u, v into stage t % S
         const int s = t % S;
         const uint32_t bar = bar_a + 8 * s;
-        mbar_expect_tx(bar, 3 * R * LY::kInCols * 8);
+        mbar_expect_tx(bar, LY::kStage);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) tma_load_2d(in_a + (s * 3 + k) * LY::kInTile, &min_[k], c0 - 1, ia + 1 + t * R, bar);
+        for (int k = 0; k < 3; ++k) tma_load_2d(ring_a + s * LY::kStage + k * LY::kField, &maps[k], c0, ja + 1 + t * R, bar);
     };
-    if (lane == 0) {
-#pragma unroll
-        for (int t = 0; t < S - 1; ++t)
-            if (t < ntiles) issue_load(t);
-    }
-
-    Lane<STRICT, false, false, false> ln;
-    ln.init(p, jl, s_dt);
-    Cell cur;
-    Face x0;
-    {
-        const size_t k0 = (size_t)(ia - 1) * P + jl, k1 = k0 + P;
-        const Cell prev = ln.cell(H[k0], U[k0], V[k0], 0.0);
-        cur = ln.cell(H[k1], U[k1], V[k1], 0.0);
-        x0 = ln.first_face(p, prev, cur, ia);
-    }
-    const bool edge = p.pole_s && (jl == p.jl_lo + 1) || p.pole_n && (jl == p.jl_hi - 1);
-    const bool cell_lane = (lane >= 1) && (lane <= kCellsPerWarp);
-    const bool warp_has_edge = __any_sync(0xffffffffu, edge && upd);
-    constexpr int kOutF = LY::kOutTile / 8;  // doubles per output field tile
-
-    for (int t = 0; t < ntiles; ++t) {
-        const int s = t % S;
-        mbar_wait(bar_a + 8 * s, (uint32_t)((t / S) & 1));
-        const int ob = t & 1;
-        if (t >= 2) {  // the store that last read out buffer `ob` must have drained it
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-        }
-        const double *ti = in_s + (size_t)s * 3 * (LY::kInTile / 8) + lane + 1;
-        double *to = out_s + (size_t)ob * 3 * kOutF + (lane - 1);
-        const int i0 = ia + t * R;
-        const bool full = (i0 + R <= ib);  // warp-uniform
-        bool done_fast = false;
-        if constexpr (!STRICT) {
-          if (full) {
-            done_fast = true;
-            // hot path: R rows in one branch-free basic block
-#pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-                const Cell nxt = ln.cell(ti[rr * LY::kInCols], ti[LY::kInTile / 8 + rr * LY::kInCols],
-                                         ti[2 * (LY::kInTile / 8) + rr * LY::kInCols], 0.0);
-                double hn, un, vn;
-                x0 = ln.advance_fast(cur, nxt, x0, p.g, hn, un, vn);
-                if (cell_lane) {
-                    to[rr * 30] = hn;
-                    to[kOutF + rr * 30] = un;
-                    to[2 * kOutF + rr * 30] = vn;
-                }
-                cur = nxt;
-            }
-          }
-        }
-        if (!done_fast) {
-#pragma unroll 1
-            for (int rr = 0; rr < R; ++rr) {
-                const int i = i0 + rr;
-                const Cell nxt = ln.cell(ti[rr * LY::kInCols], ti[LY::kInTile / 8 + rr * LY::kInCols],
-                                         ti[2 * (LY::kInTile / 8) + rr * LY::kInCols], 0.0);
-                double hn, un, vn;
-                const bool live = upd && (i < ib);
-                x0 = ln.advance(p, H, U, V, cur, nxt, x0, i, live, hn, un, vn);
-                if (cell_lane) {
-                    to[rr * 30] = hn;
-                    to[kOutF + rr * 30] = un;
-                    to[2 * kOutF + rr * 30] = vn;
-                }
-                cur = nxt;
-            }
-        }
-        // periodic-wrap rows and pole copies (numpy.py:402-404): rare, read back from the tile
-        const bool wrap_tile = (i0 <= p.M && p.M < i0 + R) || (i0 <= 2 && 2 < i0 + R);
-        if (warp_has_edge || wrap_tile) {
-#pragma unroll 1
-            for (int rr = 0; rr < R; ++rr) {
-                const int i = i0 + rr;
-                if (upd && i < ib && (edge || i == p.M || i == 2))
-                    put_cell(p, Hn, Un, Vn, i, jl, to[rr * 30], to[kOutF + rr * 30], to[2 * kOutF + rr * 30], false);
-            }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
+    if (TMA && warp_on) {
         if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) tma_store_2d(&mout[k], out_a + (ob * 3 + k) * LY::kOutTile, c0 + 1, i0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (t + S - 1 < ntiles) issue_load(t + S - 1);
+            for (int s = 0; s < S; ++s) mbar_init(bar_a + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+            for (int t = 0; t < S - 1; ++t)
+                if (t < ntiles) issue_load(t);
+        }
+        __syncwarp();
+    }
+
+    // ---- row records of latitudes ja-1 .. jb ----------------------------------------
+    double *rowc = reinterpret_cast<double *>(smem_raw);
+    double *rowd = rowc + (size_t)(p.chunk + 2) * kRowRec;
+    for (int r = threadIdx.x; r < jb - ja + 2; r += blockDim.x) {
+        build_row_record<STRICT>(p, ja - 1 + r, dt, rowc + (size_t)r * kRowRec);
+        if (DIFF && !STRICT) build_diff_record(p, ja - 1 + r, dt, rowd + (size_t)r * kRowDiff);
+    }
+    __syncthreads();
+    if (!warp_on) return;
+
+    // ---- per-lane set-up ------------------------------------------------------------
+    const int colA = c0 + 2 * lane;  // this lane's cells: (., colA) and (., colA + 1)
+    const bool vA = (lane >= 1) && (colA <= p.M + 1);
+    const bool vB = (lane <= 30) && (colA + 1 <= p.M + 1);
+    const double hdt = O::mul(0.5, dt);
+    const double hgCell = O::mul(0.5, p.g);            // numpy.py:203, 255: 0.5*g
+    const double hgK = STRICT ? hgCell : 0.25 * p.g;   // FAST faces are doubled
+    const double raK = STRICT ? p.a : 1.0 / p.a;
+    double ph_m = 0.0, ph_0 = 0.0, ph_1 = 0.0, ph_2 = 0.0;  // STRICT: phi at colA-1 .. colA+2
+    if (STRICT) {
+        ph_m = p.phi[max(colA - 1, 0)];
+        ph_0 = p.phi[colA];
+        ph_1 = p.phi[colA + 1];
+        ph_2 = p.phi[colA + 2];
+    }
+    // extra copies a cell owes: periodic ghost columns (numpy.py:402)
+    const bool wrapA = vA && (colA == p.M || colA == 2), wrapB = vB && (colA + 1 == p.M || colA + 1 == 2);
+    const bool warp_wraps = __any_sync(0xffffffffu, wrapA || wrapB);
+    const int st_both = (vA && vB) ? 1 : 0, st_onlyA = (vA && !vB) ? 1 : 0, st_onlyB = (vB && !vA) ? 1 : 0;
+    unsigned long long mxA = 0ULL, myA = 0ULL, mxB = 0ULL, myB = 0ULL;  // running CFL maxima (bit patterns)
+    int negA = 0, negB = 0;  // sign watch of the half-step depths (FAST without GUARD)
+
+    auto rec_of = [&](int jl) { return rowc + (size_t)(jl - (ja - 1)) * kRowRec; };
+    auto load_f = [&](int jl) -> double2 {
+        if (F2D) return ldg2(p.f2d + (size_t)min(jl, p.nrows - 1) * P + colA);
+        return make_double2(0.0, 0.0);
+    };
+
+    Cell curA, curB;
+    Face y0A, y0B;
+    {
+        const size_t k0 = (size_t)(ja - 1) * P + colA, k1 = k0 + P;
+        const double2 h0 = ldg2(H + k0), u0 = ldg2(U + k0), v0 = ldg2(V + k0);
+        const double2 h1 = ldg2(H + k1), u1 = ldg2(U + k1), v1 = ldg2(V + k1);
+        const double2 f0 = load_f(ja - 1), f1 = load_f(ja);
+        const double *r0 = rec_of(ja - 1), *r1 = rec_of(ja);
+        const Cell pA = make_cell<STRICT>(h0.x, u0.x, v0.x, r0[RC_C], hgCell, f0.x);
+        const Cell pB = make_cell<STRICT>(h0.y, u0.y, v0.y, r0[RC_C], hgCell, f0.y);
+        curA = make_cell<STRICT>(h1.x, u1.x, v1.x, r1[RC_C], hgCell, f1.x);
+        curB = make_cell<STRICT>(h1.y, u1.y, v1.y, r1[RC_C], hgCell, f1.y);
+        auto fy = [&](const Cell &a, const Cell &b) {
+            if (!F2D) return r0[RC_FKY];
+            return STRICT ? O::mul(0.5, O::add(b.f, a.f)) : hdt * 0.5 * (b.f + a.f);
+        };
+        y0A = y_face<STRICT, kGuard>(pA, curA, r0[RC_CY1F], r0[RC_CYF], r0[RC_KY], fy(pA, curA), r0[RC_CM], hdt, hgK, raK);
+        y0B = y_face<STRICT, kGuard>(pB, curB, r0[RC_CY1F], r0[RC_CYF], r0[RC_KY], fy(pB, curB), r0[RC_CM], hdt, hgK, raK);
+    }
+
+    // rows at which a cell owes more than its own store: zero-gradient pole rows
+    // (numpy.py:403-404) and the rows a neighbour band reads as its halo
+    int plain_lo = ja, plain_hi = jb - 1;  // rows in [plain_lo, plain_hi] need nothing special
+    if (p.pole_s) plain_lo = max(plain_lo, 2);
+    if (p.pole_n) plain_hi = min(plain_hi, p.nrows - 3);
+    if (p.world > 1) {
+        if (p.south[0][0] != nullptr) plain_lo = max(plain_lo, p.jl_first + p.halo);
+        if (p.north[0][0] != nullptr) plain_hi = min(plain_hi, p.jl_last - p.halo);
+    }
+    if (warp_wraps) plain_hi = plain_lo - 1;  // strips that feed the periodic ghost columns: every row
+
+    // One latitude: cells (jl, colA), (jl, colA+1) from `cur`, the row above in (h2,u2,v2).
+    // `hot` (a compile-time tag) = a live row in [plain_lo, plain_hi]: own stores only.
+    size_t krow = (size_t)ja * P + colA;  // element index of (jl, colA), advanced row by row
+    auto do_row = [&](auto hot_tag, int jl, double2 h2, double2 u2, double2 v2, bool live) {
+        constexpr bool HOT = decltype(hot_tag)::value;
+        const double2 *rc2 = reinterpret_cast<const double2 *>(rec_of(jl));
+        // the row record, read as 16-byte pairs (broadcast LDS.128)
+        const double2 r_c_ac = rc2[RC_C / 2], r_kx_fkx = rc2[RC_KX / 2], r_cdx_cxu = rc2[RC_CDX / 2], r_ky_fky = rc2[RC_KY / 2];
+        const double2 r_cm_cy1f = rc2[RC_CM / 2], r_cyf_cy1u = rc2[RC_CYF / 2], r_cyu_kc = rc2[RC_CYU / 2], r_fd_dy1s = rc2[RC_FD / 2];
+        const double cn = rec_of(jl)[kRowRec + RC_C];
+        const double2 f2 = load_f(jl + 1);
+        const Cell nxtA = make_cell<STRICT>(h2.x, u2.x, v2.x, cn, hgCell, f2.x);
+        const Cell nxtB = make_cell<STRICT>(h2.y, u2.y, v2.y, cn, hgCell, f2.y);
+
+        // y-faces (jl | jl+1)
+        double fyA = r_ky_fky.y, fyB = fyA;
+        if (F2D) {
+            fyA = STRICT ? O::mul(0.5, O::add(nxtA.f, curA.f)) : hdt * 0.5 * (nxtA.f + curA.f);
+            fyB = STRICT ? O::mul(0.5, O::add(nxtB.f, curB.f)) : hdt * 0.5 * (nxtB.f + curB.f);
+        }
+        const Face y1A = y_face<STRICT, kGuard>(curA, nxtA, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyA, r_cm_cy1f.x, hdt, hgK, raK);
+        const Face y1B = y_face<STRICT, kGuard>(curB, nxtB, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyB, r_cm_cy1f.x, hdt, hgK, raK);
+
+        // x-faces of this latitude: (A | B) and (B | next lane's A)
+        Cell nA;
+        nA.h = shfl_down1(curA.h);   nA.u = shfl_down1(curA.u);
+        nA.hu = shfl_down1(curA.hu); nA.hv = shfl_down1(curA.hv);
+        nA.Ux = shfl_down1(curA.Ux); nA.Vx = shfl_down1(curA.Vx);
+        nA.f = F2D ? shfl_down1(curA.f) : 0.0;
+        double cdxAB, cdxBN, cxA, cxB, dxsA = 0.0, dxsB = 0.0;
+        if (STRICT) {
+            const double ac = r_c_ac.y;
+            const double xm = O::mul(ac, ph_m), x0 = O::mul(ac, ph_0), x1 = O::mul(ac, ph_1), x2 = O::mul(ac, ph_2);
+            const double dxm = O::sub(x0, xm), dxA = O::sub(x1, x0), dxB = O::sub(x2, x1);
+            cdxAB = O::div(hdt, dxA);
+            cdxBN = O::div(hdt, dxB);
+            dxsA = O::add(dxm, dxA);
+            dxsB = O::add(dxA, dxB);
+            cxA = O::div(dt, O::mul(0.5, dxsA));
+            cxB = O::div(dt, O::mul(0.5, dxsB));
+        } else {
+            cdxAB = cdxBN = r_cdx_cxu.x;
+            cxA = cxB = r_cdx_cxu.y;
+            if (HS) dxsA = dxsB = 2.0 * r_c_ac.y * p.dphi;
+        }
+        double fxAB = r_kx_fkx.y, fxBN = fxAB;
+        if (F2D) {
+            fxAB = STRICT ? O::mul(0.5, O::add(curB.f, curA.f)) : hdt * 0.5 * (curB.f + curA.f);
+            fxBN = STRICT ? O::mul(0.5, O::add(nA.f, curB.f)) : hdt * 0.5 * (nA.f + curB.f);
+        }
+        const Face xAB = x_face<STRICT, kGuard>(curA, curB, cdxAB, r_kx_fkx.x, fxAB, hdt, hgK, raK);
+        const Face xBN = x_face<STRICT, kGuard>(curB, nA, cdxBN, r_kx_fkx.x, fxBN, hdt, hgK, raK);
+        Face xL;  // (previous lane's B | A)
+        xL.huM = shfl_up1(xBN.huM); xL.hvM = shfl_up1(xBN.hvM); xL.q = shfl_up1(xBN.q);
+        xL.F1 = shfl_up1(xBN.F1);   xL.F2 = shfl_up1(xBN.F2);
+        xL.hM = HS ? shfl_up1(xBN.hM) : 0.0;
+
+        // topography differences (numpy.py:310-317, 342-349)
+        double hsxA = 0.0, hsxB = 0.0, hsyA = 0.0, hsyB = 0.0;
+        if (HS) {
+            const double *hr = p.hs + (size_t)jl * P + colA;
+            const double *hu_ = p.hs + (size_t)min(jl + 1, p.nrows - 1) * P + colA;
+            const double *hd_ = p.hs + (size_t)max(jl - 1, 0) * P + colA;
+            const double e0 = hr[colA > 0 ? -1 : 0], e1 = hr[0], e2 = hr[1], e3 = hr[2];
+            hsxA = O::sub(e2, e0);
+            hsxB = O::sub(e3, e1);
+            hsyA = O::sub(hu_[0], hd_[0]);
+            hsyB = O::sub(hu_[1], hd_[1]);
+        }
+
+        double hnA, unA, vnA, hnB, unB, vnB;
+        const double fcA = F2D ? (STRICT ? curA.f : dt * 0.125 * curA.f) : r_fd_dy1s.x;
+        const double fcB = F2D ? (STRICT ? curB.f : dt * 0.125 * curB.f) : r_fd_dy1s.x;
+        update_cell<STRICT, HS>(curA, xL, xAB, y0A, y1A, cxA, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcA, dt, p.g, raK, hsxA, hsyA,
+                                dxsA, r_fd_dy1s.y, hnA, unA, vnA);
+        update_cell<STRICT, HS>(curB, xAB, xBN, y0B, y1B, cxB, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcB, dt, p.g, raK, hsxB, hsyB,
+                                dxsB, r_fd_dy1s.y, hnB, unB, vnB);
+
+        if (DIFF) {  // numpy.py:541-544: Laplacian of the OLD fields; u, v (not hu, hv)
+            const int iA = min(max(colA, 1), p.M + 1), iB = min(max(colA + 1, 1), p.M + 1);  // keep invalid lanes in bounds
+            const Star shA = load_star(H, p.pitch, p.nrows, p.M, jl, iA), shB = load_star(H, p.pitch, p.nrows, p.M, jl, iB);
+            const Star suA = load_star(U, p.pitch, p.nrows, p.M, jl, iA), suB = load_star(U, p.pitch, p.nrows, p.M, jl, iB);
+            const Star svA = load_star(V, p.pitch, p.nrows, p.M, jl, iA), svB = load_star(V, p.pitch, p.nrows, p.M, jl, iB);
+            if (STRICT) {
+                const double dnu = O::mul(dt, p.nu);
+                const W3 wy = y_weights(p.tab, p.nrows, jl);
+                const W3 wxA = x_weights_strict(p.phi, r_c_ac.y, iA, p.M), wxB = x_weights_strict(p.phi, r_c_ac.y, iB, p.M);
+                auto lap = [&](const Star &s, const W3 &wx) {
+                    return O::add(second_diff_strict(wx, s.xmm, s.xm, s.q0, s.xp, s.xpp),
+                                  second_diff_strict(wy, s.ymm, s.ym, s.q0, s.yp, s.ypp));
+                };
+                hnA = O::add(hnA, O::mul(dnu, lap(shA, wxA))); hnB = O::add(hnB, O::mul(dnu, lap(shB, wxB)));
+                unA = O::add(unA, O::mul(dnu, lap(suA, wxA))); unB = O::add(unB, O::mul(dnu, lap(suB, wxB)));
+                vnA = O::add(vnA, O::mul(dnu, lap(svA, wxA))); vnB = O::add(vnB, O::mul(dnu, lap(svB, wxB)));
+            } else {
+                const double *rd = rowd + (size_t)(jl - (ja - 1)) * kRowDiff;
+                const double dnu = rd[6];
+                hnA = fma(dnu, laplacian_fast(shA, rd), hnA); hnB = fma(dnu, laplacian_fast(shB, rd), hnB);
+                unA = fma(dnu, laplacian_fast(suA, rd), unA); unB = fma(dnu, laplacian_fast(suB, rd), unB);
+                vnA = fma(dnu, laplacian_fast(svA, rd), vnA); vnB = fma(dnu, laplacian_fast(svB, rd), vnB);
+            }
+        }
+
+        // CFL maxima of the new state: max(|q-c|, |q|, |q+c|) == |q| + c for c >= 0
+        if (HOT || live) {
+            const double csA = STRICT ? __dsqrt_rn(O::mul(p.g, fabs(hnA))) : fast_sqrt(p.g * fabs(hnA));
+            const double csB = STRICT ? __dsqrt_rn(O::mul(p.g, fabs(hnB))) : fast_sqrt(p.g * fabs(hnB));
+            mxA = umax64(mxA, nonneg_bits(O::add(fabs(unA), csA))); myA = umax64(myA, nonneg_bits(O::add(fabs(vnA), csA)));
+            mxB = umax64(mxB, nonneg_bits(O::add(fabs(unB), csB))); myB = umax64(myB, nonneg_bits(O::add(fabs(vnB), csB)));
+            if (!kGuard) {
+                negA |= __double2hiint(xAB.hM) | __double2hiint(y1A.hM) | __double2hiint(hnA);
+                negB |= __double2hiint(xBN.hM) | __double2hiint(y1B.hM) | __double2hiint(hnB);
+            }
+        }
+
+        // stores: the pair is 16-byte aligned; the strip's first and last column are not ours
+        if (HOT || live) {
+            st_pair(Hn + krow, hnA, hnB, st_both, st_onlyA, st_onlyB);
+            st_pair(Un + krow, unA, unB, st_both, st_onlyA, st_onlyB);
+            st_pair(Vn + krow, vnA, vnB, st_both, st_onlyA, st_onlyB);
+        }
+        if (!HOT && live) {
+            // boundary conditions (numpy.py:402-404): periodic ghost columns, zero-gradient
+            // pole rows (which also copy the ghost columns), halo rows of the neighbour bands
+            const bool south = p.pole_s && (jl == 1), north = p.pole_n && (jl == p.nrows - 2);
+            if (warp_wraps || south || north) {
+                auto put = [&](size_t kk, double hh, double uu, double vv) { Hn[kk] = hh; Un[kk] = uu; Vn[kk] = vv; };
+                auto dup = [&](bool valid, bool wraps, int col, double hh, double uu, double vv) {
+                    if (!valid) return;
+                    // a wrapping column is mirrored at column 0 (col == M) and / or M+2 (col == 2)
+                    const bool w0 = wraps && (col == p.M), w2 = wraps && (col == 2);
+                    auto row_put = [&](int row, bool centre) {
+                        if (centre) put((size_t)row * P + col, hh, uu, vv);
+                        if (w0) put((size_t)row * P, hh, uu, vv);
+                        if (w2) put((size_t)row * P + p.M + 2, hh, uu, vv);
+                    };
+                    row_put(jl, false);
+                    if (south) row_put(jl - 1, true);
+                    if (north) row_put(jl + 1, true);
+                };
+                dup(vA, wrapA, colA, hnA, unA, vnA);
+                dup(vB, wrapB, colA + 1, hnB, unB, vnB);
+            }
+            if (p.world > 1) {
+                // rows a neighbour band reads as its halo: store them into its arrays as well
+                const int ds = jl - p.jl_first, dn = p.jl_last - jl;
+                auto peer_put = [&](double *const *nb, int prow, int ppitch) {
+                    const size_t kb = (size_t)prow * ppitch + colA;
+                    auto one = [&](int col_off, bool valid, bool wraps, double hh, double uu, double vv) {
+                        if (!valid) return;
+                        nb[0][kb + col_off] = hh; nb[1][kb + col_off] = uu; nb[2][kb + col_off] = vv;
+                        const int col = colA + col_off;
+                        if (wraps && col == p.M) {
+                            const size_t kg = (size_t)prow * ppitch;
+                            nb[0][kg] = hh; nb[1][kg] = uu; nb[2][kg] = vv;
+                        }
+                        if (wraps && col == 2) {
+                            const size_t kg = (size_t)prow * ppitch + p.M + 2;
+                            nb[0][kg] = hh; nb[1][kg] = uu; nb[2][kg] = vv;
+                        }
+                    };
+                    one(0, vA, wrapA, hnA, unA, vnA);
+                    one(1, vB, wrapB, hnB, unB, vnB);
+                };
+                if (ds < p.halo && p.south[par ^ 1][0] != nullptr) peer_put(p.south[par ^ 1], p.south_row + ds, p.south_pitch);
+                if (dn < p.halo && p.north[par ^ 1][0] != nullptr) peer_put(p.north[par ^ 1], p.north_row - dn, p.north_pitch);
+            }
+        }
+        krow += P;
+        curA = nxtA; curB = nxtB;
+        y0A = y1A;   y0B = y1B;
+    };
+    using HotTag = std::integral_constant<bool, true>;
+    using RareTag = std::integral_constant<bool, false>;
+
+    // ---- the march ------------------------------------------------------------------
+    if (TMA) {
+        const double *ring = reinterpret_cast<const double *>(wbase);
+        for (int t = 0; t < ntiles; ++t) {
+            const int s = t % S;
+            mbar_wait(bar_a + 8 * s, (uint32_t)((t / S) & 1));
+            const double2 *tile = reinterpret_cast<const double2 *>(ring + (size_t)s * (LY::kStage / 8)) + lane;
+            const int j0 = ja + t * R;
+            if (j0 >= plain_lo && j0 + R - 1 <= plain_hi) {  // warp-uniform
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr)
+                    do_row(HotTag(), j0 + rr, tile[rr * (kStripCols / 2)], tile[LY::kField / 16 + rr * (kStripCols / 2)],
+                           tile[2 * (LY::kField / 16) + rr * (kStripCols / 2)], true);
+            } else {
+#pragma unroll 1
+                for (int rr = 0; rr < R; ++rr)
+                    do_row(RareTag(), j0 + rr, tile[rr * (kStripCols / 2)], tile[LY::kField / 16 + rr * (kStripCols / 2)],
+                           tile[2 * (LY::kField / 16) + rr * (kStripCols / 2)], j0 + rr < jb);
+            }
+            __syncwarp();  // every lane is done with the stage that is refilled next
+            if (lane == 0 && t + S - 1 < ntiles) issue_load(t + S - 1);
+        }
+    } else {
+#pragma unroll 1
+        for (int jl = ja; jl < jb; ++jl) {
+            const size_t k = (size_t)min(jl + 1, p.nrows - 1) * P + colA;
+            do_row(RareTag(), jl, ldg2(H + k), ldg2(U + k), ldg2(V + k), true);
         }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    ln.publish(p, lane, upd);
+
+    // ---- epilogue: publish the CFL maxima and the depth watch -------------------------
+    if (!p.fixed) {
+        unsigned long long mx = umax64(vA ? mxA : 0ULL, vB ? mxB : 0ULL);
+        unsigned long long my = umax64(vA ? myA : 0ULL, vB ? myB : 0ULL);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            mx = umax64(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+            my = umax64(my, __shfl_xor_sync(0xffffffffu, my, s));
+        }
+        if (lane == 0) {
+            Ctrl *const new_slot = p.ctrl + ((p.launch + 1) % 3);
+            atomicMax(&new_slot->ex_bits, mx);
+            atomicMax(&new_slot->ey_bits, my);
+        }
+    }
+    if (!kGuard) {
+        const bool bad = (vA && negA < 0) || (vB && negB < 0);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMin(p.err, -6);  // SWB_E_DEPTH
+    }
+}
+
+// Multi-GPU step epilogue: once every block of the step kernel has retired (stream order),
+// deposit this band's CFL maxima, stamped, in every rank's exchange block.  The system-wide
+// fence in front orders the halo rows stored by the step kernel before the stamp.
+__global__ void publish_kernel(const __grid_constant__ Params p)
+{
+    if (threadIdx.x >= p.world) return;
+    const Ctrl *new_slot = p.ctrl + ((p.launch + 1) % 3);
+    const unsigned long long ex = new_slot->ex_bits, ey = new_slot->ey_bits;
+    __threadfence_system();
+    volatile XSlot *dst = &p.xpeer[threadIdx.x]->slot[(p.launch + 1) % 3][p.rank];
+    dst->ex_bits = ex;
+    dst->ey_bits = ey;
+    __threadfence_system();
+    dst->stamp = p.stamp + 1;
 }
 
 // ------------------------------------------------------------------------------------
 // K0: CFL maxima over the FULL ghosted initial state (numpy.py:503-521), into slot 0.
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cfl_init_kernel(const double *__restrict__ H, const double *__restrict__ U,
-                                                       const double *__restrict__ V, int nrows, int jl0, int jl1,
+                                                       const double *__restrict__ V, int ncols, int jl0, int jl1,
                                                        int pitch, double g, Ctrl *slot)
 {
     unsigned long long mx = 0ULL, my = 0ULL;
-    const int width = jl1 - jl0;
-    const long long total = (long long)nrows * width;
+    const long long total = (long long)(jl1 - jl0) * ncols;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(k / width), j = jl0 + (int)(k % width);
-        const size_t a = (size_t)i * pitch + j;
+        const int jl = jl0 + (int)(k / ncols), i = (int)(k % ncols);
+        const size_t a = (size_t)jl * pitch + i;
         const double cs = __dsqrt_rn(__dmul_rn(g, fabs(H[a])));
         // the reference's three-way maximum, evaluated literally for step 1
         const double u = U[a], v = V[a];
         const unsigned long long bx0 = nonneg_bits(__dsub_rn(u, cs)), bx1 = nonneg_bits(u), bx2 = nonneg_bits(__dadd_rn(u, cs));
         const unsigned long long by0 = nonneg_bits(__dsub_rn(v, cs)), by1 = nonneg_bits(v), by2 = nonneg_bits(__dadd_rn(v, cs));
-        unsigned long long bx = bx1 > bx2 ? bx1 : bx2; bx = bx0 > bx ? bx0 : bx;
-        unsigned long long by = by1 > by2 ? by1 : by2; by = by0 > by ? by0 : by;
-        mx = bx > mx ? bx : mx;
-        my = by > my ? by : my;
+        mx = umax64(mx, umax64(bx0, umax64(bx1, bx2)));
+        my = umax64(my, umax64(by0, umax64(by1, by2)));
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
-        const unsigned long long ox = __shfl_xor_sync(0xffffffffu, mx, s);
-        const unsigned long long oy = __shfl_xor_sync(0xffffffffu, my, s);
-        mx = ox > mx ? ox : mx;
-        my = oy > my ? oy : my;
+        mx = umax64(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        my = umax64(my, __shfl_xor_sync(0xffffffffu, my, s));
     }
     if ((threadIdx.x & 31) == 0) {
         atomicMax(&slot->ex_bits, mx);
@@ -965,40 +1058,55 @@ __global__ void __launch_bounds__(256) cfl_init_kernel(const double *__restrict_
 
 // K5: max sqrt(u*u + v*v) over the full state (numpy.py:553-554).
 __global__ void __launch_bounds__(256) max_speed_kernel(const double *__restrict__ U, const double *__restrict__ V,
-                                                        int nrows, int jl0, int jl1, int pitch, unsigned long long *out)
+                                                        int ncols, int jl0, int jl1, int pitch, unsigned long long *out)
 {
     unsigned long long m = 0ULL;
-    const int width = jl1 - jl0;
-    const long long total = (long long)nrows * width;
+    const long long total = (long long)(jl1 - jl0) * ncols;
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(k / width), j = jl0 + (int)(k % width);
-        const size_t a = (size_t)i * pitch + j;
+        const int jl = jl0 + (int)(k / ncols), i = (int)(k % ncols);
+        const size_t a = (size_t)jl * pitch + i;
         const double s = __dsqrt_rn(__dadd_rn(__dmul_rn(U[a], U[a]), __dmul_rn(V[a], V[a])));
-        const unsigned long long b = nonneg_bits(s);
-        m = b > m ? b : m;
+        m = umax64(m, nonneg_bits(s));
     }
 #pragma unroll
-    for (int s = 16; s > 0; s >>= 1) {
-        const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, s);
-        m = o > m ? o : m;
-    }
+    for (int s = 16; s > 0; s >>= 1) m = umax64(m, __shfl_xor_sync(0xffffffffu, m, s));
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
 // Operator-level Laplacian (numpy.py:359-382 `compute_diffusion`), strict arithmetic.
 __global__ void __launch_bounds__(128) laplacian_kernel(const double *__restrict__ q, double *__restrict__ out, Params p)
 {
-    const int jl = p.jl_first + blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = 1 + blockIdx.y;
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int jl = p.jl_first + blockIdx.y;
     if (jl > p.jl_last || i > p.M + 1) return;
-    const size_t TS = (size_t)p.ncols;
-    LapCtx L;
-    const int jm = max(jl - 1, p.jl_lo), jp = min(jl + 1, p.jl_hi);
-    L.Aym = p.tab[T_AY * TS + jm]; L.Bym = p.tab[T_BY * TS + jm]; L.Cym = p.tab[T_CY * TS + jm];
-    L.Ay0 = p.tab[T_AY * TS + jl]; L.By0 = p.tab[T_BY * TS + jl]; L.Cy0 = p.tab[T_CY * TS + jl];
-    L.Ayp = p.tab[T_AY * TS + jp]; L.Byp = p.tab[T_BY * TS + jp]; L.Cyp = p.tab[T_CY * TS + jp];
-    L.jm1 = jm; L.jp1 = jp; L.jm2 = max(jl - 2, p.jl_lo); L.jp2 = min(jl + 2, p.jl_hi);
-    out[(size_t)i * p.pitch + jl] = laplacian_at<true>(q, p, L, p.tab[T_AC * TS + jl], i, jl);
+    using O = Op<true>;
+    const Star s = load_star(q, p.pitch, p.nrows, p.M, jl, i);
+    const W3 wy = y_weights(p.tab, p.nrows, jl);
+    const W3 wx = x_weights_strict(p.phi, p.tab[(size_t)T_AC * p.nrows + jl], i, p.M);
+    out[(size_t)jl * p.pitch + i] = O::add(second_diff_strict(wx, s.xmm, s.xm, s.q0, s.xp, s.xpp),
+                                           second_diff_strict(wy, s.ymm, s.ym, s.q0, s.yp, s.ypp));
+}
+
+// K4: layout conversion between the reference's (M+3, n) array (latitude contiguous) and
+// the device layout (n, pitch) (longitude contiguous): a tiled transpose through shared
+// memory, both sides coalesced.  dst[r][c] = src[c][r] for r < rows, c < cols.
+__global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ src, int src_pitch,
+                                                        double *__restrict__ dst, int dst_pitch, int rows, int cols)
+{
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int c = c0 + ty + k, r = r0 + tx;  // src row = c, src col = r
+        if (c < cols && r < rows) tile[ty + k][tx] = src[(size_t)c * src_pitch + r];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 32; k += 8) {
+        const int r = r0 + ty + k, c = c0 + tx;
+        if (r < rows && c < cols) dst[(size_t)r * dst_pitch + c] = tile[tx][ty + k];
+    }
 }
 
 }  // namespace swb

@@ -137,20 +137,26 @@ def _stream(device) -> ctypes.c_void_p:
 # the device-resident loop body
 # --------------------------------------------------------------------------------------
 class Stepper:
-    """Device-resident state + the fused step kernel for one grid (or latitude band).
+    """Device-resident state + the fused step kernel for one grid (or one latitude band).
 
     ``h, u, v`` (and a 2-D ``f`` / ``hs`` when given) are (M+3, N) arrays in the
-    reference layout -- numpy arrays are uploaded, CUDA tensors are copied on the device.
-    After construction ``enqueue(n)`` runs n iterations of numpy.py:496-549 without
-    involving the host; ``status()`` synchronises and reports time / step count.
+    reference layout -- numpy arrays are uploaded, CUDA tensors are used in place -- or,
+    with ``layout="device"``, CUDA tensors already in the kernels' latitude-major layout
+    (n_local, M+3).  With ``band`` (an entry of ``band_layout``) the stepper owns rows
+    ``j_begin .. j_begin+n_local-1`` only and the arrays may be either the full grid or
+    that window.  After construction ``enqueue(n)`` runs n iterations of numpy.py:496-549
+    without involving the host; ``status()`` synchronises and reports time / step count.
     """
 
     def __init__(self, latlon_grid: LatLonGrid, cart_grid: CartesianGrid, h, u, v, f, hs=None, *,
                  courant: float, final_time: float, use_diffusion: bool = True, mode: Optional[str] = None,
-                 device=None, log_capacity: int = 0):
+                 device=None, log_capacity: int = 0, band: Optional[Dict[str, int]] = None, world: int = 1,
+                 layout: str = "reference"):
         mode = DEFAULT_MODE if mode is None else mode
         if mode not in MODES:
             raise ValueError(f"mode must be one of {sorted(MODES)}, got {mode!r}")
+        if layout not in ("reference", "device"):
+            raise ValueError("layout must be 'reference' or 'device'")
         self.lib = _lib.load()
         self.device = _require_cuda(device)
         self.latlon_grid, self.cart_grid = latlon_grid, cart_grid
@@ -158,41 +164,49 @@ class Stepper:
         self.mode = mode
         self.use_diffusion = bool(use_diffusion)
         M, N = self.M, self.N
-        shape = (M + 3, N)
+        if band is None:
+            band = {"rank": 0, "j_first": 1, "j_last": N - 2, "j_begin": 0, "n_local": N}
+            world = 1
+        self.band, self.world = dict(band), int(world)
+        self.j_begin, self.n_local = int(band["j_begin"]), int(band["n_local"])
+        self.halo = (2 if self.use_diffusion else 1) if self.world > 1 else 0
+        self._layout = layout
+        self._peer_bases: List[int] = []
 
-        # Device layout: the reference's (M+3, N) arrays with `lead_pad` unused columns in front
-        # and an even pitch, so that the first updated latitude sits on a 16-byte boundary
-        # (TMA boxes must start there; include/swb200.h).
-        self.lead_pad = 1
-        self.pitch = (self.lead_pad + N + 1) // 2 * 2
-        self._cols = slice(self.lead_pad, self.lead_pad + N)
+        # Device layout: latitude-major (n_local, pitch), longitude contiguous (include/swb200.h)
+        self.pitch = int(self.lib.swb_required_pitch(M))
+        if self.pitch <= 0:
+            raise ValueError(f"bad grid size M={M}")
+        self._raw = torch.zeros((2, 3, self.n_local, self.pitch), dtype=torch.float64, device=self.device)
+        #: (2, 3, M+3, n_local) view of the two buffer sets in the reference's index order
+        self.buf = self._raw[..., : M + 3].transpose(-1, -2)
 
-        f_lat = _latitude_only(f)
-        self._f2d = None if f_lat is not None else self._padded(f)
-        self._hs = None
-        if hs is not None:
-            hs_t = self._padded(hs)
-            if bool((hs_t != 0).any()):  # flat topography only subtracts an exact zero
-                self._hs = hs_t
-
-        # two buffer sets {h,u,v}; set 0 receives the initial state
-        self._raw = torch.zeros((2, 3, M + 3, self.pitch), dtype=torch.float64, device=self.device)
-        self.buf = self._raw[..., self._cols]  # (2, 3, M+3, N) view in the reference layout
-        for k, q in enumerate((h, u, v)):
-            self.buf[0, k].copy_(self._as_tensor(q, shape), non_blocking=False)
+        # Coriolis: a latitude vector (length N, or the band's window) or a genuinely 2-D field
+        if isinstance(f, (np.ndarray, torch.Tensor)) and f.ndim == 1:
+            f_lat = np.ascontiguousarray(f.detach().cpu().numpy() if isinstance(f, torch.Tensor) else f, dtype=np.float64)
+        else:
+            f_lat = _latitude_only(f) if layout == "reference" else None
+        if f_lat is not None and len(f_lat) == self.n_local != N:  # the band's window: place it
+            full = np.zeros(N)
+            full[self.j_begin:self.j_begin + self.n_local] = f_lat
+            f_lat = full
+        if isinstance(hs, torch.Tensor):
+            hs_flat = not bool((hs != 0).any())  # flat topography only subtracts an exact zero
+        else:
+            hs_flat = hs is None or not np.any(np.asarray(hs))
 
         cfg = SwbConfig()
         cfg.struct_bytes = ctypes.sizeof(SwbConfig)
         cfg.M, cfg.N = M, N
-        cfg.j_begin, cfg.n_local, cfg.j_first, cfg.j_last, cfg.pitch = 0, N, 1, N - 2, self.pitch
-        cfg.lead_pad = self.lead_pad
+        cfg.j_begin, cfg.n_local = self.j_begin, self.n_local
+        cfg.j_first, cfg.j_last, cfg.pitch = int(band["j_first"]), int(band["j_last"]), self.pitch
         cfg.dtype, cfg.mode = _lib.SWB_F64, MODES[mode]
         cfg.use_diffusion = int(self.use_diffusion)
-        cfg.f_is_2d = int(self._f2d is not None)
-        cfg.has_hs = int(self._hs is not None)
+        cfg.f_is_2d = int(f_lat is None)
+        cfg.has_hs = int(not hs_flat)
         cfg.device = self.device.index
         cfg.log_capacity = int(log_capacity)
-        cfg.rank, cfg.world = 0, 1
+        cfg.rank, cfg.world, cfg.halo = int(band.get("rank", 0)), self.world, self.halo
         cfg.courant, cfg.final_time = float(courant), float(final_time)
         cfg.dxmin, cfg.dymin = float(cart_grid.dxmin), float(cart_grid.dymin)
         cfg.g, cfg.a, cfg.nu = EARTH_CONSTANTS.g, EARTH_CONSTANTS.a, EARTH_CONSTANTS.nu
@@ -201,37 +215,64 @@ class Stepper:
         self._ctx = ctypes.c_void_p()
         check(self.lib.swb_create(ctypes.byref(self._ctx), ctypes.byref(cfg)))
 
-        tabs = latitude_tables(latlon_grid, cart_grid, f_lat, self.use_diffusion)
+        tabs = latitude_tables(latlon_grid, cart_grid, f_lat, self.use_diffusion, self.j_begin, self.n_local)
         ct = SwbTables()
         for name in _lib.TABLE_FIELDS:
             arr = tabs.get(name)
             setattr(ct, name, arr.ctypes.data_as(_lib._dp) if arr is not None else None)
         check(self.lib.swb_set_tables(self._ctx, ctypes.byref(ct)))
 
+        # set 0 receives the initial state
+        for k, q in enumerate((h, u, v)):
+            self._load(q, self._raw[0, k])
+        self._f2d = self._load(f, None) if f_lat is None else None
+        self._hs = None if hs_flat else self._load(hs, None)
+
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
         check(self.lib.swb_bind_state(self._ctx, *(ptr(self._raw[s, k]) for s in (0, 1) for k in range(3)),
                                       ptr(self._f2d), ptr(self._hs)))
         self._cfl_ready = False
+        self._staging: Optional[torch.Tensor] = None
 
     # -- plumbing ------------------------------------------------------------------
-    def _as_tensor(self, q, shape) -> torch.Tensor:
-        if isinstance(q, torch.Tensor):
-            t = q
-        else:
-            t = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64))
-        if tuple(t.shape) != tuple(shape) or t.dtype != torch.float64:
-            raise ValueError(f"expected a float64 array of shape {shape}, got {tuple(t.shape)} {t.dtype}")
-        return t
+    def _load(self, q, dst: Optional[torch.Tensor]) -> torch.Tensor:
+        """Bring one field into the device layout (``dst`` or a fresh (n_local, pitch) array)."""
+        M, nl = self.M, self.n_local
+        if dst is None:
+            dst = torch.zeros((nl, self.pitch), dtype=torch.float64, device=self.device)
+        if self._layout == "device":
+            if not (isinstance(q, torch.Tensor) and q.is_cuda and tuple(q.shape) == (nl, M + 3) and q.dtype == torch.float64):
+                raise ValueError(f"layout='device' expects float64 CUDA tensors of shape {(nl, M + 3)}")
+            dst[:, : M + 3].copy_(q)
+            return dst
+        t = q if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64))
+        if t.dtype != torch.float64 or t.ndim != 2 or t.shape[0] != M + 3 or t.shape[1] not in (self.N, nl):
+            raise ValueError(f"expected a float64 array of shape {(M + 3, self.N)} (or the band window {(M + 3, nl)}), "
+                             f"got {tuple(t.shape)} {t.dtype}")
+        if t.shape[1] != nl:  # the full grid was given: take this band's rows
+            t = t[:, self.j_begin:self.j_begin + nl]
+        t = t.to(self.device, non_blocking=False)  # H2D (or a no-op for a CUDA tensor): plumbing
+        if t.stride(1) != 1:
+            t = t.contiguous()
+        check(self.lib.swb_to_device_layout(self._ctx, ctypes.c_void_p(t.data_ptr()), int(t.stride(0)),
+                                            ctypes.c_void_p(dst.data_ptr()), _stream(self.device)))
+        torch.cuda.current_stream(self.device).synchronize()  # `t` may be a temporary
+        return dst
 
-    def _padded(self, q) -> torch.Tensor:
-        """Copy an (M+3, N) array into a fresh device array in the padded layout."""
-        out = torch.zeros((self.M + 3, self.pitch), dtype=torch.float64, device=self.device)
-        out[:, self._cols].copy_(self._as_tensor(q, (self.M + 3, self.N)))
+    def export(self, src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Device-layout (n_local, pitch) array -> (M+3, n_local) CUDA tensor in the reference layout."""
+        if out is None:
+            out = torch.empty((self.M + 3, self.n_local), dtype=torch.float64, device=self.device)
+        check(self.lib.swb_from_device_layout(self._ctx, ctypes.c_void_p(src.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                              int(out.stride(0)), _stream(self.device)))
         return out
 
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             torch.cuda.synchronize(self.device)
+            for base in self._peer_bases:
+                self.lib.swb_ipc_close(ctypes.c_void_p(base))
+            self._peer_bases = []
             self.lib.swb_destroy(self._ctx)
             self._ctx = ctypes.c_void_p()
 
@@ -268,12 +309,22 @@ class Stepper:
         return st
 
     def state(self, current: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Device views (M+3, N) of the current h, u, v (synchronises unless ``current`` is given)."""
+        """Device views (M+3, n_local) of the current h, u, v (synchronises unless ``current`` is given)."""
         cur = self.status().current if current is None else current
         return self.buf[cur, 0], self.buf[cur, 1], self.buf[cur, 2]
 
+    def snapshot(self, current: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """K4: the buffer set ``current`` as one (3, M+3, n_local) CUDA tensor in the reference
+        layout (numpy.py:488-492, 559-563), produced on the current stream."""
+        if out is None:
+            out = torch.empty((3, self.M + 3, self.n_local), dtype=torch.float64, device=self.device)
+        for k in range(3):
+            self.export(self._raw[current, k], out[k])
+        return out
+
     def to_numpy(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-        return tuple(q.cpu().numpy() for q in self.state())
+        snap = self.snapshot(self.status().current).cpu().numpy()
+        return snap[0], snap[1], snap[2]
 
     def max_speed(self) -> float:
         """max sqrt(u^2+v^2) over the full current state (numpy.py:553-554)."""
@@ -289,15 +340,54 @@ class Stepper:
 
     def laplacian(self, q) -> torch.Tensor:
         """(D_x D_x + D_y D_y) q at the interior cells (numpy.py:359-382), as (M+1, N-2)."""
-        qd = self._padded(q)
+        qd = self._load(q, None)
         out = torch.zeros_like(qd)
         check(self.lib.swb_laplacian(self._ctx, ctypes.c_void_p(qd.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                      _stream(self.device)))
-        return out[1:-1, self.lead_pad + 1:self.lead_pad + self.N - 1]
+        return out[1:-1, 1:self.M + 2].transpose(0, 1)
 
     @property
     def launch_count(self) -> int:
         return int(self.lib.swb_launch_count(self._ctx))
+
+    # -- latitude bands (multi-GPU) ---------------------------------------------------
+    def exchange_block(self) -> Tuple[int, int]:
+        """Device address and size of the block peers deposit their CFL maxima in."""
+        ptr, nbytes = ctypes.c_void_p(), ctypes.c_uint64()
+        check(self.lib.swb_exchange_block(self._ctx, ctypes.byref(ptr), ctypes.byref(nbytes)))
+        return int(ptr.value), int(nbytes.value)
+
+    def buffer_addresses(self, base: Optional[int] = None) -> List[int]:
+        """Addresses of h0,u0,v0,h1,u1,v1 (optionally relative to another mapping's base)."""
+        b = self._raw.data_ptr() if base is None else base
+        stride = self.n_local * self.pitch * 8
+        return [b + (s * 3 + k) * stride for s in (0, 1) for k in range(3)]
+
+    def link(self, exchange_blocks: List[int], south: Optional[Dict[str, Any]], north: Optional[Dict[str, Any]]):
+        """Hand the context its peers (include/swb200.h swb_link_peers).  ``exchange_blocks``:
+        every rank's block as mapped in this process; ``south`` / ``north``: dicts with the
+        neighbour's ``bufs`` (six mapped addresses), ``j_begin`` and ``pitch``, or None."""
+        xb = (ctypes.c_void_p * len(exchange_blocks))(*exchange_blocks)
+
+        def pack(nb):
+            if nb is None:
+                return None, 0, 0
+            return (ctypes.c_void_p * 6)(*nb["bufs"]), int(nb["j_begin"]), int(nb["pitch"])
+
+        sb, sj, sp = pack(south)
+        nb_, nj, np_ = pack(north)
+        check(self.lib.swb_link_peers(self._ctx, xb, sb, sj, sp, nb_, nj, np_))
+        self._cfl_ready = False
+
+
+def link_local(steppers: List["Stepper"]):
+    """Link latitude bands that live in ONE process on ONE device (plain device pointers).
+    Serves tests and single-GPU emulation of the band path: launches of the bands are then
+    enqueued round-robin on one stream, so every wait in a step prologue is already met."""
+    blocks = [s.exchange_block()[0] for s in steppers]
+    for r, s in enumerate(steppers):
+        nb = lambda t: {"bufs": t.buffer_addresses(), "j_begin": t.j_begin, "pitch": t.pitch}  # noqa: E731
+        s.link(blocks, nb(steppers[r - 1]) if r > 0 else None, nb(steppers[r + 1]) if r + 1 < len(steppers) else None)
 
 
 # --------------------------------------------------------------------------------------
@@ -461,10 +551,18 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
         st.cfl_init()
         snaps: List[torch.Tensor] = []   # pinned (3, M+1, N) host copies, one per save point
         snap_status: List[torch.Tensor] = []
+        stage = None  # device staging of one snapshot in the reference layout (K4)
+
+        def take_snapshot(current: int) -> torch.Tensor:
+            nonlocal stage
+            stage = st.snapshot(current, stage)
+            pinned = torch.empty((3, latlon_grid.M + 1, latlon_grid.N), dtype=torch.float64).pin_memory()
+            for k in range(3):
+                pinned[k].copy_(stage[k, 1:-1, :], non_blocking=True)  # numpy.py:488-492: h[1:-1, :]
+            return pinned
+
         if save_interval > 0:
-            first = torch.empty((3, latlon_grid.M + 1, latlon_grid.N), dtype=torch.float64).pin_memory()
-            first.copy_(st.buf[0, :, 1:-1, :], non_blocking=True)
-            snaps.append(first)
+            snaps.append(take_snapshot(0))
 
         def stops():
             """Step counts at which the host must do something, in increasing order."""
@@ -492,9 +590,7 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
                     )
             if save_interval > 0 and enq % save_interval == 0:
                 # valid only if all `enq` steps ran, in which case the parity is known
-                snap = torch.empty((3, latlon_grid.M + 1, latlon_grid.N), dtype=torch.float64).pin_memory()
-                snap.copy_(st.buf[enq & 1, :, 1:-1, :], non_blocking=True)
-                snaps.append(snap)
+                snaps.append(take_snapshot(enq & 1))
                 pin = torch.zeros(_STATUS_BYTES, dtype=torch.uint8).pin_memory()
                 st.status_async(pin)
                 snap_status.append(pin)
