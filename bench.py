@@ -180,44 +180,72 @@ def run_reference_arm(args, M, N):
 # our arm
 # --------------------------------------------------------------------------------------
 def run_ours(args, M, N):
+    """One rank of the job.  N = 1: the whole M x N grid on cuda:0.  N > 1 (torchrun, one
+    process per GPU): weak scaling -- every GPU owns an M x N latitude band of the
+    M x (N * world) globe; halo rows and CFL maxima travel by in-kernel peer stores."""
     import torch
 
+    from sw_solver_b200 import bands
     from sw_solver_b200.grid import CartesianGrid, LatLonGrid
-    from sw_solver_b200.ic import ICType, coriolis_latitude, get_initial_conditions
-    from sw_solver_b200.solver import Stepper
+    from sw_solver_b200.ic import coriolis_latitude, rossby_haurwitz_window
+    from sw_solver_b200.solver import Stepper, band_layout
 
-    if args.gpus != 1:
-        raise SystemExit("multi-GPU bench path: see bench_multi (not in this build)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE is {world}: launch N > 1 with torchrun (one process per GPU)")
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
 
-    ll = LatLonGrid(M, N)
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N_glob = N * world
+    ll = LatLonGrid(M, N_glob)
     cg = CartesianGrid(ll)
-    h, u, v, _ = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
-    f = coriolis_latitude(ll)
-    pts = (M + 1) * (ll.N - 2)
-    state_bytes = 3 * (M + 3) * ll.N * 8
+    f_lat = coriolis_latitude(ll)
+    halo = 2 if args.diffusion else 1
+    band = band_layout(ll.N, world, halo)[rank] if world > 1 else None
+    j_begin, n_local = (band["j_begin"], band["n_local"]) if band else (0, ll.N)
+    pts_rank = (M + 1) * ((band["j_last"] - band["j_first"] + 1) if band else ll.N - 2)
+    pts = (M + 1) * (ll.N - 2)  # whole job, per step
+    kw = dict(courant=0.5, final_time=1e12, use_diffusion=args.diffusion, mode=args.mode, device=dev)
 
-    # pinned host copies of the initial state for the end-to-end leg
-    host = [torch.from_numpy(q).pin_memory() for q in (h, u, v)]
-    del h, u, v
-
-    st = Stepper(ll, cg, host[0], host[1], host[2], f, None, courant=0.5, final_time=1e12,
-                 use_diffusion=args.diffusion, mode=args.mode, device=dev)
+    # --- device-resident leg: the state is assembled on the GPU, in the device layout -----
+    hd, ud, vd, _ = bands.rossby_haurwitz_band(ll, j_begin, n_local, dev)
+    st = Stepper(ll, cg, hd, ud, vd, f_lat, None, band=band, world=world, layout="device", **kw)
+    del hd, ud, vd
+    if world > 1:
+        bands.link_distributed(st)
     st.cfl_init()
     st.enqueue(args.warmup)
-    torch.cuda.synchronize(dev)
+    barrier()
     launches0 = st.launch_count
 
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(0) as clk:
-        torch.cuda.synchronize(dev)
+    with ClockSampler(local_rank) as clk:
+        barrier()
         ev0.record()
         st.enqueue(args.steps)
         ev1.record()
-        torch.cuda.synchronize(dev)
-    ms = ev0.elapsed_time(ev1)
+        barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = st.launch_count - launches0
     s = st.status()
     assert s.steps == args.warmup + args.steps and not s.done and s.error == 0, (s.steps, s.done, s.error)
@@ -225,44 +253,51 @@ def run_ours(args, M, N):
     assert bool(torch.isfinite(hcur).all()), "non-finite state after the timed region"
     value = pts * args.steps / (ms * 1e-3)
     st.close()
-    del st
+    del st, hcur
+    torch.cuda.empty_cache()
 
     # --- end to end through the public host API, HOST buffers in and out -----------------
     e2e = None
     if not args.no_e2e:
+        host = [torch.from_numpy(q).pin_memory() for q in rossby_haurwitz_window(ll, j_begin, n_local)]
         out = [torch.empty_like(q).pin_memory() for q in host]
-        torch.cuda.synchronize(dev)
+        state_bytes = 3 * (M + 3) * n_local * 8
+        barrier()
         t0 = time.perf_counter()
-        st2 = Stepper(ll, cg, host[0], host[1], host[2], f, None, courant=0.5, final_time=1e12,
-                      use_diffusion=args.diffusion, mode=args.mode, device=dev)   # H2D of h, u, v
+        st2 = Stepper(ll, cg, host[0], host[1], host[2], f_lat, None, band=band, world=world, **kw)  # H2D of h, u, v
+        if world > 1:
+            bands.link_distributed(st2)
         st2.enqueue(args.steps)
         cur = st2.status().current                                                  # blocks until done
-        snap = st2.snapshot(cur)                                                   # K4: back to the reference layout
+        snap = st2.snapshot(cur)                                                    # K4: back to the reference layout
         for k in range(3):
             out[k].copy_(snap[k], non_blocking=True)                                # D2H of h, u, v
         torch.cuda.synchronize(dev)
-        el = time.perf_counter() - t0
+        el = max_over_ranks(time.perf_counter() - t0)
         st2.close()
         e2e = {"value": pts * args.steps / el, "unit": UNIT,
-               "h2d_bytes_per_step": state_bytes / args.steps, "d2h_bytes_per_step": state_bytes / args.steps,
-               "call": f"Stepper(host h,u,v) + enqueue({args.steps}) + D2H of h,u,v; {state_bytes} B each way per call",
+               "h2d_bytes_per_step": world * state_bytes / args.steps, "d2h_bytes_per_step": world * state_bytes / args.steps,
+               "call": f"per rank: Stepper(host h,u,v) + enqueue({args.steps}) + snapshot + D2H of h,u,v; "
+                       f"{state_bytes} B each way per rank per call",
                "seconds": el}
+        del host, out, snap
 
     peak, peak_src = measured_peak_gbs()
     kernel_ms = ms / args.steps
-    achieved = BYTES_PER_UPDATE_F64 * pts / (kernel_ms * 1e-3) / 1e9
+    achieved = BYTES_PER_UPDATE_F64 * pts_rank / (kernel_ms * 1e-3) / 1e9  # per GPU
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "swb::step_kernel", "kernel_ms": kernel_ms,
-                "bytes_per_launch": BYTES_PER_UPDATE_F64 * pts, "peak_source": peak_src}
+                "traffic": None, "kernel": "swb::march_kernel", "kernel_ms": kernel_ms,
+                "bytes_per_launch": BYTES_PER_UPDATE_F64 * pts_rank, "peak_source": peak_src,
+                "note": "per GPU; one march_kernel launch per step (kernel_ms = step time, CUDA events on the launch stream)"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(f"{M}x{ll.N}:{args.mode}")
+            roofline["traffic"] = json.load(open(prof)).get(f"{M}x{N}:{args.mode}")
         except Exception:
             pass
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         ns = cpu_sample_rows(M)
         probe = cpu_reference_run(M, ns, args.diffusion, 1, 1)
         nsteps = int(max(2, min(200, 12.0 / max(probe["seconds"], 1e-3))))
@@ -271,24 +306,31 @@ def run_ours(args, M, N):
                "sample": f"oracle port of numpy.py:503-549 (C, OpenMP) on a {M}x{r['N_sample']} latitude band of the "
                          f"workload, {nsteps} steps, {r['seconds']:.1f} s"}
 
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Rossby-Haurwitz {M}x{ll.N} fp64, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
-                   "mode": args.mode, "l2": "state (6.4 GB touched per step) is larger than L2; no flush needed",
-                   "pts_per_step": pts},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clk.summary(),
-    }
-    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+    if rank == 0:
+        per_gpu = f"{M}x{N} per GPU, {M}x{ll.N} globe in {world} latitude bands" if world > 1 else f"{M}x{ll.N}"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"Rossby-Haurwitz {per_gpu} fp64, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
+                       "mode": args.mode,
+                       "l2": "state (6.4 GB touched per GPU per step at the default size) is larger than L2; no flush needed",
+                       "pts_per_step": pts, "parallelism": f"lat-bands x{world}"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
+            "clocks": clk.summary(),
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
     M, N = (int(x) for x in args.grid.lower().split("x"))
     if args.impl == "reference":
-        run_reference_arm(args, M, N)
+        run_reference_arm(args, M, N * max(1, args.gpus))
     else:
         run_ours(args, M, N)
 

@@ -109,7 +109,8 @@ typedef struct swb_tables {
 /* Small status record mirrored from the device (see swb_get_status). */
 typedef struct swb_status {
     double time;       /* simulated seconds reached                                   */
-    double eigenx;     /* CFL maxima of the CURRENT state (numpy.py:503-521)          */
+    double eigenx;     /* CFL maxima of the CURRENT state (numpy.py:503-521); with
+                          several bands: of this band's rows                          */
     double eigeny;
     double last_dt;    /* dt of the most recent step                                  */
     int64_t steps;     /* completed time steps (numpy.py:500 num_steps)               */

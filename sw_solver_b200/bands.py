@@ -1,0 +1,157 @@
+"""Latitude bands across GPUs: one process per GPU, launched with torchrun.
+
+The reference is a single process on one array (src/sw_solver/numpy.py:464-494); this
+module is the plumbing of the decomposition SURVEY.md section 8(e) describes.  The globe is
+cut into ``world`` contiguous latitude bands (``solver.band_layout``).  Every rank builds a
+``Stepper`` for its band, then ``link_distributed`` exchanges CUDA IPC handles through
+``torch.distributed`` (any backend: the handles are tiny host objects) and maps
+
+* every rank's *exchange block* -- where that rank's step kernel's epilogue deposits the
+  CFL maxima of its band, stamped with the step number, and
+* the two neighbours' state buffers -- into which the step kernel stores the rows the
+  neighbour reads as halo (peer stores over NVLink),
+
+into this process.  From then on the time loop involves no host call and no NCCL
+collective: the prologue of step n+1 waits (on its own GPU's memory) until all bands'
+maxima of step n have arrived, which also orders the halo rows.  ``torch.distributed`` is
+used for set-up, barriers and the timing reduction only.
+"""
+
+import ctypes
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+from .grid import LatLonGrid
+from .ic import separable_rossby_haurwitz
+
+
+# --------------------------------------------------------------------------------------
+# pure host logic (covered by CPU / gloo tests)
+# --------------------------------------------------------------------------------------
+def neighbour_plan(infos: List[Dict[str, Any]], rank: int) -> Dict[str, Any]:
+    """Which peers' memory rank ``rank`` has to map, from the all-gathered band records.
+
+    Each record carries ``rank, j_begin, n_local, j_first, j_last, pitch`` (+ the opaque
+    handles).  Returns ``{"exchange": [ranks in order], "south": rank-1 | None,
+    "north": rank+1 | None}`` after checking that the bands tile the interior rows.
+    """
+    world = len(infos)
+    order = sorted(infos, key=lambda d: d["rank"])
+    if [d["rank"] for d in order] != list(range(world)):
+        raise ValueError("band records do not cover ranks 0..world-1 exactly once")
+    for a, b in zip(order[:-1], order[1:]):
+        if a["j_last"] + 1 != b["j_first"]:
+            raise ValueError(f"bands {a['rank']} and {b['rank']} are not contiguous in latitude")
+        if b["j_begin"] > a["j_last"] or a["j_begin"] + a["n_local"] <= b["j_first"]:
+            raise ValueError(f"bands {a['rank']} and {b['rank']} do not overlap by their halo rows")
+    if len({d["pitch"] for d in order}) != 1:
+        raise ValueError("all bands must use the same pitch")
+    return {
+        "exchange": list(range(world)),
+        "south": rank - 1 if rank > 0 else None,
+        "north": rank + 1 if rank < world - 1 else None,
+    }
+
+
+def band_record(stepper) -> Dict[str, Any]:
+    """The record a rank contributes to the all-gather (IPC handles included)."""
+    lib = stepper.lib
+
+    def export(ptr: int) -> Tuple[bytes, int]:
+        handle = ctypes.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+        off = ctypes.c_uint64()
+        check(lib.swb_ipc_export(ctypes.c_void_p(ptr), handle, ctypes.byref(off)))
+        return handle.raw, int(off.value)
+
+    xptr, _ = stepper.exchange_block()
+    xh, xo = export(xptr)
+    sh, so = export(stepper._raw.data_ptr())
+    b = stepper.band
+    return {"rank": int(b["rank"]), "j_begin": stepper.j_begin, "n_local": stepper.n_local,
+            "j_first": int(b["j_first"]), "j_last": int(b["j_last"]), "pitch": stepper.pitch,
+            "xh": xh, "xo": xo, "sh": sh, "so": so}
+
+
+# --------------------------------------------------------------------------------------
+# linking (needs CUDA)
+# --------------------------------------------------------------------------------------
+def link_distributed(stepper, group=None) -> None:
+    """All-gather the band records over ``torch.distributed`` and link ``stepper``."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world != stepper.world or rank != stepper.band["rank"]:
+        raise ValueError("the stepper's band does not match this process's rank / world size")
+    infos: List[Optional[Dict[str, Any]]] = [None] * world
+    dist.all_gather_object(infos, band_record(stepper), group=group)
+    plan = neighbour_plan(infos, rank)
+    lib, dev = stepper.lib, stepper.device.index
+
+    def open_handle(raw: bytes) -> int:
+        base = ctypes.c_void_p()
+        check(lib.swb_ipc_open(raw, dev, ctypes.byref(base)))
+        stepper._peer_bases.append(int(base.value))
+        return int(base.value)
+
+    blocks = []
+    for r in plan["exchange"]:
+        if r == rank:
+            blocks.append(stepper.exchange_block()[0])
+        else:
+            blocks.append(open_handle(infos[r]["xh"]) + infos[r]["xo"])
+
+    def neighbour(r: Optional[int]):
+        if r is None:
+            return None
+        d = infos[r]
+        base = open_handle(d["sh"]) + d["so"]
+        stride = d["n_local"] * d["pitch"] * 8
+        return {"bufs": [base + k * stride for k in range(6)], "j_begin": d["j_begin"], "pitch": d["pitch"]}
+
+    stepper.link(blocks, neighbour(plan["south"]), neighbour(plan["north"]))
+    dist.barrier(group=group)  # nobody steps before everybody is linked
+
+
+# --------------------------------------------------------------------------------------
+# band-sized initial state, assembled on the device
+# --------------------------------------------------------------------------------------
+def rossby_haurwitz_band(latlon_grid: LatLonGrid, j_begin: int, n_local: int, device) -> Tuple[torch.Tensor, ...]:
+    """h, u, v of the Rossby-Haurwitz wave (reference ic.py:53-107) for latitudes
+    ``j_begin .. j_begin+n_local-1``, as (n_local, M+3) float64 CUDA tensors in the device
+    layout, plus the Coriolis latitude vector of the WHOLE grid (numpy).
+
+    The transcendental factors are evaluated by numpy on O(M + N) points exactly as
+    ``ic.get_initial_conditions`` does; the device only forms the final products and sums,
+    one IEEE operation per torch call in the reference's order, so the result is
+    bit-identical to slicing the full-grid initial condition.
+    """
+    from .ic import coriolis_latitude
+
+    s = separable_rossby_haurwitz(latlon_grid)
+    sl = slice(j_begin, j_begin + n_local)
+    dev = torch.device(device)
+
+    def col(name):  # latitude factor -> column vector
+        return torch.from_numpy(np.ascontiguousarray(s[name][sl])).to(dev)[:, None]
+
+    def row(name):  # longitude factor -> row vector
+        return torch.from_numpy(np.ascontiguousarray(s[name])).to(dev)[None, :]
+
+    cR, c2R, sR = row("cosR"), row("cos2R"), row("sinR")
+    t = col("hB") * cR
+    t = col("hA") + t
+    t2 = col("hC") * c2R
+    t = t + t2
+    del t2
+    t = t / float(s["g"])
+    h = float(s["h0"]) + t
+    del t
+    u = col("uB") * cR
+    u = col("uA") + u
+    v = col("vB") * sR
+    return h, u, v, coriolis_latitude(latlon_grid)

@@ -38,6 +38,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         nvcc_path(),
         "-gencode", "arch=compute_100a,code=sm_100a",
         "-O3", "-std=c++17", "-lineinfo",
+        # no implicit FMA contraction: STRICT needs numpy's operation-by-operation rounding, and
+        # FAST spells every fused multiply-add out, so that all instantiations of the step kernel
+        # (hot / boundary rows, TMA / direct loads, any band decomposition) round identically
+        "-fmad=false",
         "-Xcompiler", "-fPIC", "-shared",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
         "-o", LIB,

@@ -501,10 +501,6 @@ __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int
         new_slot->last_dt = active ? dt : cur_slot->last_dt;
         new_slot->done = !(tnew < p.final_time);
         new_slot->error = 0;
-        if (p.world > 1) {  // what this launch consumed, for the status mirror
-            cur_slot->ex_bits = exb;
-            cur_slot->ey_bits = eyb;
-        }
         if (!active) {  // nothing will be accumulated: carry the maxima forward
             new_slot->ex_bits = exb;
             new_slot->ey_bits = eyb;

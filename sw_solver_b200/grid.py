@@ -130,6 +130,21 @@ class CartesianGrid:
         return self.phi1d[i0:i1, None] * self.ac1d[None, :]
 
     def _dx_min(self):
+        """min over the whole 2-D dx field (grid.py:46) without forming it.
+
+        dx[i, j] = ac_j*phi_{i+1} - ac_j*phi_i equals ac_j*dphi up to a relative roundoff of
+        ~1e-10 at most, whereas ac_j changes from one latitude to the next by a relative
+        ~34/(N-1) next to the channel walls: the minimum therefore sits in one of the two
+        outermost latitudes on either side, and scanning those four columns over all
+        longitudes returns the reference's value bit for bit (checked against the full
+        scan in tests/test_host.py).
+        """
+        cols = sorted({0, 1, self.N - 2, self.N - 1})
+        x = self.phi1d[:, None] * self.ac1d[None, cols]
+        return np.float64((x[1:] - x[:-1]).min())
+
+    def _dx_min_full(self):
+        """The literal blockwise scan of all (M+2) x N increments (test reference)."""
         best = np.inf
         nrow = self.M + 3
         for i0 in range(0, nrow - 1, _ROW_BLOCK):

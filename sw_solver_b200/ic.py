@@ -74,6 +74,19 @@ def separable_rossby_haurwitz(latlon_grid: LatLonGrid) -> Dict[str, np.ndarray]:
     }
 
 
+def rossby_haurwitz_window(latlon_grid: LatLonGrid, j_begin: int, n_local: int):
+    """h, u, v of the Rossby-Haurwitz wave on latitudes ``j_begin .. j_begin+n_local-1`` only,
+    shape (M+3, n_local): bit-identical to the same columns of ``get_initial_conditions``
+    (same products and sums in the same order), without forming the full grid."""
+    s = separable_rossby_haurwitz(latlon_grid)
+    sl = slice(j_begin, j_begin + n_local)
+    cR, c2R, sR = s["cosR"][:, None], s["cos2R"][:, None], s["sinR"][:, None]
+    h = s["h0"] + (s["hA"][None, sl] + s["hB"][None, sl] * cR + s["hC"][None, sl] * c2R) / s["g"]
+    u = s["uA"][None, sl] + s["uB"][None, sl] * cR
+    v = s["vB"][None, sl] * sR
+    return np.ascontiguousarray(h), np.ascontiguousarray(u), np.ascontiguousarray(v)
+
+
 def get_initial_conditions(ic_type: ICType, latlon_grid: LatLonGrid):
     """Return ``h, u, v, f`` on the full ghosted (M+3, N) grid (reference ic.py:22-159).
 
