@@ -173,7 +173,7 @@ def run_reference_arm(args, M, N):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------
@@ -245,7 +245,10 @@ def run_ours(args, M, N):
         st.enqueue(args.steps)
         ev1.record()
         barrier()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_local = ev0.elapsed_time(ev1)
+    ms = max_over_ranks(ms_local)
+    if os.environ.get("SWB_BENCH_VERBOSE"):
+        print(f"[bench] rank {rank}: {ms_local / args.steps:.4f} ms/step locally, clocks {clk.summary()}", file=sys.stderr, flush=True)
     launches = st.launch_count - launches0
     s = st.status()
     assert s.steps == args.warmup + args.steps and not s.done and s.error == 0, (s.steps, s.done, s.error)
@@ -321,12 +324,17 @@ def run_ours(args, M, N):
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
             "clocks": clk.summary(),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
+    # Libraries (NCCL's version banner, torchrun notices) may write to fd 1; the contract is ONE
+    # JSON line on stdout, so everything but that line is sent to stderr.
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     args = parse_args()
     M, N = (int(x) for x in args.grid.lower().split("x"))
     if args.impl == "reference":

@@ -75,25 +75,26 @@ struct swb_ctx {
 namespace {
 
 // TMA ring shapes built into the library: {latitudes per box R, stages S}
-struct TmaVariant { int R, S, minb; };
-constexpr TmaVariant kTmaVariants[] = {{2, 4, 3}, {4, 2, 3}, {2, 3, 3}, {4, 3, 2}, {2, 4, 2}, {4, 4, 2}};
+struct TmaVariant { int R, S, minb, W; };
+constexpr TmaVariant kTmaVariants[] = {{2, 4, 3, 4}, {4, 2, 3, 4}, {2, 3, 3, 4}, {4, 3, 2, 4}, {2, 4, 2, 4}, {4, 4, 2, 4},
+                                       {4, 3, 2, 5}, {2, 4, 2, 5}, {4, 2, 2, 6}, {2, 4, 2, 6}, {4, 4, 1, 8}};
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 constexpr int kDefaultTmaVariant = 5;  // R = 4, S = 4, two blocks per SM: no spills (1.26 ms/step at 16384 x 8192)
 
-template <bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB>
+template <bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
 cudaError_t launch_inst(const swb_ctx *c, dim3 grid, cudaStream_t st)
 {
     using LY = TmaLayout<R, S>;
-    const int smem = rec_bytes(c->prm.chunk, DIFF) + (TMA ? kWarpsPerBlock * LY::kWarpBytes : 0);
+    const int smem = rec_bytes(c->prm.chunk, DIFF) + (TMA ? W * LY::kWarpBytes : 0);
     static int configured[64] = {0};  // per instantiation and device: largest size opted in so far
-    auto fn = march_kernel<STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, MINB>;
+    auto fn = march_kernel<STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, MINB, W>;
     const int dev = c->cfg.device & 63;
     if (configured[dev] < smem) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured[dev] = smem;
     }
-    fn<<<grid, kWarpsPerBlock * 32, smem, st>>>(c->prm, c->maps);
+    fn<<<grid, W * 32, smem, st>>>(c->prm, c->maps);
     return cudaSuccess;
 }
 
@@ -120,12 +121,12 @@ cudaError_t launch_ldg(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool
     return diff ? launch_ldg_f<true>(c, mode, g, st, f2d, hs) : launch_ldg_f<false>(c, mode, g, st, f2d, hs);
 }
 
-template <int R, int S, int MINB>
+template <int R, int S, int MINB, int W = kWarpsPerBlock>
 cudaError_t launch_tma_rs(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
-    if (mode == SWB_STRICT) return launch_inst<true, false, false, false, true, R, S, true, 2>(c, g, st);
-    if (mode == SWB_FAST) return launch_inst<false, false, false, false, true, R, S, false, MINB>(c, g, st);
-    return launch_inst<false, false, false, false, true, R, S, true, MINB>(c, g, st);
+    if (mode == SWB_STRICT) return launch_inst<true, false, false, false, true, R, S, true, (W > 4 ? 1 : 2), W>(c, g, st);
+    if (mode == SWB_FAST) return launch_inst<false, false, false, false, true, R, S, false, MINB, W>(c, g, st);
+    return launch_inst<false, false, false, false, true, R, S, true, MINB, W>(c, g, st);
 }
 cudaError_t launch_tma(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
@@ -135,7 +136,12 @@ cudaError_t launch_tma(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
         case 2: return launch_tma_rs<2, 3, 3>(c, mode, g, st);
         case 3: return launch_tma_rs<4, 3, 2>(c, mode, g, st);
         case 4: return launch_tma_rs<2, 4, 2>(c, mode, g, st);
-        default: return launch_tma_rs<4, 4, 2>(c, mode, g, st);
+        case 5: return launch_tma_rs<4, 4, 2>(c, mode, g, st);
+        case 6: return launch_tma_rs<4, 3, 2, 5>(c, mode, g, st);
+        case 7: return launch_tma_rs<2, 4, 2, 5>(c, mode, g, st);
+        case 8: return launch_tma_rs<4, 2, 2, 6>(c, mode, g, st);
+        case 9: return launch_tma_rs<2, 4, 2, 6>(c, mode, g, st);
+        default: return launch_tma_rs<4, 4, 1, 8>(c, mode, g, st);
     }
 }
 
@@ -144,7 +150,13 @@ int launch_one(swb_ctx *c, cudaStream_t st)
     const swb_config &cfg = c->cfg;
     const Params &p = c->prm;
     const int rows = p.jl_last - p.jl_first + 1;
-    dim3 grid((unsigned)((p.nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock), (unsigned)((rows + p.chunk - 1) / p.chunk));
+    const int W = c->use_tma ? kTmaVariants[c->tma_variant].W : kWarpsPerBlock;
+    dim3 grid((unsigned)((p.nstrips + W - 1) / W), (unsigned)((rows + p.chunk - 1) / p.chunk));
+    if (c->linked && !p.fixed) {  // the maxima of all bands' previous step -> this step's slot
+        gather_kernel<<<1, 32, 0, st>>>(p);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
     if (c->use_tma) CK(launch_tma(c, cfg.mode, grid, st));
     else CK(launch_ldg(c, cfg.mode, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs));
     c->launches++;

@@ -443,9 +443,8 @@ __device__ __forceinline__ double laplacian_fast(const Star &s, const double *__
 // ------------------------------------------------------------------------------------
 // Executed by thread 0 of every block (every block needs dt); block (0,0) also advances
 // the loop state.  Returns through shared memory: dt and flags (bit 0 active, bit 1 parity).
-// With several latitude bands (world > 1) the maxima of every band's previous step are
-// read from this context's exchange block, where the peers deposited them; their arrival
-// also tells that the neighbours' halo rows are in place.
+// With several latitude bands (world > 1) `gather_kernel` has replaced the slot's maxima by
+// the maxima over all bands before this kernel starts.
 __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int *s_flags)
 {
     Ctrl *const cur_slot = p.ctrl + (p.launch % 3);
@@ -457,24 +456,7 @@ __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int
     }
     const double time = cur_slot->time;
     const long long nsteps = cur_slot->nsteps;
-    unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
-    if (p.world > 1) {
-        const volatile XSlot *xs = p.xlocal->slot[p.launch % 3];
-        const long long t0 = clock64();
-        exb = eyb = 0ULL;
-        for (int r = 0; r < p.world; ++r) {
-            while (xs[r].stamp != p.stamp) {
-                if (clock64() - t0 > p.spin_limit) {
-                    atomicMin(p.err, -4);  // SWB_E_TIMEOUT
-                    break;
-                }
-                __nanosleep(64);
-            }
-            __threadfence_system();
-            exb = umax64(exb, xs[r].ex_bits);
-            eyb = umax64(eyb, xs[r].ey_bits);
-        }
-    }
+    const unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
     const double tx = __ddiv_rn(p.dxmin, __longlong_as_double((long long)exb));
     const double ty = __ddiv_rn(p.dymin, __longlong_as_double((long long)eyb));
     const double dtmax = (tx != tx) ? tx : ((ty != ty) ? ty : (tx < ty ? tx : ty));  // np.minimum propagates NaN
@@ -652,8 +634,8 @@ __device__ __forceinline__ void st_pair(double *addr, double a, double b, int bo
 // TMA ring (R latitudes per box, S stages) or direct loads, and whether FAST evaluates the
 // reference's hMid > 0 selects (GUARD) or assumes them true and raises SWB_E_DEPTH when a
 // half-step depth turns out non-positive.
-template <bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB)
+template <bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
+__global__ void __launch_bounds__(W * 32, MINB)
 march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
 {
     using O = Op<STRICT>;
@@ -678,7 +660,7 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x * kWarpsPerBlock + warp;
+    const int strip = blockIdx.x * W + warp;
     const bool warp_on = strip < p.nstrips;
     const int ja = p.jl_first + blockIdx.y * p.chunk;  // first latitude updated
     const int jb = min(ja + p.chunk, p.jl_last + 1);   // one past the last
@@ -1005,20 +987,65 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     }
 }
 
-// Multi-GPU step epilogue: once every block of the step kernel has retired (stream order),
-// deposit this band's CFL maxima, stamped, in every rank's exchange block.  The system-wide
-// fence in front orders the halo rows stored by the step kernel before the stamp.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Multi-GPU step epilogue (one warp, after the step kernel in stream order): lane r deposits
+// this band's CFL maxima of the new state in rank r's exchange block and then releases the
+// stamp.  The system-scope fence in front orders every store of the finished step kernel --
+// the halo rows it wrote into the neighbours' arrays included -- before the stamp.
 __global__ void publish_kernel(const __grid_constant__ Params p)
 {
     if (threadIdx.x >= p.world) return;
     const Ctrl *new_slot = p.ctrl + ((p.launch + 1) % 3);
     const unsigned long long ex = new_slot->ex_bits, ey = new_slot->ey_bits;
     __threadfence_system();
-    volatile XSlot *dst = &p.xpeer[threadIdx.x]->slot[(p.launch + 1) % 3][p.rank];
+    XSlot *dst = &p.xpeer[threadIdx.x]->slot[(p.launch + 1) % 3][p.rank];
     dst->ex_bits = ex;
     dst->ey_bits = ey;
-    __threadfence_system();
-    dst->stamp = p.stamp + 1;
+    st_release_sys(&dst->stamp, p.stamp + 1);
+}
+
+// Multi-GPU step prologue (one warp, before the step kernel in stream order): lane r waits
+// (on this GPU's own memory) for rank r's stamp of the previous step, then the warp reduces
+// the bands' maxima and writes the GLOBAL maxima into the slot the step kernel reads --
+// every band derives the identical dt.  The stamps' arrival is also the halo hand-shake
+// and the write-after-read barrier of the ping-pong buffers.
+__global__ void gather_kernel(const __grid_constant__ Params p)
+{
+    const int r = threadIdx.x;
+    unsigned long long ex = 0ULL, ey = 0ULL;
+    if (r < p.world) {
+        const XSlot *xs = &p.xlocal->slot[p.launch % 3][r];
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&xs->stamp) != p.stamp) {
+            if (clock64() - t0 > p.spin_limit) {
+                atomicMin(p.err, -4);  // SWB_E_TIMEOUT
+                break;
+            }
+            __nanosleep(100);
+        }
+        ex = *reinterpret_cast<const volatile unsigned long long *>(&xs->ex_bits);
+        ey = *reinterpret_cast<const volatile unsigned long long *>(&xs->ey_bits);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        ex = umax64(ex, __shfl_xor_sync(0xffffffffu, ex, s));
+        ey = umax64(ey, __shfl_xor_sync(0xffffffffu, ey, s));
+    }
+    if (r == 0) {
+        Ctrl *cur_slot = p.ctrl + (p.launch % 3);
+        cur_slot->ex_bits = ex;
+        cur_slot->ey_bits = ey;
+    }
 }
 
 // ------------------------------------------------------------------------------------

@@ -283,3 +283,91 @@ def test_nan_state_stops_like_the_reference():
     s = st.status()
     assert s.steps == 1 and s.done and np.isnan(s.time)
     st.close()
+
+
+def test_config3_grid_against_oracle():
+    """BASELINE.json configs[3] grid (7200 x 3600, diffusion off) on one GPU: three steps
+    against the CPU oracle -- STRICT bit-for-bit (state and dt), FAST within 1e-12."""
+    M, N, nsteps = 7200, 3600, 3
+    og = so.OracleGrid(M, N)
+    h, u, v, f = so.initial_conditions(0, og)
+    h, u, v = (np.ascontiguousarray(x) for x in (h, u, v))
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    gpu = {m: Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=1e9, use_diffusion=False, mode=m,
+                      log_capacity=nsteps) for m in ("strict", "fast")}
+    stp = so.Stepper(og, f, None, False)
+    t, dts = 0.0, []
+    for _ in range(nsteps):
+        dt, t = stp.step(h, u, v, 0.5, t, 1e9)
+        dts.append(dt)
+    for m, st in gpu.items():
+        st.enqueue(nsteps)
+        s = st.status()
+        hg, ug, vg = st.to_numpy()
+        gdts, _ = st.read_log(nsteps)
+        st.close()
+        assert s.steps == nsteps and s.error == 0
+        if m == "strict":
+            assert _bits(gdts, np.asarray(dts)) and s.time == t
+            assert _bits(hg, h) and _bits(ug, u) and _bits(vg, v)
+        else:
+            assert normwise(gdts, np.asarray(dts)) < 1e-13
+            for name, a, b in (("h", hg, h), ("u", ug, u), ("v", vg, v)):
+                assert normwise(a, b) < TOL_FAST, (name, normwise(a, b))
+
+
+def test_headline_grid_properties():
+    """BASELINE.json configs[4] grid (16384 x 8192, the bench workload), where the oracle
+    would need ~40 GB: size-independent properties instead.  (1) FAST agrees with STRICT
+    (itself bit-exact to numpy on every grid the oracle reaches) within 1e-12 after two
+    steps, dt included; (2) the boundary conditions hold exactly on the device
+    (numpy.py:402-404); (3) a 64-latitude sub-band of the same longitudes, run as its own
+    grid, matches the oracle bit-for-bit in STRICT mode."""
+    from sw_solver_b200.bands import rossby_haurwitz_band
+
+    M, N, nsteps = 16384, 8192, 2
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    res = {}
+    for m in ("strict", "fast"):
+        hd, ud, vd, f_lat = rossby_haurwitz_band(ll, 0, ll.N, "cuda")
+        st = Stepper(ll, cg, hd, ud, vd, f_lat, None, courant=0.5, final_time=1e9, use_diffusion=False, mode=m,
+                     layout="device", log_capacity=nsteps)
+        del hd, ud, vd
+        st.enqueue(nsteps)
+        s = st.status()
+        assert s.steps == nsteps and s.error == 0
+        cur = s.current
+        q = st._raw[cur, :, :, : M + 3].clone()  # (3, N, M+3) device layout
+        # (2) ghost columns and pole rows
+        assert torch.equal(q[:, 1:-1, 0], q[:, 1:-1, M]) and torch.equal(q[:, 1:-1, M + 2], q[:, 1:-1, 2])
+        assert torch.equal(q[:, 0, :], q[:, 1, :]) and torch.equal(q[:, -1, :], q[:, -2, :])
+        assert bool(torch.isfinite(q).all())
+        res[m] = (q, st.read_log(nsteps)[0])
+        st.close()
+        del st
+    assert normwise(res["fast"][1], res["strict"][1]) < 1e-13
+    for k in range(3):
+        den = float(res["strict"][0][k].abs().max())
+        err = float((res["fast"][0][k] - res["strict"][0][k]).abs().max()) / den
+        assert err < TOL_FAST, (k, err)
+    del res
+    torch.cuda.empty_cache()
+
+    # (3) the same 16384 longitudes on a 64-latitude grid of its own
+    Ms, Ns = M, 64
+    og = so.OracleGrid(Ms, Ns)
+    h, u, v, f = so.initial_conditions(0, og)
+    h, u, v = (np.ascontiguousarray(x) for x in (h, u, v))
+    lls = LatLonGrid(Ms, Ns)
+    cgs = CartesianGrid(lls)
+    st = Stepper(lls, cgs, h, u, v, f, None, courant=0.5, final_time=1e9, use_diffusion=False, mode="strict")
+    stp = so.Stepper(og, f, None, False)
+    t = 0.0
+    for _ in range(3):
+        _, t = stp.step(h, u, v, 0.5, t, 1e9)
+    st.enqueue(3)
+    hg, ug, vg = st.to_numpy()
+    assert st.status().time == t and _bits(hg, h) and _bits(ug, u) and _bits(vg, v)
+    st.close()
