@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--grid", default="16384x8192")
     ap.add_argument("--mode", default="fast", choices=["fast", "strict"])
     ap.add_argument("--diffusion", action="store_true")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="state type; f32 is the optional fp32 mode (24 algorithmic bytes per update)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -225,7 +227,10 @@ def run_ours(args, M, N):
     j_begin, n_local = (band["j_begin"], band["n_local"]) if band else (0, ll.N)
     pts_rank = (M + 1) * ((band["j_last"] - band["j_first"] + 1) if band else ll.N - 2)
     pts = (M + 1) * (ll.N - 2)  # whole job, per step
-    kw = dict(courant=0.5, final_time=1e12, use_diffusion=args.diffusion, mode=args.mode, device=dev)
+    kw = dict(courant=0.5, final_time=1e12, use_diffusion=args.diffusion, mode=args.mode, device=dev,
+              dtype={"f64": "float64", "f32": "float32"}[args.dtype])
+    bytes_per_update = BYTES_PER_UPDATE_F64 if args.dtype == "f64" else BYTES_PER_UPDATE_F64 / 2
+    metric = METRIC if args.dtype == "f64" else METRIC.replace("fp64", "fp32")
 
     # --- device-resident leg: the state is assembled on the GPU, in the device layout -----
     hd, ud, vd, _ = bands.rossby_haurwitz_band(ll, j_begin, n_local, dev)
@@ -287,15 +292,15 @@ def run_ours(args, M, N):
 
     peak, peak_src = measured_peak_gbs()
     kernel_ms = ms / args.steps
-    achieved = BYTES_PER_UPDATE_F64 * pts_rank / (kernel_ms * 1e-3) / 1e9  # per GPU
+    achieved = bytes_per_update * pts_rank / (kernel_ms * 1e-3) / 1e9  # per GPU
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "swb::march_kernel", "kernel_ms": kernel_ms,
-                "bytes_per_launch": BYTES_PER_UPDATE_F64 * pts_rank, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_update * pts_rank, "peak_source": peak_src,
                 "note": "per GPU; one march_kernel launch per step (kernel_ms = step time, CUDA events on the launch stream)"}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(f"{M}x{N}:{args.mode}")
+            roofline["traffic"] = json.load(open(prof)).get(f"{M}x{N}:{args.mode}" + ("" if args.dtype == "f64" else ":f32"))
         except Exception:
             pass
 
@@ -314,10 +319,10 @@ def run_ours(args, M, N):
     if rank == 0:
         per_gpu = f"{M}x{N} per GPU, {M}x{ll.N} globe in {world} latitude bands" if world > 1 else f"{M}x{ll.N}"
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"Rossby-Haurwitz {per_gpu} fp64, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"Rossby-Haurwitz {per_gpu} {'fp64' if args.dtype == 'f64' else 'fp32'}, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
                        "mode": args.mode,
                        "l2": "state (6.4 GB touched per GPU per step at the default size) is larger than L2; no flush needed",
                        "pts_per_step": pts, "parallelism": f"lat-bands x{world}"},

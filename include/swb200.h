@@ -15,8 +15,10 @@
  *    [jl = local latitude 0..n_local-1][i = longitude 0..M+2], longitude contiguous,
  *    `pitch` elements between consecutive latitudes (the transpose of the reference's
  *    (M+3, N) array; swb_import_state / swb_export_state convert on the device).  pitch
- *    must be at least swb_required_pitch(M) -- the kernels read whole 64-column strips --
- *    and even, bases 16-byte aligned; the padding columns are never written;
+ *    must be at least swb_required_pitch(M, dtype) -- the kernels read whole 64-column
+ *    strips -- bases 16-byte aligned; the padding columns are never written.  State
+ *    arrays hold doubles (SWB_F64) or floats (SWB_F32: FAST arithmetic, latitude-only
+ *    Coriolis, flat topography; every metric / dt factor is still formed in fp64);
  *  - table pointers passed to swb_set_tables are HOST pointers (copied);
  *  - `stream` is a cudaStream_t passed as void*; calls only enqueue work unless stated;
  *  - the caller (PyTorch on the Python side) owns every state buffer and keeps it alive
@@ -130,8 +132,9 @@ int swb_destroy(swb_ctx *ctx);
 
 int swb_set_tables(swb_ctx *ctx, const swb_tables *tabs);
 
-/* Smallest legal `pitch` for a grid with M longitudes (a multiple of 16 elements). */
-int swb_required_pitch(int M);
+/* Smallest legal `pitch` for a grid with M longitudes and state type `dtype` (a multiple of
+ * 16 elements). */
+int swb_required_pitch(int M, int dtype);
 
 /* Bind the two buffer sets the path ping-pongs between (set 0 holds the initial state),
  * plus the optional 2-D Coriolis array and topography (device pointers or NULL), all

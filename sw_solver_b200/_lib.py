@@ -14,6 +14,7 @@ _dp = ctypes.POINTER(ctypes.c_double)
 SWB_F64, SWB_F32 = 0, 1
 SWB_STRICT, SWB_FAST, SWB_FAST_GUARDED = 0, 1, 2
 MODES = {"strict": SWB_STRICT, "fast": SWB_FAST, "fast_guarded": SWB_FAST_GUARDED}
+DTYPES = {"float64": SWB_F64, "float32": SWB_F32}
 SWB_E_TIMEOUT, SWB_E_DEPTH = -4, -6
 IPC_HANDLE_BYTES = 64
 
@@ -55,7 +56,7 @@ SYMBOLS = {
     "swb_create": (ctypes.c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(SwbConfig)]),
     "swb_destroy": (ctypes.c_int, [c_void_p]),
     "swb_set_tables": (ctypes.c_int, [c_void_p, ctypes.POINTER(SwbTables)]),
-    "swb_required_pitch": (ctypes.c_int, [ctypes.c_int]),
+    "swb_required_pitch": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "swb_bind_state": (ctypes.c_int, [c_void_p] + [c_void_p] * 8),
     "swb_to_device_layout": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, c_void_p, c_void_p]),
     "swb_from_device_layout": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int, c_void_p]),

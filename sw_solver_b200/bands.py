@@ -110,7 +110,7 @@ def link_distributed(stepper, group=None) -> None:
             return None
         d = infos[r]
         base = open_handle(d["sh"]) + d["so"]
-        stride = d["n_local"] * d["pitch"] * 8
+        stride = d["n_local"] * d["pitch"] * stepper._raw.element_size()
         return {"bufs": [base + k * stride for k in range(6)], "j_begin": d["j_begin"], "pitch": d["pitch"]}
 
     stepper.link(blocks, neighbour(plan["south"]), neighbour(plan["north"]))

@@ -41,12 +41,13 @@ int cuda_fail(cudaError_t e, const char *where)
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
-int nstrips_of(int M) { return (M + 1 + kStripValid - 1) / kStripValid; }
+int valid_cols(int dtype) { return dtype == SWB_F32 ? kStripValidF32 : kStripValid; }
+int nstrips_of(int M, int dtype) { return (M + 1 + valid_cols(dtype) - 1) / valid_cols(dtype); }
 
-int required_pitch(int M)
+int required_pitch(int M, int dtype)
 {
-    // the last strip reads 64 columns (+2 for the topography differences); round to 128 bytes
-    const int need = kStripValid * (nstrips_of(M) - 1) + kStripCols + 2;
+    // the last strip reads 64 columns (+2 for the topography differences); round to 16 elements
+    const int need = valid_cols(dtype) * (nstrips_of(M, dtype) - 1) + kStripCols + 2;
     return (need + 15) / 16 * 16;
 }
 
@@ -68,7 +69,7 @@ struct swb_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     bool use_tma = false;
-    int tma_variant = 0;  // index into kTmaVariants
+    int tma_variant = 0;  // index into kTmaVariants (fp64) / kTmaVariantsF32
     TmaMaps maps;
 };
 
@@ -81,13 +82,13 @@ constexpr TmaVariant kTmaVariants[] = {{2, 4, 3, 4}, {4, 2, 3, 4}, {2, 3, 3, 4},
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 constexpr int kDefaultTmaVariant = 5;  // R = 4, S = 4, two blocks per SM: no spills (1.26 ms/step at 16384 x 8192)
 
-template <bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
+template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
 cudaError_t launch_inst(const swb_ctx *c, dim3 grid, cudaStream_t st)
 {
-    using LY = TmaLayout<R, S>;
+    using LY = TmaLayout<R, S, T>;
     const int smem = rec_bytes(c->prm.chunk, DIFF) + (TMA ? W * LY::kWarpBytes : 0);
     static int configured[64] = {0};  // per instantiation and device: largest size opted in so far
-    auto fn = march_kernel<STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, MINB, W>;
+    auto fn = march_kernel<T, STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, MINB, W>;
     const int dev = c->cfg.device & 63;
     if (configured[dev] < smem) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -102,9 +103,9 @@ cudaError_t launch_inst(const swb_ctx *c, dim3 grid, cudaStream_t st)
 template <bool DIFF, bool F2D, bool HS>
 cudaError_t launch_ldg_m(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
-    if (mode == SWB_STRICT) return launch_inst<true, DIFF, F2D, HS, false, 1, 1, true, 2>(c, g, st);
-    if (mode == SWB_FAST) return launch_inst<false, DIFF, F2D, HS, false, 1, 1, false, 2>(c, g, st);
-    return launch_inst<false, DIFF, F2D, HS, false, 1, 1, true, 2>(c, g, st);
+    if (mode == SWB_STRICT) return launch_inst<double, true, DIFF, F2D, HS, false, 1, 1, true, 2>(c, g, st);
+    if (mode == SWB_FAST) return launch_inst<double, false, DIFF, F2D, HS, false, 1, 1, false, 2>(c, g, st);
+    return launch_inst<double, false, DIFF, F2D, HS, false, 1, 1, true, 2>(c, g, st);
 }
 template <bool DIFF, bool F2D>
 cudaError_t launch_ldg_h(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool hs)
@@ -124,9 +125,9 @@ cudaError_t launch_ldg(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool
 template <int R, int S, int MINB, int W = kWarpsPerBlock>
 cudaError_t launch_tma_rs(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
-    if (mode == SWB_STRICT) return launch_inst<true, false, false, false, true, R, S, true, (W > 4 ? 1 : 2), W>(c, g, st);
-    if (mode == SWB_FAST) return launch_inst<false, false, false, false, true, R, S, false, MINB, W>(c, g, st);
-    return launch_inst<false, false, false, false, true, R, S, true, MINB, W>(c, g, st);
+    if (mode == SWB_STRICT) return launch_inst<double, true, false, false, false, true, R, S, true, (W > 4 ? 1 : 2), W>(c, g, st);
+    if (mode == SWB_FAST) return launch_inst<double, false, false, false, false, true, R, S, false, MINB, W>(c, g, st);
+    return launch_inst<double, false, false, false, false, true, R, S, true, MINB, W>(c, g, st);
 }
 cudaError_t launch_tma(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
@@ -145,20 +146,57 @@ cudaError_t launch_tma(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
     }
 }
 
+// fp32 mode: FAST arithmetic only, latitude-only Coriolis, flat topography
+constexpr TmaVariant kTmaVariantsF32[] = {{4, 4, 2, 4}, {4, 3, 3, 4}, {4, 3, 4, 4}, {2, 4, 4, 4}};
+constexpr int kNumTmaVariantsF32 = (int)(sizeof(kTmaVariantsF32) / sizeof(kTmaVariantsF32[0]));
+constexpr int kDefaultTmaVariantF32 = 2;  // R = 4, S = 3, four blocks per SM (0.68 ms/step at 16384 x 8192)
+
+template <int R, int S, int MINB>
+cudaError_t launch_tma_f32_rs(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
+{
+    if (mode == SWB_FAST) return launch_inst<float, false, false, false, false, true, R, S, false, MINB>(c, g, st);
+    return launch_inst<float, false, false, false, false, true, R, S, true, MINB>(c, g, st);
+}
+cudaError_t launch_tma_f32(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
+{
+    switch (c->tma_variant) {
+        case 0: return launch_tma_f32_rs<4, 4, 2>(c, mode, g, st);
+        case 1: return launch_tma_f32_rs<4, 3, 3>(c, mode, g, st);
+        case 2: return launch_tma_f32_rs<4, 3, 4>(c, mode, g, st);
+        default: return launch_tma_f32_rs<2, 4, 4>(c, mode, g, st);
+    }
+}
+cudaError_t launch_ldg_f32(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool diff)
+{
+    if (diff) {
+        if (mode == SWB_FAST) return launch_inst<float, false, true, false, false, false, 1, 1, false, 2>(c, g, st);
+        return launch_inst<float, false, true, false, false, false, 1, 1, true, 2>(c, g, st);
+    }
+    if (mode == SWB_FAST) return launch_inst<float, false, false, false, false, false, 1, 1, false, 2>(c, g, st);
+    return launch_inst<float, false, false, false, false, false, 1, 1, true, 2>(c, g, st);
+}
+
 int launch_one(swb_ctx *c, cudaStream_t st)
 {
     const swb_config &cfg = c->cfg;
     const Params &p = c->prm;
     const int rows = p.jl_last - p.jl_first + 1;
-    const int W = c->use_tma ? kTmaVariants[c->tma_variant].W : kWarpsPerBlock;
+    const bool f32 = cfg.dtype == SWB_F32;
+    const int W = (c->use_tma && !f32) ? kTmaVariants[c->tma_variant].W : kWarpsPerBlock;
     dim3 grid((unsigned)((p.nstrips + W - 1) / W), (unsigned)((rows + p.chunk - 1) / p.chunk));
     if (c->linked && !p.fixed) {  // the maxima of all bands' previous step -> this step's slot
         gather_kernel<<<1, 32, 0, st>>>(p);
         c->launches++;
         CK(cudaGetLastError());
     }
-    if (c->use_tma) CK(launch_tma(c, cfg.mode, grid, st));
-    else CK(launch_ldg(c, cfg.mode, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs));
+    if (f32) {
+        if (c->use_tma) CK(launch_tma_f32(c, cfg.mode, grid, st));
+        else CK(launch_ldg_f32(c, cfg.mode, grid, st, cfg.use_diffusion));
+    } else if (c->use_tma) {
+        CK(launch_tma(c, cfg.mode, grid, st));
+    } else {
+        CK(launch_ldg(c, cfg.mode, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs));
+    }
     c->launches++;
     CK(cudaGetLastError());
     if (c->linked && !p.fixed) {
@@ -174,7 +212,7 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D fp64 tensor map over a (rows x cols) window of a state array with `pitch` elements per row
-int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_cols, uint32_t box_rows)
+int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_cols, uint32_t box_rows, bool f32)
 {
     static encode_tiled_fn encode = nullptr;
     if (!encode) {
@@ -185,10 +223,10 @@ int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_
         encode = (encode_tiled_fn)fn;
     }
     const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {pitch * sizeof(double)};
+    const cuuint64_t strides[1] = {pitch * (f32 ? sizeof(float) : sizeof(double))};
     const cuuint32_t box[2] = {box_cols, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = encode(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[160];
@@ -215,7 +253,7 @@ extern "C" {
 
 int swb_abi_version(void) { return SWB_ABI_VERSION; }
 const char *swb_last_error(void) { return g_err.c_str(); }
-int swb_required_pitch(int M) { return M >= 2 ? required_pitch(M) : SWB_E_INVALID; }
+int swb_required_pitch(int M, int dtype) { return (M >= 2 && (dtype == SWB_F64 || dtype == SWB_F32)) ? required_pitch(M, dtype) : SWB_E_INVALID; }
 
 int swb_create(swb_ctx **out, const swb_config *cfg)
 {
@@ -223,10 +261,12 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     *out = nullptr;
     if (cfg->struct_bytes != (int32_t)sizeof(swb_config)) return fail(SWB_E_INVALID, "swb_create: swb_config size mismatch (ABI)");
     if (cfg->M < 2 || cfg->N < 2 || (cfg->N & 1)) return fail(SWB_E_INVALID, "swb_create: need M >= 2 and an even N >= 2");
-    if (cfg->dtype != SWB_F64) return fail(SWB_E_INVALID, "swb_create: only SWB_F64 is built in this version");
+    if (cfg->dtype != SWB_F64 && cfg->dtype != SWB_F32) return fail(SWB_E_INVALID, "swb_create: bad dtype");
+    if (cfg->dtype == SWB_F32 && (cfg->mode == SWB_STRICT || cfg->f_is_2d || cfg->has_hs))
+        return fail(SWB_E_INVALID, "swb_create: the fp32 mode serves FAST arithmetic with latitude-only Coriolis and flat topography");
     if (cfg->mode != SWB_STRICT && cfg->mode != SWB_FAST && cfg->mode != SWB_FAST_GUARDED) return fail(SWB_E_INVALID, "swb_create: bad mode");
     if (cfg->n_local < 3) return fail(SWB_E_INVALID, "swb_create: a band needs at least three latitude rows");
-    if (cfg->pitch < required_pitch(cfg->M) || (cfg->pitch & 1)) return fail(SWB_E_INVALID, "swb_create: pitch must be even and >= swb_required_pitch(M)");
+    if (cfg->pitch < required_pitch(cfg->M, cfg->dtype) || (cfg->pitch & 3)) return fail(SWB_E_INVALID, "swb_create: pitch must be a multiple of 4 and >= swb_required_pitch(M, dtype)");
     if (cfg->j_begin < 0 || cfg->j_begin + cfg->n_local > cfg->N) return fail(SWB_E_INVALID, "swb_create: band outside the grid");
     if (cfg->j_first < 1 || cfg->j_last > cfg->N - 2 || cfg->j_first > cfg->j_last) return fail(SWB_E_INVALID, "swb_create: bad j_first / j_last");
     if (cfg->j_first - 1 < cfg->j_begin || cfg->j_last + 1 >= cfg->j_begin + cfg->n_local)
@@ -292,7 +332,7 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     p.jl_last = cfg->j_last - cfg->j_begin;
     p.pole_s = (cfg->j_begin == 0);
     p.pole_n = (cfg->j_begin + cfg->n_local == cfg->N);
-    p.nstrips = nstrips_of(p.M);
+    p.nstrips = nstrips_of(p.M, cfg->dtype);
     p.chunk = pick_chunk(p.jl_last - p.jl_first + 1, p.nstrips, c->sm_count);
     if (const char *ch = getenv("SWB_CHUNK")) {  // tuning knob: a power of two in [4, 128]
         const int v = atoi(ch);
@@ -360,10 +400,10 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     void *all[8] = {h0, u0, v0, h1, u1, v1, const_cast<void *>(f2d), const_cast<void *>(hs)};
     for (void *q : all)
         if (q && ((uintptr_t)q % 16) != 0) return fail(SWB_E_INVALID, "swb_bind_state: arrays must be 16-byte aligned");
-    p.buf[0][0] = (double *)h0; p.buf[0][1] = (double *)u0; p.buf[0][2] = (double *)v0;
-    p.buf[1][0] = (double *)h1; p.buf[1][1] = (double *)u1; p.buf[1][2] = (double *)v1;
-    p.f2d = (const double *)f2d;
-    p.hs = (const double *)hs;
+    p.buf[0][0] = h0; p.buf[0][1] = u0; p.buf[0][2] = v0;
+    p.buf[1][0] = h1; p.buf[1][1] = u1; p.buf[1][2] = v1;
+    p.f2d = f2d;
+    p.hs = hs;
     c->state_bound = true;
     c->cfl_ready = false;
 
@@ -375,15 +415,16 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     c->use_tma = plain && !(force && strcmp(force, "ldg") == 0);
     if (force && strcmp(force, "tma") == 0 && !c->use_tma) return fail(SWB_E_INVALID, "SWB_KERNEL=tma but this configuration cannot use the TMA kernel");
     if (c->use_tma) {
-        const char *v = getenv("SWB_TMA_VARIANT");
-        c->tma_variant = v ? atoi(v) : kDefaultTmaVariant;
-        if (c->tma_variant < 0 || c->tma_variant >= kNumTmaVariants) return fail(SWB_E_INVALID, "bad SWB_TMA_VARIANT");
-        const TmaVariant tv = kTmaVariants[c->tma_variant];
+        const bool f32 = c->cfg.dtype == SWB_F32;
+        const char *v = getenv(f32 ? "SWB_TMA_VARIANT_F32" : "SWB_TMA_VARIANT");
+        c->tma_variant = v ? atoi(v) : (f32 ? kDefaultTmaVariantF32 : kDefaultTmaVariant);
+        if (c->tma_variant < 0 || c->tma_variant >= (f32 ? kNumTmaVariantsF32 : kNumTmaVariants)) return fail(SWB_E_INVALID, "bad SWB_TMA_VARIANT");
+        const TmaVariant tv = f32 ? kTmaVariantsF32[c->tma_variant] : kTmaVariants[c->tma_variant];
         CK(cudaSetDevice(c->cfg.device));
         for (int s = 0; s < 2; ++s)
             for (int k = 0; k < 3; ++k) {
                 int rc = make_map(&c->maps.in[s][k], p.buf[s][k], (uint64_t)(p.M + 3), (uint64_t)p.nrows, (uint64_t)p.pitch, kStripCols,
-                                  (uint32_t)tv.R);
+                                  (uint32_t)tv.R, f32);
                 if (rc) return rc;
             }
     }
@@ -397,7 +438,10 @@ int swb_to_device_layout(swb_ctx *c, const void *ref, int ref_pitch, void *dev, 
     CK(cudaSetDevice(c->cfg.device));
     const int rows = c->cfg.n_local, cols = c->cfg.M + 3;
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
-    transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)ref, ref_pitch, (double *)dev, c->cfg.pitch, rows, cols);
+    if (c->cfg.dtype == SWB_F32)
+        transpose_kernel<double, float><<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)ref, ref_pitch, (float *)dev, c->cfg.pitch, rows, cols);
+    else
+        transpose_kernel<double, double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)ref, ref_pitch, (double *)dev, c->cfg.pitch, rows, cols);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -410,7 +454,10 @@ int swb_from_device_layout(swb_ctx *c, const void *dev, void *ref, int ref_pitch
     CK(cudaSetDevice(c->cfg.device));
     const int rows = c->cfg.M + 3, cols = c->cfg.n_local;
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
-    transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)dev, c->cfg.pitch, (double *)ref, ref_pitch, rows, cols);
+    if (c->cfg.dtype == SWB_F32)
+        transpose_kernel<float, double><<<grid, 256, 0, (cudaStream_t)stream>>>((const float *)dev, c->cfg.pitch, (double *)ref, ref_pitch, rows, cols);
+    else
+        transpose_kernel<double, double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double *)dev, c->cfg.pitch, (double *)ref, ref_pitch, rows, cols);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -430,7 +477,12 @@ int swb_cfl_init(swb_ctx *c, void *stream)
     // initial values); rows that are another band's interior are scanned by that band.
     const int jl0 = p.pole_s ? 0 : p.jl_first, jl1 = p.pole_n ? p.nrows : p.jl_last + 1;
     const int blocks = c->sm_count * 8;
-    cfl_init_kernel<<<blocks, 256, 0, st>>>(p.buf[0][0], p.buf[0][1], p.buf[0][2], p.M + 3, jl0, jl1, p.pitch, p.g, c->d_ctrl);
+    if (c->cfg.dtype == SWB_F32)
+        cfl_init_kernel<float><<<blocks, 256, 0, st>>>((const float *)p.buf[0][0], (const float *)p.buf[0][1], (const float *)p.buf[0][2], p.M + 3, jl0, jl1,
+                                                       p.pitch, p.g, c->d_ctrl);
+    else
+        cfl_init_kernel<double><<<blocks, 256, 0, st>>>((const double *)p.buf[0][0], (const double *)p.buf[0][1], (const double *)p.buf[0][2], p.M + 3, jl0,
+                                                        jl1, p.pitch, p.g, c->d_ctrl);
     c->launches++;
     CK(cudaGetLastError());
     c->launch = 0;
@@ -481,6 +533,7 @@ int swb_laplacian(swb_ctx *c, const void *q, void *out, void *stream)
 {
     if (!c || !q || !out) return fail(SWB_E_INVALID, "swb_laplacian: null argument");
     if (!c->tables_set || !c->cfg.use_diffusion) return fail(SWB_E_STATE, "swb_laplacian: needs tables with diffusion weights");
+    if (c->cfg.dtype != SWB_F64) return fail(SWB_E_STATE, "swb_laplacian: the operator-level Laplacian is fp64 (strict)");
     CK(cudaSetDevice(c->cfg.device));
     const Params &p = c->prm;
     dim3 grid((unsigned)((p.M + 1 + 127) / 128), (unsigned)(p.jl_last - p.jl_first + 1));
@@ -529,7 +582,10 @@ int swb_max_speed(swb_ctx *c, double *out_host, void *stream)
     const int cur = s.current;
     CK(cudaMemsetAsync(c->d_scratch, 0, sizeof(unsigned long long), st));
     const int jl0 = p.pole_s ? 0 : p.jl_first, jl1 = p.pole_n ? p.nrows : p.jl_last + 1;
-    max_speed_kernel<<<c->sm_count * 8, 256, 0, st>>>(p.buf[cur][1], p.buf[cur][2], p.M + 3, jl0, jl1, p.pitch, c->d_scratch);
+    if (c->cfg.dtype == SWB_F32)
+        max_speed_kernel<float><<<c->sm_count * 8, 256, 0, st>>>((const float *)p.buf[cur][1], (const float *)p.buf[cur][2], p.M + 3, jl0, jl1, p.pitch, c->d_scratch);
+    else
+        max_speed_kernel<double><<<c->sm_count * 8, 256, 0, st>>>((const double *)p.buf[cur][1], (const double *)p.buf[cur][2], p.M + 3, jl0, jl1, p.pitch, c->d_scratch);
     c->launches++;
     CK(cudaGetLastError());
     unsigned long long bits = 0;
@@ -619,8 +675,8 @@ int swb_link_peers(swb_ctx *c, void *const *exchange_blocks, void *const south_b
     }
     for (int s = 0; s < 2; ++s)
         for (int k = 0; k < 3; ++k) {
-            p.south[s][k] = has_s ? (double *)south_bufs[s * 3 + k] : nullptr;
-            p.north[s][k] = has_n ? (double *)north_bufs[s * 3 + k] : nullptr;
+            p.south[s][k] = has_s ? south_bufs[s * 3 + k] : nullptr;
+            p.north[s][k] = has_n ? north_bufs[s * 3 + k] : nullptr;
             if ((has_s && !p.south[s][k]) || (has_n && !p.north[s][k])) return fail(SWB_E_INVALID, "swb_link_peers: null neighbour buffer");
         }
     // our first updated row (global j_first) is the south neighbour's first halo row above

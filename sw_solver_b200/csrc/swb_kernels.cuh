@@ -32,7 +32,8 @@ namespace swb {
 
 constexpr int kWarpsPerBlock = 4;
 constexpr int kStripCols = 64;   // longitudes held by a warp (2 per lane)
-constexpr int kStripValid = 62;  // longitudes updated by a warp (columns 1..62 of the strip)
+constexpr int kStripValid = 62;  // longitudes updated by a warp (columns 1..62 of the strip), fp64
+constexpr int kStripValidF32 = 60;  // fp32: strips must start on 16-byte columns (TMA), i.e. multiples of 4
 constexpr int kMaxChunk = 128;   // latitudes marched by one warp, at most
 constexpr int kRowRec = 16;      // doubles per row record
 constexpr int kRowDiff = 8;      // doubles per diffusion row record
@@ -88,9 +89,9 @@ struct XBlock {
 };
 
 struct Params {
-    double *buf[2][3];  // two buffer sets {h,u,v}; set (nsteps & 1) holds the current state
-    const double *f2d;  // (nrows, pitch) or null
-    const double *hs;   // (nrows, pitch) or null
+    void *buf[2][3];    // two buffer sets {h,u,v} (fp64 or fp32); set (nsteps & 1) holds the current state
+    const void *f2d;    // (nrows, pitch) or null
+    const void *hs;     // (nrows, pitch) or null
     const double *phi;  // M+3 (+ padding)
     const double *tab;  // T_COUNT x nrows
     Ctrl *ctrl;         // 3 slots
@@ -112,8 +113,8 @@ struct Params {
     unsigned long long stamp;       // launch sequence number (monotone, never wraps in practice)
     XBlock *xlocal;                 // this context's exchange block
     XBlock *xpeer[kMaxRanks];       // every rank's exchange block as mapped here (self included)
-    double *south[2][3];            // south neighbour's buffer sets (peer mapped) or null
-    double *north[2][3];
+    void *south[2][3];              // south neighbour's buffer sets (peer mapped) or null
+    void *north[2][3];
     int south_row, north_row;       // row index, in the neighbour's arrays, of the halo row we fill
     int south_pitch, north_pitch;
     int halo;                       // rows exchanged per side (1, or 2 with diffusion)
@@ -125,13 +126,23 @@ struct Params {
 // ------------------------------------------------------------------------------------
 // STRICT: IEEE round-to-nearest, never contracted -> numpy's ufunc-by-ufunc evaluation.
 // FAST:   plain operators (nvcc contracts a*b+c into DFMA) and explicit fma.
-template <bool STRICT>
+// T is the arithmetic type of the state: double, or float in the optional fp32 mode (FAST only).
+template <bool STRICT, typename T = double>
 struct Op {
-    static __device__ __forceinline__ double add(double a, double b) { return STRICT ? __dadd_rn(a, b) : a + b; }
-    static __device__ __forceinline__ double sub(double a, double b) { return STRICT ? __dsub_rn(a, b) : a - b; }
-    static __device__ __forceinline__ double mul(double a, double b) { return STRICT ? __dmul_rn(a, b) : a * b; }
-    static __device__ __forceinline__ double div(double a, double b) { return STRICT ? __ddiv_rn(a, b) : a / b; }
+    static __device__ __forceinline__ T add(T a, T b) { return STRICT ? (T)__dadd_rn(a, b) : a + b; }
+    static __device__ __forceinline__ T sub(T a, T b) { return STRICT ? (T)__dsub_rn(a, b) : a - b; }
+    static __device__ __forceinline__ T mul(T a, T b) { return STRICT ? (T)__dmul_rn(a, b) : a * b; }
+    static __device__ __forceinline__ T div(T a, T b) { return STRICT ? (T)__ddiv_rn(a, b) : a / b; }
 };
+
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+template <typename T> using vec2_t = typename Vec2<T>::type;
+template <typename T> struct BitsOf;
+template <> struct BitsOf<double> { using type = unsigned long long; };
+template <> struct BitsOf<float> { using type = unsigned int; };
+template <typename T> using bits_t = typename BitsOf<T>::type;
 
 // 1/x to ~1 ulp from the hardware seed (MUFU.RCP64H, ~2^-20) and one cubic Newton step:
 // r(1 + e + e^2) with e = 1 - x r leaves a relative error e^3.
@@ -159,6 +170,22 @@ __device__ __forceinline__ double fast_sqrt(double x)
     return fma(d, hy, s);
 }
 
+// fp32: MUFU.RCP (~1 ulp, biased) + one Newton step -- the residual is then far below half an
+// ulp, so r is the correctly rounded reciprocal almost always and errors do not pile up
+// coherently over thousands of steps; MUFU.SQRT alone serves the CFL estimate.
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ unsigned long long nonneg_bits(double v)
 {
     // |v| as an unsigned integer: monotone for finite values and +inf, and every NaN maps
@@ -167,36 +194,45 @@ __device__ __forceinline__ unsigned long long nonneg_bits(double v)
     return ((unsigned long long)(unsigned)(__double2hiint(v) & 0x7fffffff) << 32) | (unsigned)__double2loint(v);
 }
 
-__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+__device__ __forceinline__ unsigned int nonneg_bits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
+// the same ordering key widened to the fp64 pattern the control slots hold
+__device__ __forceinline__ unsigned long long widen_bits(unsigned long long b) { return b; }
+__device__ __forceinline__ unsigned long long widen_bits(unsigned int b) { return nonneg_bits((double)__uint_as_float(b)); }
 
-__device__ __forceinline__ double shfl_down1(double x) { return __shfl_down_sync(0xffffffffu, x, 1); }
-__device__ __forceinline__ double shfl_up1(double x) { return __shfl_up_sync(0xffffffffu, x, 1); }
+__device__ __forceinline__ unsigned long long umax64(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
+__device__ __forceinline__ unsigned int umax64(unsigned int a, unsigned int b) { return a > b ? a : b; }
+__device__ __forceinline__ int hi_word(double x) { return __double2hiint(x); }
+__device__ __forceinline__ int hi_word(float x) { return __float_as_int(x); }
+
+template <typename T> __device__ __forceinline__ T shfl_down1(T x) { return __shfl_down_sync(0xffffffffu, x, 1); }
+template <typename T> __device__ __forceinline__ T shfl_up1(T x) { return __shfl_up_sync(0xffffffffu, x, 1); }
 
 // ------------------------------------------------------------------------------------
 // per-cell products (numpy.py:185-188, 203, 220, 237, 254-255)
 // ------------------------------------------------------------------------------------
+template <typename T>
 struct Cell {
-    double h, u;
-    double hu, hv;   // h*u, h*v
-    double Ux, Vx;   // hu*u + (hg*h)*h ; hu*v
-    double hw;       // h*(v*c)          ("hv1")
-    double Uy, Vy1;  // hu*(v*c) ; hv*(v*c)
-    double pr;       // (hg*h)*h         ("Vy2", also the pressure part of Ux)
-    double f;        // Coriolis at the cell (only when it is a 2-D field)
+    T h, u, v;
+    T hu, hv;   // h*u, h*v
+    T Ux, Vx;   // hu*u + (hg*h)*h ; hu*v
+    T hw;       // h*(v*c)          ("hv1")
+    T Uy, Vy1;  // hu*(v*c) ; hv*(v*c)
+    T pr;       // (hg*h)*h         ("Vy2", also the pressure part of Ux)
+    T f;        // Coriolis at the cell (only when it is a 2-D field)
 };
 
-template <bool STRICT>
-__device__ __forceinline__ Cell make_cell(double h, double u, double v, double c, double hg, double f)
+template <bool STRICT, typename T>
+__device__ __forceinline__ Cell<T> make_cell(T h, T u, T v, T c, T hg, T f)
 {
-    using O = Op<STRICT>;
-    Cell q;
-    q.h = h; q.u = u; q.f = f;
+    using O = Op<STRICT, T>;
+    Cell<T> q;
+    q.h = h; q.u = u; q.v = v; q.f = f;
     q.hu = O::mul(h, u);
     q.hv = O::mul(h, v);
     q.pr = O::mul(O::mul(hg, h), h);
     q.Ux = STRICT ? O::add(O::mul(q.hu, u), q.pr) : fma(q.hu, u, q.pr);
     q.Vx = O::mul(q.hu, v);
-    const double w = O::mul(v, c);
+    const T w = O::mul(v, c);
     q.hw = O::mul(h, w);
     q.Uy = O::mul(q.hu, w);
     q.Vy1 = O::mul(q.hv, w);
@@ -205,16 +241,18 @@ __device__ __forceinline__ Cell make_cell(double h, double u, double v, double c
 
 // Face record.  STRICT stores the reference's quantities; FAST stores hM, huM, hvM and the
 // fluxes DOUBLED (a factor 2 is exact), with the 0.5 folded into the update coefficients.
+template <typename T>
 struct Face {
-    double hM, huM, hvM;
-    double q;           // huM / hM, unguarded (numpy.py:302-305)
-    double F1, F2, F3;  // x: UxMid, VxMid, - ; y: UyMid, Vy1Mid, Vy2Mid
-    double hvc;         // y only: hvMidy * cMidy
+    T hM, huM, hvM;
+    T q;           // huM / hM, unguarded (numpy.py:302-305)
+    T F1, F2, F3;  // x: UxMid, VxMid, - ; y: UyMid, Vy1Mid, Vy2Mid
+    T hvc;         // y only: hvMidy * cMidy
 };
 
 // hM > 0 on the integer pipe (false for -0, +0 and negative values; NaN is not an issue:
 // a NaN state stops the loop through the CFL maxima)
 __device__ __forceinline__ bool positive(double x) { return __double_as_longlong(x) > 0; }
+__device__ __forceinline__ bool positive(float x) { return __float_as_int(x) > 0; }
 
 // x-face between (i, j) = `a` and (i+1, j) = `b`.  numpy.py:193-195, 203-217, 237-251,
 // 287-291, 321.
@@ -222,40 +260,39 @@ __device__ __forceinline__ bool positive(double x) { return __double_as_longlong
 //   FAST:   cdx = dt/dx_j;      kt = hdt*0.5*tan/a;          fK = hdt*f
 // GUARD evaluates the reference's `hMid > 0` selects; without it they are assumed true
 // (positive layer depth) and the caller watches the sign of hM instead.
-template <bool STRICT, bool GUARD>
-__device__ __forceinline__ Face x_face(const Cell &a, const Cell &b, double cdx, double kt, double fK,
-                                       double hdt, double hg, double ra)
+template <bool STRICT, bool GUARD, typename T>
+__device__ __forceinline__ Face<T> x_face(const Cell<T> &a, const Cell<T> &b, T cdx, T kt, T fK, T hdt, T hg, T ra)
 {
-    using O = Op<STRICT>;
-    Face F;
+    using O = Op<STRICT, T>;
+    Face<T> F;
     if (STRICT) {
-        const double P = O::add(fK, O::div(O::mul(O::mul(0.5, O::add(b.u, a.u)), kt), ra));  // ra = a
-        const double K = O::mul(hdt, P);
-        const double shu = O::mul(0.5, O::add(b.hu, a.hu));
-        const double shv = O::mul(0.5, O::add(b.hv, a.hv));
-        F.hM = O::sub(O::mul(0.5, O::add(b.h, a.h)), O::mul(cdx, O::sub(b.hu, a.hu)));
+        const T P = O::add(fK, O::div(O::mul(O::mul(T(0.5), O::add(b.u, a.u)), kt), ra));  // ra = a
+        const T K = O::mul(hdt, P);
+        const T shu = O::mul(T(0.5), O::add(b.hu, a.hu));
+        const T shv = O::mul(T(0.5), O::add(b.hv, a.hv));
+        F.hM = O::sub(O::mul(T(0.5), O::add(b.h, a.h)), O::mul(cdx, O::sub(b.hu, a.hu)));
         F.huM = O::add(O::sub(shu, O::mul(cdx, O::sub(b.Ux, a.Ux))), O::mul(K, shv));
         F.hvM = O::sub(O::sub(shv, O::mul(cdx, O::sub(b.Vx, a.Vx))), O::mul(K, shu));
         F.q = O::div(F.huM, F.hM);
-        const double pres = O::mul(O::mul(hg, F.hM), F.hM);
+        const T pres = O::mul(O::mul(hg, F.hM), F.hM);
         const bool pos = F.hM > 0.0;
         F.F1 = pos ? O::add(O::div(O::mul(F.huM, F.huM), F.hM), pres) : pres;
-        F.F2 = pos ? O::div(O::mul(F.hvM, F.huM), F.hM) : 0.0;
+        F.F2 = pos ? O::div(O::mul(F.hvM, F.huM), F.hM) : T(0);
     } else {
-        const double K = fma(b.u + a.u, kt, fK);
-        const double shu = b.hu + a.hu, shv = b.hv + a.hv;
+        const T K = fma(b.u + a.u, kt, fK);
+        const T shu = b.hu + a.hu, shv = b.hv + a.hv;
         F.hM = fma(-cdx, b.hu - a.hu, b.h + a.h);             // 2 hMidx
         F.huM = fma(K, shv, fma(-cdx, b.Ux - a.Ux, shu));     // 2 huMidx
         F.hvM = fma(-K, shu, fma(-cdx, b.Vx - a.Vx, shv));    // 2 hvMidx
-        const double r = fast_rcp(F.hM);
+        const T r = fast_rcp(F.hM);
         F.q = F.huM * r;
-        const double pres = (hg * F.hM) * F.hM;               // hg here is g/4: 2*(g/2)*hM^2
-        const double qg = (!GUARD || positive(F.hM)) ? F.q : 0.0;
+        const T pres = (hg * F.hM) * F.hM;               // hg here is g/4: 2*(g/2)*hM^2
+        const T qg = (!GUARD || positive(F.hM)) ? F.q : T(0);
         F.F1 = fma(F.huM, qg, pres);                          // 2 UxMid
         F.F2 = F.hvM * qg;                                    // 2 VxMid
     }
-    F.F3 = 0.0;
-    F.hvc = 0.0;
+    F.F3 = T(0);
+    F.hvc = T(0);
     return F;
 }
 
@@ -263,40 +300,39 @@ __device__ __forceinline__ Face x_face(const Cell &a, const Cell &b, double cdx,
 // 292, 322-323.
 //   STRICT: c1 = hdt/dy1_j, c2 = hdt/dy_j, kt = tgMidy_j, fK = 0.5*(f_b+f_a)
 //   FAST:   c1 = dt/dy1_j,  c2 = dt/dy_j,  kt = hdt*0.5*tgMidy/a, fK = hdt*0.5*(f_b+f_a)
-template <bool STRICT, bool GUARD>
-__device__ __forceinline__ Face y_face(const Cell &a, const Cell &b, double c1, double c2, double kt, double fK,
-                                       double cm, double hdt, double hg, double ra)
+template <bool STRICT, bool GUARD, typename T>
+__device__ __forceinline__ Face<T> y_face(const Cell<T> &a, const Cell<T> &b, T c1, T c2, T kt, T fK, T cm, T hdt, T hg, T ra)
 {
-    using O = Op<STRICT>;
-    Face F;
+    using O = Op<STRICT, T>;
+    Face<T> F;
     if (STRICT) {
-        const double P = O::add(fK, O::div(O::mul(O::mul(0.5, O::add(b.u, a.u)), kt), ra));
-        const double K = O::mul(hdt, P);
-        const double shu = O::mul(0.5, O::add(b.hu, a.hu));
-        const double shv = O::mul(0.5, O::add(b.hv, a.hv));
-        F.hM = O::sub(O::mul(0.5, O::add(b.h, a.h)), O::mul(c1, O::sub(b.hw, a.hw)));
+        const T P = O::add(fK, O::div(O::mul(O::mul(T(0.5), O::add(b.u, a.u)), kt), ra));
+        const T K = O::mul(hdt, P);
+        const T shu = O::mul(T(0.5), O::add(b.hu, a.hu));
+        const T shv = O::mul(T(0.5), O::add(b.hv, a.hv));
+        F.hM = O::sub(O::mul(T(0.5), O::add(b.h, a.h)), O::mul(c1, O::sub(b.hw, a.hw)));
         F.huM = O::add(O::sub(shu, O::mul(c1, O::sub(b.Uy, a.Uy))), O::mul(K, shv));
         F.hvM = O::sub(O::sub(O::sub(shv, O::mul(c1, O::sub(b.Vy1, a.Vy1))), O::mul(c2, O::sub(b.pr, a.pr))),
                        O::mul(K, shu));
         F.q = O::div(F.huM, F.hM);
         F.hvc = O::mul(F.hvM, cm);
         const bool pos = F.hM > 0.0;
-        F.F1 = pos ? O::div(O::mul(F.hvc, F.huM), F.hM) : 0.0;
-        F.F2 = pos ? O::mul(O::div(O::mul(F.hvM, F.hvM), F.hM), cm) : 0.0;
+        F.F1 = pos ? O::div(O::mul(F.hvc, F.huM), F.hM) : T(0);
+        F.F2 = pos ? O::mul(O::div(O::mul(F.hvM, F.hvM), F.hM), cm) : T(0);
         F.F3 = O::mul(O::mul(hg, F.hM), F.hM);
     } else {
-        const double K = fma(b.u + a.u, kt, fK);
-        const double shu = b.hu + a.hu, shv = b.hv + a.hv;
+        const T K = fma(b.u + a.u, kt, fK);
+        const T shu = b.hu + a.hu, shv = b.hv + a.hv;
         F.hM = fma(-c1, b.hw - a.hw, b.h + a.h);
         F.huM = fma(K, shv, fma(-c1, b.Uy - a.Uy, shu));
         F.hvM = fma(-K, shu, fma(-c2, b.pr - a.pr, fma(-c1, b.Vy1 - a.Vy1, shv)));
-        const double r = fast_rcp(F.hM);
+        const T r = fast_rcp(F.hM);
         F.q = F.huM * r;
         F.hvc = F.hvM * cm;
-        const double t = F.hvM * r;
+        const T t = F.hvM * r;
         const bool pos = !GUARD || positive(F.hM);
-        F.F1 = F.hvc * (pos ? F.q : 0.0);          // 2 UyMid
-        F.F2 = F.hvc * (pos ? t : 0.0);            // 2 Vy1Mid
+        F.F1 = F.hvc * (pos ? F.q : T(0));          // 2 UyMid
+        F.F2 = F.hvc * (pos ? t : T(0));            // 2 Vy1Mid
         F.F3 = (hg * F.hM) * F.hM;                 // 2 Vy2Mid (hg = g/4)
     }
     return F;
@@ -306,48 +342,62 @@ __device__ __forceinline__ Face y_face(const Cell &a, const Cell &b, double c1, 
 //   STRICT: cx = dt/dxc[i,j], cy1u = dt/dy1c_j, cyu = dt/dyc_j, kc = tan(theta_j), fc = f
 //   FAST:   cx = 0.5*dt/dx_j, cy1u, cyu halved, kc = dt/64*tan/a, fc = dt/8*f
 // hsx = hs[i+1,j]-hs[i-1,j], hsy = hs[i,j+1]-hs[i,j-1], dxs = dx[i-1,j]+dx[i,j], dy1s = dy1_{j-1}+dy1_j.
-template <bool STRICT, bool HS>
-__device__ __forceinline__ void update_cell(const Cell &cur, const Face &x0, const Face &x1, const Face &y0, const Face &y1,
-                                            double cx, double cy1u, double cyu, double kc, double fc, double dt, double g,
-                                            double ra, double hsx, double hsy, double dxs, double dy1s, double &hn,
-                                            double &un, double &vn)
+template <bool STRICT, bool HS, typename T>
+__device__ __forceinline__ void update_cell(const Cell<T> &cur, const Face<T> &x0, const Face<T> &x1, const Face<T> &y0,
+                                            const Face<T> &y1, T cx, T cy1u, T cyu, T kc, T fc, T dt, T g, T ra, T hsx, T hsy,
+                                            T dxs, T dy1s, T &hn, T &un, T &vn)
 {
-    using O = Op<STRICT>;
+    using O = Op<STRICT, T>;
     if (STRICT) {
         hn = O::sub(O::sub(cur.h, O::mul(cx, O::sub(x1.huM, x0.huM))), O::mul(cy1u, O::sub(y1.hvc, y0.hvc)));
-        const double qs = O::add(O::add(O::add(x0.q, x1.q), y0.q), y1.q);
-        const double Fc = O::add(fc, O::div(O::mul(O::mul(0.25, qs), kc), ra));
-        const double D = O::mul(O::mul(dt, Fc), 0.25);
-        const double shv = O::add(O::add(O::add(x0.hvM, x1.hvM), y0.hvM), y1.hvM);
-        const double shu = O::add(O::add(O::add(x0.huM, x1.huM), y0.huM), y1.huM);
-        double hun = O::add(O::sub(O::sub(cur.hu, O::mul(cx, O::sub(x1.F1, x0.F1))), O::mul(cy1u, O::sub(y1.F1, y0.F1))),
+        const T qs = O::add(O::add(O::add(x0.q, x1.q), y0.q), y1.q);
+        const T Fc = O::add(fc, O::div(O::mul(O::mul(T(0.25), qs), kc), ra));
+        const T D = O::mul(O::mul(dt, Fc), T(0.25));
+        const T shv = O::add(O::add(O::add(x0.hvM, x1.hvM), y0.hvM), y1.hvM);
+        const T shu = O::add(O::add(O::add(x0.huM, x1.huM), y0.huM), y1.huM);
+        T hun = O::add(O::sub(O::sub(cur.hu, O::mul(cx, O::sub(x1.F1, x0.F1))), O::mul(cy1u, O::sub(y1.F1, y0.F1))),
                             O::mul(D, shv));
-        double hvn = O::sub(O::sub(O::sub(O::sub(cur.hv, O::mul(cx, O::sub(x1.F2, x0.F2))), O::mul(cy1u, O::sub(y1.F2, y0.F2))),
+        T hvn = O::sub(O::sub(O::sub(O::sub(cur.hv, O::mul(cx, O::sub(x1.F2, x0.F2))), O::mul(cy1u, O::sub(y1.F2, y0.F2))),
                                    O::mul(cyu, O::sub(y1.F3, y0.F3))),
                             O::mul(D, shu));
         if (HS) {  // numpy.py:310-317, 342-349
-            const double hsum = O::add(O::add(O::add(x0.hM, x1.hM), y0.hM), y1.hM);
-            const double gq = O::mul(O::mul(O::mul(dt, g), 0.25), hsum);
+            const T hsum = O::add(O::add(O::add(x0.hM, x1.hM), y0.hM), y1.hM);
+            const T gq = O::mul(O::mul(O::mul(dt, g), T(0.25)), hsum);
             hun = O::sub(hun, O::div(O::mul(gq, hsx), dxs));
             hvn = O::sub(hvn, O::div(O::mul(gq, hsy), dy1s));
         }
         un = O::div(hun, hn);
         vn = O::div(hvn, hn);
+    } else if (sizeof(T) == 4) {
+        // fp32: increment form.  h' = h + dh, (hu)' = hu + dhu  =>  u' = u + (dhu - u dh) / h':
+        // the increments are ~1e-3 of the fields, so their rounding errors stay far below an
+        // ulp of u, v instead of the ~2 ulp per step the quotient (hu)'/h' costs in fp32.
+        const T dh = fma(-cy1u, y1.hvc - y0.hvc, -cx * (x1.huM - x0.huM));
+        hn = cur.h + dh;
+        const T qs = (x0.q + x1.q) + (y0.q + y1.q);
+        const T D = fma(qs, kc, fc);
+        const T shv = (x0.hvM + x1.hvM) + (y0.hvM + y1.hvM);
+        const T shu = (x0.huM + x1.huM) + (y0.huM + y1.huM);
+        const T dhu = fma(D, shv, fma(-cy1u, y1.F1 - y0.F1, -cx * (x1.F1 - x0.F1)));
+        const T dhv = fma(-D, shu, fma(-cyu, y1.F3 - y0.F3, fma(-cy1u, y1.F2 - y0.F2, -cx * (x1.F2 - x0.F2))));
+        const T r = fast_rcp(hn);
+        un = fma(fma(-cur.u, dh, dhu), r, cur.u);
+        vn = fma(fma(-cur.v, dh, dhv), r, cur.v);
     } else {
         hn = fma(-cy1u, y1.hvc - y0.hvc, fma(-cx, x1.huM - x0.huM, cur.h));
-        const double qs = (x0.q + x1.q) + (y0.q + y1.q);
-        const double D = fma(qs, kc, fc);  // 0.5 * dt * Fc * 0.25
-        const double shv = (x0.hvM + x1.hvM) + (y0.hvM + y1.hvM);
-        const double shu = (x0.huM + x1.huM) + (y0.huM + y1.huM);
-        double hun = fma(D, shv, fma(-cy1u, y1.F1 - y0.F1, fma(-cx, x1.F1 - x0.F1, cur.hu)));
-        double hvn = fma(-D, shu, fma(-cyu, y1.F3 - y0.F3, fma(-cy1u, y1.F2 - y0.F2, fma(-cx, x1.F2 - x0.F2, cur.hv))));
+        const T qs = (x0.q + x1.q) + (y0.q + y1.q);
+        const T D = fma(qs, kc, fc);  // 0.5 * dt * Fc * 0.25
+        const T shv = (x0.hvM + x1.hvM) + (y0.hvM + y1.hvM);
+        const T shu = (x0.huM + x1.huM) + (y0.huM + y1.huM);
+        T hun = fma(D, shv, fma(-cy1u, y1.F1 - y0.F1, fma(-cx, x1.F1 - x0.F1, cur.hu)));
+        T hvn = fma(-D, shu, fma(-cyu, y1.F3 - y0.F3, fma(-cy1u, y1.F2 - y0.F2, fma(-cx, x1.F2 - x0.F2, cur.hv))));
         if (HS) {
-            const double hsum = (x0.hM + x1.hM) + (y0.hM + y1.hM);  // doubled
-            const double gq = dt * g * 0.125 * hsum;
+            const T hsum = (x0.hM + x1.hM) + (y0.hM + y1.hM);  // doubled
+            const T gq = dt * g * T(0.125) * hsum;
             hun -= gq * hsx / dxs;
             hvn -= gq * hsy / dy1s;
         }
-        const double r = fast_rcp(hn);
+        const T r = fast_rcp(hn);
         un = hun * r;
         vn = hvn * r;
     }
@@ -410,18 +460,20 @@ __device__ __forceinline__ W3 y_weights(const double *__restrict__ tab, int nrow
 
 // the five stencil values of q along each axis around (jl, i), with the reference's
 // extension (numpy.py:376-381): periodic in longitude, duplicated rows in latitude
+template <typename T>
 struct Star {
-    double q0, xm, xp, xmm, xpp, ym, yp, ymm, ypp;
+    T q0, xm, xp, xmm, xpp, ym, yp, ymm, ypp;
 };
-__device__ __forceinline__ Star load_star(const double *__restrict__ q, int pitch, int nrows, int M, int jl, int i)
+template <typename T>
+__device__ __forceinline__ Star<T> load_star(const T *__restrict__ q, int pitch, int nrows, int M, int jl, int i)
 {
     const size_t P = (size_t)pitch;
     const int im2 = (i - 2 < 0) ? M - 1 : i - 2;  // numpy.py:376-378
     const int ip2 = (i + 2 > M + 2) ? 3 : i + 2;
     const int jm1 = max(jl - 1, 0), jp1 = min(jl + 1, nrows - 1);
     const int jm2 = max(jl - 2, 0), jp2 = min(jl + 2, nrows - 1);
-    Star s;
-    const double *row = q + (size_t)jl * P;
+    Star<T> s;
+    const T *row = q + (size_t)jl * P;
     s.q0 = row[i];
     s.xm = row[i - 1]; s.xp = row[i + 1];
     s.xmm = row[im2];  s.xpp = row[ip2];
@@ -431,10 +483,11 @@ __device__ __forceinline__ Star load_star(const double *__restrict__ q, int pitc
 }
 
 // FAST diffusion row record: w[0..4] combined latitude weights, [5] = 1/(2 dx_j)^2, [6] = dt*nu
-__device__ __forceinline__ double laplacian_fast(const Star &s, const double *__restrict__ rd)
+template <typename T>
+__device__ __forceinline__ T laplacian_fast(const Star<T> &s, const T *__restrict__ rd)
 {
-    const double qxx = rd[5] * fma(-2.0, s.q0, s.xpp + s.xmm);
-    const double qyy = fma(rd[0], s.ymm, fma(rd[1], s.ym, fma(rd[2], s.q0, fma(rd[3], s.yp, rd[4] * s.ypp))));
+    const T qxx = rd[5] * fma(T(-2.0), s.q0, s.xpp + s.xmm);
+    const T qyy = fma(rd[0], s.ymm, fma(rd[1], s.ym, fma(rd[2], s.q0, fma(rd[3], s.yp, rd[4] * s.ypp))));
     return qxx + qyy;
 }
 
@@ -594,9 +647,9 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
                  ::"r"(dst), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
-template <int R, int S>
+template <int R, int S, typename T = double>
 struct TmaLayout {
-    static constexpr int kField = R * kStripCols * 8;  // one field, one stage
+    static constexpr int kField = R * kStripCols * (int)sizeof(T);  // one field, one stage
     static constexpr int kStage = 3 * kField;
     static constexpr int kRing = S * kStage;
     static constexpr int kBars = 128;
@@ -610,6 +663,9 @@ __host__ __device__ constexpr int rec_bytes(int chunk, bool diff)
 }
 
 __device__ __forceinline__ double2 ldg2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ float2 ldg2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
 
 // Store a lane's pair of values without branching: both (one 16-byte store), or only the
 // first / only the second (the strip's edge lanes and the right end of the grid).
@@ -626,6 +682,20 @@ __device__ __forceinline__ void st_pair(double *addr, double a, double b, int bo
         "@pc st.global.f64 [%0+8], %2;\n\t"
         "}" ::"l"(addr), "d"(a), "d"(b), "r"(both), "r"(only_a), "r"(only_b) : "memory");
 }
+__device__ __forceinline__ void st_pair(float *addr, float a, float b, int both, int only_a, int only_b)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pb, pa, pc;\n\t"
+        "setp.ne.s32 pb, %3, 0;\n\t"
+        "setp.ne.s32 pa, %4, 0;\n\t"
+        "setp.ne.s32 pc, %5, 0;\n\t"
+        "@pb st.global.v2.f32 [%0], {%1, %2};\n\t"
+        "@pa st.global.f32 [%0], %1;\n\t"
+        "@pc st.global.f32 [%0+4], %2;\n\t"
+        "}" ::"l"(addr), "f"(a), "f"(b), "r"(both), "r"(only_a), "r"(only_b) : "memory");
+}
+
 
 // ------------------------------------------------------------------------------------
 // the fused step kernel
@@ -634,12 +704,15 @@ __device__ __forceinline__ void st_pair(double *addr, double a, double b, int bo
 // TMA ring (R latitudes per box, S stages) or direct loads, and whether FAST evaluates the
 // reference's hMid > 0 selects (GUARD) or assumes them true and raises SWB_E_DEPTH when a
 // half-step depth turns out non-positive.
-template <bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
+template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
 __global__ void __launch_bounds__(W * 32, MINB)
 march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
 {
-    using O = Op<STRICT>;
-    using LY = TmaLayout<R, S>;
+    static_assert(!STRICT || sizeof(T) == 8, "STRICT reproduces numpy's float64 arithmetic");
+    using O = Op<STRICT, T>;
+    using LY = TmaLayout<R, S, T>;
+    using V2 = vec2_t<T>;
+    constexpr int kValid = sizeof(T) == 8 ? kStripValid : kStripValidF32;
     constexpr bool kGuard = STRICT || GUARD;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ double s_dt;
@@ -649,14 +722,15 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     const int flags = s_flags;
     if (!(flags & 1)) return;
     const int par = (flags >> 1) & 1;
-    const double dt = s_dt;
+    const T dt = (T)s_dt;
+    const T g_ = (T)p.g;
 
-    const double *__restrict__ H = p.buf[par][0];
-    const double *__restrict__ U = p.buf[par][1];
-    const double *__restrict__ V = p.buf[par][2];
-    double *__restrict__ Hn = p.buf[par ^ 1][0];
-    double *__restrict__ Un = p.buf[par ^ 1][1];
-    double *__restrict__ Vn = p.buf[par ^ 1][2];
+    const T *__restrict__ H = (const T *)p.buf[par][0];
+    const T *__restrict__ U = (const T *)p.buf[par][1];
+    const T *__restrict__ V = (const T *)p.buf[par][2];
+    T *__restrict__ Hn = (T *)p.buf[par ^ 1][0];
+    T *__restrict__ Un = (T *)p.buf[par ^ 1][1];
+    T *__restrict__ Vn = (T *)p.buf[par ^ 1][2];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -664,7 +738,7 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     const bool warp_on = strip < p.nstrips;
     const int ja = p.jl_first + blockIdx.y * p.chunk;  // first latitude updated
     const int jb = min(ja + p.chunk, p.jl_last + 1);   // one past the last
-    const int c0 = kStripValid * strip;
+    const int c0 = kValid * strip;
     const size_t P = (size_t)p.pitch;
 
     // ---- TMA ring: start the first loads before anything else ----------------------
@@ -693,58 +767,66 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     }
 
     // ---- row records of latitudes ja-1 .. jb ----------------------------------------
-    double *rowc = reinterpret_cast<double *>(smem_raw);
-    double *rowd = rowc + (size_t)(p.chunk + 2) * kRowRec;
+    T *rowc = reinterpret_cast<T *>(smem_raw);
+    T *rowd = rowc + (size_t)(p.chunk + 2) * kRowRec;
     for (int r = threadIdx.x; r < jb - ja + 2; r += blockDim.x) {
-        build_row_record<STRICT>(p, ja - 1 + r, dt, rowc + (size_t)r * kRowRec);
-        if (DIFF && !STRICT) build_diff_record(p, ja - 1 + r, dt, rowd + (size_t)r * kRowDiff);
+        double rec[kRowRec];  // built in fp64 whatever T is (hard part 6), rounded once
+        build_row_record<STRICT>(p, ja - 1 + r, s_dt, rec);
+#pragma unroll
+        for (int k = 0; k < kRowRec; ++k) rowc[(size_t)r * kRowRec + k] = (T)rec[k];
+        if (DIFF && !STRICT) {
+            double rd[kRowDiff];
+            build_diff_record(p, ja - 1 + r, s_dt, rd);
+#pragma unroll
+            for (int k = 0; k < kRowDiff; ++k) rowd[(size_t)r * kRowDiff + k] = (T)rd[k];
+        }
     }
     __syncthreads();
     if (!warp_on) return;
 
     // ---- per-lane set-up ------------------------------------------------------------
     const int colA = c0 + 2 * lane;  // this lane's cells: (., colA) and (., colA + 1)
-    const bool vA = (lane >= 1) && (colA <= p.M + 1);
-    const bool vB = (lane <= 30) && (colA + 1 <= p.M + 1);
-    const double hdt = O::mul(0.5, dt);
-    const double hgCell = O::mul(0.5, p.g);            // numpy.py:203, 255: 0.5*g
-    const double hgK = STRICT ? hgCell : 0.25 * p.g;   // FAST faces are doubled
-    const double raK = STRICT ? p.a : 1.0 / p.a;
-    double ph_m = 0.0, ph_0 = 0.0, ph_1 = 0.0, ph_2 = 0.0;  // STRICT: phi at colA-1 .. colA+2
+    const bool vA = (lane >= 1) && (colA <= c0 + kValid) && (colA <= p.M + 1);
+    const bool vB = (colA + 1 <= c0 + kValid) && (colA + 1 <= p.M + 1);
+    const T hdt = O::mul(T(0.5), dt);
+    const T hgCell = O::mul(T(0.5), g_);               // numpy.py:203, 255: 0.5*g
+    const T hgK = STRICT ? hgCell : T(0.25) * g_;      // FAST faces are doubled
+    const T raK = STRICT ? (T)p.a : (T)(1.0 / p.a);
+    T ph_m = 0, ph_0 = 0, ph_1 = 0, ph_2 = 0;  // STRICT: phi at colA-1 .. colA+2
     if (STRICT) {
-        ph_m = p.phi[max(colA - 1, 0)];
-        ph_0 = p.phi[colA];
-        ph_1 = p.phi[colA + 1];
-        ph_2 = p.phi[colA + 2];
+        ph_m = (T)p.phi[max(colA - 1, 0)];
+        ph_0 = (T)p.phi[colA];
+        ph_1 = (T)p.phi[colA + 1];
+        ph_2 = (T)p.phi[colA + 2];
     }
     // extra copies a cell owes: periodic ghost columns (numpy.py:402)
     const bool wrapA = vA && (colA == p.M || colA == 2), wrapB = vB && (colA + 1 == p.M || colA + 1 == 2);
     const bool warp_wraps = __any_sync(0xffffffffu, wrapA || wrapB);
     const int st_both = (vA && vB) ? 1 : 0, st_onlyA = (vA && !vB) ? 1 : 0, st_onlyB = (vB && !vA) ? 1 : 0;
-    unsigned long long mxA = 0ULL, myA = 0ULL, mxB = 0ULL, myB = 0ULL;  // running CFL maxima (bit patterns)
+    bits_t<T> mxA = 0, myA = 0, mxB = 0, myB = 0;  // running CFL maxima (bit patterns)
     int negA = 0, negB = 0;  // sign watch of the half-step depths (FAST without GUARD)
 
     auto rec_of = [&](int jl) { return rowc + (size_t)(jl - (ja - 1)) * kRowRec; };
-    auto load_f = [&](int jl) -> double2 {
-        if (F2D) return ldg2(p.f2d + (size_t)min(jl, p.nrows - 1) * P + colA);
-        return make_double2(0.0, 0.0);
+    auto load_f = [&](int jl) -> V2 {
+        if (F2D) return ldg2((const T *)p.f2d + (size_t)min(jl, p.nrows - 1) * P + colA);
+        return mk2(T(0), T(0));
     };
 
-    Cell curA, curB;
-    Face y0A, y0B;
+    Cell<T> curA, curB;
+    Face<T> y0A, y0B;
     {
         const size_t k0 = (size_t)(ja - 1) * P + colA, k1 = k0 + P;
-        const double2 h0 = ldg2(H + k0), u0 = ldg2(U + k0), v0 = ldg2(V + k0);
-        const double2 h1 = ldg2(H + k1), u1 = ldg2(U + k1), v1 = ldg2(V + k1);
-        const double2 f0 = load_f(ja - 1), f1 = load_f(ja);
-        const double *r0 = rec_of(ja - 1), *r1 = rec_of(ja);
-        const Cell pA = make_cell<STRICT>(h0.x, u0.x, v0.x, r0[RC_C], hgCell, f0.x);
-        const Cell pB = make_cell<STRICT>(h0.y, u0.y, v0.y, r0[RC_C], hgCell, f0.y);
+        const V2 h0 = ldg2(H + k0), u0 = ldg2(U + k0), v0 = ldg2(V + k0);
+        const V2 h1 = ldg2(H + k1), u1 = ldg2(U + k1), v1 = ldg2(V + k1);
+        const V2 f0 = load_f(ja - 1), f1 = load_f(ja);
+        const T *r0 = rec_of(ja - 1), *r1 = rec_of(ja);
+        const Cell<T> pA = make_cell<STRICT>(h0.x, u0.x, v0.x, r0[RC_C], hgCell, f0.x);
+        const Cell<T> pB = make_cell<STRICT>(h0.y, u0.y, v0.y, r0[RC_C], hgCell, f0.y);
         curA = make_cell<STRICT>(h1.x, u1.x, v1.x, r1[RC_C], hgCell, f1.x);
         curB = make_cell<STRICT>(h1.y, u1.y, v1.y, r1[RC_C], hgCell, f1.y);
-        auto fy = [&](const Cell &a, const Cell &b) {
+        auto fy = [&](const Cell<T> &a, const Cell<T> &b) -> T {
             if (!F2D) return r0[RC_FKY];
-            return STRICT ? O::mul(0.5, O::add(b.f, a.f)) : hdt * 0.5 * (b.f + a.f);
+            return STRICT ? O::mul(T(0.5), O::add(b.f, a.f)) : hdt * T(0.5) * (b.f + a.f);
         };
         y0A = y_face<STRICT, kGuard>(pA, curA, r0[RC_CY1F], r0[RC_CYF], r0[RC_KY], fy(pA, curA), r0[RC_CM], hdt, hgK, raK);
         y0B = y_face<STRICT, kGuard>(pB, curB, r0[RC_CY1F], r0[RC_CYF], r0[RC_KY], fy(pB, curB), r0[RC_CM], hdt, hgK, raK);
@@ -764,91 +846,91 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     // One latitude: cells (jl, colA), (jl, colA+1) from `cur`, the row above in (h2,u2,v2).
     // `hot` (a compile-time tag) = a live row in [plain_lo, plain_hi]: own stores only.
     size_t krow = (size_t)ja * P + colA;  // element index of (jl, colA), advanced row by row
-    auto do_row = [&](auto hot_tag, int jl, double2 h2, double2 u2, double2 v2, bool live) {
+    auto do_row = [&](auto hot_tag, int jl, V2 h2, V2 u2, V2 v2, bool live) {
         constexpr bool HOT = decltype(hot_tag)::value;
-        const double2 *rc2 = reinterpret_cast<const double2 *>(rec_of(jl));
+        const V2 *rc2 = reinterpret_cast<const V2 *>(rec_of(jl));
         // the row record, read as 16-byte pairs (broadcast LDS.128)
-        const double2 r_c_ac = rc2[RC_C / 2], r_kx_fkx = rc2[RC_KX / 2], r_cdx_cxu = rc2[RC_CDX / 2], r_ky_fky = rc2[RC_KY / 2];
-        const double2 r_cm_cy1f = rc2[RC_CM / 2], r_cyf_cy1u = rc2[RC_CYF / 2], r_cyu_kc = rc2[RC_CYU / 2], r_fd_dy1s = rc2[RC_FD / 2];
-        const double cn = rec_of(jl)[kRowRec + RC_C];
-        const double2 f2 = load_f(jl + 1);
-        const Cell nxtA = make_cell<STRICT>(h2.x, u2.x, v2.x, cn, hgCell, f2.x);
-        const Cell nxtB = make_cell<STRICT>(h2.y, u2.y, v2.y, cn, hgCell, f2.y);
+        const V2 r_c_ac = rc2[RC_C / 2], r_kx_fkx = rc2[RC_KX / 2], r_cdx_cxu = rc2[RC_CDX / 2], r_ky_fky = rc2[RC_KY / 2];
+        const V2 r_cm_cy1f = rc2[RC_CM / 2], r_cyf_cy1u = rc2[RC_CYF / 2], r_cyu_kc = rc2[RC_CYU / 2], r_fd_dy1s = rc2[RC_FD / 2];
+        const T cn = rec_of(jl)[kRowRec + RC_C];
+        const V2 f2 = load_f(jl + 1);
+        const Cell<T> nxtA = make_cell<STRICT>(h2.x, u2.x, v2.x, cn, hgCell, f2.x);
+        const Cell<T> nxtB = make_cell<STRICT>(h2.y, u2.y, v2.y, cn, hgCell, f2.y);
 
         // y-faces (jl | jl+1)
-        double fyA = r_ky_fky.y, fyB = fyA;
+        T fyA = r_ky_fky.y, fyB = fyA;
         if (F2D) {
-            fyA = STRICT ? O::mul(0.5, O::add(nxtA.f, curA.f)) : hdt * 0.5 * (nxtA.f + curA.f);
-            fyB = STRICT ? O::mul(0.5, O::add(nxtB.f, curB.f)) : hdt * 0.5 * (nxtB.f + curB.f);
+            fyA = STRICT ? O::mul(T(0.5), O::add(nxtA.f, curA.f)) : hdt * T(0.5) * (nxtA.f + curA.f);
+            fyB = STRICT ? O::mul(T(0.5), O::add(nxtB.f, curB.f)) : hdt * T(0.5) * (nxtB.f + curB.f);
         }
-        const Face y1A = y_face<STRICT, kGuard>(curA, nxtA, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyA, r_cm_cy1f.x, hdt, hgK, raK);
-        const Face y1B = y_face<STRICT, kGuard>(curB, nxtB, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyB, r_cm_cy1f.x, hdt, hgK, raK);
+        const Face<T> y1A = y_face<STRICT, kGuard>(curA, nxtA, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyA, r_cm_cy1f.x, hdt, hgK, raK);
+        const Face<T> y1B = y_face<STRICT, kGuard>(curB, nxtB, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyB, r_cm_cy1f.x, hdt, hgK, raK);
 
         // x-faces of this latitude: (A | B) and (B | next lane's A)
-        Cell nA;
+        Cell<T> nA;
         nA.h = shfl_down1(curA.h);   nA.u = shfl_down1(curA.u);
         nA.hu = shfl_down1(curA.hu); nA.hv = shfl_down1(curA.hv);
         nA.Ux = shfl_down1(curA.Ux); nA.Vx = shfl_down1(curA.Vx);
-        nA.f = F2D ? shfl_down1(curA.f) : 0.0;
-        double cdxAB, cdxBN, cxA, cxB, dxsA = 0.0, dxsB = 0.0;
+        nA.f = F2D ? shfl_down1(curA.f) : T(0);
+        T cdxAB, cdxBN, cxA, cxB, dxsA = 0, dxsB = 0;
         if (STRICT) {
-            const double ac = r_c_ac.y;
-            const double xm = O::mul(ac, ph_m), x0 = O::mul(ac, ph_0), x1 = O::mul(ac, ph_1), x2 = O::mul(ac, ph_2);
-            const double dxm = O::sub(x0, xm), dxA = O::sub(x1, x0), dxB = O::sub(x2, x1);
+            const T ac = r_c_ac.y;
+            const T xm = O::mul(ac, ph_m), x0 = O::mul(ac, ph_0), x1 = O::mul(ac, ph_1), x2 = O::mul(ac, ph_2);
+            const T dxm = O::sub(x0, xm), dxA = O::sub(x1, x0), dxB = O::sub(x2, x1);
             cdxAB = O::div(hdt, dxA);
             cdxBN = O::div(hdt, dxB);
             dxsA = O::add(dxm, dxA);
             dxsB = O::add(dxA, dxB);
-            cxA = O::div(dt, O::mul(0.5, dxsA));
-            cxB = O::div(dt, O::mul(0.5, dxsB));
+            cxA = O::div(dt, O::mul(T(0.5), dxsA));
+            cxB = O::div(dt, O::mul(T(0.5), dxsB));
         } else {
             cdxAB = cdxBN = r_cdx_cxu.x;
             cxA = cxB = r_cdx_cxu.y;
-            if (HS) dxsA = dxsB = 2.0 * r_c_ac.y * p.dphi;
+            if (HS) dxsA = dxsB = T(2.0) * r_c_ac.y * (T)p.dphi;
         }
-        double fxAB = r_kx_fkx.y, fxBN = fxAB;
+        T fxAB = r_kx_fkx.y, fxBN = fxAB;
         if (F2D) {
-            fxAB = STRICT ? O::mul(0.5, O::add(curB.f, curA.f)) : hdt * 0.5 * (curB.f + curA.f);
-            fxBN = STRICT ? O::mul(0.5, O::add(nA.f, curB.f)) : hdt * 0.5 * (nA.f + curB.f);
+            fxAB = STRICT ? O::mul(T(0.5), O::add(curB.f, curA.f)) : hdt * T(0.5) * (curB.f + curA.f);
+            fxBN = STRICT ? O::mul(T(0.5), O::add(nA.f, curB.f)) : hdt * T(0.5) * (nA.f + curB.f);
         }
-        const Face xAB = x_face<STRICT, kGuard>(curA, curB, cdxAB, r_kx_fkx.x, fxAB, hdt, hgK, raK);
-        const Face xBN = x_face<STRICT, kGuard>(curB, nA, cdxBN, r_kx_fkx.x, fxBN, hdt, hgK, raK);
-        Face xL;  // (previous lane's B | A)
+        const Face<T> xAB = x_face<STRICT, kGuard>(curA, curB, cdxAB, r_kx_fkx.x, fxAB, hdt, hgK, raK);
+        const Face<T> xBN = x_face<STRICT, kGuard>(curB, nA, cdxBN, r_kx_fkx.x, fxBN, hdt, hgK, raK);
+        Face<T> xL;  // (previous lane's B | A)
         xL.huM = shfl_up1(xBN.huM); xL.hvM = shfl_up1(xBN.hvM); xL.q = shfl_up1(xBN.q);
         xL.F1 = shfl_up1(xBN.F1);   xL.F2 = shfl_up1(xBN.F2);
-        xL.hM = HS ? shfl_up1(xBN.hM) : 0.0;
+        xL.hM = HS ? shfl_up1(xBN.hM) : T(0);
 
         // topography differences (numpy.py:310-317, 342-349)
-        double hsxA = 0.0, hsxB = 0.0, hsyA = 0.0, hsyB = 0.0;
+        T hsxA = 0, hsxB = 0, hsyA = 0, hsyB = 0;
         if (HS) {
-            const double *hr = p.hs + (size_t)jl * P + colA;
-            const double *hu_ = p.hs + (size_t)min(jl + 1, p.nrows - 1) * P + colA;
-            const double *hd_ = p.hs + (size_t)max(jl - 1, 0) * P + colA;
-            const double e0 = hr[colA > 0 ? -1 : 0], e1 = hr[0], e2 = hr[1], e3 = hr[2];
+            const T *hr = (const T *)p.hs + (size_t)jl * P + colA;
+            const T *hu_ = (const T *)p.hs + (size_t)min(jl + 1, p.nrows - 1) * P + colA;
+            const T *hd_ = (const T *)p.hs + (size_t)max(jl - 1, 0) * P + colA;
+            const T e0 = hr[colA > 0 ? -1 : 0], e1 = hr[0], e2 = hr[1], e3 = hr[2];
             hsxA = O::sub(e2, e0);
             hsxB = O::sub(e3, e1);
             hsyA = O::sub(hu_[0], hd_[0]);
             hsyB = O::sub(hu_[1], hd_[1]);
         }
 
-        double hnA, unA, vnA, hnB, unB, vnB;
-        const double fcA = F2D ? (STRICT ? curA.f : dt * 0.125 * curA.f) : r_fd_dy1s.x;
-        const double fcB = F2D ? (STRICT ? curB.f : dt * 0.125 * curB.f) : r_fd_dy1s.x;
-        update_cell<STRICT, HS>(curA, xL, xAB, y0A, y1A, cxA, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcA, dt, p.g, raK, hsxA, hsyA,
+        T hnA, unA, vnA, hnB, unB, vnB;
+        const T fcA = F2D ? (STRICT ? curA.f : dt * T(0.125) * curA.f) : r_fd_dy1s.x;
+        const T fcB = F2D ? (STRICT ? curB.f : dt * T(0.125) * curB.f) : r_fd_dy1s.x;
+        update_cell<STRICT, HS>(curA, xL, xAB, y0A, y1A, cxA, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcA, dt, g_, raK, hsxA, hsyA,
                                 dxsA, r_fd_dy1s.y, hnA, unA, vnA);
-        update_cell<STRICT, HS>(curB, xAB, xBN, y0B, y1B, cxB, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcB, dt, p.g, raK, hsxB, hsyB,
+        update_cell<STRICT, HS>(curB, xAB, xBN, y0B, y1B, cxB, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcB, dt, g_, raK, hsxB, hsyB,
                                 dxsB, r_fd_dy1s.y, hnB, unB, vnB);
 
         if (DIFF) {  // numpy.py:541-544: Laplacian of the OLD fields; u, v (not hu, hv)
             const int iA = min(max(colA, 1), p.M + 1), iB = min(max(colA + 1, 1), p.M + 1);  // keep invalid lanes in bounds
-            const Star shA = load_star(H, p.pitch, p.nrows, p.M, jl, iA), shB = load_star(H, p.pitch, p.nrows, p.M, jl, iB);
-            const Star suA = load_star(U, p.pitch, p.nrows, p.M, jl, iA), suB = load_star(U, p.pitch, p.nrows, p.M, jl, iB);
-            const Star svA = load_star(V, p.pitch, p.nrows, p.M, jl, iA), svB = load_star(V, p.pitch, p.nrows, p.M, jl, iB);
+            const Star<T> shA = load_star(H, p.pitch, p.nrows, p.M, jl, iA), shB = load_star(H, p.pitch, p.nrows, p.M, jl, iB);
+            const Star<T> suA = load_star(U, p.pitch, p.nrows, p.M, jl, iA), suB = load_star(U, p.pitch, p.nrows, p.M, jl, iB);
+            const Star<T> svA = load_star(V, p.pitch, p.nrows, p.M, jl, iA), svB = load_star(V, p.pitch, p.nrows, p.M, jl, iB);
             if (STRICT) {
-                const double dnu = O::mul(dt, p.nu);
+                const T dnu = O::mul(dt, (T)p.nu);
                 const W3 wy = y_weights(p.tab, p.nrows, jl);
                 const W3 wxA = x_weights_strict(p.phi, r_c_ac.y, iA, p.M), wxB = x_weights_strict(p.phi, r_c_ac.y, iB, p.M);
-                auto lap = [&](const Star &s, const W3 &wx) {
+                auto lap = [&](const Star<T> &s, const W3 &wx) -> T {
                     return O::add(second_diff_strict(wx, s.xmm, s.xm, s.q0, s.xp, s.xpp),
                                   second_diff_strict(wy, s.ymm, s.ym, s.q0, s.yp, s.ypp));
                 };
@@ -856,8 +938,8 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
                 unA = O::add(unA, O::mul(dnu, lap(suA, wxA))); unB = O::add(unB, O::mul(dnu, lap(suB, wxB)));
                 vnA = O::add(vnA, O::mul(dnu, lap(svA, wxA))); vnB = O::add(vnB, O::mul(dnu, lap(svB, wxB)));
             } else {
-                const double *rd = rowd + (size_t)(jl - (ja - 1)) * kRowDiff;
-                const double dnu = rd[6];
+                const T *rd = rowd + (size_t)(jl - (ja - 1)) * kRowDiff;
+                const T dnu = rd[6];
                 hnA = fma(dnu, laplacian_fast(shA, rd), hnA); hnB = fma(dnu, laplacian_fast(shB, rd), hnB);
                 unA = fma(dnu, laplacian_fast(suA, rd), unA); unB = fma(dnu, laplacian_fast(suB, rd), unB);
                 vnA = fma(dnu, laplacian_fast(svA, rd), vnA); vnB = fma(dnu, laplacian_fast(svB, rd), vnB);
@@ -866,13 +948,13 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
 
         // CFL maxima of the new state: max(|q-c|, |q|, |q+c|) == |q| + c for c >= 0
         if (HOT || live) {
-            const double csA = STRICT ? __dsqrt_rn(O::mul(p.g, fabs(hnA))) : fast_sqrt(p.g * fabs(hnA));
-            const double csB = STRICT ? __dsqrt_rn(O::mul(p.g, fabs(hnB))) : fast_sqrt(p.g * fabs(hnB));
+            const T csA = STRICT ? (T)__dsqrt_rn(O::mul(g_, fabs(hnA))) : fast_sqrt(g_ * fabs(hnA));
+            const T csB = STRICT ? (T)__dsqrt_rn(O::mul(g_, fabs(hnB))) : fast_sqrt(g_ * fabs(hnB));
             mxA = umax64(mxA, nonneg_bits(O::add(fabs(unA), csA))); myA = umax64(myA, nonneg_bits(O::add(fabs(vnA), csA)));
             mxB = umax64(mxB, nonneg_bits(O::add(fabs(unB), csB))); myB = umax64(myB, nonneg_bits(O::add(fabs(vnB), csB)));
             if (!kGuard) {
-                negA |= __double2hiint(xAB.hM) | __double2hiint(y1A.hM) | __double2hiint(hnA);
-                negB |= __double2hiint(xBN.hM) | __double2hiint(y1B.hM) | __double2hiint(hnB);
+                negA |= hi_word(xAB.hM) | hi_word(y1A.hM) | hi_word(hnA);
+                negB |= hi_word(xBN.hM) | hi_word(y1B.hM) | hi_word(hnB);
             }
         }
 
@@ -887,8 +969,8 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
             // pole rows (which also copy the ghost columns), halo rows of the neighbour bands
             const bool south = p.pole_s && (jl == 1), north = p.pole_n && (jl == p.nrows - 2);
             if (warp_wraps || south || north) {
-                auto put = [&](size_t kk, double hh, double uu, double vv) { Hn[kk] = hh; Un[kk] = uu; Vn[kk] = vv; };
-                auto dup = [&](bool valid, bool wraps, int col, double hh, double uu, double vv) {
+                auto put = [&](size_t kk, T hh, T uu, T vv) { Hn[kk] = hh; Un[kk] = uu; Vn[kk] = vv; };
+                auto dup = [&](bool valid, bool wraps, int col, T hh, T uu, T vv) {
                     if (!valid) return;
                     // a wrapping column is mirrored at column 0 (col == M) and / or M+2 (col == 2)
                     const bool w0 = wraps && (col == p.M), w2 = wraps && (col == 2);
@@ -907,9 +989,9 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
             if (p.world > 1) {
                 // rows a neighbour band reads as its halo: store them into its arrays as well
                 const int ds = jl - p.jl_first, dn = p.jl_last - jl;
-                auto peer_put = [&](double *const *nb, int prow, int ppitch) {
+                auto peer_put = [&](T *const *nb, int prow, int ppitch) {
                     const size_t kb = (size_t)prow * ppitch + colA;
-                    auto one = [&](int col_off, bool valid, bool wraps, double hh, double uu, double vv) {
+                    auto one = [&](int col_off, bool valid, bool wraps, T hh, T uu, T vv) {
                         if (!valid) return;
                         nb[0][kb + col_off] = hh; nb[1][kb + col_off] = uu; nb[2][kb + col_off] = vv;
                         const int col = colA + col_off;
@@ -925,8 +1007,8 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
                     one(0, vA, wrapA, hnA, unA, vnA);
                     one(1, vB, wrapB, hnB, unB, vnB);
                 };
-                if (ds < p.halo && p.south[par ^ 1][0] != nullptr) peer_put(p.south[par ^ 1], p.south_row + ds, p.south_pitch);
-                if (dn < p.halo && p.north[par ^ 1][0] != nullptr) peer_put(p.north[par ^ 1], p.north_row - dn, p.north_pitch);
+                if (ds < p.halo && p.south[par ^ 1][0] != nullptr) peer_put(reinterpret_cast<T *const *>(p.south[par ^ 1]), p.south_row + ds, p.south_pitch);
+                if (dn < p.halo && p.north[par ^ 1][0] != nullptr) peer_put(reinterpret_cast<T *const *>(p.north[par ^ 1]), p.north_row - dn, p.north_pitch);
             }
         }
         krow += P;
@@ -938,22 +1020,21 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
 
     // ---- the march ------------------------------------------------------------------
     if (TMA) {
-        const double *ring = reinterpret_cast<const double *>(wbase);
+        constexpr int kFieldV = LY::kField / (int)sizeof(V2), kRowV = kStripCols / 2;  // strides in lane pairs
         for (int t = 0; t < ntiles; ++t) {
             const int s = t % S;
             mbar_wait(bar_a + 8 * s, (uint32_t)((t / S) & 1));
-            const double2 *tile = reinterpret_cast<const double2 *>(ring + (size_t)s * (LY::kStage / 8)) + lane;
+            const V2 *tile = reinterpret_cast<const V2 *>(wbase + (size_t)s * LY::kStage) + lane;
             const int j0 = ja + t * R;
             if (j0 >= plain_lo && j0 + R - 1 <= plain_hi) {  // warp-uniform
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr)
-                    do_row(HotTag(), j0 + rr, tile[rr * (kStripCols / 2)], tile[LY::kField / 16 + rr * (kStripCols / 2)],
-                           tile[2 * (LY::kField / 16) + rr * (kStripCols / 2)], true);
+                    do_row(HotTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true);
             } else {
 #pragma unroll 1
                 for (int rr = 0; rr < R; ++rr)
-                    do_row(RareTag(), j0 + rr, tile[rr * (kStripCols / 2)], tile[LY::kField / 16 + rr * (kStripCols / 2)],
-                           tile[2 * (LY::kField / 16) + rr * (kStripCols / 2)], j0 + rr < jb);
+                    do_row(RareTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV],
+                           j0 + rr < jb);
             }
             __syncwarp();  // every lane is done with the stage that is refilled next
             if (lane == 0 && t + S - 1 < ntiles) issue_load(t + S - 1);
@@ -968,8 +1049,8 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
 
     // ---- epilogue: publish the CFL maxima and the depth watch -------------------------
     if (!p.fixed) {
-        unsigned long long mx = umax64(vA ? mxA : 0ULL, vB ? mxB : 0ULL);
-        unsigned long long my = umax64(vA ? myA : 0ULL, vB ? myB : 0ULL);
+        bits_t<T> mx = umax64(vA ? mxA : bits_t<T>(0), vB ? mxB : bits_t<T>(0));
+        bits_t<T> my = umax64(vA ? myA : bits_t<T>(0), vB ? myB : bits_t<T>(0));
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) {
             mx = umax64(mx, __shfl_xor_sync(0xffffffffu, mx, s));
@@ -977,8 +1058,8 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
         }
         if (lane == 0) {
             Ctrl *const new_slot = p.ctrl + ((p.launch + 1) % 3);
-            atomicMax(&new_slot->ex_bits, mx);
-            atomicMax(&new_slot->ey_bits, my);
+            atomicMax(&new_slot->ex_bits, widen_bits(mx));
+            atomicMax(&new_slot->ey_bits, widen_bits(my));
         }
     }
     if (!kGuard) {
@@ -1051,8 +1132,9 @@ __global__ void gather_kernel(const __grid_constant__ Params p)
 // ------------------------------------------------------------------------------------
 // K0: CFL maxima over the FULL ghosted initial state (numpy.py:503-521), into slot 0.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) cfl_init_kernel(const double *__restrict__ H, const double *__restrict__ U,
-                                                       const double *__restrict__ V, int ncols, int jl0, int jl1,
+template <typename T>
+__global__ void __launch_bounds__(256) cfl_init_kernel(const T *__restrict__ H, const T *__restrict__ U,
+                                                       const T *__restrict__ V, int ncols, int jl0, int jl1,
                                                        int pitch, double g, Ctrl *slot)
 {
     unsigned long long mx = 0ULL, my = 0ULL;
@@ -1060,7 +1142,7 @@ __global__ void __launch_bounds__(256) cfl_init_kernel(const double *__restrict_
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
         const int jl = jl0 + (int)(k / ncols), i = (int)(k % ncols);
         const size_t a = (size_t)jl * pitch + i;
-        const double cs = __dsqrt_rn(__dmul_rn(g, fabs(H[a])));
+        const double cs = __dsqrt_rn(__dmul_rn(g, fabs((double)H[a])));
         // the reference's three-way maximum, evaluated literally for step 1
         const double u = U[a], v = V[a];
         const unsigned long long bx0 = nonneg_bits(__dsub_rn(u, cs)), bx1 = nonneg_bits(u), bx2 = nonneg_bits(__dadd_rn(u, cs));
@@ -1080,7 +1162,8 @@ __global__ void __launch_bounds__(256) cfl_init_kernel(const double *__restrict_
 }
 
 // K5: max sqrt(u*u + v*v) over the full state (numpy.py:553-554).
-__global__ void __launch_bounds__(256) max_speed_kernel(const double *__restrict__ U, const double *__restrict__ V,
+template <typename T>
+__global__ void __launch_bounds__(256) max_speed_kernel(const T *__restrict__ U, const T *__restrict__ V,
                                                         int ncols, int jl0, int jl1, int pitch, unsigned long long *out)
 {
     unsigned long long m = 0ULL;
@@ -1088,7 +1171,8 @@ __global__ void __launch_bounds__(256) max_speed_kernel(const double *__restrict
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
         const int jl = jl0 + (int)(k / ncols), i = (int)(k % ncols);
         const size_t a = (size_t)jl * pitch + i;
-        const double s = __dsqrt_rn(__dadd_rn(__dmul_rn(U[a], U[a]), __dmul_rn(V[a], V[a])));
+        const double uu = U[a], vv = V[a];
+        const double s = __dsqrt_rn(__dadd_rn(__dmul_rn(uu, uu), __dmul_rn(vv, vv)));
         m = umax64(m, nonneg_bits(s));
     }
 #pragma unroll
@@ -1103,7 +1187,7 @@ __global__ void __launch_bounds__(128) laplacian_kernel(const double *__restrict
     const int jl = p.jl_first + blockIdx.y;
     if (jl > p.jl_last || i > p.M + 1) return;
     using O = Op<true>;
-    const Star s = load_star(q, p.pitch, p.nrows, p.M, jl, i);
+    const Star<double> s = load_star(q, p.pitch, p.nrows, p.M, jl, i);
     const W3 wy = y_weights(p.tab, p.nrows, jl);
     const W3 wx = x_weights_strict(p.phi, p.tab[(size_t)T_AC * p.nrows + jl], i, p.M);
     out[(size_t)jl * p.pitch + i] = O::add(second_diff_strict(wx, s.xmm, s.xm, s.q0, s.xp, s.xpp),
@@ -1112,9 +1196,11 @@ __global__ void __launch_bounds__(128) laplacian_kernel(const double *__restrict
 
 // K4: layout conversion between the reference's (M+3, n) array (latitude contiguous) and
 // the device layout (n, pitch) (longitude contiguous): a tiled transpose through shared
-// memory, both sides coalesced.  dst[r][c] = src[c][r] for r < rows, c < cols.
-__global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict__ src, int src_pitch,
-                                                        double *__restrict__ dst, int dst_pitch, int rows, int cols)
+// memory, both sides coalesced.  dst[r][c] = src[c][r] for r < rows, c < cols; converts between
+// the reference's float64 and the state type on the way.
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) transpose_kernel(const TS *__restrict__ src, int src_pitch,
+                                                        TD *__restrict__ dst, int dst_pitch, int rows, int cols)
 {
     __shared__ double tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
@@ -1128,7 +1214,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double *__restrict
 #pragma unroll
     for (int k = 0; k < 32; k += 8) {
         const int r = r0 + ty + k, c = c0 + tx;
-        if (r < rows && c < cols) dst[(size_t)r * dst_pitch + c] = tile[tx][ty + k];
+        if (r < rows && c < cols) dst[(size_t)r * dst_pitch + c] = (TD)tile[tx][ty + k];
     }
 }
 

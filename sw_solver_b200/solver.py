@@ -24,7 +24,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MODES, SwbConfig, SwbError, SwbStatus, SwbTables, check
+from ._lib import DTYPES, MODES, SwbConfig, SwbError, SwbStatus, SwbTables, check
 from .grid import CartesianGrid, LatLonGrid
 from .ic import ICType, coriolis_latitude, get_initial_conditions
 from .utils import EARTH_CONSTANTS, FloatArray2D, FloatT
@@ -151,10 +151,17 @@ class Stepper:
     def __init__(self, latlon_grid: LatLonGrid, cart_grid: CartesianGrid, h, u, v, f, hs=None, *,
                  courant: float, final_time: float, use_diffusion: bool = True, mode: Optional[str] = None,
                  device=None, log_capacity: int = 0, band: Optional[Dict[str, int]] = None, world: int = 1,
-                 layout: str = "reference"):
+                 layout: str = "reference", dtype: str = "float64"):
         mode = DEFAULT_MODE if mode is None else mode
         if mode not in MODES:
             raise ValueError(f"mode must be one of {sorted(MODES)}, got {mode!r}")
+        dtype = {"f64": "float64", "f32": "float32"}.get(str(dtype), str(dtype)).replace("torch.", "")
+        if dtype not in DTYPES:
+            raise ValueError(f"dtype must be 'float64' or 'float32', got {dtype!r}")
+        if dtype == "float32" and mode == "strict":
+            raise ValueError("the fp32 mode has no strict (bit-exact float64) arithmetic; use mode='fast'")
+        self.dtype = dtype
+        self._tdtype = torch.float64 if dtype == "float64" else torch.float32
         if layout not in ("reference", "device"):
             raise ValueError("layout must be 'reference' or 'device'")
         self.lib = _lib.load()
@@ -174,10 +181,10 @@ class Stepper:
         self._peer_bases: List[int] = []
 
         # Device layout: latitude-major (n_local, pitch), longitude contiguous (include/swb200.h)
-        self.pitch = int(self.lib.swb_required_pitch(M))
+        self.pitch = int(self.lib.swb_required_pitch(M, DTYPES[dtype]))
         if self.pitch <= 0:
             raise ValueError(f"bad grid size M={M}")
-        self._raw = torch.zeros((2, 3, self.n_local, self.pitch), dtype=torch.float64, device=self.device)
+        self._raw = torch.zeros((2, 3, self.n_local, self.pitch), dtype=self._tdtype, device=self.device)
         #: (2, 3, M+3, n_local) view of the two buffer sets in the reference's index order
         self.buf = self._raw[..., : M + 3].transpose(-1, -2)
 
@@ -200,7 +207,7 @@ class Stepper:
         cfg.M, cfg.N = M, N
         cfg.j_begin, cfg.n_local = self.j_begin, self.n_local
         cfg.j_first, cfg.j_last, cfg.pitch = int(band["j_first"]), int(band["j_last"]), self.pitch
-        cfg.dtype, cfg.mode = _lib.SWB_F64, MODES[mode]
+        cfg.dtype, cfg.mode = DTYPES[dtype], MODES[mode]
         cfg.use_diffusion = int(self.use_diffusion)
         cfg.f_is_2d = int(f_lat is None)
         cfg.has_hs = int(not hs_flat)
@@ -239,11 +246,11 @@ class Stepper:
         """Bring one field into the device layout (``dst`` or a fresh (n_local, pitch) array)."""
         M, nl = self.M, self.n_local
         if dst is None:
-            dst = torch.zeros((nl, self.pitch), dtype=torch.float64, device=self.device)
+            dst = torch.zeros((nl, self.pitch), dtype=self._tdtype, device=self.device)
         if self._layout == "device":
             if not (isinstance(q, torch.Tensor) and q.is_cuda and tuple(q.shape) == (nl, M + 3) and q.dtype == torch.float64):
                 raise ValueError(f"layout='device' expects float64 CUDA tensors of shape {(nl, M + 3)}")
-            dst[:, : M + 3].copy_(q)
+            dst[:, : M + 3].copy_(q)  # rounds to the state type in the fp32 mode
             return dst
         t = q if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64))
         if t.dtype != torch.float64 or t.ndim != 2 or t.shape[0] != M + 3 or t.shape[1] not in (self.N, nl):
@@ -360,7 +367,7 @@ class Stepper:
     def buffer_addresses(self, base: Optional[int] = None) -> List[int]:
         """Addresses of h0,u0,v0,h1,u1,v1 (optionally relative to another mapping's base)."""
         b = self._raw.data_ptr() if base is None else base
-        stride = self.n_local * self.pitch * 8
+        stride = self.n_local * self.pitch * self._raw.element_size()
         return [b + (s * 3 + k) * stride for s in (0, 1) for k in range(3)]
 
     def link(self, exchange_blocks: List[int], south: Optional[Dict[str, Any]], north: Optional[Dict[str, Any]]):
@@ -513,7 +520,7 @@ def _read_status(pinned: torch.Tensor) -> SwbStatus:
 
 def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, courant: float,
           use_diffusion: bool = True, save_data: Optional[Dict[str, Any]] = None, print_interval: int = -1, *,
-          mode: Optional[str] = None, device=None, batch_steps: int = 512
+          mode: Optional[str] = None, device=None, batch_steps: int = 512, dtype: str = "float64"
           ) -> Tuple[FloatArray2D, FloatArray2D, FloatArray2D]:
     """Drop-in for ``sw_solver.numpy.solve`` (numpy.py:409-575) on a B200.
 
@@ -522,8 +529,10 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
     order (grid ValueError, negative ``sim_days`` ValueError, non-``ICType`` TypeError).
     Returns the full ghosted (M+3, N) float64 arrays h, u, v as numpy arrays.
 
-    Backend-only keywords: ``mode`` ("fast" | "strict"), ``device``, ``batch_steps`` (how
-    many steps are enqueued between two non-blocking termination checks).
+    Backend-only keywords: ``mode`` ("fast" | "fast_guarded" | "strict"), ``device``,
+    ``batch_steps`` (how many steps are enqueued between two non-blocking termination
+    checks), ``dtype`` ("float64" | "float32": the optional fp32 state; results are still
+    returned as float64 arrays, within 1e-5 of the reference over benchmark-length runs).
     """
     save_data = save_data if save_data is not None else {}
 
@@ -546,7 +555,7 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
 
     save_interval = int(save_data.get("interval", 0))
     st = Stepper(latlon_grid, cart_grid, h, u, v, f, None, courant=courant, final_time=final_time,
-                 use_diffusion=use_diffusion, mode=mode, device=dev)
+                 use_diffusion=use_diffusion, mode=mode, device=dev, dtype=dtype)
     try:
         st.cfl_init()
         snaps: List[torch.Tensor] = []   # pinned (3, M+1, N) host copies, one per save point

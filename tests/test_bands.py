@@ -86,13 +86,13 @@ def test_gloo_world2_band_record_exchange(tmp_path):
 # --------------------------------------------------------------------------------------
 # GPU: several bands on one device
 # --------------------------------------------------------------------------------------
-def _run_bands(M, N, ic, diff, mode, world, nsteps):
+def _run_bands(M, N, ic, diff, mode, world, nsteps, dtype="float64"):
     from sw_solver_b200.solver import Stepper, link_local
 
     ll = LatLonGrid(M, N)
     cg = CartesianGrid(ll)
     h, u, v, f = get_initial_conditions(ICType(ic), ll)
-    kw = dict(courant=0.5, final_time=1e9, use_diffusion=diff, mode=mode)
+    kw = dict(courant=0.5, final_time=1e9, use_diffusion=diff, mode=mode, dtype=dtype)
     one = Stepper(ll, cg, h, u, v, f, None, **kw)
     one.enqueue(nsteps)
     ref = one.to_numpy()
@@ -126,14 +126,16 @@ def _run_bands(M, N, ic, diff, mode, world, nsteps):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("M,N,ic,diff,mode,world,nsteps", [
-    (96, 64, 0, False, "strict", 2, 12),
-    (96, 64, 0, True, "strict", 3, 12),
-    (200, 130, 1, True, "fast", 4, 10),     # 2-D Coriolis, ragged band sizes
-    (360, 180, 0, False, "fast", 8, 25),    # the TMA kernel on every band
+@pytest.mark.parametrize("M,N,ic,diff,mode,world,nsteps,dtype", [
+    (96, 64, 0, False, "strict", 2, 12, "float64"),
+    (96, 64, 0, True, "strict", 3, 12, "float64"),
+    (200, 130, 1, True, "fast", 4, 10, "float64"),     # 2-D Coriolis, ragged band sizes
+    (360, 180, 0, False, "fast", 8, 25, "float64"),    # the TMA kernel on every band
+    (360, 180, 0, False, "fast", 4, 25, "float32"),    # fp32 state, TMA kernel
+    (200, 130, 0, True, "fast", 3, 10, "float32"),     # fp32 state, diffusion
 ])
-def test_bands_are_bit_identical_to_one_band(M, N, ic, diff, mode, world, nsteps):
-    ref, out, s_ref, stats = _run_bands(M, N, ic, diff, mode, world, nsteps)
+def test_bands_are_bit_identical_to_one_band(M, N, ic, diff, mode, world, nsteps, dtype):
+    ref, out, s_ref, stats = _run_bands(M, N, ic, diff, mode, world, nsteps, dtype)
     for s in stats:
         assert s.steps == s_ref.steps == nsteps and s.time == s_ref.time and s.error == 0
     # a band's status carries the CFL maxima of ITS rows; their maximum is the global one

@@ -371,3 +371,52 @@ def test_headline_grid_properties():
     hg, ug, vg = st.to_numpy()
     assert st.status().time == t and _bits(hg, h) and _bits(ug, u) and _bits(vg, v)
     st.close()
+
+
+TOL_FP32 = 1e-5  # north-star tolerance of the optional fp32 mode
+
+
+@pytest.mark.parametrize("M,N,diff,nsteps", [(360, 180, False, 100), (1440, 720, True, 20), (333, 97, True, 30)])
+def test_fp32_mode_against_oracle(M, N, diff, nsteps):
+    """The optional fp32 state (FAST arithmetic, metric / dt factors formed in fp64): within
+    1e-5 (normwise) of the fp64 oracle, dt history included."""
+    og = so.OracleGrid(M, N)
+    h, u, v, f = so.initial_conditions(0, og)
+    h, u, v = (np.ascontiguousarray(x) for x in (h, u, v))
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=1e9, use_diffusion=diff, mode="fast",
+                 dtype="float32", log_capacity=nsteps)
+    stp = so.Stepper(og, f, None, diff)
+    t, dts = 0.0, []
+    for _ in range(nsteps):
+        dt, t = stp.step(h, u, v, 0.5, t, 1e9)
+        dts.append(dt)
+    st.enqueue(nsteps)
+    s = st.status()
+    assert s.steps == nsteps and s.error == 0
+    assert st.state()[0].dtype == torch.float32
+    hg, ug, vg = st.to_numpy()
+    gdts, _ = st.read_log(nsteps)
+    st.close()
+    assert hg.dtype == np.float64
+    assert normwise(gdts, np.asarray(dts)) < TOL_FP32 and abs(s.time - t) < TOL_FP32 * t
+    for name, a, b in (("h", hg, h), ("u", ug, u), ("v", vg, v)):
+        assert normwise(a, b) < TOL_FP32, (name, normwise(a, b))
+    # boundary conditions hold exactly in the stored state
+    for q in (hg, ug, vg):
+        assert np.array_equal(q[0, 1:-1], q[M, 1:-1]) and np.array_equal(q[M + 2, 1:-1], q[2, 1:-1])
+        assert np.array_equal(q[:, 0], q[:, 1]) and np.array_equal(q[:, -1], q[:, -2])
+
+
+def test_fp32_mode_driver_and_limits(golden_ref10):
+    sd = {"interval": 392}
+    solve(10, 10, ICType.RossbyHaurwitzWave, 2, 0.5, True, save_data=sd, dtype="float32")
+    for name in ("h", "u", "v"):
+        assert sd[name].shape == golden_ref10[name].shape and sd[name].dtype == np.float64
+        assert normwise(sd[name], golden_ref10[name]) < 5e-5, (name, normwise(sd[name], golden_ref10[name]))  # 392 steps
+    assert abs(sd["t"][-1] - golden_ref10["t"][-1]) < 1e-3
+    with pytest.raises(ValueError):
+        solve(10, 10, ICType.RossbyHaurwitzWave, 0.1, 0.5, dtype="float32", mode="strict")
+    with pytest.raises(swb.solver.SwbError):  # 2-D Coriolis needs the fp64 kernels
+        solve(10, 10, ICType.ZonalGeostrophicFlow, 0.1, 0.5, dtype="float32")

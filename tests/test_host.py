@@ -159,7 +159,7 @@ def test_no_cpu_fallback():
     L = _lib.load()
     cfg = _lib.SwbConfig()
     cfg.struct_bytes = ctypes.sizeof(cfg)
-    cfg.M, cfg.N, cfg.n_local, cfg.pitch, cfg.j_first, cfg.j_last, cfg.world = 10, 10, 10, L.swb_required_pitch(10), 1, 8, 1
+    cfg.M, cfg.N, cfg.n_local, cfg.pitch, cfg.j_first, cfg.j_last, cfg.world = 10, 10, 10, L.swb_required_pitch(10, 0), 1, 8, 1
     ctx = ctypes.c_void_p()
     assert L.swb_create(ctypes.byref(ctx), ctypes.byref(cfg)) == -3
     assert b"no CUDA device" in L.swb_last_error()
