@@ -69,6 +69,7 @@ struct swb_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     bool use_tma = false;
+    bool cfl_filter = false;  // march_kernel<..., CFLF> + cfl_fixup_kernel (fp64 FAST, large grids)
     int tma_variant = 0;  // index into kTmaVariants (fp64) / kTmaVariantsF32
     TmaMaps maps;
 };
@@ -82,13 +83,14 @@ constexpr TmaVariant kTmaVariants[] = {{2, 4, 3, 4}, {4, 2, 3, 4}, {2, 3, 3, 4},
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 constexpr int kDefaultTmaVariant = 5;  // R = 4, S = 4, two blocks per SM: no spills (1.26 ms/step at 16384 x 8192)
 
-template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
+template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
+          bool CFLF = false>
 cudaError_t launch_inst(const swb_ctx *c, dim3 grid, cudaStream_t st)
 {
     using LY = TmaLayout<R, S, T>;
     const int smem = rec_bytes(c->prm.chunk, DIFF) + (TMA ? W * LY::kWarpBytes : 0);
     static int configured[64] = {0};  // per instantiation and device: largest size opted in so far
-    auto fn = march_kernel<T, STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, MINB, W>;
+    auto fn = march_kernel<T, STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, MINB, W, CFLF>;
     const int dev = c->cfg.device & 63;
     if (configured[dev] < smem) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -131,6 +133,10 @@ cudaError_t launch_tma_rs(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 }
 cudaError_t launch_tma(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
+    if (c->cfl_filter) {  // default ring shape only
+        if (mode == SWB_FAST) return launch_inst<double, false, false, false, false, true, 4, 4, false, 2, kWarpsPerBlock, true>(c, g, st);
+        return launch_inst<double, false, false, false, false, true, 4, 4, true, 2, kWarpsPerBlock, true>(c, g, st);
+    }
     switch (c->tma_variant) {
         case 0: return launch_tma_rs<2, 4, 3>(c, mode, g, st);
         case 1: return launch_tma_rs<4, 2, 3>(c, mode, g, st);
@@ -199,6 +205,11 @@ int launch_one(swb_ctx *c, cudaStream_t st)
     }
     c->launches++;
     CK(cudaGetLastError());
+    if (c->cfl_filter && !p.fixed) {  // returns at once unless the filter found no valid maximum
+        cfl_fixup_kernel<<<c->sm_count * 4, 256, 0, st>>>(p);
+        c->launches++;
+        CK(cudaGetLastError());
+    }
     if (c->linked && !p.fixed) {
         publish_kernel<<<1, 32, 0, st>>>(p);
         c->launches++;
@@ -413,6 +424,7 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     const char *force = getenv("SWB_KERNEL");
     const bool plain = !c->cfg.use_diffusion && !c->cfg.f_is_2d && !c->cfg.has_hs;
     c->use_tma = plain && !(force && strcmp(force, "ldg") == 0);
+    c->cfl_filter = false;
     if (force && strcmp(force, "tma") == 0 && !c->use_tma) return fail(SWB_E_INVALID, "SWB_KERNEL=tma but this configuration cannot use the TMA kernel");
     if (c->use_tma) {
         const bool f32 = c->cfg.dtype == SWB_F32;
@@ -420,6 +432,11 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
         c->tma_variant = v ? atoi(v) : (f32 ? kDefaultTmaVariantF32 : kDefaultTmaVariant);
         if (c->tma_variant < 0 || c->tma_variant >= (f32 ? kNumTmaVariantsF32 : kNumTmaVariants)) return fail(SWB_E_INVALID, "bad SWB_TMA_VARIANT");
         const TmaVariant tv = f32 ? kTmaVariantsF32[c->tma_variant] : kTmaVariants[c->tma_variant];
+        // CFL filter: worth its extra (normally empty) launch per step on grids whose step takes
+        // far longer than a launch; SWB_CFL_FILTER=0/1 overrides
+        const long long cells = (long long)(p.M + 1) * (p.jl_last - p.jl_first + 1);
+        c->cfl_filter = !f32 && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && cells >= 4000000LL;
+        if (const char *e = getenv("SWB_CFL_FILTER")) c->cfl_filter = !f32 && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && atoi(e) != 0;
         CK(cudaSetDevice(c->cfg.device));
         for (int s = 0; s < 2; ++s)
             for (int k = 0; k < 3; ++k) {

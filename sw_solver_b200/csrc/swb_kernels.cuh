@@ -530,6 +530,7 @@ __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int
         Ctrl *const clr_slot = p.ctrl + ((p.launch + 2) % 3);
         clr_slot->ex_bits = 0ULL;
         clr_slot->ey_bits = 0ULL;
+        clr_slot->reserved = 0;  // found-mask of the CFL filter (march_kernel<..., CFLF>)
         new_slot->time = tnew;
         new_slot->nsteps = nsteps + (active ? 1 : 0);
         new_slot->current = (int)((nsteps + (active ? 1 : 0)) & 1);
@@ -539,6 +540,7 @@ __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int
         if (!active) {  // nothing will be accumulated: carry the maxima forward
             new_slot->ex_bits = exb;
             new_slot->ey_bits = eyb;
+            new_slot->reserved = 3;
         } else if (p.log != nullptr && nsteps < (long long)p.log_cap) {
             p.log[nsteps] = dt;
             p.log[(size_t)p.log_cap + nsteps] = tnew;
@@ -697,6 +699,51 @@ __device__ __forceinline__ void st_pair(float *addr, float a, float b, int both,
 }
 
 
+// |u| + sqrt(g|h|) and |v| + sqrt(g|h|) of one cell as ordering keys (FAST arithmetic)
+template <typename T>
+__device__ __forceinline__ void cfl_keys_fast(T h, T u, T v, T g, bits_t<T> &kx, bits_t<T> &ky)
+{
+    const T cs = fast_sqrt(g * fabs(h));
+    kx = nonneg_bits(fabs(u) + cs);
+    ky = nonneg_bits(fabs(v) + cs);
+}
+
+// CFL filter (fp64 FAST, large grids).  The exact keys above cost 10 FP64-pipe instructions
+// per cell; all the step needs is their MAXIMUM, which moves by ~1e-5 per step.  So every
+// cell first forms a cheap estimate -- the MUFU.RSQ64H seed instead of the refined root, 4
+// instructions -- and only cells whose estimate reaches the trigger threshold (the band's
+// previous maximum less 2^-9) are evaluated exactly, from the values just stored.  A result
+// counts only if it reaches the validity threshold (previous maximum less 2^-10): every
+// cell at or above it is guaranteed to trigger (the seed errs by < 2^-20), so the maximum
+// found is the exact one.  If nothing valid was found -- the maximum fell by more than
+// 2^-10 within one step -- `cfl_fixup_kernel` recomputes it over the whole band.
+struct CflFilter {
+    int trig_x, trig_y;                  // hi words of the trigger thresholds
+    unsigned long long valid_x, valid_y; // validity thresholds (bit patterns)
+};
+__device__ __forceinline__ CflFilter make_cfl_filter(unsigned long long exb, unsigned long long eyb)
+{
+    CflFilter f;
+    const double ex = __longlong_as_double((long long)exb), ey = __longlong_as_double((long long)eyb);
+    auto trig = [](double m) {
+        const double t = m * (1.0 - 1.0 / 512.0);
+        return (t > 0.0 && t < 1e300) ? __double2hiint(t) : 0;  // unknown / non-finite: everything triggers
+    };
+    auto valid = [](double m) {
+        const double t = m * (1.0 - 1.0 / 1024.0);
+        return (t > 0.0 && t < 1e300) ? (unsigned long long)__double_as_longlong(t) : 0ULL;
+    };
+    f.trig_x = trig(ex); f.trig_y = trig(ey);
+    f.valid_x = valid(ex); f.valid_y = valid(ey);
+    return f;
+}
+__device__ __forceinline__ double rsqrt_seed(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
 // ------------------------------------------------------------------------------------
 // the fused step kernel
 // ------------------------------------------------------------------------------------
@@ -704,11 +751,13 @@ __device__ __forceinline__ void st_pair(float *addr, float a, float b, int both,
 // TMA ring (R latitudes per box, S stages) or direct loads, and whether FAST evaluates the
 // reference's hMid > 0 selects (GUARD) or assumes them true and raises SWB_E_DEPTH when a
 // half-step depth turns out non-positive.
-template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
+template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
+          bool CFLF = false>
 __global__ void __launch_bounds__(W * 32, MINB)
 march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
 {
     static_assert(!STRICT || sizeof(T) == 8, "STRICT reproduces numpy's float64 arithmetic");
+    static_assert(!CFLF || (!STRICT && TMA && sizeof(T) == 8), "the CFL filter serves the fp64 FAST TMA kernel");
     using O = Op<STRICT, T>;
     using LY = TmaLayout<R, S, T>;
     using V2 = vec2_t<T>;
@@ -717,7 +766,21 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ double s_dt;
     __shared__ int s_flags;
-    if (threadIdx.x == 0) step_prologue(p, &s_dt, &s_flags);
+    __shared__ CflFilter s_filter;
+    if (threadIdx.x == 0) {
+        step_prologue(p, &s_dt, &s_flags);
+        if (CFLF) {
+            // thresholds from THIS band's maxima of the current state (with several bands the
+            // slot holds the global maxima; the band's own live in its exchange block)
+            const Ctrl *cur_slot = p.ctrl + (p.launch % 3);
+            unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
+            if (p.world > 1) {
+                exb = p.xlocal->slot[p.launch % 3][p.rank].ex_bits;
+                eyb = p.xlocal->slot[p.launch % 3][p.rank].ey_bits;
+            }
+            s_filter = p.fixed ? make_cfl_filter(0ULL, 0ULL) : make_cfl_filter(exb, eyb);
+        }
+    }
     __syncthreads();
     const int flags = s_flags;
     if (!(flags & 1)) return;
@@ -804,6 +867,8 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     const bool warp_wraps = __any_sync(0xffffffffu, wrapA || wrapB);
     const int st_both = (vA && vB) ? 1 : 0, st_onlyA = (vA && !vB) ? 1 : 0, st_onlyB = (vB && !vA) ? 1 : 0;
     bits_t<T> mxA = 0, myA = 0, mxB = 0, myB = 0;  // running CFL maxima (bit patterns)
+    const int trig_x = CFLF ? s_filter.trig_x : 0, trig_y = CFLF ? s_filter.trig_y : 0;
+    bool trig = false;  // CFLF: some cell of the current tile reached a trigger threshold
     int negA = 0, negB = 0;  // sign watch of the half-step depths (FAST without GUARD)
 
     auto rec_of = [&](int jl) { return rowc + (size_t)(jl - (ja - 1)) * kRowRec; };
@@ -947,15 +1012,30 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
         }
 
         // CFL maxima of the new state: max(|q-c|, |q|, |q+c|) == |q| + c for c >= 0
-        if (HOT || live) {
-            const T csA = STRICT ? (T)__dsqrt_rn(O::mul(g_, fabs(hnA))) : fast_sqrt(g_ * fabs(hnA));
-            const T csB = STRICT ? (T)__dsqrt_rn(O::mul(g_, fabs(hnB))) : fast_sqrt(g_ * fabs(hnB));
-            mxA = umax64(mxA, nonneg_bits(O::add(fabs(unA), csA))); myA = umax64(myA, nonneg_bits(O::add(fabs(vnA), csA)));
-            mxB = umax64(mxB, nonneg_bits(O::add(fabs(unB), csB))); myB = umax64(myB, nonneg_bits(O::add(fabs(vnB), csB)));
-            if (!kGuard) {
-                negA |= hi_word(xAB.hM) | hi_word(y1A.hM) | hi_word(hnA);
-                negB |= hi_word(xBN.hM) | hi_word(y1B.hM) | hi_word(hnB);
+        if (CFLF && HOT) {
+            // estimate only; tiles in which an estimate reaches the trigger threshold are
+            // re-evaluated exactly after their last row (see CflFilter)
+            const T xA = g_ * fabs(hnA), xB = g_ * fabs(hnB);
+            const T cA = xA * (T)rsqrt_seed((double)xA), cB = xB * (T)rsqrt_seed((double)xB);
+            // (bitwise | on purpose: no short-circuit branches inside the hot tile)
+            trig = trig | ((hi_word(fabs(unA) + cA) & 0x7fffffff) >= trig_x) | ((hi_word(fabs(vnA) + cA) & 0x7fffffff) >= trig_y) |
+                   ((hi_word(fabs(unB) + cB) & 0x7fffffff) >= trig_x) | ((hi_word(fabs(vnB) + cB) & 0x7fffffff) >= trig_y);
+        } else if (HOT || live) {
+            bits_t<T> kxA, kyA, kxB, kyB;
+            if (STRICT) {
+                const T csA = (T)__dsqrt_rn(O::mul(g_, fabs(hnA))), csB = (T)__dsqrt_rn(O::mul(g_, fabs(hnB)));
+                kxA = nonneg_bits(O::add(fabs(unA), csA)); kyA = nonneg_bits(O::add(fabs(vnA), csA));
+                kxB = nonneg_bits(O::add(fabs(unB), csB)); kyB = nonneg_bits(O::add(fabs(vnB), csB));
+            } else {
+                cfl_keys_fast(hnA, unA, vnA, g_, kxA, kyA);
+                cfl_keys_fast(hnB, unB, vnB, g_, kxB, kyB);
             }
+            mxA = umax64(mxA, kxA); myA = umax64(myA, kyA);
+            mxB = umax64(mxB, kxB); myB = umax64(myB, kyB);
+        }
+        if (!kGuard && (HOT || live)) {
+            negA |= hi_word(xAB.hM) | hi_word(y1A.hM) | hi_word(hnA);
+            negB |= hi_word(xBN.hM) | hi_word(y1B.hM) | hi_word(hnB);
         }
 
         // stores: the pair is 16-byte aligned; the strip's first and last column are not ours
@@ -1030,6 +1110,21 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr)
                     do_row(HotTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true);
+                if (CFLF) {
+                    if (__any_sync(0xffffffffu, trig)) {  // rare: exact keys of the tile's cells, from the values just stored
+#pragma unroll 1
+                        for (int rr = 0; rr < R; ++rr) {
+                            const size_t k = (size_t)(j0 + rr) * P + colA;
+                            const V2 hh = ldg2(Hn + k), uu = ldg2(Un + k), vv = ldg2(Vn + k);
+                            bits_t<T> kxA, kyA, kxB, kyB;
+                            cfl_keys_fast(hh.x, uu.x, vv.x, g_, kxA, kyA);
+                            cfl_keys_fast(hh.y, uu.y, vv.y, g_, kxB, kyB);
+                            mxA = umax64(mxA, kxA); myA = umax64(myA, kyA);
+                            mxB = umax64(mxB, kxB); myB = umax64(myB, kyB);
+                        }
+                    }
+                    trig = false;
+                }
             } else {
 #pragma unroll 1
                 for (int rr = 0; rr < R; ++rr)
@@ -1058,8 +1153,17 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
         }
         if (lane == 0) {
             Ctrl *const new_slot = p.ctrl + ((p.launch + 1) % 3);
-            atomicMax(&new_slot->ex_bits, widen_bits(mx));
-            atomicMax(&new_slot->ey_bits, widen_bits(my));
+            if (CFLF) {
+                // most warps hold nothing: their cells stayed below the trigger threshold
+                const unsigned long long wx = widen_bits(mx), wy = widen_bits(my);
+                if (wx != 0ULL) atomicMax(&new_slot->ex_bits, wx);
+                if (wy != 0ULL) atomicMax(&new_slot->ey_bits, wy);
+                const int found = (wx >= s_filter.valid_x && wx != 0ULL ? 1 : 0) | (wy >= s_filter.valid_y && wy != 0ULL ? 2 : 0);
+                if (found) atomicOr(&new_slot->reserved, found);
+            } else {
+                atomicMax(&new_slot->ex_bits, widen_bits(mx));
+                atomicMax(&new_slot->ey_bits, widen_bits(my));
+            }
         }
     }
     if (!kGuard) {
@@ -1126,6 +1230,40 @@ __global__ void gather_kernel(const __grid_constant__ Params p)
         Ctrl *cur_slot = p.ctrl + (p.launch % 3);
         cur_slot->ex_bits = ex;
         cur_slot->ey_bits = ey;
+    }
+}
+
+// CFL filter fix-up (after a step kernel with CFLF, in stream order): nothing to do when both
+// maxima were found valid (the normal case: every block reads the mask and returns);
+// otherwise the exact keys of every updated cell of the band, with the arithmetic of the
+// step kernel.  Ghost columns and pole rows are copies of updated cells.
+__global__ void __launch_bounds__(256) cfl_fixup_kernel(const __grid_constant__ Params p)
+{
+    Ctrl *new_slot = p.ctrl + ((p.launch + 1) % 3);
+    if ((new_slot->reserved & 3) == 3) return;
+    const int cur = new_slot->current;
+    const double *__restrict__ H = (const double *)p.buf[cur][0];
+    const double *__restrict__ U = (const double *)p.buf[cur][1];
+    const double *__restrict__ V = (const double *)p.buf[cur][2];
+    unsigned long long mx = 0ULL, my = 0ULL;
+    const int ncols = p.M + 1, nrows = p.jl_last - p.jl_first + 1;
+    const long long total = (long long)nrows * ncols;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+        const int jl = p.jl_first + (int)(k / ncols), i = 1 + (int)(k % ncols);
+        const size_t a = (size_t)jl * p.pitch + i;
+        unsigned long long kx, ky;
+        cfl_keys_fast(H[a], U[a], V[a], p.g, kx, ky);
+        mx = umax64(mx, kx);
+        my = umax64(my, ky);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        mx = umax64(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        my = umax64(my, __shfl_xor_sync(0xffffffffu, my, s));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&new_slot->ex_bits, mx);
+        atomicMax(&new_slot->ey_bits, my);
     }
 }
 

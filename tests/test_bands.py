@@ -133,8 +133,12 @@ def _run_bands(M, N, ic, diff, mode, world, nsteps, dtype="float64"):
     (360, 180, 0, False, "fast", 8, 25, "float64"),    # the TMA kernel on every band
     (360, 180, 0, False, "fast", 4, 25, "float32"),    # fp32 state, TMA kernel
     (200, 130, 0, True, "fast", 3, 10, "float32"),     # fp32 state, diffusion
+    (360, 180, 0, False, "fast+cflf", 5, 25, "float64"),  # CFL filter forced on: per-band thresholds
 ])
-def test_bands_are_bit_identical_to_one_band(M, N, ic, diff, mode, world, nsteps, dtype):
+def test_bands_are_bit_identical_to_one_band(M, N, ic, diff, mode, world, nsteps, dtype, monkeypatch):
+    if mode.endswith("+cflf"):
+        mode = mode.split("+")[0]
+        monkeypatch.setenv("SWB_CFL_FILTER", "1")
     ref, out, s_ref, stats = _run_bands(M, N, ic, diff, mode, world, nsteps, dtype)
     for s in stats:
         assert s.steps == s_ref.steps == nsteps and s.time == s_ref.time and s.error == 0

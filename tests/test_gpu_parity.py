@@ -420,3 +420,36 @@ def test_fp32_mode_driver_and_limits(golden_ref10):
         solve(10, 10, ICType.RossbyHaurwitzWave, 0.1, 0.5, dtype="float32", mode="strict")
     with pytest.raises(swb.solver.SwbError):  # 2-D Coriolis needs the fp64 kernels
         solve(10, 10, ICType.ZonalGeostrophicFlow, 0.1, 0.5, dtype="float32")
+
+
+def test_cfl_filter_is_exact(monkeypatch):
+    """The CFL filter (estimate every cell, evaluate exactly only near the previous maximum,
+    full fix-up pass when the maximum fell by more than 2^-10 in a step) must return the SAME
+    maxima as evaluating every cell: identical dt history and state, bit for bit.  A rough
+    random state makes the maxima jump both ways, so trigger, validity and fix-up paths all
+    run; the smooth wave covers the common path."""
+    rng = np.random.default_rng(7)
+    for M, N, rough, nsteps in ((200, 96, True, 30), (500, 260, False, 40)):
+        ll = LatLonGrid(M, N)
+        cg = CartesianGrid(ll)
+        h, u, v, f = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+        if rough:
+            h = h + 300.0 * rng.uniform(-1, 1, h.shape)
+            u = u + 30.0 * rng.standard_normal(u.shape)
+            v = v + 30.0 * rng.standard_normal(v.shape)
+        out = {}
+        for flag in ("0", "1"):
+            monkeypatch.setenv("SWB_CFL_FILTER", flag)
+            st = Stepper(ll, cg, h, u, v, f, None, courant=0.4, final_time=1e9, use_diffusion=False, mode="fast",
+                         log_capacity=nsteps)
+            st.enqueue(nsteps)
+            s = st.status()
+            assert s.steps == nsteps and s.error == 0
+            out[flag] = (st.to_numpy(), st.read_log(nsteps), s.time, st.launch_count)
+            st.close()
+        (q0, log0, t0, n0), (q1, log1, t1, n1) = out["0"], out["1"]
+        assert n1 > n0  # the filtered run really took the other kernel (+ fix-up launches)
+        assert _bits(log0[0], log1[0]) and _bits(log0[1], log1[1]) and t0 == t1
+        assert all(_bits(a, b) for a, b in zip(q0, q1))
+        if rough:
+            assert np.ptp(log0[0]) > 1e-3 * log0[0].mean()  # dt really moved: the maxima were not static
