@@ -247,14 +247,16 @@ int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_
     return 0;
 }
 
-// marching length: long enough to amortise the two-row start-up, short enough to fill
-// the machine with several waves of blocks.
+// Marching length.  A lone warp needs ~0.8 us per latitude (one long dependent chain), and a
+// march starts with two extra rows, so: the longest chunk (<= 64 rows: two blocks of records
+// + rings fit one SM) that still fills about one wave of blocks (2 per SM); small grids end
+// up with 2-row marches, large ones with 64 (measured).
 int pick_chunk(int rows, int nstrips, int sm_count)
 {
-    const long long want_blocks = (long long)sm_count * 3 * 4;  // >= 4 waves at 3 blocks/SM
+    const long long want_blocks = (long long)sm_count * 2 * 9 / 10;
     const int gx = (nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    int chunk = 64;  // with the default ring, two blocks of 64-row records + rings fit one SM
-    while (chunk > 4 && (long long)gx * ((rows + chunk - 1) / chunk) < want_blocks) chunk >>= 1;
+    int chunk = 64;
+    while (chunk > 2 && (long long)gx * ((rows + chunk - 1) / chunk) < want_blocks) chunk >>= 1;
     return chunk;
 }
 
@@ -345,9 +347,9 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     p.pole_n = (cfg->j_begin + cfg->n_local == cfg->N);
     p.nstrips = nstrips_of(p.M, cfg->dtype);
     p.chunk = pick_chunk(p.jl_last - p.jl_first + 1, p.nstrips, c->sm_count);
-    if (const char *ch = getenv("SWB_CHUNK")) {  // tuning knob: a power of two in [4, 128]
+    if (const char *ch = getenv("SWB_CHUNK")) {  // tuning knob: a power of two in [1, 128]
         const int v = atoi(ch);
-        if (v >= 4 && v <= kMaxChunk && (v & (v - 1)) == 0) p.chunk = v;
+        if (v >= 1 && v <= kMaxChunk && (v & (v - 1)) == 0) p.chunk = v;
     }
     p.courant = cfg->courant;
     p.final_time = cfg->final_time;
