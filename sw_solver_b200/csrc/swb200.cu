@@ -46,8 +46,8 @@ int nstrips_of(int M, int dtype) { return (M + 1 + valid_cols(dtype) - 1) / vali
 
 int required_pitch(int M, int dtype)
 {
-    // the last strip reads 64 columns (+2 for the topography differences); round to 16 elements
-    const int need = valid_cols(dtype) * (nstrips_of(M, dtype) - 1) + kStripCols + 2;
+    // the last strip reads 64 columns (+4 for the diffusion star / topography differences); round to 16 elements
+    const int need = valid_cols(dtype) * (nstrips_of(M, dtype) - 1) + kStripCols + 4;
     return (need + 15) / 16 * 16;
 }
 
@@ -78,10 +78,10 @@ namespace {
 
 // TMA ring shapes built into the library: {latitudes per box R, stages S}
 struct TmaVariant { int R, S, minb, W; };
-constexpr TmaVariant kTmaVariants[] = {{2, 4, 3, 4}, {4, 2, 3, 4}, {2, 3, 3, 4}, {4, 3, 2, 4}, {2, 4, 2, 4}, {4, 4, 2, 4},
-                                       {4, 3, 2, 5}, {2, 4, 2, 5}, {4, 2, 2, 6}, {2, 4, 2, 6}, {4, 4, 1, 8}};
+// (three blocks per SM -- 168 registers -- spill and lose 25-40 %)
+constexpr TmaVariant kTmaVariants[] = {{4, 4, 2, 4}, {4, 3, 2, 4}, {2, 4, 2, 4}, {4, 4, 1, 8}};
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
-constexpr int kDefaultTmaVariant = 5;  // R = 4, S = 4, two blocks per SM: no spills (1.26 ms/step at 16384 x 8192)
+constexpr int kDefaultTmaVariant = 0;  // R = 4, S = 4, two blocks per SM: no spills (1.26 ms/step at 16384 x 8192)
 
 template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
           bool CFLF = false>
@@ -137,17 +137,15 @@ cudaError_t launch_tma(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
         if (mode == SWB_FAST) return launch_inst<double, false, false, false, false, true, 4, 4, false, 2, kWarpsPerBlock, true>(c, g, st);
         return launch_inst<double, false, false, false, false, true, 4, 4, true, 2, kWarpsPerBlock, true>(c, g, st);
     }
+    if (c->cfg.use_diffusion) {  // the ring feeds the Lax-Wendroff stream; the diffusion star reads L2
+        if (mode == SWB_STRICT) return launch_inst<double, true, true, false, false, true, 4, 3, true, 2>(c, g, st);
+        if (mode == SWB_FAST) return launch_inst<double, false, true, false, false, true, 4, 3, false, 2>(c, g, st);
+        return launch_inst<double, false, true, false, false, true, 4, 3, true, 2>(c, g, st);
+    }
     switch (c->tma_variant) {
-        case 0: return launch_tma_rs<2, 4, 3>(c, mode, g, st);
-        case 1: return launch_tma_rs<4, 2, 3>(c, mode, g, st);
-        case 2: return launch_tma_rs<2, 3, 3>(c, mode, g, st);
-        case 3: return launch_tma_rs<4, 3, 2>(c, mode, g, st);
-        case 4: return launch_tma_rs<2, 4, 2>(c, mode, g, st);
-        case 5: return launch_tma_rs<4, 4, 2>(c, mode, g, st);
-        case 6: return launch_tma_rs<4, 3, 2, 5>(c, mode, g, st);
-        case 7: return launch_tma_rs<2, 4, 2, 5>(c, mode, g, st);
-        case 8: return launch_tma_rs<4, 2, 2, 6>(c, mode, g, st);
-        case 9: return launch_tma_rs<2, 4, 2, 6>(c, mode, g, st);
+        case 0: return launch_tma_rs<4, 4, 2>(c, mode, g, st);
+        case 1: return launch_tma_rs<4, 3, 2>(c, mode, g, st);
+        case 2: return launch_tma_rs<2, 4, 2>(c, mode, g, st);
         default: return launch_tma_rs<4, 4, 1, 8>(c, mode, g, st);
     }
 }
@@ -165,6 +163,10 @@ cudaError_t launch_tma_f32_rs(const swb_ctx *c, int mode, dim3 g, cudaStream_t s
 }
 cudaError_t launch_tma_f32(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
+    if (c->cfg.use_diffusion) {
+        if (mode == SWB_FAST) return launch_inst<float, false, true, false, false, true, 4, 3, false, 2>(c, g, st);
+        return launch_inst<float, false, true, false, false, true, 4, 3, true, 2>(c, g, st);
+    }
     switch (c->tma_variant) {
         case 0: return launch_tma_f32_rs<4, 4, 2>(c, mode, g, st);
         case 1: return launch_tma_f32_rs<4, 3, 3>(c, mode, g, st);
@@ -188,7 +190,7 @@ int launch_one(swb_ctx *c, cudaStream_t st)
     const Params &p = c->prm;
     const int rows = p.jl_last - p.jl_first + 1;
     const bool f32 = cfg.dtype == SWB_F32;
-    const int W = (c->use_tma && !f32) ? kTmaVariants[c->tma_variant].W : kWarpsPerBlock;
+    const int W = (c->use_tma && !f32 && !cfg.use_diffusion) ? kTmaVariants[c->tma_variant].W : kWarpsPerBlock;
     dim3 grid((unsigned)((p.nstrips + W - 1) / W), (unsigned)((rows + p.chunk - 1) / p.chunk));
     if (c->linked && !p.fixed) {  // the maxima of all bands' previous step -> this step's slot
         gather_kernel<<<1, 32, 0, st>>>(p);
@@ -351,6 +353,7 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
         const int v = atoi(ch);
         if (v >= 1 && v <= kMaxChunk && (v & (v - 1)) == 0) p.chunk = v;
     }
+    if (const char *fr = getenv("SWB_FORCE_RARE")) p.force_rare = atoi(fr) != 0;
     p.courant = cfg->courant;
     p.final_time = cfg->final_time;
     p.dxmin = cfg->dxmin;
@@ -420,12 +423,16 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     c->state_bound = true;
     c->cfl_ready = false;
 
-    // The TMA ring serves the plain variant (flat topography, latitude-only Coriolis, no
-    // diffusion); SWB_KERNEL=ldg forces the direct-load kernel, SWB_TMA_VARIANT picks a
-    // ring shape.
+    // The TMA ring serves flat topography with latitude-only Coriolis (with or without
+    // diffusion); SWB_KERNEL=ldg forces the direct-load kernel, SWB_TMA_VARIANT picks a ring
+    // shape.
     const char *force = getenv("SWB_KERNEL");
-    const bool plain = !c->cfg.use_diffusion && !c->cfg.f_is_2d && !c->cfg.has_hs;
+    const bool plain = !c->cfg.f_is_2d && !c->cfg.has_hs;  // diffusion included: its star is read separately
     c->use_tma = plain && !(force && strcmp(force, "ldg") == 0);
+    // with diffusion the ring pays off on grids beyond the L2 only (measured: 1440 x 720 30 vs 33 us,
+    // 7200 x 3600 645 vs 515 us per step)
+    if (c->cfg.use_diffusion && (long long)(p.M + 1) * (p.jl_last - p.jl_first + 1) < 2000000LL && !(force && strcmp(force, "tma") == 0))
+        c->use_tma = false;
     c->cfl_filter = false;
     if (force && strcmp(force, "tma") == 0 && !c->use_tma) return fail(SWB_E_INVALID, "SWB_KERNEL=tma but this configuration cannot use the TMA kernel");
     if (c->use_tma) {
@@ -433,12 +440,13 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
         const char *v = getenv(f32 ? "SWB_TMA_VARIANT_F32" : "SWB_TMA_VARIANT");
         c->tma_variant = v ? atoi(v) : (f32 ? kDefaultTmaVariantF32 : kDefaultTmaVariant);
         if (c->tma_variant < 0 || c->tma_variant >= (f32 ? kNumTmaVariantsF32 : kNumTmaVariants)) return fail(SWB_E_INVALID, "bad SWB_TMA_VARIANT");
-        const TmaVariant tv = f32 ? kTmaVariantsF32[c->tma_variant] : kTmaVariants[c->tma_variant];
+        TmaVariant tv = f32 ? kTmaVariantsF32[c->tma_variant] : kTmaVariants[c->tma_variant];
+        if (c->cfg.use_diffusion) tv = TmaVariant{4, 3, 2, 4};
         // CFL filter: worth its extra (normally empty) launch per step on grids whose step takes
         // far longer than a launch; SWB_CFL_FILTER=0/1 overrides
         const long long cells = (long long)(p.M + 1) * (p.jl_last - p.jl_first + 1);
-        c->cfl_filter = !f32 && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && cells >= 4000000LL;
-        if (const char *e = getenv("SWB_CFL_FILTER")) c->cfl_filter = !f32 && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && atoi(e) != 0;
+        c->cfl_filter = !f32 && !c->cfg.use_diffusion && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && cells >= 4000000LL;
+        if (const char *e = getenv("SWB_CFL_FILTER")) c->cfl_filter = !f32 && !c->cfg.use_diffusion && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && atoi(e) != 0;
         CK(cudaSetDevice(c->cfg.device));
         for (int s = 0; s < 2; ++s)
             for (int k = 0; k < 3; ++k) {

@@ -106,6 +106,7 @@ struct Params {
     int nstrips;            // warps needed along longitude
     int launch;             // launch index L (mod 3 cycle)
     int fixed;              // 1: use fixed_dt, buffers 0 -> 1, no bookkeeping
+    int force_rare;         // tuning / test knob (SWB_FORCE_RARE=1): every row takes the boundary-row body
     double fixed_dt;
     double courant, final_time, dxmin, dymin, g, a, nu, dphi;
     // multi-GPU (world > 1): peers' exchange blocks and neighbour halo rows
@@ -139,6 +140,10 @@ template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 template <typename T> using vec2_t = typename Vec2<T>::type;
+__device__ __forceinline__ double2 ldg2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ float2 ldg2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
+__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
 template <typename T> struct BitsOf;
 template <> struct BitsOf<double> { using type = unsigned long long; };
 template <> struct BitsOf<float> { using type = unsigned int; };
@@ -482,6 +487,23 @@ __device__ __forceinline__ Star<T> load_star(const T *__restrict__ q, int pitch,
     return s;
 }
 
+// The same for a lane's pair of cells (jl, colA), (jl, colA+1) away from every boundary: six
+// 16-byte loads per field instead of eighteen scalar ones; the centre values come from
+// registers.
+template <typename T>
+__device__ __forceinline__ void load_star_pair(const T *__restrict__ q, int pitch, int jl, int colA, T q0A, T q0B,
+                                               Star<T> &sA, Star<T> &sB)
+{
+    const size_t P = (size_t)pitch;
+    const T *row = q + (size_t)jl * P + colA;
+    const vec2_t<T> L = ldg2(row - 2), Rr = ldg2(row + 2);
+    const vec2_t<T> m2 = ldg2(row - 2 * P), m1 = ldg2(row - P), p1 = ldg2(row + P), p2 = ldg2(row + 2 * P);
+    sA.q0 = q0A; sA.xmm = L.x; sA.xm = L.y; sA.xp = q0B;  sA.xpp = Rr.x;
+    sB.q0 = q0B; sB.xmm = L.y; sB.xm = q0A; sB.xp = Rr.x; sB.xpp = Rr.y;
+    sA.ymm = m2.x; sA.ym = m1.x; sA.yp = p1.x; sA.ypp = p2.x;
+    sB.ymm = m2.y; sB.ym = m1.y; sB.yp = p1.y; sB.ypp = p2.y;
+}
+
 // FAST diffusion row record: w[0..4] combined latitude weights, [5] = 1/(2 dx_j)^2, [6] = dt*nu
 template <typename T>
 __device__ __forceinline__ T laplacian_fast(const Star<T> &s, const T *__restrict__ rd)
@@ -664,10 +686,6 @@ __host__ __device__ constexpr int rec_bytes(int chunk, bool diff)
     return (((chunk + 2) * (kRowRec + (diff ? kRowDiff : 0)) * 8) + 1023) / 1024 * 1024;
 }
 
-__device__ __forceinline__ double2 ldg2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
-__device__ __forceinline__ float2 ldg2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
-__device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
-__device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
 
 // Store a lane's pair of values without branching: both (one 16-byte store), or only the
 // first / only the second (the strip's edge lanes and the right end of the grid).
@@ -864,7 +882,9 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     }
     // extra copies a cell owes: periodic ghost columns (numpy.py:402)
     const bool wrapA = vA && (colA == p.M || colA == 2), wrapB = vB && (colA + 1 == p.M || colA + 1 == 2);
-    const bool warp_wraps = __any_sync(0xffffffffu, wrapA || wrapB);
+    // with diffusion, column M+1 reaches across the periodic seam too (its i+2 is column 3)
+    const bool seam = DIFF && ((vA && colA == p.M + 1) || (vB && colA + 1 == p.M + 1));
+    const bool warp_wraps = __any_sync(0xffffffffu, wrapA || wrapB || seam);
     const int st_both = (vA && vB) ? 1 : 0, st_onlyA = (vA && !vB) ? 1 : 0, st_onlyB = (vB && !vA) ? 1 : 0;
     bits_t<T> mxA = 0, myA = 0, mxB = 0, myB = 0;  // running CFL maxima (bit patterns)
     const int trig_x = CFLF ? s_filter.trig_x : 0, trig_y = CFLF ? s_filter.trig_y : 0;
@@ -906,7 +926,7 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
         if (p.south[0][0] != nullptr) plain_lo = max(plain_lo, p.jl_first + p.halo);
         if (p.north[0][0] != nullptr) plain_hi = min(plain_hi, p.jl_last - p.halo);
     }
-    if (warp_wraps) plain_hi = plain_lo - 1;  // strips that feed the periodic ghost columns: every row
+    if (warp_wraps || p.force_rare) plain_hi = plain_lo - 1;  // strips that feed the periodic ghost columns: every row
 
     // One latitude: cells (jl, colA), (jl, colA+1) from `cur`, the row above in (h2,u2,v2).
     // `hot` (a compile-time tag) = a live row in [plain_lo, plain_hi]: own stores only.
@@ -988,9 +1008,16 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
 
         if (DIFF) {  // numpy.py:541-544: Laplacian of the OLD fields; u, v (not hu, hv)
             const int iA = min(max(colA, 1), p.M + 1), iB = min(max(colA + 1, 1), p.M + 1);  // keep invalid lanes in bounds
-            const Star<T> shA = load_star(H, p.pitch, p.nrows, p.M, jl, iA), shB = load_star(H, p.pitch, p.nrows, p.M, jl, iB);
-            const Star<T> suA = load_star(U, p.pitch, p.nrows, p.M, jl, iA), suB = load_star(U, p.pitch, p.nrows, p.M, jl, iB);
-            const Star<T> svA = load_star(V, p.pitch, p.nrows, p.M, jl, iA), svB = load_star(V, p.pitch, p.nrows, p.M, jl, iB);
+            Star<T> shA, shB, suA, suB, svA, svB;
+            if (HOT) {  // no pole row, no periodic column within reach: plain neighbours
+                load_star_pair(H, p.pitch, jl, colA, curA.h, curB.h, shA, shB);
+                load_star_pair(U, p.pitch, jl, colA, curA.u, curB.u, suA, suB);
+                load_star_pair(V, p.pitch, jl, colA, curA.v, curB.v, svA, svB);
+            } else {
+                shA = load_star(H, p.pitch, p.nrows, p.M, jl, iA); shB = load_star(H, p.pitch, p.nrows, p.M, jl, iB);
+                suA = load_star(U, p.pitch, p.nrows, p.M, jl, iA); suB = load_star(U, p.pitch, p.nrows, p.M, jl, iB);
+                svA = load_star(V, p.pitch, p.nrows, p.M, jl, iA); svB = load_star(V, p.pitch, p.nrows, p.M, jl, iB);
+            }
             if (STRICT) {
                 const T dnu = O::mul(dt, (T)p.nu);
                 const W3 wy = y_weights(p.tab, p.nrows, jl);
@@ -1138,7 +1165,8 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
 #pragma unroll 1
         for (int jl = ja; jl < jb; ++jl) {
             const size_t k = (size_t)min(jl + 1, p.nrows - 1) * P + colA;
-            do_row(RareTag(), jl, ldg2(H + k), ldg2(U + k), ldg2(V + k), true);
+            if (jl >= plain_lo && jl <= plain_hi) do_row(HotTag(), jl, ldg2(H + k), ldg2(U + k), ldg2(V + k), true);
+            else do_row(RareTag(), jl, ldg2(H + k), ldg2(U + k), ldg2(V + k), true);
         }
     }
 
