@@ -1,6 +1,6 @@
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from sw_solver_b200.grid import CartesianGrid, LatLonGrid
 from sw_solver_b200.ic import ICType, get_initial_conditions
 from sw_solver_b200.solver import Stepper, band_layout, link_local
