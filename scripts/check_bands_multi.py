@@ -67,6 +67,26 @@ def main():
         else:
             dist.send(mine, dst=0)
         dist.barrier()
+    # the driver itself: solve() under torchrun == solve() on one GPU, save_data included
+    from sw_solver_b200.ic import ICType
+    from sw_solver_b200.solver import solve
+
+    for (M, N, ic, days, diff, mode, interval) in ((96, 64, ICType.RossbyHaurwitzWave, 0.02, True, "strict", 5),
+                                                    (200, 130, ICType.ZonalGeostrophicFlow, 0.01, False, "fast", 7),
+                                                    (1440, 720, ICType.RossbyHaurwitzWave, 0.002, True, "fast", 10)):
+        sd = {"interval": interval}
+        h, u, v = solve(M, N, ic, days, 0.5, diff, save_data=sd, mode=mode)
+        if rank == 0:
+            sd1 = {"interval": interval}
+            h1, u1, v1 = solve(M, N, ic, days, 0.5, diff, save_data=sd1, mode=mode, distributed=False)
+            ok = all(np.array_equal(a, b) for a, b in ((h, h1), (u, u1), (v, v1)))
+            ok = ok and sorted(sd) == sorted(sd1) and all(np.array_equal(sd[k], sd1[k]) for k in ("h", "u", "v", "t", "phi", "theta"))
+            print(f"solve() x{world} {M}x{N} {ic.name} diffusion={diff} mode={mode}: "
+                  f"{'BIT-IDENTICAL to one GPU' if ok else 'MISMATCH'} ({len(sd1['t'])} snapshots, t_end = {sd1['t'][-1]:.3f} s)", flush=True)
+            ok_all = ok_all and ok
+        else:
+            assert sd == {"interval": interval} and h.shape[0] == M + 3
+        dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok_all else 1)
 

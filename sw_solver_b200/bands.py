@@ -148,7 +148,9 @@ def rossby_haurwitz_band(latlon_grid: LatLonGrid, j_begin: int, n_local: int, de
     t2 = col("hC") * c2R
     t = t + t2
     del t2
-    t = t / float(s["g"])
+    # a DEVICE divisor: torch turns `tensor / python_scalar` into a multiplication by the
+    # reciprocal, which is not the reference's IEEE division
+    t = t / torch.tensor(float(s["g"]), dtype=torch.float64, device=dev)
     h = float(s["h0"]) + t
     del t
     u = col("uB") * cR

@@ -518,10 +518,22 @@ def _read_status(pinned: torch.Tensor) -> SwbStatus:
     return SwbStatus.from_buffer_copy(pinned.numpy().tobytes()[:_STATUS_BYTES])
 
 
+def _dist_world(distributed: Optional[bool]):
+    """(dist module, rank, world) when the band path applies, else (None, 0, 1)."""
+    import torch.distributed as dist
+
+    on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if distributed is True and not on:
+        raise RuntimeError("distributed=True needs torch.distributed initialised with more than one rank (torchrun)")
+    if distributed is False or not on:
+        return None, 0, 1
+    return dist, dist.get_rank(), dist.get_world_size()
+
+
 def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, courant: float,
           use_diffusion: bool = True, save_data: Optional[Dict[str, Any]] = None, print_interval: int = -1, *,
-          mode: Optional[str] = None, device=None, batch_steps: int = 512, dtype: str = "float64"
-          ) -> Tuple[FloatArray2D, FloatArray2D, FloatArray2D]:
+          mode: Optional[str] = None, device=None, batch_steps: int = 512, dtype: str = "float64",
+          distributed: Optional[bool] = None) -> Tuple[FloatArray2D, FloatArray2D, FloatArray2D]:
     """Drop-in for ``sw_solver.numpy.solve`` (numpy.py:409-575) on a B200.
 
     Same positional parameters, same ``save_data`` contract (keys h, u, v, t, phi, theta
@@ -532,7 +544,11 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
     Backend-only keywords: ``mode`` ("fast" | "fast_guarded" | "strict"), ``device``,
     ``batch_steps`` (how many steps are enqueued between two non-blocking termination
     checks), ``dtype`` ("float64" | "float32": the optional fp32 state; results are still
-    returned as float64 arrays, within 1e-5 of the reference over benchmark-length runs).
+    returned as float64 arrays, within 1e-5 of the reference over benchmark-length runs),
+    ``distributed`` (None: latitude bands over all ranks whenever ``torch.distributed`` is
+    initialised with more than one rank -- one process per GPU, e.g. under torchrun; every
+    rank makes the same call; rank 0 receives the full arrays and ``save_data``, the other
+    ranks their own band's window (M+3, n_local) and an untouched ``save_data``).
     """
     save_data = save_data if save_data is not None else {}
 
@@ -548,24 +564,45 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
             f"Invalid problem IC: {ic_type}. See code documentation for implemented initial conditions."
         )
     dev = _require_cuda(device)
+    dist, rank, world = _dist_world(distributed)
+    M, N = latlon_grid.M, latlon_grid.N
 
-    h, u, v, f = get_initial_conditions(ic_type, latlon_grid)
-    if ic_type == ICType.RossbyHaurwitzWave:
-        f = coriolis_latitude(latlon_grid)
+    band = None
+    if world > 1:
+        band = band_layout(N, world, 2 if use_diffusion else 1)[rank]
+    j_begin, n_local = (band["j_begin"], band["n_local"]) if band else (0, N)
+
+    layout = "reference"
+    if ic_type == ICType.RossbyHaurwitzWave and (world > 1 or (M + 3) * N > (1 << 24)):
+        # large grids / bands: assemble the state on the device from the 1-D factors
+        # (bit-identical to get_initial_conditions; nothing of size M x N on the host)
+        from .bands import rossby_haurwitz_band
+
+        h, u, v, f = rossby_haurwitz_band(latlon_grid, j_begin, n_local, dev)
+        layout = "device"
+    else:
+        h, u, v, f = get_initial_conditions(ic_type, latlon_grid)
+        if ic_type == ICType.RossbyHaurwitzWave:
+            f = coriolis_latitude(latlon_grid)
 
     save_interval = int(save_data.get("interval", 0))
     st = Stepper(latlon_grid, cart_grid, h, u, v, f, None, courant=courant, final_time=final_time,
-                 use_diffusion=use_diffusion, mode=mode, device=dev, dtype=dtype)
+                 use_diffusion=use_diffusion, mode=mode, device=dev, dtype=dtype, band=band, world=world, layout=layout)
+    del h, u, v
     try:
+        if world > 1:
+            from .bands import link_distributed
+
+            link_distributed(st)
         st.cfl_init()
-        snaps: List[torch.Tensor] = []   # pinned (3, M+1, N) host copies, one per save point
+        snaps: List[torch.Tensor] = []   # pinned (3, M+1, n_local) host copies, one per save point
         snap_status: List[torch.Tensor] = []
         stage = None  # device staging of one snapshot in the reference layout (K4)
 
         def take_snapshot(current: int) -> torch.Tensor:
             nonlocal stage
             stage = st.snapshot(current, stage)
-            pinned = torch.empty((3, latlon_grid.M + 1, latlon_grid.N), dtype=torch.float64).pin_memory()
+            pinned = torch.empty((3, M + 1, n_local), dtype=torch.float64).pin_memory()
             for k in range(3):
                 pinned[k].copy_(stage[k, 1:-1, :], non_blocking=True)  # numpy.py:488-492: h[1:-1, :]
             return pinned
@@ -584,19 +621,30 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
                 yield nxt
                 n = nxt
 
+        def max_speed() -> float:
+            m = st.max_speed()
+            if dist is not None:  # numpy's max propagates NaN: so does this one
+                t = torch.tensor([float("inf") if m != m else m], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                m = float("nan") if t.item() == float("inf") else t.item()
+            return m
+
+        # Every rank sees the same time / step count / termination flag (identical dt on all
+        # bands), so the control flow below is the same on every rank.
         ring: List[Tuple[int, torch.Tensor, torch.cuda.Event]] = []
         enq = 0
-        finished: Optional[SwbStatus] = None
         for target in stops():
             st.enqueue(target - enq)
             enq = target
             if print_interval > 0 and enq % print_interval == 0:
                 s = st.status()
                 if s.steps == enq:  # the loop was still running at this step
-                    print(
-                        f"Time = {s.time / 3600.0:6.2f} hours (max {int(final_time / 3600.0)}); "
-                        f"max(|u|) = {st.max_speed():16.16f}"
-                    )
+                    speed = max_speed()
+                    if rank == 0:
+                        print(
+                            f"Time = {s.time / 3600.0:6.2f} hours (max {int(final_time / 3600.0)}); "
+                            f"max(|u|) = {speed:16.16f}"
+                        )
             if save_interval > 0 and enq % save_interval == 0:
                 # valid only if all `enq` steps ran, in which case the parity is known
                 snaps.append(take_snapshot(enq & 1))
@@ -612,29 +660,61 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
             if len(ring) >= 2:
                 _, pin0, ev0 = ring.pop(0)
                 ev0.synchronize()
-                s0 = _read_status(pin0)
-                if s0.done:
-                    finished = s0
+                if _read_status(pin0).done:
                     break
         final = st.status()
         if final.error:
-            raise SwbError(final.error, "device-side error flag raised during the time loop")
+            raise SwbError(final.error, "device-side error flag raised during the time loop "
+                                        "(SWB_E_DEPTH: use mode='fast_guarded' or 'strict'; SWB_E_TIMEOUT: a peer GPU never answered)")
         hh, uu, vv = st.to_numpy()
 
+        keep: List[torch.Tensor] = []
+        tsave: List[float] = []
         if save_interval > 0:
             torch.cuda.synchronize(dev)
-            keep = [snaps[0]]
-            tsave = [0.0]
+            keep, tsave = [snaps[0]], [0.0]
             for k, pin in enumerate(snap_status):
                 s = _read_status(pin)
                 if s.steps == (k + 1) * save_interval:  # numpy.py:559: taken while the loop ran
                     keep.append(snaps[k + 1])
                     tsave.append(s.time)
+
+        if world > 1:
+            hh, uu, vv, keep = _gather_bands(dist, dev, band, world, N, (hh, uu, vv), keep)
+
+        if save_interval > 0 and rank == 0:
             for idx, name in enumerate(("h", "u", "v")):
-                save_data[name] = np.stack([s[idx].numpy() for s in keep], axis=2)
+                save_data[name] = np.stack([np.asarray(s[idx]) for s in keep], axis=2)
             save_data["t"] = np.asarray(tsave)
             save_data["phi"] = latlon_grid.phi
             save_data["theta"] = latlon_grid.theta
     finally:
         st.close()
     return hh, uu, vv
+
+
+def _gather_bands(dist, dev, band, world, N, state, snaps):
+    """Collect the rows every band owns on rank 0: the final (M+3, N) state and the kept
+    snapshots.  Other ranks keep their windows.  Plumbing only (NCCL send / recv)."""
+    rank = band["rank"]
+    lo = 0 if rank == 0 else band["j_first"]
+    hi = N if rank == world - 1 else band["j_last"] + 1
+    own = slice(lo - band["j_begin"], hi - band["j_begin"])
+    items = [np.stack(state)] + [np.asarray(s) for s in snaps]  # (3, rows_i, n_local) each
+    spans = [None] * world
+    dist.all_gather_object(spans, (lo, hi))
+    if rank != 0:
+        for a in items:
+            dist.send(torch.from_numpy(np.ascontiguousarray(a[:, :, own])).to(dev), dst=0)
+        return state[0], state[1], state[2], snaps
+    out = []
+    for a in items:
+        full = np.empty(a.shape[:2] + (N,), dtype=np.float64)
+        full[:, :, lo:hi] = a[:, :, own]
+        for r in range(1, world):
+            rlo, rhi = spans[r]
+            buf = torch.empty(a.shape[:2] + (rhi - rlo,), dtype=torch.float64, device=dev)
+            dist.recv(buf, src=r)
+            full[:, :, rlo:rhi] = buf.cpu().numpy()
+        out.append(full)
+    return out[0][0], out[0][1], out[0][2], out[1:]

@@ -146,3 +146,18 @@ def test_bands_are_bit_identical_to_one_band(M, N, ic, diff, mode, world, nsteps
     assert max(s.eigenx for s in stats) == s_ref.eigenx and max(s.eigeny for s in stats) == s_ref.eigeny
     for k in range(3):
         assert np.array_equal(out[k], ref[k]), k
+
+
+@pytest.mark.gpu
+def test_device_side_initial_state_is_bit_identical():
+    """bands.rossby_haurwitz_band (state assembled on the GPU from 1-D factors) against the
+    host path ic.get_initial_conditions, which tests/test_host.py pins to the reference."""
+    from sw_solver_b200.bands import rossby_haurwitz_band
+
+    for M, N, jb, nl in ((96, 64, 0, 64), (333, 98, 17, 40), (1440, 720, 700, 20)):
+        ll = LatLonGrid(M, N)
+        h, u, v, _ = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+        hd, ud, vd, f = rossby_haurwitz_band(ll, jb, nl, "cuda")
+        for a, b in ((hd, h), (ud, u), (vd, v)):
+            assert np.array_equal(a.cpu().numpy().T, b[:, jb:jb + nl])
+        assert f.shape == (ll.N,)
