@@ -138,7 +138,10 @@ int swb_required_pitch(int M, int dtype);
 
 /* Bind the two buffer sets the path ping-pongs between (set 0 holds the initial state),
  * plus the optional 2-D Coriolis array and topography (device pointers or NULL), all
- * (n_local, pitch) arrays in the latitude-major device layout. */
+ * (n_local, pitch) arrays in the latitude-major device layout.  The TMA-fed kernels read
+ * h, u, v of a buffer set through one 3-D tensor map: they are used when u - h == v - u (a
+ * positive multiple of 16 bytes) in both sets -- e.g. one (3, n_local, pitch) allocation per
+ * set; any other placement runs the direct-load kernels. */
 int swb_bind_state(swb_ctx *ctx, void *h0, void *u0, void *v0, void *h1, void *u1, void *v1,
                    const void *f2d, const void *hs);
 
@@ -186,6 +189,12 @@ int swb_read_log(swb_ctx *ctx, double *dt_out, double *time_out, int count, void
 
 /* Number of kernels this context has launched so far (for bench.py's gpu_launches). */
 int64_t swb_launch_count(const swb_ctx *ctx);
+
+/* 1 if swb_enqueue_steps runs each batch of steps as ONE cooperative launch of the resident
+ * kernel (grids whose blocks all fit the GPU at once: the loop of numpy.py:496-549 then never
+ * leaves the device, a grid barrier replaces the launch per step), else 0.  Decided by
+ * swb_bind_state; the environment variable SWB_RESIDENT=0 keeps the launch-per-step kernel. */
+int swb_resident(const swb_ctx *ctx);
 
 /* ---- multi-GPU (one process per GPU, latitude bands) ------------------------------ */
 

@@ -46,6 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
         "-o", LIB,
     ] + SOURCES
+    cmd[1:1] = os.environ.get("SWB_NVCC_FLAGS", "").split()  # dev builds, e.g. -DSWB_RES_TIMING
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

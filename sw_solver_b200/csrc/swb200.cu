@@ -72,6 +72,12 @@ struct swb_ctx {
     bool cfl_filter = false;  // march_kernel<..., CFLF> + cfl_fixup_kernel (fp64 FAST, large grids)
     int tma_variant = 0;  // index into kTmaVariants (fp64) / kTmaVariantsF32
     TmaMaps maps;
+    // resident_kernel (grids that fit the GPU as one wave of blocks): the whole batch of steps in one launch
+    int base_chunk = 2;  // marching length of march_kernel (the resident kernel picks its own)
+    bool resident = false;
+    const void *res_fn = nullptr;
+    int res_smem = 0;
+    dim3 res_grid;
 };
 
 namespace {
@@ -220,12 +226,91 @@ int launch_one(swb_ctx *c, cudaStream_t st)
     return 0;
 }
 
+// ---- resident_kernel: instantiations and set-up --------------------------------------
+constexpr int kResMaxChunk = 32;  // two sets of row records + the rings of two blocks fit one SM
+
+struct ResKernel { const void *fn; int smem; };
+template <bool STRICT, bool DIFF, bool TMA, bool GUARD>
+ResKernel res_kernel_inst(int chunk)
+{
+    using LY = TmaLayout<4, 4, double>;
+    auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? 4 : 1), GUARD, 2>;
+    return ResKernel{(const void *)fn, 2 * rec_bytes(chunk, DIFF) + (TMA ? kWarpsPerBlock * LY::kWarpBytes : kWarpsPerBlock * kFirstRowsBytes)};
+}
+ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk)
+{
+    if (tma) return mode == SWB_FAST ? res_kernel_inst<false, false, true, false>(chunk) : res_kernel_inst<false, false, true, true>(chunk);
+    if (mode == SWB_STRICT) return diff ? res_kernel_inst<true, true, false, true>(chunk) : res_kernel_inst<true, false, false, true>(chunk);
+    if (mode == SWB_FAST) return diff ? res_kernel_inst<false, true, false, false>(chunk) : res_kernel_inst<false, false, false, false>(chunk);
+    return diff ? res_kernel_inst<false, true, false, true>(chunk) : res_kernel_inst<false, false, false, true>(chunk);
+}
+
+// Decide whether this context's grid runs resident (fp64, one band, latitude-only Coriolis,
+// flat topography, all blocks co-resident with marches of at most kResMaxChunk rows) and
+// size the launch.  SWB_RESIDENT=0 keeps the launch-per-step kernel, SWB_RES_CHUNK / SWB_KERNEL
+// (ldg | tma) override the choices below (tuning and tests).
+int setup_resident(swb_ctx *c)
+{
+    c->resident = false;
+    const swb_config &cfg = c->cfg;
+    Params &p = c->prm;
+    if (cfg.world != 1 || cfg.dtype != SWB_F64 || cfg.f_is_2d || cfg.has_hs) return 0;
+    if (const char *e = getenv("SWB_RESIDENT"))
+        if (atoi(e) == 0) return 0;
+    const int rows = p.jl_last - p.jl_first + 1;
+    const int gx = (p.nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const bool tma_ok = c->use_tma && !cfg.use_diffusion && cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant;
+    const char *force = getenv("SWB_KERNEL");
+    int forced_chunk = 0;
+    if (const char *e = getenv("SWB_RES_CHUNK")) forced_chunk = atoi(e);
+    auto capacity = [&](bool tma, int *cap) -> int {
+        const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, kResMaxChunk);
+        CK(cudaFuncSetAttribute(rk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rk.smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk.fn, kWarpsPerBlock * 32, (size_t)rk.smem));
+        *cap = nb * c->sm_count;
+        return 0;
+    };
+    auto chunk_for = [&](int cap, int mult) -> int {  // shortest march (a multiple of `mult`) with gx * ceil(rows / chunk) <= cap
+        const int ny = cap / gx;
+        if (ny < 1) return 0;
+        int ch = (rows + ny - 1) / ny;
+        if (forced_chunk > 0) ch = forced_chunk;
+        ch = (ch + mult - 1) / mult * mult;
+        if (ch > kResMaxChunk || (long long)gx * ((rows + ch - 1) / ch) > cap) return 0;
+        return ch;
+    };
+    int cap = 0, chunk = 0;
+    bool tma = false;
+    int rc = capacity(false, &cap);
+    if (rc) return rc;
+    chunk = chunk_for(cap, 1);
+    // marches of 8 rows and more: the TMA ring with its unrolled four-row tiles (measured)
+    if (tma_ok && (chunk >= 8 || chunk == 0 || (force && strcmp(force, "tma") == 0))) {
+        int cap_t = 0;
+        rc = capacity(true, &cap_t);
+        if (rc) return rc;
+        const int ch_t = chunk_for(cap_t, 4);
+        if (ch_t > 0) { tma = true; chunk = ch_t; cap = cap_t; }
+    }
+    if (chunk <= 0) return 0;
+    const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, chunk);
+    c->res_fn = rk.fn;
+    c->res_smem = rk.smem;
+    c->res_grid = dim3((unsigned)gx, (unsigned)((rows + chunk - 1) / chunk));
+    p.chunk = chunk;
+    c->resident = true;
+    return 0;
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// 2-D fp64 tensor map over a (rows x cols) window of a state array with `pitch` elements per row
-int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_t pitch, uint32_t box_cols, uint32_t box_rows, bool f32)
+// 3-D tensor map over the h, u, v arrays of one buffer set: (cols x rows x 3 fields), `pitch`
+// elements per row and `field_stride` bytes between consecutive fields
+int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_t pitch, uint64_t field_stride, uint32_t box_cols,
+             uint32_t box_rows, bool f32)
 {
     static encode_tiled_fn encode = nullptr;
     if (!encode) {
@@ -235,11 +320,11 @@ int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_
         if (!fn) return fail(SWB_E_NODEVICE, "cuTensorMapEncodeTiled is not available in this driver");
         encode = (encode_tiled_fn)fn;
     }
-    const cuuint64_t dims[2] = {cols, rows};
-    const cuuint64_t strides[1] = {pitch * (f32 ? sizeof(float) : sizeof(double))};
-    const cuuint32_t box[2] = {box_cols, box_rows};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t dims[3] = {cols, rows, 3};
+    const cuuint64_t strides[2] = {pitch * (f32 ? sizeof(float) : sizeof(double)), field_stride};
+    const cuuint32_t box[3] = {box_cols, box_rows, 3};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(out, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[160];
@@ -353,6 +438,7 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
         const int v = atoi(ch);
         if (v >= 1 && v <= kMaxChunk && (v & (v - 1)) == 0) p.chunk = v;
     }
+    c->base_chunk = p.chunk;
     if (const char *fr = getenv("SWB_FORCE_RARE")) p.force_rare = atoi(fr) != 0;
     p.courant = cfg->courant;
     p.final_time = cfg->final_time;
@@ -428,7 +514,10 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     // shape.
     const char *force = getenv("SWB_KERNEL");
     const bool plain = !c->cfg.f_is_2d && !c->cfg.has_hs;  // diffusion included: its star is read separately
-    c->use_tma = plain && !(force && strcmp(force, "ldg") == 0);
+    // one tensor box carries h, u and v: the three arrays of a buffer set must be equally spaced
+    const ptrdiff_t fs0 = (char *)u0 - (char *)h0, fs1 = (char *)u1 - (char *)h1;
+    const bool spaced = fs0 > 0 && (char *)v0 - (char *)u0 == fs0 && fs1 > 0 && (char *)v1 - (char *)u1 == fs1 && fs0 % 16 == 0 && fs1 % 16 == 0;
+    c->use_tma = plain && spaced && !(force && strcmp(force, "ldg") == 0);
     // with diffusion the ring pays off on grids beyond the L2 only (measured: 1440 x 720 30 vs 33 us,
     // 7200 x 3600 645 vs 515 us per step)
     if (c->cfg.use_diffusion && (long long)(p.M + 1) * (p.jl_last - p.jl_first + 1) < 2000000LL && !(force && strcmp(force, "tma") == 0))
@@ -448,15 +537,17 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
         c->cfl_filter = !f32 && !c->cfg.use_diffusion && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && cells >= 4000000LL;
         if (const char *e = getenv("SWB_CFL_FILTER")) c->cfl_filter = !f32 && !c->cfg.use_diffusion && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && atoi(e) != 0;
         CK(cudaSetDevice(c->cfg.device));
-        for (int s = 0; s < 2; ++s)
-            for (int k = 0; k < 3; ++k) {
-                int rc = make_map(&c->maps.in[s][k], p.buf[s][k], (uint64_t)(p.M + 3), (uint64_t)p.nrows, (uint64_t)p.pitch, kStripCols,
-                                  (uint32_t)tv.R, f32);
-                if (rc) return rc;
-            }
+        for (int s = 0; s < 2; ++s) {
+            int rc = make_map(&c->maps.in[s], p.buf[s][0], (uint64_t)(p.M + 3), (uint64_t)p.nrows, (uint64_t)p.pitch, (uint64_t)(s ? fs1 : fs0),
+                              kStripCols, (uint32_t)tv.R, f32);
+            if (rc) return rc;
+        }
     }
-    return 0;
+    p.chunk = c->base_chunk;
+    return setup_resident(c);
 }
+
+int swb_resident(const swb_ctx *c) { return (c && c->resident) ? 1 : 0; }
 
 int swb_to_device_layout(swb_ctx *c, const void *ref, int ref_pitch, void *dev, void *stream)
 {
@@ -532,6 +623,54 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
     CK(cudaSetDevice(c->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
     c->prm.fixed = 0;
+    if (c->resident) {  // the whole batch in one cooperative launch
+        int left = n;
+        while (left > 0) {
+            const int m = left < (1 << 20) ? left : (1 << 20);
+            c->prm.launch = c->launch;
+            c->prm.nsteps = m;
+            CK(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned int), st));
+            void *args[2] = {(void *)&c->prm, (void *)&c->maps};
+#ifdef SWB_RES_TIMING
+            const size_t nb = (size_t)c->res_grid.x * c->res_grid.y;
+            if (!c->prm.dbg) CK(cudaMalloc(&c->prm.dbg, nb * 16 * sizeof(long long)));
+            CK(cudaMemsetAsync(c->prm.dbg, 0, nb * 16 * sizeof(long long), st));
+#endif
+            CK(cudaLaunchCooperativeKernel(c->res_fn, c->res_grid, dim3(kWarpsPerBlock * 32), args, (size_t)c->res_smem, st));
+#ifdef SWB_RES_TIMING
+            if (m >= 100) {  // phase durations (SM clock ticks) of the launch's last-but-one step: mean and max over blocks
+                std::vector<long long> hst(nb * 16);
+                CK(cudaStreamSynchronize(st));
+                CK(cudaMemcpy(hst.data(), c->prm.dbg, nb * 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+                const char *names[7] = {"prologue", "records", "startup", "march", "epilogue+sync", "fence+arrive", "wait"};
+                fprintf(stderr, "[res-timing] grid %u x %u chunk %d:", c->res_grid.x, c->res_grid.y, c->prm.chunk);
+                for (int k = 0; k < 7; ++k) {
+                    double sum = 0, mx = 0;
+                    for (size_t b = 0; b < nb; ++b) {
+                        const double d = (double)(hst[b * 16 + k + 1] - hst[b * 16 + k]);
+                        sum += d;
+                        if (d > mx) mx = d;
+                    }
+                    fprintf(stderr, " %s %.0f/%.0f", names[k], sum / nb, mx);
+                }
+                fprintf(stderr, "\n");
+                if (const char *path = getenv("SWB_RES_TIMING_FILE")) {  // raw stamps: nb x 16 int64 (0..7 clock64 per phase, 8 = SM id) after a 3-int header
+                    if (FILE *f = fopen(path, "wb")) {
+                        const int hdr[4] = {(int)c->res_grid.x, (int)c->res_grid.y, c->prm.chunk, 0};
+                        fwrite(hdr, sizeof(int), 4, f);
+                        fwrite(hst.data(), sizeof(long long), nb * 16, f);
+                        fclose(f);
+                    }
+                }
+            }
+#endif
+            c->launches++;
+            c->launch = (c->launch + m) % 3000000;
+            c->seq += (unsigned long long)m;
+            left -= m;
+        }
+        return 0;
+    }
     for (int k = 0; k < n; ++k) {
         c->prm.launch = c->launch;
         c->prm.stamp = c->seq;

@@ -96,7 +96,7 @@ struct Params {
     const double *tab;  // T_COUNT x nrows
     Ctrl *ctrl;         // 3 slots
     int *err;           // sticky device-side error word (0 or a negative SWB_E_*)
-    unsigned int *done_ctr;  // 3 counters: blocks of launch L that finished (multi-GPU epilogue)
+    unsigned int *done_ctr;  // grid-barrier arrival counter of resident_kernel (zeroed before each launch)
     double *log;        // 2 x log_cap: dt then time, or null
     int log_cap;
     int M, nrows, pitch;    // nrows = local latitudes (halo / pole rows included)
@@ -105,6 +105,8 @@ struct Params {
     int chunk;              // latitudes marched by one warp
     int nstrips;            // warps needed along longitude
     int launch;             // launch index L (mod 3 cycle)
+    int nsteps;             // resident_kernel: time steps run by this one launch
+    long long *dbg;         // SWB_RES_TIMING builds: per block 8 clock64 stamps of one step (dev instrumentation)
     int fixed;              // 1: use fixed_dt, buffers 0 -> 1, no bookkeeping
     int force_rare;         // tuning / test knob (SWB_FORCE_RARE=1): every row takes the boundary-row body
     double fixed_dt;
@@ -142,6 +144,21 @@ template <> struct Vec2<float> { using type = float2; };
 template <typename T> using vec2_t = typename Vec2<T>::type;
 __device__ __forceinline__ double2 ldg2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ float2 ldg2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
+// COH: the state is rewritten by other SMs while the kernel runs (resident_kernel) -- read it
+// at the L2 (ld.global.cg), never through the non-coherent L1 path.
+template <bool COH, typename T>
+__device__ __forceinline__ typename Vec2<T>::type ld2(const T *p)
+{
+    using V = typename Vec2<T>::type;
+    if (COH) return __ldcg(reinterpret_cast<const V *>(p));
+    return *reinterpret_cast<const V *>(p);
+}
+template <bool COH, typename T>
+__device__ __forceinline__ T ld1(const T *p)
+{
+    if (COH) return __ldcg(p);
+    return *p;
+}
 __device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
 __device__ __forceinline__ float2 mk2(float a, float b) { return make_float2(a, b); }
 template <typename T> struct BitsOf;
@@ -469,7 +486,7 @@ template <typename T>
 struct Star {
     T q0, xm, xp, xmm, xpp, ym, yp, ymm, ypp;
 };
-template <typename T>
+template <typename T, bool COH = false>
 __device__ __forceinline__ Star<T> load_star(const T *__restrict__ q, int pitch, int nrows, int M, int jl, int i)
 {
     const size_t P = (size_t)pitch;
@@ -479,25 +496,25 @@ __device__ __forceinline__ Star<T> load_star(const T *__restrict__ q, int pitch,
     const int jm2 = max(jl - 2, 0), jp2 = min(jl + 2, nrows - 1);
     Star<T> s;
     const T *row = q + (size_t)jl * P;
-    s.q0 = row[i];
-    s.xm = row[i - 1]; s.xp = row[i + 1];
-    s.xmm = row[im2];  s.xpp = row[ip2];
-    s.ym = q[(size_t)jm1 * P + i]; s.yp = q[(size_t)jp1 * P + i];
-    s.ymm = q[(size_t)jm2 * P + i]; s.ypp = q[(size_t)jp2 * P + i];
+    s.q0 = ld1<COH>(row + i);
+    s.xm = ld1<COH>(row + i - 1); s.xp = ld1<COH>(row + i + 1);
+    s.xmm = ld1<COH>(row + im2);  s.xpp = ld1<COH>(row + ip2);
+    s.ym = ld1<COH>(q + (size_t)jm1 * P + i); s.yp = ld1<COH>(q + (size_t)jp1 * P + i);
+    s.ymm = ld1<COH>(q + (size_t)jm2 * P + i); s.ypp = ld1<COH>(q + (size_t)jp2 * P + i);
     return s;
 }
 
 // The same for a lane's pair of cells (jl, colA), (jl, colA+1) away from every boundary: six
 // 16-byte loads per field instead of eighteen scalar ones; the centre values come from
 // registers.
-template <typename T>
+template <typename T, bool COH = false>
 __device__ __forceinline__ void load_star_pair(const T *__restrict__ q, int pitch, int jl, int colA, T q0A, T q0B,
                                                Star<T> &sA, Star<T> &sB)
 {
     const size_t P = (size_t)pitch;
     const T *row = q + (size_t)jl * P + colA;
-    const vec2_t<T> L = ldg2(row - 2), Rr = ldg2(row + 2);
-    const vec2_t<T> m2 = ldg2(row - 2 * P), m1 = ldg2(row - P), p1 = ldg2(row + P), p2 = ldg2(row + 2 * P);
+    const vec2_t<T> L = ld2<COH>(row - 2), Rr = ld2<COH>(row + 2);
+    const vec2_t<T> m2 = ld2<COH>(row - 2 * P), m1 = ld2<COH>(row - P), p1 = ld2<COH>(row + P), p2 = ld2<COH>(row + 2 * P);
     sA.q0 = q0A; sA.xmm = L.x; sA.xm = L.y; sA.xp = q0B;  sA.xpp = Rr.x;
     sB.q0 = q0B; sB.xmm = L.y; sB.xm = q0A; sB.xp = Rr.x; sB.xpp = Rr.y;
     sA.ymm = m2.x; sA.ym = m1.x; sA.yp = p1.x; sA.ypp = p2.x;
@@ -520,18 +537,22 @@ __device__ __forceinline__ T laplacian_fast(const Star<T> &s, const T *__restric
 // the loop state.  Returns through shared memory: dt and flags (bit 0 active, bit 1 parity).
 // With several latitude bands (world > 1) `gather_kernel` has replaced the slot's maxima by
 // the maxima over all bands before this kernel starts.
-__device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int *s_flags)
+// RES (resident_kernel): the launch stops at the first inactive step, so that step leaves
+// the carried-forward state in BOTH other slots -- whatever launch index comes next reads it.
+template <bool RES>
+__device__ __forceinline__ void step_prologue(const Params &p, int launch, double *s_dt, int *s_flags)
 {
-    Ctrl *const cur_slot = p.ctrl + (p.launch % 3);
-    Ctrl *const new_slot = p.ctrl + ((p.launch + 1) % 3);
+    Ctrl *const cur_slot = p.ctrl + (launch % 3);
+    Ctrl *const new_slot = p.ctrl + ((launch + 1) % 3);
     if (p.fixed) {
         *s_dt = p.fixed_dt;
         *s_flags = 1;
         return;
     }
-    const double time = cur_slot->time;
-    const long long nsteps = cur_slot->nsteps;
-    const unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
+    // (RES: written by other SMs earlier in this launch -- read at the L2)
+    const double time = ld1<RES>(&cur_slot->time);
+    const long long nsteps = ld1<RES>(&cur_slot->nsteps);
+    const unsigned long long exb = ld1<RES>(&cur_slot->ex_bits), eyb = ld1<RES>(&cur_slot->ey_bits);
     const double tx = __ddiv_rn(p.dxmin, __longlong_as_double((long long)exb));
     const double ty = __ddiv_rn(p.dymin, __longlong_as_double((long long)eyb));
     const double dtmax = (tx != tx) ? tx : ((ty != ty) ? ty : (tx < ty ? tx : ty));  // np.minimum propagates NaN
@@ -549,20 +570,21 @@ __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int
     *s_dt = dt;
     *s_flags = (active ? 1 : 0) | (int)((nsteps & 1) << 1);
     if (blockIdx.x == 0 && blockIdx.y == 0) {
-        Ctrl *const clr_slot = p.ctrl + ((p.launch + 2) % 3);
+        Ctrl *const clr_slot = p.ctrl + ((launch + 2) % 3);
         clr_slot->ex_bits = 0ULL;
         clr_slot->ey_bits = 0ULL;
         clr_slot->reserved = 0;  // found-mask of the CFL filter (march_kernel<..., CFLF>)
         new_slot->time = tnew;
         new_slot->nsteps = nsteps + (active ? 1 : 0);
         new_slot->current = (int)((nsteps + (active ? 1 : 0)) & 1);
-        new_slot->last_dt = active ? dt : cur_slot->last_dt;
+        new_slot->last_dt = active ? dt : ld1<RES>(&cur_slot->last_dt);
         new_slot->done = !(tnew < p.final_time);
         new_slot->error = 0;
         if (!active) {  // nothing will be accumulated: carry the maxima forward
             new_slot->ex_bits = exb;
             new_slot->ey_bits = eyb;
             new_slot->reserved = 3;
+            if (RES) *clr_slot = *new_slot;
         } else if (p.log != nullptr && nsteps < (long long)p.log_cap) {
             p.log[nsteps] = dt;
             p.log[(size_t)p.log_cap + nsteps] = tnew;
@@ -570,9 +592,15 @@ __device__ __forceinline__ void step_prologue(const Params &p, double *s_dt, int
     }
 }
 
-// Row record of local latitude jl (clamped into the array) for time step dt.
+// Row records are built in two stages so that a resident kernel can keep the first one:
+//   stage 1 (`build_row_pre`): everything that does not depend on dt -- table look-ups and,
+//            in FAST mode, the reciprocals of the metric spacings;
+//   stage 2 (`scale_row_record`): the record of this time step.  FAST: one multiplication by dt
+//            per slot; STRICT: the reference's own quotients hdt/dy1, hdt/dy, dt/dy1c, dt/dyc.
+// march_kernel runs both stages every step, resident_kernel stage 1 once per launch: the
+// arithmetic, and therefore every bit of the result, is the same.
 template <bool STRICT>
-__device__ __forceinline__ void build_row_record(const Params &p, int jl, double dt, double *__restrict__ rec)
+__device__ __forceinline__ void build_row_pre(const Params &p, int jl, double *__restrict__ pre)
 {
     using O = Op<STRICT>;
     const int nr = p.nrows;
@@ -583,44 +611,59 @@ __device__ __forceinline__ void build_row_record(const Params &p, int jl, double
     const double tgm = tab[(size_t)T_TGMIDY * nr + j], cm = tab[(size_t)T_CMIDY * nr + j];
     const double dy = tab[(size_t)T_DY * nr + j], dy1 = tab[(size_t)T_DY1 * nr + j];
     const double dyc = tab[(size_t)T_DYC * nr + j], dy1c = tab[(size_t)T_DY1C * nr + j];
-    const double hdt = O::mul(0.5, dt);
-    rec[RC_C] = c;
-    rec[RC_AC] = ac;
-    rec[RC_CM] = cm;
-    rec[RC_DY1S] = O::add(tab[(size_t)T_DY1 * nr + jm], dy1);
+    pre[RC_C] = c;
+    pre[RC_AC] = ac;
+    pre[RC_CM] = cm;
+    pre[RC_DY1S] = O::add(tab[(size_t)T_DY1 * nr + jm], dy1);
     if (STRICT) {
-        rec[RC_KX] = tg;   // tgMidx == tan(theta_j): 0.5*(theta+theta) is exact (grid.py:107)
-        rec[RC_FKX] = f_j; // 0.5*(f+f) is exact
-        rec[RC_CDX] = 0.0;
-        rec[RC_CXU] = 0.0;
-        rec[RC_KY] = tgm;
-        rec[RC_FKY] = O::mul(0.5, O::add(f_jp, f_j));
-        rec[RC_CY1F] = O::div(hdt, dy1);
-        rec[RC_CYF] = O::div(hdt, dy);
-        rec[RC_CY1U] = O::div(dt, dy1c);
-        rec[RC_CYU] = O::div(dt, dyc);
-        rec[RC_KC] = tg;
-        rec[RC_FD] = f_j;
+        pre[RC_KX] = tg;   // tgMidx == tan(theta_j): 0.5*(theta+theta) is exact (grid.py:107)
+        pre[RC_FKX] = f_j; // 0.5*(f+f) is exact
+        pre[RC_CDX] = 0.0;
+        pre[RC_CXU] = 0.0;
+        pre[RC_KY] = tgm;
+        pre[RC_FKY] = O::mul(0.5, O::add(f_jp, f_j));
+        pre[RC_CY1F] = dy1;
+        pre[RC_CYF] = dy;
+        pre[RC_CY1U] = dy1c;
+        pre[RC_CYU] = dyc;
+        pre[RC_KC] = tg;
+        pre[RC_FD] = f_j;
     } else {
+        // (times dt in stage 2; hdt = dt/2 and the doubled face values are folded in here)
         const double ra = 1.0 / p.a;
-        const double dxa = ac * p.dphi;  // analytic dx_j (the reference's differs by roundoff only)
-        rec[RC_KX] = hdt * 0.5 * tg * ra;
-        rec[RC_FKX] = hdt * f_j;
-        rec[RC_CDX] = dt / dxa;
-        rec[RC_CXU] = 0.5 * dt / dxa;
-        rec[RC_KY] = hdt * 0.5 * tgm * ra;
-        rec[RC_FKY] = hdt * 0.5 * (f_jp + f_j);
-        rec[RC_CY1F] = dt / dy1;
-        rec[RC_CYF] = dt / dy;
-        rec[RC_CY1U] = 0.5 * dt / dy1c;
-        rec[RC_CYU] = 0.5 * dt / dyc;
-        rec[RC_KC] = dt * 0.25 * 0.5 * 0.25 * tg * ra;  // (dt*0.25) * 0.5[doubled sums] * 0.25 * tg/a
-        rec[RC_FD] = dt * 0.25 * 0.5 * f_j;
+        const double rdx = 1.0 / (ac * p.dphi);  // analytic dx_j (the reference's differs by roundoff only)
+        pre[RC_KX] = 0.25 * tg * ra;             // hdt * 0.5 * tan / a
+        pre[RC_FKX] = 0.5 * f_j;                 // hdt * f
+        pre[RC_CDX] = rdx;                       // dt / dx
+        pre[RC_CXU] = 0.5 * rdx;                 // 0.5 dt / dx
+        pre[RC_KY] = 0.25 * tgm * ra;
+        pre[RC_FKY] = 0.25 * (f_jp + f_j);       // hdt * 0.5 * (f_j + f_j+1)
+        pre[RC_CY1F] = 1.0 / dy1;
+        pre[RC_CYF] = 1.0 / dy;
+        pre[RC_CY1U] = 0.5 / dy1c;
+        pre[RC_CYU] = 0.5 / dyc;
+        pre[RC_KC] = 0.03125 * tg * ra;          // (dt*0.25) * 0.5[doubled sums] * 0.25 * tan/a
+        pre[RC_FD] = 0.125 * f_j;                // (dt*0.25) * 0.5 * f
     }
 }
 
-// FAST diffusion record of local latitude jl
-__device__ __forceinline__ void build_diff_record(const Params &p, int jl, double dt, double *__restrict__ rd)
+// slot k of the record of time step dt from slot k of the dt-independent record
+template <bool STRICT>
+__device__ __forceinline__ double scale_row_slot(int k, double pre, double dt)
+{
+    using O = Op<STRICT>;
+    if (STRICT) {
+        if (k == RC_CY1F || k == RC_CYF) return O::div(O::mul(0.5, dt), pre);  // hdt / dy1, hdt / dy
+        if (k == RC_CY1U || k == RC_CYU) return O::div(dt, pre);               // dt / dy1c, dt / dyc
+        return pre;
+    }
+    constexpr unsigned kPlain = (1u << RC_C) | (1u << RC_AC) | (1u << RC_CM) | (1u << RC_DY1S);
+    return ((kPlain >> k) & 1u) ? pre : dt * pre;
+}
+
+// FAST diffusion record of local latitude jl: [0..4] combined latitude weights,
+// [5] = 1/(2 dx_j)^2 (both independent of dt), [6] = dt*nu (stage 2)
+__device__ __forceinline__ void build_diff_pre(const Params &p, int jl, double *__restrict__ rd)
 {
     const int nr = p.nrows;
     const int j = min(max(jl, 0), nr - 1);
@@ -632,7 +675,7 @@ __device__ __forceinline__ void build_diff_record(const Params &p, int jl, doubl
     rd[4] = w.B[1] * w.B[2];
     const double dxa = p.tab[(size_t)T_AC * nr + j] * p.dphi;
     rd[5] = 0.25 / (dxa * dxa);
-    rd[6] = dt * p.nu;
+    rd[6] = p.nu;
     rd[7] = 0.0;
 }
 
@@ -640,7 +683,7 @@ __device__ __forceinline__ void build_diff_record(const Params &p, int jl, doubl
 // TMA plumbing
 // ------------------------------------------------------------------------------------
 struct TmaMaps {
-    CUtensorMap in[2][3];  // box {64, R} over (M+3, nrows) of each buffer set's h, u, v
+    CUtensorMap in[2];  // per buffer set: box {64 longitudes, R latitudes, 3 fields} over (M+3, nrows, {h, u, v})
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
@@ -670,6 +713,20 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+// 16 bytes global -> shared without passing through registers (LDGSTS, L2 only)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+constexpr int kFirstRowsBytes = 6 * 32 * 16;  // per warp: h, u, v pairs of the march's first two latitudes
 
 template <int R, int S, typename T = double>
 struct TmaLayout {
@@ -716,6 +773,16 @@ __device__ __forceinline__ void st_pair(float *addr, float a, float b, int both,
         "}" ::"l"(addr), "f"(a), "f"(b), "r"(both), "r"(only_a), "r"(only_b) : "memory");
 }
 
+
+// one predicated scalar store (no branch: the unrolled tile stays one basic block)
+__device__ __forceinline__ void st_if(double *addr, double a, int pred)
+{
+    asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %2, 0;\n\t@pp st.global.f64 [%0], %1;\n\t}" ::"l"(addr), "d"(a), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void st_if(float *addr, float a, int pred)
+{
+    asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %2, 0;\n\t@pp st.global.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(a), "r"(pred) : "memory");
+}
 
 // |u| + sqrt(g|h|) and |v| + sqrt(g|h|) of one cell as ordering keys (FAST arithmetic)
 template <typename T>
@@ -769,49 +836,39 @@ __device__ __forceinline__ double rsqrt_seed(double x)
 // TMA ring (R latitudes per box, S stages) or direct loads, and whether FAST evaluates the
 // reference's hMid > 0 selects (GUARD) or assumes them true and raises SWB_E_DEPTH when a
 // half-step depth turns out non-positive.
-template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
-          bool CFLF = false>
-__global__ void __launch_bounds__(W * 32, MINB)
-march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
+#ifdef SWB_RES_TIMING
+__device__ __forceinline__ unsigned swb_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define SWB_STAMP(k)                                                                                       \
+    do {                                                                                                   \
+        if (RES && p.dbg != nullptr && threadIdx.x == 0 && launch == p.launch + p.nsteps - 2)              \
+            p.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = ((k) == 8) ? (long long)swb_smid() : clock64();                     \
+    } while (0)
+#else
+#define SWB_STAMP(k) do { } while (0)
+#endif
+
+// One time step of the block's tile; the body of both step kernels below.  RES = called from
+// resident_kernel's loop: coherent (L2) loads of the state, dt-independent row records and
+// mbarriers kept across steps (`first` = the launch's first step sets them up; `tbase` counts
+// the TMA tiles this warp consumed so far, which fixes ring stage and mbarrier parity), ghost
+// columns and pole rows handled inside the unrolled tiles (in a single wave of blocks the
+// slowest warp sets the step time), the block's CFL maxima gathered in `s_max`.
+// `par_io` (RES): buffer set holding the current state if the caller knows it (>= 0) -- the
+// first loads then start before dt is known -- and on return the set holding the new state.
+// Returns false when the loop has ended (time >= final_time) -- uniform over the grid.
+template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int W, bool CFLF, bool RES>
+__device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, const int launch, const bool first, int &tbase,
+                                           int &par_io, unsigned char *smem_raw, double &s_dt, int &s_flags, CflFilter &s_filter,
+                                           unsigned long long *s_max)
 {
     static_assert(!STRICT || sizeof(T) == 8, "STRICT reproduces numpy's float64 arithmetic");
     static_assert(!CFLF || (!STRICT && TMA && sizeof(T) == 8), "the CFL filter serves the fp64 FAST TMA kernel");
+    static_assert(!RES || (sizeof(T) == 8 && !F2D && !HS && !CFLF), "resident_kernel: fp64, latitude-only Coriolis, flat topography");
     using O = Op<STRICT, T>;
     using LY = TmaLayout<R, S, T>;
     using V2 = vec2_t<T>;
     constexpr int kValid = sizeof(T) == 8 ? kStripValid : kStripValidF32;
     constexpr bool kGuard = STRICT || GUARD;
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ double s_dt;
-    __shared__ int s_flags;
-    __shared__ CflFilter s_filter;
-    if (threadIdx.x == 0) {
-        step_prologue(p, &s_dt, &s_flags);
-        if (CFLF) {
-            // thresholds from THIS band's maxima of the current state (with several bands the
-            // slot holds the global maxima; the band's own live in its exchange block)
-            const Ctrl *cur_slot = p.ctrl + (p.launch % 3);
-            unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
-            if (p.world > 1) {
-                exb = p.xlocal->slot[p.launch % 3][p.rank].ex_bits;
-                eyb = p.xlocal->slot[p.launch % 3][p.rank].ey_bits;
-            }
-            s_filter = p.fixed ? make_cfl_filter(0ULL, 0ULL) : make_cfl_filter(exb, eyb);
-        }
-    }
-    __syncthreads();
-    const int flags = s_flags;
-    if (!(flags & 1)) return;
-    const int par = (flags >> 1) & 1;
-    const T dt = (T)s_dt;
-    const T g_ = (T)p.g;
-
-    const T *__restrict__ H = (const T *)p.buf[par][0];
-    const T *__restrict__ U = (const T *)p.buf[par][1];
-    const T *__restrict__ V = (const T *)p.buf[par][2];
-    T *__restrict__ Hn = (T *)p.buf[par ^ 1][0];
-    T *__restrict__ Un = (T *)p.buf[par ^ 1][1];
-    T *__restrict__ Vn = (T *)p.buf[par ^ 1][2];
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -820,53 +877,157 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     const int ja = p.jl_first + blockIdx.y * p.chunk;  // first latitude updated
     const int jb = min(ja + p.chunk, p.jl_last + 1);   // one past the last
     const int c0 = kValid * strip;
+    const int colA = c0 + 2 * lane;  // this lane's cells: (., colA) and (., colA + 1)
     const size_t P = (size_t)p.pitch;
 
-    // ---- TMA ring: start the first loads before anything else ----------------------
-    const int recb = rec_bytes(p.chunk, DIFF);
+    // ---- TMA ring and the march's first two latitudes ----------------------------------
+    const int recb = rec_bytes(p.chunk, DIFF) * (RES ? 2 : 1);  // RES: the dt-independent records follow
     unsigned char *wbase = smem_raw + recb + (size_t)warp * LY::kWarpBytes;
     const uint32_t ring_a = smem_u32(wbase), bar_a = ring_a + LY::kRing;
-    const CUtensorMap *maps = tm.in[par];
     const int ntiles = (jb - ja + R - 1) / R;
-    auto issue_load = [&](int t) {  // lane 0 only: latitudes ja+1+tR .. of h, u, v into stage t % S
-        const int s = t % S;
+    const int tb = RES ? tbase : 0;  // tiles consumed before this step
+    int par = 0;
+    const T *__restrict__ H, *__restrict__ U, *__restrict__ V;
+    T *__restrict__ Hn, *__restrict__ Un, *__restrict__ Vn;
+    const CUtensorMap *maps;
+    auto bind = [&](int pr) {
+        par = pr;
+        H = (const T *)p.buf[pr][0]; U = (const T *)p.buf[pr][1]; V = (const T *)p.buf[pr][2];
+        Hn = (T *)p.buf[pr ^ 1][0]; Un = (T *)p.buf[pr ^ 1][1]; Vn = (T *)p.buf[pr ^ 1][2];
+        maps = &tm.in[pr];
+    };
+    auto issue_load = [&](int t) {  // lane 0 only: latitudes ja+1+tR .. of h, u, v into stage (tb + t) % S
+        const int s = (tb + t) % S;
         const uint32_t bar = bar_a + 8 * s;
         mbar_expect_tx(bar, LY::kStage);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) tma_load_2d(ring_a + s * LY::kStage + k * LY::kField, &maps[k], c0, ja + 1 + t * R, bar);
+        tma_load_3d(ring_a + s * LY::kStage, maps, c0, ja + 1 + t * R, 0, bar);  // h, u, v of R latitudes in one box
     };
-    if (TMA && warp_on) {
-        if (lane == 0) {
+    // tiles [t_lo, t_hi) of the ring's first S-1
+    auto start_ring = [&](int t_lo, int t_hi) {
+        if (TMA && warp_on) {
+            if (lane == 0) {
+                if ((!RES || first) && t_lo == 0) {
 #pragma unroll
-            for (int s = 0; s < S; ++s) mbar_init(bar_a + 8 * s, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                    for (int s = 0; s < S; ++s) mbar_init(bar_a + 8 * s, 1);
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                }
 #pragma unroll
-            for (int t = 0; t < S - 1; ++t)
-                if (t < ntiles) issue_load(t);
+                for (int t = 0; t < S - 1; ++t)
+                    if (t >= t_lo && t < t_hi && t < ntiles) issue_load(t);
+            }
+            __syncwarp();
         }
-        __syncwarp();
+    };
+    V2 h0, u0, v0, h1, u1, v1;  // latitudes ja-1 and ja
+    auto load_first_rows = [&]() {
+        const size_t k0 = (size_t)(ja - 1) * P + colA, k1 = k0 + P;
+        h0 = ld2<RES>(H + k0); u0 = ld2<RES>(U + k0); v0 = ld2<RES>(V + k0);
+        h1 = ld2<RES>(H + k1); u1 = ld2<RES>(U + k1); v1 = ld2<RES>(V + k1);
+    };
+    // RES, early: the same twelve values parked in shared memory by asynchronous copies (each lane
+    // copies and later reads its own 6 x 16 bytes) -- in the ring stage that is not in flight yet
+    // (TMA), or in a staging area behind the records
+    unsigned char *stg = (TMA ? wbase + (size_t)((tb + S - 1) % S) * LY::kStage : smem_raw + recb + (size_t)warp * kFirstRowsBytes) + lane * 16;
+    auto first_rows_async = [&]() {
+        const size_t k0 = (size_t)(ja - 1) * P + colA, k1 = k0 + P;
+        const uint32_t d = smem_u32(stg);
+        cp_async16(d, H + k0); cp_async16(d + 512, U + k0); cp_async16(d + 1024, V + k0);
+        cp_async16(d + 1536, H + k1); cp_async16(d + 2048, U + k1); cp_async16(d + 2560, V + k1);
+    };
+    auto first_rows_landed = [&]() {
+        cp_async_wait_all();
+        const V2 *q = reinterpret_cast<const V2 *>(stg);
+        h0 = q[0]; u0 = q[32]; v0 = q[64]; h1 = q[96]; u1 = q[128]; v1 = q[160];
+    };
+    // RES, second step onwards: the parity is known, so the first tile is requested while thread 0
+    // works out dt (only the first: the SM's whole share of the state arrives in microseconds anyway,
+    // and a deeper prefetch by every warp at once only queues up in front of the first tiles)
+    const bool early = RES && par_io >= 0;
+    if (early) {
+        bind(par_io);
+        if (warp != 0) {  // (warp 0: after the prologue -- its lane 0 is the prologue's thread)
+            start_ring(0, 1);
+            if (warp_on) first_rows_async();
+        }
     }
+    SWB_STAMP(9);
+
+    if (threadIdx.x == 0) {
+        step_prologue<RES>(p, launch, &s_dt, &s_flags);
+        if (RES) s_max[0] = s_max[1] = 0ULL;
+        if (CFLF) {
+            // thresholds from THIS band's maxima of the current state (with several bands the
+            // slot holds the global maxima; the band's own live in its exchange block)
+            const Ctrl *cur_slot = p.ctrl + (launch % 3);
+            unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
+            if (p.world > 1) {
+                exb = p.xlocal->slot[launch % 3][p.rank].ex_bits;
+                eyb = p.xlocal->slot[launch % 3][p.rank].ey_bits;
+            }
+            s_filter = p.fixed ? make_cfl_filter(0ULL, 0ULL) : make_cfl_filter(exb, eyb);
+        }
+    }
+    SWB_STAMP(10);
+    if (early && warp == 0) {
+        start_ring(0, 1);
+        first_rows_async();
+    }
+    SWB_STAMP(11);
+    __syncthreads();
+    SWB_STAMP(1);
+    const int flags = s_flags;
+    if (!(flags & 1)) {
+        if (early && TMA && warp_on && lane == 0)  // the load already under way must land before the block may exit
+            mbar_wait(bar_a + 8 * (tb % S), (uint32_t)((tb / S) & 1));
+        return false;
+    }
+    if (!early) bind((flags >> 1) & 1);
+    start_ring(early ? 1 : 0, S - 1);
+    if (RES) par_io = par ^ 1;
+    const T dt = (T)s_dt;
+    const T g_ = (T)p.g;
 
     // ---- row records of latitudes ja-1 .. jb ----------------------------------------
+    // (built in fp64 whatever T is -- SURVEY 7, hard part 6 -- and rounded once)
     T *rowc = reinterpret_cast<T *>(smem_raw);
     T *rowd = rowc + (size_t)(p.chunk + 2) * kRowRec;
-    for (int r = threadIdx.x; r < jb - ja + 2; r += blockDim.x) {
-        double rec[kRowRec];  // built in fp64 whatever T is (hard part 6), rounded once
-        build_row_record<STRICT>(p, ja - 1 + r, s_dt, rec);
+    if (RES) {
+        double *prec = reinterpret_cast<double *>(smem_raw + rec_bytes(p.chunk, DIFF));
+        double *pred = prec + (size_t)(p.chunk + 2) * kRowRec;
+        const int nrec = jb - ja + 2;
+        if (first) {
+            for (int r = threadIdx.x; r < nrec; r += blockDim.x) {
+                build_row_pre<STRICT>(p, ja - 1 + r, prec + (size_t)r * kRowRec);
+                if (DIFF && !STRICT) build_diff_pre(p, ja - 1 + r, pred + (size_t)r * kRowDiff);
+            }
+            __syncthreads();
+        }
+        const double dt64 = s_dt;
+        for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) rowc[e] = (T)scale_row_slot<STRICT>(e % kRowRec, prec[e], dt64);
+        if (DIFF && !STRICT)
+            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == 6 ? dt64 * pred[e] : pred[e]);
+    } else {
+        for (int r = threadIdx.x; r < jb - ja + 2; r += blockDim.x) {
+            double pre[kRowRec];
+            build_row_pre<STRICT>(p, ja - 1 + r, pre);
 #pragma unroll
-        for (int k = 0; k < kRowRec; ++k) rowc[(size_t)r * kRowRec + k] = (T)rec[k];
-        if (DIFF && !STRICT) {
-            double rd[kRowDiff];
-            build_diff_record(p, ja - 1 + r, s_dt, rd);
+            for (int k = 0; k < kRowRec; ++k) rowc[(size_t)r * kRowRec + k] = (T)scale_row_slot<STRICT>(k, pre[k], s_dt);
+            if (DIFF && !STRICT) {
+                double rd[kRowDiff];
+                build_diff_pre(p, ja - 1 + r, rd);
 #pragma unroll
-            for (int k = 0; k < kRowDiff; ++k) rowd[(size_t)r * kRowDiff + k] = (T)rd[k];
+                for (int k = 0; k < kRowDiff; ++k) rowd[(size_t)r * kRowDiff + k] = (T)(k == 6 ? s_dt * rd[6] : rd[k]);
+            }
         }
     }
     __syncthreads();
-    if (!warp_on) return;
+    SWB_STAMP(2);
+    if (!warp_on) return true;
+    if (RES) tbase = tb + ntiles;
+    if (early) first_rows_landed();
+    else load_first_rows();
 
     // ---- per-lane set-up ------------------------------------------------------------
-    const int colA = c0 + 2 * lane;  // this lane's cells: (., colA) and (., colA + 1)
     const bool vA = (lane >= 1) && (colA <= c0 + kValid) && (colA <= p.M + 1);
     const bool vB = (colA + 1 <= c0 + kValid) && (colA + 1 <= p.M + 1);
     const T hdt = O::mul(T(0.5), dt);
@@ -886,6 +1047,12 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     const bool seam = DIFF && ((vA && colA == p.M + 1) || (vB && colA + 1 == p.M + 1));
     const bool warp_wraps = __any_sync(0xffffffffu, wrapA || wrapB || seam);
     const int st_both = (vA && vB) ? 1 : 0, st_onlyA = (vA && !vB) ? 1 : 0, st_onlyB = (vB && !vA) ? 1 : 0;
+    // resident kernel: the ghost-column copy of a wrapping cell as one predicated store per field
+    // (column M -> column 0, column 2 -> column M+2; M >= 4 so that no column is both)
+    const bool res_wrap = RES && p.M >= 4;
+    const int gpA = (res_wrap && wrapA) ? 1 : 0, gpB = (res_wrap && wrapB) ? 1 : 0;
+    const long long goA = (long long)((colA == p.M) ? 0 : p.M + 2) - colA;      // element offset from (jl, colA) to A's ghost column
+    const long long goB = (long long)((colA + 1 == p.M) ? 0 : p.M + 2) - colA;  // ... and to B's
     bits_t<T> mxA = 0, myA = 0, mxB = 0, myB = 0;  // running CFL maxima (bit patterns)
     const int trig_x = CFLF ? s_filter.trig_x : 0, trig_y = CFLF ? s_filter.trig_y : 0;
     bool trig = false;  // CFLF: some cell of the current tile reached a trigger threshold
@@ -900,9 +1067,6 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     Cell<T> curA, curB;
     Face<T> y0A, y0B;
     {
-        const size_t k0 = (size_t)(ja - 1) * P + colA, k1 = k0 + P;
-        const V2 h0 = ldg2(H + k0), u0 = ldg2(U + k0), v0 = ldg2(V + k0);
-        const V2 h1 = ldg2(H + k1), u1 = ldg2(U + k1), v1 = ldg2(V + k1);
         const V2 f0 = load_f(ja - 1), f1 = load_f(ja);
         const T *r0 = rec_of(ja - 1), *r1 = rec_of(ja);
         const Cell<T> pA = make_cell<STRICT>(h0.x, u0.x, v0.x, r0[RC_C], hgCell, f0.x);
@@ -927,12 +1091,17 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
         if (p.north[0][0] != nullptr) plain_hi = min(plain_hi, p.jl_last - p.halo);
     }
     if (warp_wraps || p.force_rare) plain_hi = plain_lo - 1;  // strips that feed the periodic ghost columns: every row
+    // resident kernel: only the pole rows (and degenerate grids) leave the fast body
+    int res_lo = p.pole_s ? 2 : 0, res_hi = p.pole_n ? p.nrows - 3 : p.nrows;
+    if (p.force_rare || (warp_wraps && !res_wrap)) res_hi = res_lo - 1;
 
     // One latitude: cells (jl, colA), (jl, colA+1) from `cur`, the row above in (h2,u2,v2).
     // `hot` (a compile-time tag) = a live row in [plain_lo, plain_hi]: own stores only.
     size_t krow = (size_t)ja * P + colA;  // element index of (jl, colA), advanced row by row
     auto do_row = [&](auto hot_tag, int jl, V2 h2, V2 u2, V2 v2, bool live) {
         constexpr bool HOT = decltype(hot_tag)::value;
+        // resident kernel: ghost columns and pole rows are served inside the fast (unrolled) body
+        constexpr bool EXTRA = RES && HOT;
         const V2 *rc2 = reinterpret_cast<const V2 *>(rec_of(jl));
         // the row record, read as 16-byte pairs (broadcast LDS.128)
         const V2 r_c_ac = rc2[RC_C / 2], r_kx_fkx = rc2[RC_KX / 2], r_cdx_cxu = rc2[RC_CDX / 2], r_ky_fky = rc2[RC_KY / 2];
@@ -1009,14 +1178,15 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
         if (DIFF) {  // numpy.py:541-544: Laplacian of the OLD fields; u, v (not hu, hv)
             const int iA = min(max(colA, 1), p.M + 1), iB = min(max(colA + 1, 1), p.M + 1);  // keep invalid lanes in bounds
             Star<T> shA, shB, suA, suB, svA, svB;
-            if (HOT) {  // no pole row, no periodic column within reach: plain neighbours
-                load_star_pair(H, p.pitch, jl, colA, curA.h, curB.h, shA, shB);
-                load_star_pair(U, p.pitch, jl, colA, curA.u, curB.u, suA, suB);
-                load_star_pair(V, p.pitch, jl, colA, curA.v, curB.v, svA, svB);
+            // HOT: no pole row, no periodic column within reach: plain neighbours (EXTRA: checked per row)
+            if (HOT && (!EXTRA || (!warp_wraps && jl >= 2 && jl <= p.nrows - 3))) {
+                load_star_pair<T, RES>(H, p.pitch, jl, colA, curA.h, curB.h, shA, shB);
+                load_star_pair<T, RES>(U, p.pitch, jl, colA, curA.u, curB.u, suA, suB);
+                load_star_pair<T, RES>(V, p.pitch, jl, colA, curA.v, curB.v, svA, svB);
             } else {
-                shA = load_star(H, p.pitch, p.nrows, p.M, jl, iA); shB = load_star(H, p.pitch, p.nrows, p.M, jl, iB);
-                suA = load_star(U, p.pitch, p.nrows, p.M, jl, iA); suB = load_star(U, p.pitch, p.nrows, p.M, jl, iB);
-                svA = load_star(V, p.pitch, p.nrows, p.M, jl, iA); svB = load_star(V, p.pitch, p.nrows, p.M, jl, iB);
+                shA = load_star<T, RES>(H, p.pitch, p.nrows, p.M, jl, iA); shB = load_star<T, RES>(H, p.pitch, p.nrows, p.M, jl, iB);
+                suA = load_star<T, RES>(U, p.pitch, p.nrows, p.M, jl, iA); suB = load_star<T, RES>(U, p.pitch, p.nrows, p.M, jl, iB);
+                svA = load_star<T, RES>(V, p.pitch, p.nrows, p.M, jl, iA); svB = load_star<T, RES>(V, p.pitch, p.nrows, p.M, jl, iB);
             }
             if (STRICT) {
                 const T dnu = O::mul(dt, (T)p.nu);
@@ -1070,6 +1240,10 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
             st_pair(Hn + krow, hnA, hnB, st_both, st_onlyA, st_onlyB);
             st_pair(Un + krow, unA, unB, st_both, st_onlyA, st_onlyB);
             st_pair(Vn + krow, vnA, vnB, st_both, st_onlyA, st_onlyB);
+        }
+        if (EXTRA) {  // periodic ghost columns (numpy.py:402), branch-free; pole rows never come here
+            st_if(Hn + krow + goA, hnA, gpA); st_if(Un + krow + goA, unA, gpA); st_if(Vn + krow + goA, vnA, gpA);
+            st_if(Hn + krow + goB, hnB, gpB); st_if(Un + krow + goB, unB, gpB); st_if(Vn + krow + goB, vnB, gpB);
         }
         if (!HOT && live) {
             // boundary conditions (numpy.py:402-404): periodic ghost columns, zero-gradient
@@ -1126,14 +1300,16 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     using RareTag = std::integral_constant<bool, false>;
 
     // ---- the march ------------------------------------------------------------------
+    SWB_STAMP(3);
     if (TMA) {
         constexpr int kFieldV = LY::kField / (int)sizeof(V2), kRowV = kStripCols / 2;  // strides in lane pairs
         for (int t = 0; t < ntiles; ++t) {
-            const int s = t % S;
-            mbar_wait(bar_a + 8 * s, (uint32_t)((t / S) & 1));
+            const int s = (tb + t) % S;
+            mbar_wait(bar_a + 8 * s, (uint32_t)(((tb + t) / S) & 1));
             const V2 *tile = reinterpret_cast<const V2 *>(wbase + (size_t)s * LY::kStage) + lane;
             const int j0 = ja + t * R;
-            if (j0 >= plain_lo && j0 + R - 1 <= plain_hi) {  // warp-uniform
+            // warp-uniform; the resident kernel's fast body serves every complete tile
+            if (RES ? (j0 + R <= jb && j0 >= res_lo && j0 + R - 1 <= res_hi) : (j0 >= plain_lo && j0 + R - 1 <= plain_hi)) {
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr)
                     do_row(HotTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true);
@@ -1165,12 +1341,13 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
 #pragma unroll 1
         for (int jl = ja; jl < jb; ++jl) {
             const size_t k = (size_t)min(jl + 1, p.nrows - 1) * P + colA;
-            if (jl >= plain_lo && jl <= plain_hi) do_row(HotTag(), jl, ldg2(H + k), ldg2(U + k), ldg2(V + k), true);
-            else do_row(RareTag(), jl, ldg2(H + k), ldg2(U + k), ldg2(V + k), true);
+            if (RES ? (jl >= res_lo && jl <= res_hi) : (jl >= plain_lo && jl <= plain_hi)) do_row(HotTag(), jl, ld2<RES>(H + k), ld2<RES>(U + k), ld2<RES>(V + k), true);
+            else do_row(RareTag(), jl, ld2<RES>(H + k), ld2<RES>(U + k), ld2<RES>(V + k), true);
         }
     }
 
     // ---- epilogue: publish the CFL maxima and the depth watch -------------------------
+    SWB_STAMP(4);
     if (!p.fixed) {
         bits_t<T> mx = umax64(vA ? mxA : bits_t<T>(0), vB ? mxB : bits_t<T>(0));
         bits_t<T> my = umax64(vA ? myA : bits_t<T>(0), vB ? myB : bits_t<T>(0));
@@ -1180,8 +1357,11 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
             my = umax64(my, __shfl_xor_sync(0xffffffffu, my, s));
         }
         if (lane == 0) {
-            Ctrl *const new_slot = p.ctrl + ((p.launch + 1) % 3);
-            if (CFLF) {
+            Ctrl *const new_slot = p.ctrl + ((launch + 1) % 3);
+            if (RES) {  // per block first; resident_kernel forwards the block's maxima behind its barrier's __syncthreads
+                atomicMax(&s_max[0], widen_bits(mx));
+                atomicMax(&s_max[1], widen_bits(my));
+            } else if (CFLF) {
                 // most warps hold nothing: their cells stayed below the trigger threshold
                 const unsigned long long wx = widen_bits(mx), wy = widen_bits(my);
                 if (wx != 0ULL) atomicMax(&new_slot->ex_bits, wx);
@@ -1197,6 +1377,80 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     if (!kGuard) {
         const bool bad = (vA && negA < 0) || (vB && negB < 0);
         if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMin(p.err, -6);  // SWB_E_DEPTH
+    }
+    return true;
+}
+
+// One launch per time step (any grid size, any band decomposition).
+template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
+          bool CFLF = false>
+__global__ void __launch_bounds__(W * 32, MINB)
+march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ double s_dt;
+    __shared__ int s_flags;
+    __shared__ CflFilter s_filter;
+    int tbase = 0, par = -1;
+    march_step<T, STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, W, CFLF, false>(p, tm, p.launch, true, tbase, par, smem_raw, s_dt, s_flags, s_filter,
+                                                                           nullptr);
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grids that fit the GPU as ONE wave of blocks (360 x 180, 1440 x 720 -- the
+// state lives in the L2, a step takes microseconds and a launch per step would cost as much
+// again): the whole time loop of numpy.py:496-549 in one cooperative launch.  Every block
+// keeps its tile; a step ends in a grid barrier (one arrival atomic per block, release /
+// acquire at gpu scope), behind which the next step reads the CFL maxima -- accumulated by
+// the same atomics as in march_kernel -- and its neighbours' new rows and columns straight
+// from the L2.  Same step body, same arithmetic: bit-identical to a launch per step.
+template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
+__global__ void __launch_bounds__(W * 32, MINB)
+resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
+{
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ double s_dt;
+    __shared__ int s_flags;
+    __shared__ CflFilter s_filter;
+    __shared__ unsigned long long s_max[2];
+    const unsigned int nblocks = gridDim.x * gridDim.y;
+    int tbase = 0, par = -1;
+    for (int s = 0; s < p.nsteps; ++s) {
+#ifdef SWB_RES_TIMING
+        constexpr bool RES = true;
+        const int launch = p.launch + s;
+        SWB_STAMP(0);
+        SWB_STAMP(8);
+#endif
+        const bool active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true>(p, tm, p.launch + s, s == 0, tbase, par, smem_raw,
+                                                                                                     s_dt, s_flags, s_filter, s_max);
+        if (!active) break;
+        // Grid barrier: all stores and atomics of step s happen before any load of step s+1.
+        // (TMA: every thread first orders its generic-proxy stores before the async-proxy reads
+        // the next step's tensor loads are.)
+        if (TMA) asm volatile("fence.proxy.async.global;" ::: "memory");
+        __syncthreads();
+        SWB_STAMP(5);
+        if (threadIdx.x == 0) {
+            Ctrl *const new_slot = p.ctrl + ((p.launch + s + 1) % 3);
+            atomicMax(&new_slot->ex_bits, s_max[0]);
+            atomicMax(&new_slot->ey_bits, s_max[1]);
+            if (s + 1 < p.nsteps) {
+                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.done_ctr) : "memory");
+                SWB_STAMP(6);
+                const unsigned int target = (unsigned int)(s + 1) * nblocks;
+                while ((int)(ld_acquire_gpu(p.done_ctr) - target) < 0) {
+                }
+                SWB_STAMP(7);
+            }
+        }
+        __syncthreads();
     }
 }
 

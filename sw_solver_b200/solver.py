@@ -357,6 +357,12 @@ class Stepper:
     def launch_count(self) -> int:
         return int(self.lib.swb_launch_count(self._ctx))
 
+    @property
+    def resident(self) -> bool:
+        """True when ``enqueue(n)`` is ONE launch of the resident kernel (grids that fit the
+        GPU as one wave of blocks) instead of one launch per step."""
+        return bool(self.lib.swb_resident(self._ctx))
+
     # -- latitude bands (multi-GPU) ---------------------------------------------------
     def exchange_block(self) -> Tuple[int, int]:
         """Device address and size of the block peers deposit their CFL maxima in."""

@@ -429,6 +429,7 @@ def test_cfl_filter_is_exact(monkeypatch):
     random state makes the maxima jump both ways, so trigger, validity and fix-up paths all
     run; the smooth wave covers the common path."""
     rng = np.random.default_rng(7)
+    monkeypatch.setenv("SWB_RESIDENT", "0")  # the filter serves the launch-per-step kernel (large grids)
     for M, N, rough, nsteps in ((200, 96, True, 30), (500, 260, False, 40)):
         ll = LatLonGrid(M, N)
         cg = CartesianGrid(ll)
@@ -453,3 +454,93 @@ def test_cfl_filter_is_exact(monkeypatch):
         assert all(_bits(a, b) for a, b in zip(q0, q1))
         if rough:
             assert np.ptp(log0[0]) > 1e-3 * log0[0].mean()  # dt really moved: the maxima were not static
+
+
+# ---- resident kernel: one cooperative launch per batch of steps --------
+def _run_batches(M, N, ic, diff, mode, batches, final_time, resident, monkeypatch, extra_env=None):
+    monkeypatch.setenv("SWB_RESIDENT", "1" if resident else "0")
+    for k, v in (extra_env or {}).items():
+        monkeypatch.setenv(k, v)
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    h, u, v, f = get_initial_conditions(ic, ll)
+    st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=final_time, use_diffusion=diff, mode=mode, log_capacity=256)
+    assert st.resident == resident
+    trace = []
+    for n in batches:
+        st.enqueue(n)
+        s = st.status()
+        trace.append((int(s.steps), float(s.time), int(s.done), int(s.current), float(s.last_dt)))
+    out = st.to_numpy()
+    log = st.read_log(min(int(s.steps), 256))
+    launches = st.launch_count
+    st.close()
+    for k in (extra_env or {}):
+        monkeypatch.delenv(k)
+    return out, trace, log, launches
+
+
+@pytest.mark.parametrize("M,N,ic,diff,mode", [
+    (10, 10, ICType.RossbyHaurwitzWave, True, "strict"),
+    (10, 10, ICType.RossbyHaurwitzWave, False, "fast"),
+    (64, 48, ICType.RossbyHaurwitzWave, True, "fast"),
+    (131, 30, ICType.RossbyHaurwitzWave, True, "fast_guarded"),
+    (360, 180, ICType.RossbyHaurwitzWave, False, "fast"),
+    (360, 180, ICType.RossbyHaurwitzWave, False, "strict"),
+    (333, 97, ICType.RossbyHaurwitzWave, True, "strict"),
+    (1440, 720, ICType.RossbyHaurwitzWave, True, "fast"),
+    (1440, 720, ICType.RossbyHaurwitzWave, False, "fast"),          # TMA ring inside the resident loop
+    (1440, 720, ICType.RossbyHaurwitzWave, False, "fast_guarded"),
+])
+def test_resident_kernel_is_bit_identical_to_launch_per_step(M, N, ic, diff, mode, monkeypatch):
+    """The same step body behind a grid barrier instead of a launch: every bit of the state,
+    the time, the dt history and the step count must agree, however the steps are batched."""
+    batches = [1, 2, 7, 30, 1, 23]
+    ref, tr_ref, log_ref, n_ref = _run_batches(M, N, ic, diff, mode, batches, 1e12, False, monkeypatch)
+    res, tr_res, log_res, n_res = _run_batches(M, N, ic, diff, mode, batches, 1e12, True, monkeypatch)
+    assert tr_res == tr_ref
+    for a, b in zip(log_res, log_ref):
+        assert _bits(a, b)
+    for name, a, b in zip("huv", res, ref):
+        assert _bits(a, b), (name, _worst(a, b))
+    assert n_res < n_ref and n_res <= 3 * 3 + len(batches)  # three layout conversions, K0, one launch per batch
+
+
+def test_resident_kernel_marching_lengths_and_load_paths(monkeypatch):
+    """Forced marching lengths (1 row ... several tiles) and both load paths give the same bits."""
+    M, N, batches = 500, 100, [5, 20]
+    ref, tr_ref, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, False, "fast", batches, 1e12, False, monkeypatch)
+    for env in ({"SWB_RES_CHUNK": "1", "SWB_KERNEL": "ldg"}, {"SWB_RES_CHUNK": "3", "SWB_KERNEL": "ldg"},
+                {"SWB_RES_CHUNK": "4", "SWB_KERNEL": "tma"}, {"SWB_RES_CHUNK": "12", "SWB_KERNEL": "tma"},
+                {"SWB_RES_CHUNK": "32", "SWB_KERNEL": "tma"}):
+        res, tr, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, False, "fast", batches, 1e12, True, monkeypatch, env)
+        assert tr == tr_ref, env
+        for name, a, b in zip("huv", res, ref):
+            assert _bits(a, b), (env, name, _worst(a, b))
+
+
+def test_resident_kernel_stops_at_final_time(monkeypatch):
+    """The loop ends inside a batch (numpy.py:496, 528-532): the launch stops there, later
+    batches are no-ops, and time / step count / state equal the launch-per-step run."""
+    M, N = 64, 48
+    final_time = 3600.0  # ~52 steps
+    batches = [40, 40, 5, 1]
+    ref, tr_ref, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, "fast", batches, final_time, False, monkeypatch)
+    res, tr_res, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, "fast", batches, final_time, True, monkeypatch)
+    assert tr_ref[0][2] == 0 and tr_ref[1][2] == 1 and tr_ref[1][1] == final_time
+    assert tr_res == tr_ref
+    for name, a, b in zip("huv", res, ref):
+        assert _bits(a, b), name
+
+
+def test_large_grids_keep_the_launch_per_step_kernel():
+    ll = LatLonGrid(7200, 3600)
+    cg = CartesianGrid(ll)
+    from sw_solver_b200 import bands
+    from sw_solver_b200.ic import coriolis_latitude
+
+    hd, ud, vd, _ = bands.rossby_haurwitz_band(ll, 0, ll.N, torch.device("cuda", 0))
+    st = Stepper(ll, cg, hd, ud, vd, coriolis_latitude(ll), None, courant=0.5, final_time=1e12, use_diffusion=False,
+                 mode="fast", layout="device")
+    assert not st.resident
+    st.close()
