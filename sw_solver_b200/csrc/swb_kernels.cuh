@@ -144,19 +144,25 @@ template <> struct Vec2<float> { using type = float2; };
 template <typename T> using vec2_t = typename Vec2<T>::type;
 __device__ __forceinline__ double2 ldg2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ float2 ldg2(const float *p) { return *reinterpret_cast<const float2 *>(p); }
-// COH: the state is rewritten by other SMs while the kernel runs (resident_kernel) -- read it
-// at the L2 (ld.global.cg), never through the non-coherent L1 path.
-template <bool COH, typename T>
+// How the state is read.  LD_PLAIN: the compiler's choice (read-only data path when it can prove
+// the arrays constant -- march_kernel).  resident_kernel rewrites the state while it runs, so it
+// names the path: LD_CG = at the L2 (single-use rows, control words), LD_CA = through the L1 (the
+// diffusion star: every row is re-read by four other latitudes) -- coherent because the grid
+// barrier's acquire invalidates the L1 (LDG.STRONG.GPU + CCTL.IVALL) before the next step reads.
+enum LdPath { LD_PLAIN = 0, LD_CG = 1, LD_CA = 2 };
+template <int LD, typename T>
 __device__ __forceinline__ typename Vec2<T>::type ld2(const T *p)
 {
     using V = typename Vec2<T>::type;
-    if (COH) return __ldcg(reinterpret_cast<const V *>(p));
+    if (LD == LD_CG) return __ldcg(reinterpret_cast<const V *>(p));
+    if (LD == LD_CA) return __ldca(reinterpret_cast<const V *>(p));
     return *reinterpret_cast<const V *>(p);
 }
-template <bool COH, typename T>
+template <int LD, typename T>
 __device__ __forceinline__ T ld1(const T *p)
 {
-    if (COH) return __ldcg(p);
+    if (LD == LD_CG) return __ldcg(p);
+    if (LD == LD_CA) return __ldca(p);
     return *p;
 }
 __device__ __forceinline__ double2 mk2(double a, double b) { return make_double2(a, b); }
@@ -486,7 +492,7 @@ template <typename T>
 struct Star {
     T q0, xm, xp, xmm, xpp, ym, yp, ymm, ypp;
 };
-template <typename T, bool COH = false>
+template <typename T, int LD = LD_PLAIN>
 __device__ __forceinline__ Star<T> load_star(const T *__restrict__ q, int pitch, int nrows, int M, int jl, int i)
 {
     const size_t P = (size_t)pitch;
@@ -496,25 +502,25 @@ __device__ __forceinline__ Star<T> load_star(const T *__restrict__ q, int pitch,
     const int jm2 = max(jl - 2, 0), jp2 = min(jl + 2, nrows - 1);
     Star<T> s;
     const T *row = q + (size_t)jl * P;
-    s.q0 = ld1<COH>(row + i);
-    s.xm = ld1<COH>(row + i - 1); s.xp = ld1<COH>(row + i + 1);
-    s.xmm = ld1<COH>(row + im2);  s.xpp = ld1<COH>(row + ip2);
-    s.ym = ld1<COH>(q + (size_t)jm1 * P + i); s.yp = ld1<COH>(q + (size_t)jp1 * P + i);
-    s.ymm = ld1<COH>(q + (size_t)jm2 * P + i); s.ypp = ld1<COH>(q + (size_t)jp2 * P + i);
+    s.q0 = ld1<LD>(row + i);
+    s.xm = ld1<LD>(row + i - 1); s.xp = ld1<LD>(row + i + 1);
+    s.xmm = ld1<LD>(row + im2);  s.xpp = ld1<LD>(row + ip2);
+    s.ym = ld1<LD>(q + (size_t)jm1 * P + i); s.yp = ld1<LD>(q + (size_t)jp1 * P + i);
+    s.ymm = ld1<LD>(q + (size_t)jm2 * P + i); s.ypp = ld1<LD>(q + (size_t)jp2 * P + i);
     return s;
 }
 
 // The same for a lane's pair of cells (jl, colA), (jl, colA+1) away from every boundary: six
 // 16-byte loads per field instead of eighteen scalar ones; the centre values come from
 // registers.
-template <typename T, bool COH = false>
+template <typename T, int LD = LD_PLAIN>
 __device__ __forceinline__ void load_star_pair(const T *__restrict__ q, int pitch, int jl, int colA, T q0A, T q0B,
                                                Star<T> &sA, Star<T> &sB)
 {
     const size_t P = (size_t)pitch;
     const T *row = q + (size_t)jl * P + colA;
-    const vec2_t<T> L = ld2<COH>(row - 2), Rr = ld2<COH>(row + 2);
-    const vec2_t<T> m2 = ld2<COH>(row - 2 * P), m1 = ld2<COH>(row - P), p1 = ld2<COH>(row + P), p2 = ld2<COH>(row + 2 * P);
+    const vec2_t<T> L = ld2<LD>(row - 2), Rr = ld2<LD>(row + 2);
+    const vec2_t<T> m2 = ld2<LD>(row - 2 * P), m1 = ld2<LD>(row - P), p1 = ld2<LD>(row + P), p2 = ld2<LD>(row + 2 * P);
     sA.q0 = q0A; sA.xmm = L.x; sA.xm = L.y; sA.xp = q0B;  sA.xpp = Rr.x;
     sB.q0 = q0B; sB.xmm = L.y; sB.xm = q0A; sB.xp = Rr.x; sB.xpp = Rr.y;
     sA.ymm = m2.x; sA.ym = m1.x; sA.yp = p1.x; sA.ypp = p2.x;
@@ -550,9 +556,9 @@ __device__ __forceinline__ void step_prologue(const Params &p, int launch, doubl
         return;
     }
     // (RES: written by other SMs earlier in this launch -- read at the L2)
-    const double time = ld1<RES>(&cur_slot->time);
-    const long long nsteps = ld1<RES>(&cur_slot->nsteps);
-    const unsigned long long exb = ld1<RES>(&cur_slot->ex_bits), eyb = ld1<RES>(&cur_slot->ey_bits);
+    const double time = ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->time);
+    const long long nsteps = ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->nsteps);
+    const unsigned long long exb = ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->ex_bits), eyb = ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->ey_bits);
     const double tx = __ddiv_rn(p.dxmin, __longlong_as_double((long long)exb));
     const double ty = __ddiv_rn(p.dymin, __longlong_as_double((long long)eyb));
     const double dtmax = (tx != tx) ? tx : ((ty != ty) ? ty : (tx < ty ? tx : ty));  // np.minimum propagates NaN
@@ -577,7 +583,7 @@ __device__ __forceinline__ void step_prologue(const Params &p, int launch, doubl
         new_slot->time = tnew;
         new_slot->nsteps = nsteps + (active ? 1 : 0);
         new_slot->current = (int)((nsteps + (active ? 1 : 0)) & 1);
-        new_slot->last_dt = active ? dt : ld1<RES>(&cur_slot->last_dt);
+        new_slot->last_dt = active ? dt : ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->last_dt);
         new_slot->done = !(tnew < p.final_time);
         new_slot->error = 0;
         if (!active) {  // nothing will be accumulated: carry the maxima forward
@@ -869,6 +875,8 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     using V2 = vec2_t<T>;
     constexpr int kValid = sizeof(T) == 8 ? kStripValid : kStripValidF32;
     constexpr bool kGuard = STRICT || GUARD;
+    constexpr int kLdStar = RES ? LD_CA : LD_PLAIN;                   // diffusion star
+    constexpr int kLdRow = RES ? (DIFF ? LD_CA : LD_CG) : LD_PLAIN;   // the march's own rows
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -921,8 +929,8 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     V2 h0, u0, v0, h1, u1, v1;  // latitudes ja-1 and ja
     auto load_first_rows = [&]() {
         const size_t k0 = (size_t)(ja - 1) * P + colA, k1 = k0 + P;
-        h0 = ld2<RES>(H + k0); u0 = ld2<RES>(U + k0); v0 = ld2<RES>(V + k0);
-        h1 = ld2<RES>(H + k1); u1 = ld2<RES>(U + k1); v1 = ld2<RES>(V + k1);
+        h0 = ld2<kLdRow>(H + k0); u0 = ld2<kLdRow>(U + k0); v0 = ld2<kLdRow>(V + k0);
+        h1 = ld2<kLdRow>(H + k1); u1 = ld2<kLdRow>(U + k1); v1 = ld2<kLdRow>(V + k1);
     };
     // RES, early: the same twelve values parked in shared memory by asynchronous copies (each lane
     // copies and later reads its own 6 x 16 bytes) -- in the ring stage that is not in flight yet
@@ -1180,13 +1188,13 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             Star<T> shA, shB, suA, suB, svA, svB;
             // HOT: no pole row, no periodic column within reach: plain neighbours (EXTRA: checked per row)
             if (HOT && (!EXTRA || (!warp_wraps && jl >= 2 && jl <= p.nrows - 3))) {
-                load_star_pair<T, RES>(H, p.pitch, jl, colA, curA.h, curB.h, shA, shB);
-                load_star_pair<T, RES>(U, p.pitch, jl, colA, curA.u, curB.u, suA, suB);
-                load_star_pair<T, RES>(V, p.pitch, jl, colA, curA.v, curB.v, svA, svB);
+                load_star_pair<T, kLdStar>(H, p.pitch, jl, colA, curA.h, curB.h, shA, shB);
+                load_star_pair<T, kLdStar>(U, p.pitch, jl, colA, curA.u, curB.u, suA, suB);
+                load_star_pair<T, kLdStar>(V, p.pitch, jl, colA, curA.v, curB.v, svA, svB);
             } else {
-                shA = load_star<T, RES>(H, p.pitch, p.nrows, p.M, jl, iA); shB = load_star<T, RES>(H, p.pitch, p.nrows, p.M, jl, iB);
-                suA = load_star<T, RES>(U, p.pitch, p.nrows, p.M, jl, iA); suB = load_star<T, RES>(U, p.pitch, p.nrows, p.M, jl, iB);
-                svA = load_star<T, RES>(V, p.pitch, p.nrows, p.M, jl, iA); svB = load_star<T, RES>(V, p.pitch, p.nrows, p.M, jl, iB);
+                shA = load_star<T, kLdStar>(H, p.pitch, p.nrows, p.M, jl, iA); shB = load_star<T, kLdStar>(H, p.pitch, p.nrows, p.M, jl, iB);
+                suA = load_star<T, kLdStar>(U, p.pitch, p.nrows, p.M, jl, iA); suB = load_star<T, kLdStar>(U, p.pitch, p.nrows, p.M, jl, iB);
+                svA = load_star<T, kLdStar>(V, p.pitch, p.nrows, p.M, jl, iA); svB = load_star<T, kLdStar>(V, p.pitch, p.nrows, p.M, jl, iB);
             }
             if (STRICT) {
                 const T dnu = O::mul(dt, (T)p.nu);
@@ -1341,8 +1349,8 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
 #pragma unroll 1
         for (int jl = ja; jl < jb; ++jl) {
             const size_t k = (size_t)min(jl + 1, p.nrows - 1) * P + colA;
-            if (RES ? (jl >= res_lo && jl <= res_hi) : (jl >= plain_lo && jl <= plain_hi)) do_row(HotTag(), jl, ld2<RES>(H + k), ld2<RES>(U + k), ld2<RES>(V + k), true);
-            else do_row(RareTag(), jl, ld2<RES>(H + k), ld2<RES>(U + k), ld2<RES>(V + k), true);
+            if (RES ? (jl >= res_lo && jl <= res_hi) : (jl >= plain_lo && jl <= plain_hi)) do_row(HotTag(), jl, ld2<kLdRow>(H + k), ld2<kLdRow>(U + k), ld2<kLdRow>(V + k), true);
+            else do_row(RareTag(), jl, ld2<kLdRow>(H + k), ld2<kLdRow>(U + k), ld2<kLdRow>(V + k), true);
         }
     }
 
