@@ -55,6 +55,7 @@ def parse_args():
                     help="state type; f32 is the optional fp32 mode (24 algorithmic bytes per update)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="skip the L2-resident configurations (BASELINE.json configs 1 and 2)")
     return ap.parse_args()
 
 
@@ -181,6 +182,42 @@ def run_reference_arm(args, M, N):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+def small_configs(dev):
+    """BASELINE.json configs 1 and 2 (L2-resident grids, N = 1): step time through the same
+    `Stepper.enqueue` call; these grids run the resident kernel (one cooperative launch per
+    batch of steps).  Informational: the headline line is the 16384 x 8192 workload."""
+    import torch
+
+    from sw_solver_b200.grid import CartesianGrid, LatLonGrid
+    from sw_solver_b200.ic import ICType, get_initial_conditions
+    from sw_solver_b200.solver import Stepper
+
+    out = []
+    for M, N, diff, steps in ((360, 180, False, 4000), (1440, 720, True, 2000)):
+        ll = LatLonGrid(M, N)
+        cg = CartesianGrid(ll)
+        h, u, v, f = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+        st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=1e12, use_diffusion=diff, mode="fast", device=dev)
+        st.enqueue(200)
+        torch.cuda.synchronize(dev)
+        l0 = st.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st.enqueue(steps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        s = st.status()
+        assert s.steps == 200 + steps and s.error == 0
+        pts = (M + 1) * (ll.N - 2)
+        out.append({"workload": f"Rossby-Haurwitz {M}x{ll.N} fp64, diffusion {'on' if diff else 'off'}", "steps": steps,
+                    "us_per_step": 1e3 * ms / steps, "value": pts * steps / (ms * 1e-3), "unit": UNIT,
+                    "kernel": "swb::resident_kernel" if st.resident else "swb::march_kernel",
+                    "gpu_launches": int(st.launch_count - l0)})
+        st.close()
+    return out
+
+
 def run_ours(args, M, N):
     """One rank of the job.  N = 1: the whole M x N grid on cuda:0.  N > 1 (torchrun, one
     process per GPU): weak scaling -- every GPU owns an M x N latitude band of the
@@ -260,6 +297,7 @@ def run_ours(args, M, N):
     hcur = st.state()[0]
     assert bool(torch.isfinite(hcur).all()), "non-finite state after the timed region"
     value = pts * args.steps / (ms * 1e-3)
+    resident = st.resident
     st.close()
     del st, hcur
     torch.cuda.empty_cache()
@@ -294,9 +332,11 @@ def run_ours(args, M, N):
     kernel_ms = ms / args.steps
     achieved = bytes_per_update * pts_rank / (kernel_ms * 1e-3) / 1e9  # per GPU
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "swb::march_kernel", "kernel_ms": kernel_ms,
+                "traffic": None, "kernel": "swb::resident_kernel" if resident else "swb::march_kernel", "kernel_ms": kernel_ms,
                 "bytes_per_launch": bytes_per_update * pts_rank, "peak_source": peak_src,
-                "note": "per GPU; one march_kernel launch per step (kernel_ms = step time, CUDA events on the launch stream)"}
+                "note": ("per GPU; one resident_kernel launch for all timed steps (kernel_ms = step time, CUDA events on the launch stream)"
+                         if resident else
+                         "per GPU; one march_kernel launch per step (kernel_ms = step time, CUDA events on the launch stream)")}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -314,6 +354,10 @@ def run_ours(args, M, N):
                "sample": f"oracle port of numpy.py:503-549 (C, OpenMP) on a {M}x{r['N_sample']} latitude band of the "
                          f"workload, {nsteps} steps, {r['seconds']:.1f} s"}
 
+    small = None
+    if world == 1 and not args.no_small:
+        small = small_configs(dev)
+
     if dist is not None:
         dist.barrier()
     if rank == 0:
@@ -324,10 +368,12 @@ def run_ours(args, M, N):
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"Rossby-Haurwitz {per_gpu} {'fp64' if args.dtype == 'f64' else 'fp32'}, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
                        "mode": args.mode,
-                       "l2": "state (6.4 GB touched per GPU per step at the default size) is larger than L2; no flush needed",
+                       "l2": (f"state ({2 * bytes_per_update / 2 * pts_rank / 1e9:.2f} GB touched per GPU per step) is larger than the 126 MB L2; no flush needed"
+                              if bytes_per_update * pts_rank > 4 * 126e6 else
+                              "state fits the L2: this grid is L2-resident by nature (no flush; the roofline fraction is not an HBM figure)"),
                        "pts_per_step": pts, "parallelism": f"lat-bands x{world}"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
-            "clocks": clk.summary(),
+            "clocks": clk.summary(), "l2_resident_configs": small,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -91,7 +91,12 @@ def load():
     global _lib
     if _lib is None:
         path = _build.LIB
-        if _build.needs_build():
+        alt = os.environ.get("SWB_LIB")  # dev: an alternative build of the same sources (e.g. -DSWB_RES_TIMING)
+        if alt:
+            if not os.path.exists(alt):
+                raise ImportError(f"SWB_LIB={alt} does not exist")
+            path = alt
+        elif _build.needs_build():
             try:
                 path = _build.build()
             except RuntimeError:

@@ -31,8 +31,8 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = LIB) -> str:
+    if out == LIB and not force and not needs_build():
         return LIB
     cmd = [
         nvcc_path(),
@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-fmad=false",
         "-Xcompiler", "-fPIC", "-shared",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-        "-o", LIB,
+        "-o", out,
     ] + SOURCES
     cmd[1:1] = os.environ.get("SWB_NVCC_FLAGS", "").split()  # dev builds, e.g. -DSWB_RES_TIMING
     if verbose:
@@ -55,8 +55,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    outs = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=outs[0] if outs else LIB))
