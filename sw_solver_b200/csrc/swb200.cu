@@ -93,7 +93,7 @@ template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R
           bool CFLF = false>
 cudaError_t launch_inst(const swb_ctx *c, dim3 grid, cudaStream_t st)
 {
-    using LY = TmaLayout<R, S, T>;
+    using LY = TmaLayout<R, S, T, box_cols<T, DIFF, TMA>()>;
     const int smem = rec_bytes(c->prm.chunk, DIFF) + (TMA ? W * LY::kWarpBytes : 0);
     static int configured[64] = {0};  // per instantiation and device: largest size opted in so far
     auto fn = march_kernel<T, STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, MINB, W, CFLF>;
@@ -233,12 +233,14 @@ struct ResKernel { const void *fn; int smem; };
 template <bool STRICT, bool DIFF, bool TMA, bool GUARD>
 ResKernel res_kernel_inst(int chunk)
 {
-    using LY = TmaLayout<4, 4, double>;
-    auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? 4 : 1), GUARD, 2>;
+    constexpr int S = DIFF ? 3 : 4;  // (with diffusion: three stages of wider boxes, as in march_kernel)
+    using LY = TmaLayout<4, S, double, box_cols<double, DIFF, TMA>()>;
+    auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? S : 1), GUARD, 2>;
     return ResKernel{(const void *)fn, 2 * rec_bytes(chunk, DIFF) + (TMA ? kWarpsPerBlock * LY::kWarpBytes : kWarpsPerBlock * kFirstRowsBytes)};
 }
 ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk)
 {
+    if (tma && diff) return mode == SWB_FAST ? res_kernel_inst<false, true, true, false>(chunk) : res_kernel_inst<false, true, true, true>(chunk);
     if (tma) return mode == SWB_FAST ? res_kernel_inst<false, false, true, false>(chunk) : res_kernel_inst<false, false, true, true>(chunk);
     if (mode == SWB_STRICT) return diff ? res_kernel_inst<true, true, false, true>(chunk) : res_kernel_inst<true, false, false, true>(chunk);
     if (mode == SWB_FAST) return diff ? res_kernel_inst<false, true, false, false>(chunk) : res_kernel_inst<false, false, false, false>(chunk);
@@ -259,7 +261,7 @@ int setup_resident(swb_ctx *c)
         if (atoi(e) == 0) return 0;
     const int rows = p.jl_last - p.jl_first + 1;
     const int gx = (p.nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const bool tma_ok = c->use_tma && !cfg.use_diffusion && cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant;
+    const bool tma_ok = c->use_tma && cfg.mode != SWB_STRICT && (cfg.use_diffusion || c->tma_variant == kDefaultTmaVariant);
     const char *force = getenv("SWB_KERNEL");
     int forced_chunk = 0;
     if (const char *e = getenv("SWB_RES_CHUNK")) forced_chunk = atoi(e);
@@ -538,8 +540,9 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
         if (const char *e = getenv("SWB_CFL_FILTER")) c->cfl_filter = !f32 && !c->cfg.use_diffusion && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && atoi(e) != 0;
         CK(cudaSetDevice(c->cfg.device));
         for (int s = 0; s < 2; ++s) {
+            // (fp64 with diffusion: the box also carries the star's two columns either side)
             int rc = make_map(&c->maps.in[s], p.buf[s][0], (uint64_t)(p.M + 3), (uint64_t)p.nrows, (uint64_t)p.pitch, (uint64_t)(s ? fs1 : fs0),
-                              kStripCols, (uint32_t)tv.R, f32);
+                              (uint32_t)((c->cfg.use_diffusion && !f32) ? box_cols<double, true, true>() : kStripCols), (uint32_t)tv.R, f32);
             if (rc) return rc;
         }
     }

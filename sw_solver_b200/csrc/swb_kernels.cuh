@@ -734,9 +734,14 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 constexpr int kFirstRowsBytes = 6 * 32 * 16;  // per warp: h, u, v pairs of the march's first two latitudes
 
-template <int R, int S, typename T = double>
+// Columns of a TMA box: the strip, plus two columns either side when the diffusion star is read
+// from the ring as well (fp64 with diffusion: SSTAR in march_step)
+template <typename T, bool DIFF, bool TMA>
+__host__ __device__ constexpr int box_cols() { return (DIFF && TMA && sizeof(T) == 8) ? kStripCols + 4 : kStripCols; }
+
+template <int R, int S, typename T = double, int COLS = kStripCols>
 struct TmaLayout {
-    static constexpr int kField = R * kStripCols * (int)sizeof(T);  // one field, one stage
+    static constexpr int kField = R * COLS * (int)sizeof(T);  // one field, one stage
     static constexpr int kStage = 3 * kField;
     static constexpr int kRing = S * kStage;
     static constexpr int kBars = 128;
@@ -842,6 +847,13 @@ __device__ __forceinline__ double rsqrt_seed(double x)
 // TMA ring (R latitudes per box, S stages) or direct loads, and whether FAST evaluates the
 // reference's hMid > 0 selects (GUARD) or assumes them true and raises SWB_E_DEPTH when a
 // half-step depth turns out non-positive.
+// SSTAR: where a lane finds its pair of latitudes jl-2, jl-1, jl and jl+2 in the ring (field 0;
+// latitude jl+1 is the row the march streams anyway)
+template <typename V2>
+struct StarRows {
+    const V2 *m2, *m1, *c0, *p2;
+};
+
 #ifdef SWB_RES_TIMING
 __device__ __forceinline__ unsigned swb_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
 #define SWB_STAMP(k)                                                                                       \
@@ -871,7 +883,14 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     static_assert(!CFLF || (!STRICT && TMA && sizeof(T) == 8), "the CFL filter serves the fp64 FAST TMA kernel");
     static_assert(!RES || (sizeof(T) == 8 && !F2D && !HS && !CFLF), "resident_kernel: fp64, latitude-only Coriolis, flat topography");
     using O = Op<STRICT, T>;
-    using LY = TmaLayout<R, S, T>;
+    // SSTAR: the diffusion star comes out of the ring too -- boxes two columns wider on either
+    // side, one tile more at either end of the march, tiles t-1, t, t+1 resident while tile t
+    // is marched (S >= 3)
+    constexpr bool SSTAR = DIFF && TMA && sizeof(T) == 8;
+    constexpr int kBoxCols = box_cols<T, DIFF, TMA>();
+    constexpr int kLead = SSTAR ? 1 : 0;  // ring tile u holds latitudes ja+1+(u-kLead)R ..; the march consumes u = kLead ..
+    static_assert(!SSTAR || (S >= 3 && R == 4), "the star needs three four-row tiles in the ring");
+    using LY = TmaLayout<R, S, T, kBoxCols>;
     using V2 = vec2_t<T>;
     constexpr int kValid = sizeof(T) == 8 ? kStripValid : kStripValidF32;
     constexpr bool kGuard = STRICT || GUARD;
@@ -892,8 +911,11 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     const int recb = rec_bytes(p.chunk, DIFF) * (RES ? 2 : 1);  // RES: the dt-independent records follow
     unsigned char *wbase = smem_raw + recb + (size_t)warp * LY::kWarpBytes;
     const uint32_t ring_a = smem_u32(wbase), bar_a = ring_a + LY::kRing;
-    const int ntiles = (jb - ja + R - 1) / R;
-    const int tb = RES ? tbase : 0;  // tiles consumed before this step
+    const int ntiles = (jb - ja + R - 1) / R;  // tiles marched
+    // tiles loaded: with SSTAR one before (latitudes ja-3 .. ja) and, when the last marched
+    // tile ends on jb, one after (the star of latitude jb-1 reaches jb+1)
+    const int nload = ntiles + (SSTAR ? 1 + ((ntiles * R < jb - ja + 1) ? 1 : 0) : 0);
+    const int tb = RES ? tbase : 0;  // ring tiles consumed before this step
     int par = 0;
     const T *__restrict__ H, *__restrict__ U, *__restrict__ V;
     T *__restrict__ Hn, *__restrict__ Un, *__restrict__ Vn;
@@ -904,24 +926,26 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         Hn = (T *)p.buf[pr ^ 1][0]; Un = (T *)p.buf[pr ^ 1][1]; Vn = (T *)p.buf[pr ^ 1][2];
         maps = &tm.in[pr];
     };
-    auto issue_load = [&](int t) {  // lane 0 only: latitudes ja+1+tR .. of h, u, v into stage (tb + t) % S
-        const int s = (tb + t) % S;
+    auto stage_of = [&](int u) { return (tb + u) % S; };
+    auto wait_tile = [&](int u) { mbar_wait(bar_a + 8 * stage_of(u), (uint32_t)(((tb + u) / S) & 1)); };
+    auto issue_load = [&](int u) {  // lane 0 only: ring tile u -- h, u, v of R latitudes in one box (out-of-range parts read as zero)
+        const int s = stage_of(u);
         const uint32_t bar = bar_a + 8 * s;
         mbar_expect_tx(bar, LY::kStage);
-        tma_load_3d(ring_a + s * LY::kStage, maps, c0, ja + 1 + t * R, 0, bar);  // h, u, v of R latitudes in one box
+        tma_load_3d(ring_a + s * LY::kStage, maps, c0 - (SSTAR ? 2 : 0), ja + 1 + (u - kLead) * R, 0, bar);
     };
-    // tiles [t_lo, t_hi) of the ring's first S-1
-    auto start_ring = [&](int t_lo, int t_hi) {
+    constexpr int kFirstIssue = S - 1 + kLead;  // tiles requested before the march starts
+    auto start_ring = [&](int u_lo, int u_hi) {
         if (TMA && warp_on) {
             if (lane == 0) {
-                if ((!RES || first) && t_lo == 0) {
+                if ((!RES || first) && u_lo == 0) {
 #pragma unroll
                     for (int s = 0; s < S; ++s) mbar_init(bar_a + 8 * s, 1);
                     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
                 }
 #pragma unroll
-                for (int t = 0; t < S - 1; ++t)
-                    if (t >= t_lo && t < t_hi && t < ntiles) issue_load(t);
+                for (int u = 0; u < kFirstIssue; ++u)
+                    if (u >= u_lo && u < u_hi && u < nload) issue_load(u);
             }
             __syncwarp();
         }
@@ -936,6 +960,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     // copies and later reads its own 6 x 16 bytes) -- in the ring stage that is not in flight yet
     // (TMA), or in a staging area behind the records
     unsigned char *stg = (TMA ? wbase + (size_t)((tb + S - 1) % S) * LY::kStage : smem_raw + recb + (size_t)warp * kFirstRowsBytes) + lane * 16;
+    constexpr int kEarly = 1 + kLead;  // tiles requested before dt is known (RES); SSTAR: its first tile holds the first rows
     auto first_rows_async = [&]() {
         const size_t k0 = (size_t)(ja - 1) * P + colA, k1 = k0 + P;
         const uint32_t d = smem_u32(stg);
@@ -954,8 +979,8 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     if (early) {
         bind(par_io);
         if (warp != 0) {  // (warp 0: after the prologue -- its lane 0 is the prologue's thread)
-            start_ring(0, 1);
-            if (warp_on) first_rows_async();
+            start_ring(0, kEarly);
+            if (warp_on && !SSTAR) first_rows_async();
         }
     }
     SWB_STAMP(9);
@@ -977,20 +1002,20 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     }
     SWB_STAMP(10);
     if (early && warp == 0) {
-        start_ring(0, 1);
-        first_rows_async();
+        start_ring(0, kEarly);
+        if (!SSTAR) first_rows_async();
     }
     SWB_STAMP(11);
     __syncthreads();
     SWB_STAMP(1);
     const int flags = s_flags;
     if (!(flags & 1)) {
-        if (early && TMA && warp_on && lane == 0)  // the load already under way must land before the block may exit
-            mbar_wait(bar_a + 8 * (tb % S), (uint32_t)((tb / S) & 1));
+        if (early && TMA && warp_on && lane == 0)  // the loads already under way must land before the block may exit
+            for (int u = 0; u < kEarly && u < nload; ++u) wait_tile(u);
         return false;
     }
     if (!early) bind((flags >> 1) & 1);
-    start_ring(early ? 1 : 0, S - 1);
+    start_ring(early ? kEarly : 0, kFirstIssue);
     if (RES) par_io = par ^ 1;
     const T dt = (T)s_dt;
     const T g_ = (T)p.g;
@@ -1031,9 +1056,21 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     __syncthreads();
     SWB_STAMP(2);
     if (!warp_on) return true;
-    if (RES) tbase = tb + ntiles;
-    if (early) first_rows_landed();
-    else load_first_rows();
+    if (RES) tbase = tb + nload;
+    constexpr int kFieldV = LY::kField / (int)sizeof(V2), kRowV = kBoxCols / 2;  // ring strides in lane pairs
+    auto tile_of = [&](int u) {  // this lane's pair in row 0, field 0 of ring tile u
+        return reinterpret_cast<const V2 *>(wbase + (size_t)stage_of(u) * LY::kStage) + lane + (SSTAR ? 1 : 0);
+    };
+    if (SSTAR) {  // latitudes ja-1, ja: the last two rows of the leading tile
+        wait_tile(0);
+        const V2 *q = tile_of(0);
+        h0 = q[(R - 2) * kRowV]; u0 = q[kFieldV + (R - 2) * kRowV]; v0 = q[2 * kFieldV + (R - 2) * kRowV];
+        h1 = q[(R - 1) * kRowV]; u1 = q[kFieldV + (R - 1) * kRowV]; v1 = q[2 * kFieldV + (R - 1) * kRowV];
+    } else if (early) {
+        first_rows_landed();
+    } else {
+        load_first_rows();
+    }
 
     // ---- per-lane set-up ------------------------------------------------------------
     const bool vA = (lane >= 1) && (colA <= c0 + kValid) && (colA <= p.M + 1);
@@ -1106,7 +1143,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     // One latitude: cells (jl, colA), (jl, colA+1) from `cur`, the row above in (h2,u2,v2).
     // `hot` (a compile-time tag) = a live row in [plain_lo, plain_hi]: own stores only.
     size_t krow = (size_t)ja * P + colA;  // element index of (jl, colA), advanced row by row
-    auto do_row = [&](auto hot_tag, int jl, V2 h2, V2 u2, V2 v2, bool live) {
+    auto do_row = [&](auto hot_tag, int jl, V2 h2, V2 u2, V2 v2, bool live, const StarRows<V2> &sr) {
         constexpr bool HOT = decltype(hot_tag)::value;
         // resident kernel: ghost columns and pole rows are served inside the fast (unrolled) body
         constexpr bool EXTRA = RES && HOT;
@@ -1187,7 +1224,21 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             const int iA = min(max(colA, 1), p.M + 1), iB = min(max(colA + 1, 1), p.M + 1);  // keep invalid lanes in bounds
             Star<T> shA, shB, suA, suB, svA, svB;
             // HOT: no pole row, no periodic column within reach: plain neighbours (EXTRA: checked per row)
-            if (HOT && (!EXTRA || (!warp_wraps && jl >= 2 && jl <= p.nrows - 3))) {
+            if (HOT && SSTAR && (!EXTRA || !warp_wraps)) {
+                // out of the ring: per field the pairs left and right of the lane's own and the
+                // lane's pairs two and one latitudes below and two above (LDS.128, conflict-free)
+                auto star = [&](int fld, T q0A, T q0B, V2 p1, Star<T> &sA, Star<T> &sB) {
+                    const V2 L = sr.c0[fld * kFieldV - 1], Rr = sr.c0[fld * kFieldV + 1];
+                    const V2 m2 = sr.m2[fld * kFieldV], m1 = sr.m1[fld * kFieldV], p2 = sr.p2[fld * kFieldV];
+                    sA.q0 = q0A; sA.xmm = L.x; sA.xm = L.y; sA.xp = q0B;  sA.xpp = Rr.x;
+                    sB.q0 = q0B; sB.xmm = L.y; sB.xm = q0A; sB.xp = Rr.x; sB.xpp = Rr.y;
+                    sA.ymm = m2.x; sA.ym = m1.x; sA.yp = p1.x; sA.ypp = p2.x;
+                    sB.ymm = m2.y; sB.ym = m1.y; sB.yp = p1.y; sB.ypp = p2.y;
+                };
+                star(0, curA.h, curB.h, h2, shA, shB);
+                star(1, curA.u, curB.u, u2, suA, suB);
+                star(2, curA.v, curB.v, v2, svA, svB);
+            } else if (HOT && (!EXTRA || (!warp_wraps && jl >= 2 && jl <= p.nrows - 3))) {
                 load_star_pair<T, kLdStar>(H, p.pitch, jl, colA, curA.h, curB.h, shA, shB);
                 load_star_pair<T, kLdStar>(U, p.pitch, jl, colA, curA.u, curB.u, suA, suB);
                 load_star_pair<T, kLdStar>(V, p.pitch, jl, colA, curA.v, curB.v, svA, svB);
@@ -1309,18 +1360,35 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
 
     // ---- the march ------------------------------------------------------------------
     SWB_STAMP(3);
+    const StarRows<V2> no_star{nullptr, nullptr, nullptr, nullptr};
     if (TMA) {
-        constexpr int kFieldV = LY::kField / (int)sizeof(V2), kRowV = kStripCols / 2;  // strides in lane pairs
+        if (SSTAR) wait_tile(1);
         for (int t = 0; t < ntiles; ++t) {
-            const int s = (tb + t) % S;
-            mbar_wait(bar_a + 8 * s, (uint32_t)(((tb + t) / S) & 1));
-            const V2 *tile = reinterpret_cast<const V2 *>(wbase + (size_t)s * LY::kStage) + lane;
+            const int u = t + kLead;
+            if (!SSTAR) wait_tile(u);
+            const V2 *tile = tile_of(u);
+            const V2 *tprev = SSTAR ? tile_of(u - 1) : tile, *tnext = SSTAR ? tile_of(u + 1) : tile;
+            // row i of the marched tile, reaching into its neighbours in the ring (i is a constant after unrolling)
+            auto ring_row = [&](int i) { return i < 0 ? tprev + (i + R) * kRowV : (i >= R ? tnext + (i - R) * kRowV : tile + i * kRowV); };
+            // SSTAR ring protocol: tile u-1 is dead once row R-2 of tile u is done (the last row reaches
+            // into tiles u and u+1 only), so its stage is refilled THERE -- and tile u+1, requested at the
+            // same point of the previous tile, is awaited there: a whole tile of slack with three stages.
+            auto turn_ring = [&]() {
+                __syncwarp();
+                if (lane == 0 && u + S - 1 < nload) issue_load(u + S - 1);
+                if (u + 1 < nload) wait_tile(u + 1);
+            };
             const int j0 = ja + t * R;
             // warp-uniform; the resident kernel's fast body serves every complete tile
-            if (RES ? (j0 + R <= jb && j0 >= res_lo && j0 + R - 1 <= res_hi) : (j0 >= plain_lo && j0 + R - 1 <= plain_hi)) {
+            const bool hot_tile = RES ? (j0 + R <= jb && j0 >= res_lo && j0 + R - 1 <= res_hi) : (j0 >= plain_lo && j0 + R - 1 <= plain_hi);
+            if (hot_tile) {
 #pragma unroll
-                for (int rr = 0; rr < R; ++rr)
-                    do_row(HotTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true);
+                for (int rr = 0; rr < R; ++rr) {
+                    if (SSTAR && rr == R - 1) turn_ring();
+                    // the streamed row rr is latitude jl+1: jl-2, jl-1, jl, jl+2 are rows rr-3, rr-2, rr-1, rr+1
+                    const StarRows<V2> sr{ring_row(rr - 3), ring_row(rr - 2), ring_row(rr - 1), ring_row(rr + 1)};
+                    do_row(HotTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true, SSTAR ? sr : no_star);
+                }
                 if (CFLF) {
                     if (__any_sync(0xffffffffu, trig)) {  // rare: exact keys of the tile's cells, from the values just stored
 #pragma unroll 1
@@ -1340,17 +1408,21 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
 #pragma unroll 1
                 for (int rr = 0; rr < R; ++rr)
                     do_row(RareTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV],
-                           j0 + rr < jb);
+                           j0 + rr < jb, no_star);
             }
-            __syncwarp();  // every lane is done with the stage that is refilled next
-            if (lane == 0 && t + S - 1 < ntiles) issue_load(t + S - 1);
+            if (SSTAR) {
+                if (!hot_tile) turn_ring();
+            } else {
+                __syncwarp();  // every lane is done with the stage that is refilled next
+                if (lane == 0 && u + S - 1 < nload) issue_load(u + S - 1);
+            }
         }
     } else {
 #pragma unroll 1
         for (int jl = ja; jl < jb; ++jl) {
             const size_t k = (size_t)min(jl + 1, p.nrows - 1) * P + colA;
-            if (RES ? (jl >= res_lo && jl <= res_hi) : (jl >= plain_lo && jl <= plain_hi)) do_row(HotTag(), jl, ld2<kLdRow>(H + k), ld2<kLdRow>(U + k), ld2<kLdRow>(V + k), true);
-            else do_row(RareTag(), jl, ld2<kLdRow>(H + k), ld2<kLdRow>(U + k), ld2<kLdRow>(V + k), true);
+            if (RES ? (jl >= res_lo && jl <= res_hi) : (jl >= plain_lo && jl <= plain_hi)) do_row(HotTag(), jl, ld2<kLdRow>(H + k), ld2<kLdRow>(U + k), ld2<kLdRow>(V + k), true, no_star);
+            else do_row(RareTag(), jl, ld2<kLdRow>(H + k), ld2<kLdRow>(U + k), ld2<kLdRow>(V + k), true, no_star);
         }
     }
 

@@ -544,3 +544,22 @@ def test_large_grids_keep_the_launch_per_step_kernel():
                  mode="fast", layout="device")
     assert not st.resident
     st.close()
+
+
+@pytest.mark.parametrize("M,N,mode", [(500, 100, "fast"), (333, 97, "strict"), (700, 260, "fast_guarded"), (62, 40, "fast"), (125, 34, "fast")])
+def test_diffusion_star_from_the_ring_is_bit_identical(M, N, mode, monkeypatch):
+    """With diffusion the TMA kernels read the radius-2 star out of the shared-memory ring
+    (boxes two columns wider, one tile more at either end of a march).  Same arithmetic as the
+    direct-load kernels: launch-per-step and resident, every marching length, same bits."""
+    batches = [3, 10, 6]
+    ref, tr_ref, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, mode, batches, 1e12, False, monkeypatch, {"SWB_KERNEL": "ldg"})
+    for resident, env in ((False, {"SWB_KERNEL": "tma", "SWB_CHUNK": "4"}), (False, {"SWB_KERNEL": "tma", "SWB_CHUNK": "8"}),
+                          (False, {"SWB_KERNEL": "tma", "SWB_CHUNK": "32"}), (False, {"SWB_KERNEL": "tma", "SWB_CHUNK": "2"}),
+                          (True, {"SWB_KERNEL": "tma", "SWB_RES_CHUNK": "4"}), (True, {"SWB_KERNEL": "tma", "SWB_RES_CHUNK": "16"}),
+                          (True, {"SWB_KERNEL": "tma"})):
+        if resident and mode == "strict":
+            continue  # (the resident TMA kernel serves the FAST modes; strict runs resident with direct loads)
+        res, tr, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, mode, batches, 1e12, resident, monkeypatch, env)
+        assert tr == tr_ref, env
+        for name, a, b in zip("huv", res, ref):
+            assert _bits(a, b), (resident, env, name, _worst(a, b))
