@@ -1224,7 +1224,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             const int iA = min(max(colA, 1), p.M + 1), iB = min(max(colA + 1, 1), p.M + 1);  // keep invalid lanes in bounds
             Star<T> shA, shB, suA, suB, svA, svB;
             // HOT: no pole row, no periodic column within reach: plain neighbours (EXTRA: checked per row)
-            if (HOT && SSTAR && (!EXTRA || !warp_wraps)) {
+            if (HOT && SSTAR) {
                 // out of the ring: per field the pairs left and right of the lane's own and the
                 // lane's pairs two and one latitudes below and two above (LDS.128, conflict-free)
                 auto star = [&](int fld, T q0A, T q0B, V2 p1, Star<T> &sA, Star<T> &sB) {
@@ -1238,7 +1238,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                 star(0, curA.h, curB.h, h2, shA, shB);
                 star(1, curA.u, curB.u, u2, suA, suB);
                 star(2, curA.v, curB.v, v2, svA, svB);
-            } else if (HOT && (!EXTRA || (!warp_wraps && jl >= 2 && jl <= p.nrows - 3))) {
+            } else if (HOT && (!EXTRA || !warp_wraps)) {  // (direct loads: the seam strips keep the general star -- patching costs registers here)
                 load_star_pair<T, kLdStar>(H, p.pitch, jl, colA, curA.h, curB.h, shA, shB);
                 load_star_pair<T, kLdStar>(U, p.pitch, jl, colA, curA.u, curB.u, suA, suB);
                 load_star_pair<T, kLdStar>(V, p.pitch, jl, colA, curA.v, curB.v, svA, svB);
@@ -1246,6 +1246,16 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                 shA = load_star<T, kLdStar>(H, p.pitch, p.nrows, p.M, jl, iA); shB = load_star<T, kLdStar>(H, p.pitch, p.nrows, p.M, jl, iB);
                 suA = load_star<T, kLdStar>(U, p.pitch, p.nrows, p.M, jl, iA); suB = load_star<T, kLdStar>(U, p.pitch, p.nrows, p.M, jl, iB);
                 svA = load_star<T, kLdStar>(V, p.pitch, p.nrows, p.M, jl, iA); svB = load_star<T, kLdStar>(V, p.pitch, p.nrows, p.M, jl, iB);
+            }
+            if (EXTRA && SSTAR && warp_wraps) {
+                // resident kernel: the strips at the periodic seam read the ring too; the two
+                // neighbours that lie across the seam are fetched on top (numpy.py:376-378: column 1
+                // reaches back to column M-1, column M+1 forward to column 3)
+                const bool b1 = vB && (colA + 1 == 1), ae = vA && (colA == p.M + 1), be = vB && (colA + 1 == p.M + 1);
+                const size_t kr = (size_t)jl * P;
+                if (b1) { shB.xmm = ld1<kLdStar>(H + kr + p.M - 1); suB.xmm = ld1<kLdStar>(U + kr + p.M - 1); svB.xmm = ld1<kLdStar>(V + kr + p.M - 1); }
+                if (ae) { shA.xpp = ld1<kLdStar>(H + kr + 3); suA.xpp = ld1<kLdStar>(U + kr + 3); svA.xpp = ld1<kLdStar>(V + kr + 3); }
+                if (be) { shB.xpp = ld1<kLdStar>(H + kr + 3); suB.xpp = ld1<kLdStar>(U + kr + 3); svB.xpp = ld1<kLdStar>(V + kr + 3); }
             }
             if (STRICT) {
                 const T dnu = O::mul(dt, (T)p.nu);
