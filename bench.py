@@ -215,6 +215,16 @@ def small_configs(dev):
                     "kernel": "swb::resident_kernel" if st.resident else "swb::march_kernel",
                     "gpu_launches": int(st.launch_count - l0)})
         st.close()
+    # the reference's own call, end to end (grid + initial state on the host, H2D, time loop, D2H)
+    from sw_solver_b200.solver import solve
+
+    solve(360, 180, ICType.RossbyHaurwitzWave, 0.01, 0.5, False)  # warm-up (library load, allocator)
+    t0 = time.perf_counter()
+    sd = {"interval": 10 ** 9}
+    solve(360, 180, ICType.RossbyHaurwitzWave, 1.0, 0.5, False, save_data=sd)
+    wall = time.perf_counter() - t0
+    out.append({"workload": "solve(360, 180, RossbyHaurwitzWave, sim_days=1, courant=0.5, use_diffusion=False) -- the reference's call",
+                "wall_seconds": wall, "note": "about 7.5 k adaptive steps; the numpy reference runs 21 ms per step on this grid (SURVEY 6)"})
     return out
 
 

@@ -57,7 +57,7 @@ struct swb_ctx {
     swb_config cfg;
     Params prm;
     bool tables_set = false, state_bound = false, cfl_ready = false, linked = false;
-    double *d_phi = nullptr, *d_tab = nullptr, *d_log = nullptr;
+    double *d_phi = nullptr, *d_tab = nullptr, *d_log = nullptr, *d_pre = nullptr, *d_pred = nullptr;
     Ctrl *d_ctrl = nullptr;
     int *d_err = nullptr;
     unsigned int *d_done = nullptr;
@@ -402,6 +402,8 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     CK(cudaMemset(c->d_phi, 0, sizeof(double) * nphi));
     CK(cudaMalloc(&c->d_tab, sizeof(double) * (size_t)T_COUNT * nloc));
     CK(cudaMemset(c->d_tab, 0, sizeof(double) * (size_t)T_COUNT * nloc));
+    CK(cudaMalloc(&c->d_pre, sizeof(double) * (size_t)kRowRec * nloc));
+    if (cfg->use_diffusion && cfg->mode != SWB_STRICT) CK(cudaMalloc(&c->d_pred, sizeof(double) * (size_t)kRowDiff * nloc));
     CK(cudaMalloc(&c->d_ctrl, sizeof(Ctrl) * 3));
     CK(cudaMemset(c->d_ctrl, 0, sizeof(Ctrl) * 3));
     CK(cudaMalloc(&c->d_err, sizeof(int)));
@@ -422,6 +424,8 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     memset(&p, 0, sizeof p);
     p.phi = c->d_phi;
     p.tab = c->d_tab;
+    p.pre = c->d_pre;
+    p.pred = c->d_pred;
     p.ctrl = c->d_ctrl;
     p.err = c->d_err;
     p.done_ctr = c->d_done;
@@ -465,12 +469,15 @@ int swb_destroy(swb_ctx *c)
     cudaSetDevice(c->cfg.device);
     cudaFree(c->d_phi);
     cudaFree(c->d_tab);
+    cudaFree(c->d_pre);
+    cudaFree(c->d_pred);
     cudaFree(c->d_ctrl);
     cudaFree(c->d_err);
     cudaFree(c->d_done);
     cudaFree(c->d_xblock);
     cudaFree(c->d_scratch);
     cudaFree(c->d_log);
+    cudaFree(c->prm.dbg);
     cudaFreeHost(c->h_status);
     delete c;
     return 0;
@@ -491,6 +498,13 @@ int swb_set_tables(swb_ctx *c, const swb_tables *t)
         if (src[k]) memcpy(&host[(size_t)k * nloc], src[k], sizeof(double) * nloc);
     CK(cudaMemcpy(c->d_tab, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_phi, t->phi, sizeof(double) * (size_t)(c->cfg.M + 3), cudaMemcpyHostToDevice));
+    // the dt-independent stage of the row records, once
+    const int nb = (c->cfg.n_local + 127) / 128;
+    if (c->cfg.mode == SWB_STRICT) prerec_kernel<true><<<nb, 128>>>(c->prm, c->d_pre, nullptr);
+    else prerec_kernel<false><<<nb, 128>>>(c->prm, c->d_pre, c->d_pred);
+    c->launches++;
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
     c->tables_set = true;
     return 0;
 }
@@ -639,7 +653,16 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
             if (!c->prm.dbg) CK(cudaMalloc(&c->prm.dbg, nb * 16 * sizeof(long long)));
             CK(cudaMemsetAsync(c->prm.dbg, 0, nb * 16 * sizeof(long long), st));
 #endif
-            CK(cudaLaunchCooperativeKernel(c->res_fn, c->res_grid, dim3(kWarpsPerBlock * 32), args, (size_t)c->res_smem, st));
+            cudaError_t le = cudaLaunchCooperativeKernel(c->res_fn, c->res_grid, dim3(kWarpsPerBlock * 32), args, (size_t)c->res_smem, st);
+            if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported) {
+                // the device cannot hold the whole grid right now (shared with another context, MIG
+                // slice, ...): this context goes back to one launch per step, for good
+                (void)cudaGetLastError();
+                c->resident = false;
+                c->prm.chunk = c->base_chunk;
+                break;
+            }
+            CK(le);
 #ifdef SWB_RES_TIMING
             if (m >= 100) {  // phase durations (SM clock ticks) of the launch's last-but-one step: mean and max over blocks
                 std::vector<long long> hst(nb * 16);
@@ -672,7 +695,8 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
             c->seq += (unsigned long long)m;
             left -= m;
         }
-        return 0;
+        if (c->resident) return 0;
+        n = left;
     }
     for (int k = 0; k < n; ++k) {
         c->prm.launch = c->launch;

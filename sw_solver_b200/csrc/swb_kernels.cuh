@@ -94,6 +94,8 @@ struct Params {
     const void *hs;     // (nrows, pitch) or null
     const double *phi;  // M+3 (+ padding)
     const double *tab;  // T_COUNT x nrows
+    const double *pre;  // nrows x kRowRec: dt-independent stage of the row records (prerec_kernel)
+    const double *pred; // nrows x kRowDiff: the same for the FAST diffusion records, or null
     Ctrl *ctrl;         // 3 slots
     int *err;           // sticky device-side error word (0 or a negative SWB_E_*)
     unsigned int *done_ctr;  // grid-barrier arrival counter of resident_kernel (zeroed before each launch)
@@ -1024,34 +1026,29 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     // (built in fp64 whatever T is -- SURVEY 7, hard part 6 -- and rounded once)
     T *rowc = reinterpret_cast<T *>(smem_raw);
     T *rowd = rowc + (size_t)(p.chunk + 2) * kRowRec;
-    if (RES) {
-        double *prec = reinterpret_cast<double *>(smem_raw + rec_bytes(p.chunk, DIFF));
-        double *pred = prec + (size_t)(p.chunk + 2) * kRowRec;
+    {
+        // stage 1 (everything that does not depend on dt: look-ups, reciprocals of the metric
+        // spacings) was computed once per context by prerec_kernel; stage 2 is one multiplication
+        // per slot (STRICT: the reference's own quotients), spread over the block's threads.  The
+        // resident kernel keeps its rows' stage 1 in shared memory.
         const int nrec = jb - ja + 2;
-        if (first) {
-            for (int r = threadIdx.x; r < nrec; r += blockDim.x) {
-                build_row_pre<STRICT>(p, ja - 1 + r, prec + (size_t)r * kRowRec);
-                if (DIFF && !STRICT) build_diff_pre(p, ja - 1 + r, pred + (size_t)r * kRowDiff);
+        const double *src = p.pre + (size_t)(ja - 1) * kRowRec, *srcd = (DIFF && !STRICT) ? p.pred + (size_t)(ja - 1) * kRowDiff : nullptr;
+        if (RES) {
+            double *prec = reinterpret_cast<double *>(smem_raw + rec_bytes(p.chunk, DIFF));
+            double *pred = prec + (size_t)(p.chunk + 2) * kRowRec;
+            if (first) {
+                for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) prec[e] = src[e];
+                if (DIFF && !STRICT)
+                    for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) pred[e] = srcd[e];
+                __syncthreads();
             }
-            __syncthreads();
+            src = prec;
+            srcd = pred;
         }
         const double dt64 = s_dt;
-        for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) rowc[e] = (T)scale_row_slot<STRICT>(e % kRowRec, prec[e], dt64);
+        for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) rowc[e] = (T)scale_row_slot<STRICT>(e % kRowRec, src[e], dt64);
         if (DIFF && !STRICT)
-            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == 6 ? dt64 * pred[e] : pred[e]);
-    } else {
-        for (int r = threadIdx.x; r < jb - ja + 2; r += blockDim.x) {
-            double pre[kRowRec];
-            build_row_pre<STRICT>(p, ja - 1 + r, pre);
-#pragma unroll
-            for (int k = 0; k < kRowRec; ++k) rowc[(size_t)r * kRowRec + k] = (T)scale_row_slot<STRICT>(k, pre[k], s_dt);
-            if (DIFF && !STRICT) {
-                double rd[kRowDiff];
-                build_diff_pre(p, ja - 1 + r, rd);
-#pragma unroll
-                for (int k = 0; k < kRowDiff; ++k) rowd[(size_t)r * kRowDiff + k] = (T)(k == 6 ? s_dt * rd[6] : rd[k]);
-            }
-        }
+            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == 6 ? dt64 * srcd[e] : srcd[e]);
     }
     __syncthreads();
     SWB_STAMP(2);
@@ -1636,6 +1633,24 @@ __global__ void __launch_bounds__(256) cfl_fixup_kernel(const __grid_constant__ 
     if ((threadIdx.x & 31) == 0) {
         atomicMax(&new_slot->ex_bits, mx);
         atomicMax(&new_slot->ey_bits, my);
+    }
+}
+
+// Stage 1 of the row records for every local latitude, once per context (swb_set_tables).
+template <bool STRICT>
+__global__ void __launch_bounds__(128) prerec_kernel(const __grid_constant__ Params p, double *__restrict__ pre, double *__restrict__ pred)
+{
+    const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jl >= p.nrows) return;
+    double rec[kRowRec];
+    build_row_pre<STRICT>(p, jl, rec);
+#pragma unroll
+    for (int k = 0; k < kRowRec; ++k) pre[(size_t)jl * kRowRec + k] = rec[k];
+    if (pred != nullptr) {
+        double rd[kRowDiff];
+        build_diff_pre(p, jl, rd);
+#pragma unroll
+        for (int k = 0; k < kRowDiff; ++k) pred[(size_t)jl * kRowDiff + k] = rd[k];
     }
 }
 
