@@ -1,5 +1,5 @@
 set -x
-CMD="python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline"
+CMD="python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-small"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 && \
