@@ -68,7 +68,7 @@ def main():
         M, N = (int(x) for x in case.rstrip("d").split("x"))
         ref = None
         for var in args.variants.split(","):
-            env = {"SWB_RESIDENT": 0 if var == "march" else 1}
+            env = {"SWB_RESIDENT": 0 if var.split("-")[0] == "march" else 1}
             for tok in var.split("-")[1:]:
                 if tok in ("ldg", "tma"):
                     env["SWB_KERNEL"] = tok

@@ -68,7 +68,9 @@ struct swb_ctx {
     unsigned long long seq = 1;      // stamp of the next step launch (multi-GPU)
     int64_t launches = 0;
     int sm_count = 148;
-    bool use_tma = false;
+    bool use_tma = false;    // march_kernel reads through the TMA ring
+    bool tma_ready = false;  // tensor maps built (the placement of the arrays allows it)
+    bool res_tma = false;    // resident_kernel reads through the TMA ring
     bool cfl_filter = false;  // march_kernel<..., CFLF> + cfl_fixup_kernel (fp64 FAST, large grids)
     int tma_variant = 0;  // index into kTmaVariants (fp64) / kTmaVariantsF32
     TmaMaps maps;
@@ -261,7 +263,7 @@ int setup_resident(swb_ctx *c)
         if (atoi(e) == 0) return 0;
     const int rows = p.jl_last - p.jl_first + 1;
     const int gx = (p.nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const bool tma_ok = c->use_tma && cfg.mode != SWB_STRICT && (cfg.use_diffusion || c->tma_variant == kDefaultTmaVariant);
+    const bool tma_ok = c->res_tma && cfg.mode != SWB_STRICT && (cfg.use_diffusion || c->tma_variant == kDefaultTmaVariant);
     const char *force = getenv("SWB_KERNEL");
     int forced_chunk = 0;
     if (const char *e = getenv("SWB_RES_CHUNK")) forced_chunk = atoi(e);
@@ -533,14 +535,19 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     // one tensor box carries h, u and v: the three arrays of a buffer set must be equally spaced
     const ptrdiff_t fs0 = (char *)u0 - (char *)h0, fs1 = (char *)u1 - (char *)h1;
     const bool spaced = fs0 > 0 && (char *)v0 - (char *)u0 == fs0 && fs1 > 0 && (char *)v1 - (char *)u1 == fs1 && fs0 % 16 == 0 && fs1 % 16 == 0;
-    c->use_tma = plain && spaced && !(force && strcmp(force, "ldg") == 0);
-    // with diffusion the ring pays off on grids beyond the L2 only (measured: 1440 x 720 30 vs 33 us,
-    // 7200 x 3600 645 vs 515 us per step)
-    if (c->cfg.use_diffusion && (long long)(p.M + 1) * (p.jl_last - p.jl_first + 1) < 2000000LL && !(force && strcmp(force, "tma") == 0))
-        c->use_tma = false;
+    const bool force_tma = force && strcmp(force, "tma") == 0;
+    c->tma_ready = plain && spaced && !(force && strcmp(force, "ldg") == 0);
+    c->use_tma = c->tma_ready;
+    // With diffusion the ring (which then feeds the star as well) pays off from a size on; below it
+    // the direct loads' L1 hits win.  Measured us/step, direct vs ring -- one launch per step:
+    // 1440 x 720 29.3 / 32.8, 2000 x 1000 69.7 / 61.1, 4000 x 2000 232 / 198; resident kernel:
+    // 1000 x 500 17.2 / 20.6, 1440 x 720 27.1 / 25.7, 2000 x 1000 68.2 / 45.9.
+    const long long ncell = (long long)(p.M + 1) * (p.jl_last - p.jl_first + 1);
+    c->res_tma = c->tma_ready && (!c->cfg.use_diffusion || ncell >= 1000000LL || force_tma);
+    if (c->cfg.use_diffusion && ncell < 2000000LL && !force_tma) c->use_tma = false;
     c->cfl_filter = false;
-    if (force && strcmp(force, "tma") == 0 && !c->use_tma) return fail(SWB_E_INVALID, "SWB_KERNEL=tma but this configuration cannot use the TMA kernel");
-    if (c->use_tma) {
+    if (force_tma && !c->use_tma) return fail(SWB_E_INVALID, "SWB_KERNEL=tma but this configuration cannot use the TMA kernel");
+    if (c->tma_ready) {
         const bool f32 = c->cfg.dtype == SWB_F32;
         const char *v = getenv(f32 ? "SWB_TMA_VARIANT_F32" : "SWB_TMA_VARIANT");
         c->tma_variant = v ? atoi(v) : (f32 ? kDefaultTmaVariantF32 : kDefaultTmaVariant);

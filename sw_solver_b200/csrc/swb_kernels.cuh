@@ -1137,6 +1137,36 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     int res_lo = p.pole_s ? 2 : 0, res_hi = p.pole_n ? p.nrows - 3 : p.nrows;
     if (p.force_rare || (warp_wraps && !res_wrap)) res_hi = res_lo - 1;
 
+    // Resident kernel, ring-fed star, strips at the periodic seam: the two neighbours that lie
+    // across the seam (numpy.py:376-378: column 1 reaches back to column M-1, column M+1 forward
+    // to column 3) are written INTO the landed tile, in place of the out-of-range / padding
+    // columns the box brought -- once per tile, latencies overlapped -- so that these strips run
+    // the same branch-free body as all others.  The lane that writes a value is the lane that
+    // reads it (its pair to the left / right), hence no synchronisation.
+    const bool seam_b1 = vB && (colA + 1 == 1), seam_ae = vA && (colA == p.M + 1), seam_be = vB && (colA + 1 == p.M + 1);
+    auto patch_tile = [&](int u) {
+        if (!(RES && SSTAR) || !warp_wraps || !res_wrap) return;
+        if (seam_b1 || seam_ae || seam_be) {
+            T *base = reinterpret_cast<T *>(wbase + (size_t)stage_of(u) * LY::kStage) + (2 * lane + 2);  // box element of (row 0, colA)
+            const int src_col = seam_b1 ? p.M - 1 : 3;
+            const int dst_off = seam_b1 ? -1 : (seam_ae ? 2 : 3);  // column -1, or M+3, relative to colA
+            const int row0 = ja + 1 + (u - kLead) * R;
+            T val[3][R];
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const size_t k = (size_t)min(max(row0 + r, 0), p.nrows - 1) * P + src_col;
+                    val[f][r] = ld1<kLdStar>((f == 0 ? H : (f == 1 ? U : V)) + k);
+                }
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+#pragma unroll
+                for (int r = 0; r < R; ++r) base[(f * R + r) * kBoxCols + dst_off] = val[f][r];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes before the stage's next tensor load
+        }
+    };
+
     // One latitude: cells (jl, colA), (jl, colA+1) from `cur`, the row above in (h2,u2,v2).
     // `hot` (a compile-time tag) = a live row in [plain_lo, plain_hi]: own stores only.
     size_t krow = (size_t)ja * P + colA;  // element index of (jl, colA), advanced row by row
@@ -1243,16 +1273,6 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                 shA = load_star<T, kLdStar>(H, p.pitch, p.nrows, p.M, jl, iA); shB = load_star<T, kLdStar>(H, p.pitch, p.nrows, p.M, jl, iB);
                 suA = load_star<T, kLdStar>(U, p.pitch, p.nrows, p.M, jl, iA); suB = load_star<T, kLdStar>(U, p.pitch, p.nrows, p.M, jl, iB);
                 svA = load_star<T, kLdStar>(V, p.pitch, p.nrows, p.M, jl, iA); svB = load_star<T, kLdStar>(V, p.pitch, p.nrows, p.M, jl, iB);
-            }
-            if (EXTRA && SSTAR && warp_wraps) {
-                // resident kernel: the strips at the periodic seam read the ring too; the two
-                // neighbours that lie across the seam are fetched on top (numpy.py:376-378: column 1
-                // reaches back to column M-1, column M+1 forward to column 3)
-                const bool b1 = vB && (colA + 1 == 1), ae = vA && (colA == p.M + 1), be = vB && (colA + 1 == p.M + 1);
-                const size_t kr = (size_t)jl * P;
-                if (b1) { shB.xmm = ld1<kLdStar>(H + kr + p.M - 1); suB.xmm = ld1<kLdStar>(U + kr + p.M - 1); svB.xmm = ld1<kLdStar>(V + kr + p.M - 1); }
-                if (ae) { shA.xpp = ld1<kLdStar>(H + kr + 3); suA.xpp = ld1<kLdStar>(U + kr + 3); svA.xpp = ld1<kLdStar>(V + kr + 3); }
-                if (be) { shB.xpp = ld1<kLdStar>(H + kr + 3); suB.xpp = ld1<kLdStar>(U + kr + 3); svB.xpp = ld1<kLdStar>(V + kr + 3); }
             }
             if (STRICT) {
                 const T dnu = O::mul(dt, (T)p.nu);
@@ -1369,7 +1389,11 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     SWB_STAMP(3);
     const StarRows<V2> no_star{nullptr, nullptr, nullptr, nullptr};
     if (TMA) {
-        if (SSTAR) wait_tile(1);
+        if (SSTAR) {
+            wait_tile(1);
+            patch_tile(0);
+            patch_tile(1);
+        }
         for (int t = 0; t < ntiles; ++t) {
             const int u = t + kLead;
             if (!SSTAR) wait_tile(u);
@@ -1383,7 +1407,10 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             auto turn_ring = [&]() {
                 __syncwarp();
                 if (lane == 0 && u + S - 1 < nload) issue_load(u + S - 1);
-                if (u + 1 < nload) wait_tile(u + 1);
+                if (u + 1 < nload) {
+                    wait_tile(u + 1);
+                    patch_tile(u + 1);
+                }
             };
             const int j0 = ja + t * R;
             // warp-uniform; the resident kernel's fast body serves every complete tile
@@ -1532,12 +1559,19 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
                 asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.done_ctr) : "memory");
                 SWB_STAMP(6);
                 const unsigned int target = (unsigned int)(s + 1) * nblocks;
+                const long long t0 = clock64();
                 while ((int)(ld_acquire_gpu(p.done_ctr) - target) < 0) {
+                    if (clock64() - t0 > p.spin_limit) {  // never in a healthy run: turn a lost block into an error, not a hang
+                        atomicMin(p.err, -4);             // SWB_E_TIMEOUT
+                        s_flags = -1;
+                        break;
+                    }
                 }
                 SWB_STAMP(7);
             }
         }
         __syncthreads();
+        if (s_flags == -1) break;
     }
 }
 
