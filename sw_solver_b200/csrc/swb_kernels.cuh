@@ -1026,29 +1026,42 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     // (built in fp64 whatever T is -- SURVEY 7, hard part 6 -- and rounded once)
     T *rowc = reinterpret_cast<T *>(smem_raw);
     T *rowd = rowc + (size_t)(p.chunk + 2) * kRowRec;
-    {
+    if (RES) {
         // stage 1 (everything that does not depend on dt: look-ups, reciprocals of the metric
-        // spacings) was computed once per context by prerec_kernel; stage 2 is one multiplication
-        // per slot (STRICT: the reference's own quotients), spread over the block's threads.  The
-        // resident kernel keeps its rows' stage 1 in shared memory.
+        // spacings) was computed once per context by prerec_kernel and is kept in shared memory for
+        // the launch; stage 2 is one multiplication per slot (STRICT: the reference's own
+        // quotients), spread over the block's threads.
         const int nrec = jb - ja + 2;
-        const double *src = p.pre + (size_t)(ja - 1) * kRowRec, *srcd = (DIFF && !STRICT) ? p.pred + (size_t)(ja - 1) * kRowDiff : nullptr;
-        if (RES) {
-            double *prec = reinterpret_cast<double *>(smem_raw + rec_bytes(p.chunk, DIFF));
-            double *pred = prec + (size_t)(p.chunk + 2) * kRowRec;
-            if (first) {
-                for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) prec[e] = src[e];
-                if (DIFF && !STRICT)
-                    for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) pred[e] = srcd[e];
-                __syncthreads();
+        double *prec = reinterpret_cast<double *>(smem_raw + rec_bytes(p.chunk, DIFF));
+        double *pred = prec + (size_t)(p.chunk + 2) * kRowRec;
+        if (first) {
+            const double *src = p.pre + (size_t)(ja - 1) * kRowRec;
+            for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) prec[e] = src[e];
+            if (DIFF && !STRICT) {
+                const double *srcd = p.pred + (size_t)(ja - 1) * kRowDiff;
+                for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) pred[e] = srcd[e];
             }
-            src = prec;
-            srcd = pred;
+            __syncthreads();
         }
         const double dt64 = s_dt;
-        for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) rowc[e] = (T)scale_row_slot<STRICT>(e % kRowRec, src[e], dt64);
+        for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) rowc[e] = (T)scale_row_slot<STRICT>(e % kRowRec, prec[e], dt64);
         if (DIFF && !STRICT)
-            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == 6 ? dt64 * srcd[e] : srcd[e]);
+            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == 6 ? dt64 * pred[e] : pred[e]);
+    } else {
+        // one launch per step: both stages here, one latitude per thread (the same arithmetic; a
+        // table look-up instead was tried and cost the hot loop registers)
+        for (int r = threadIdx.x; r < jb - ja + 2; r += blockDim.x) {
+            double pre[kRowRec];
+            build_row_pre<STRICT>(p, ja - 1 + r, pre);
+#pragma unroll
+            for (int k = 0; k < kRowRec; ++k) rowc[(size_t)r * kRowRec + k] = (T)scale_row_slot<STRICT>(k, pre[k], s_dt);
+            if (DIFF && !STRICT) {
+                double rd[kRowDiff];
+                build_diff_pre(p, ja - 1 + r, rd);
+#pragma unroll
+                for (int k = 0; k < kRowDiff; ++k) rowd[(size_t)r * kRowDiff + k] = (T)(k == 6 ? s_dt * rd[6] : rd[k]);
+            }
+        }
     }
     __syncthreads();
     SWB_STAMP(2);
