@@ -229,20 +229,28 @@ int launch_one(swb_ctx *c, cudaStream_t st)
 }
 
 // ---- resident_kernel: instantiations and set-up --------------------------------------
-constexpr int kResMaxChunk = 32;  // two sets of row records + the rings of two blocks fit one SM
+// Longest marches: with the dt-independent row records kept in shared memory (direct-load kernels,
+// short marches) 32 rows; beyond that the TMA kernels scale the records straight from the
+// per-context table, and what two blocks per SM leave of the shared memory next to their rings
+// holds the records of 96 rows (128 with the three-stage diffusion ring).
+constexpr int kResPreSmemChunk = 32;
+constexpr int kResFourStageChunk = 96;  // no diffusion: four ring stages up to here, three beyond
+constexpr int res_max_chunk(bool tma, bool /*diff*/) { return !tma ? kResPreSmemChunk : 128; }
 
 struct ResKernel { const void *fn; int smem; };
-template <bool STRICT, bool DIFF, bool TMA, bool GUARD>
+template <bool STRICT, bool DIFF, bool TMA, bool GUARD, int S = (DIFF ? 3 : 4)>  // (with diffusion: three stages of wider boxes, as in march_kernel)
 ResKernel res_kernel_inst(int chunk)
 {
-    constexpr int S = DIFF ? 3 : 4;  // (with diffusion: three stages of wider boxes, as in march_kernel)
     using LY = TmaLayout<4, S, double, box_cols<double, DIFF, TMA>()>;
     auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? S : 1), GUARD, 2>;
-    return ResKernel{(const void *)fn, 2 * rec_bytes(chunk, DIFF) + (TMA ? kWarpsPerBlock * LY::kWarpBytes : kWarpsPerBlock * kFirstRowsBytes)};
+    return ResKernel{(const void *)fn, (chunk <= kResPreSmemChunk ? 2 : 1) * rec_bytes(chunk, DIFF) +
+                                           (TMA ? kWarpsPerBlock * LY::kWarpBytes : kWarpsPerBlock * kFirstRowsBytes)};
 }
 ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk)
 {
     if (tma && diff) return mode == SWB_FAST ? res_kernel_inst<false, true, true, false>(chunk) : res_kernel_inst<false, true, true, true>(chunk);
+    if (tma && chunk > kResFourStageChunk)
+        return mode == SWB_FAST ? res_kernel_inst<false, false, true, false, 3>(chunk) : res_kernel_inst<false, false, true, true, 3>(chunk);
     if (tma) return mode == SWB_FAST ? res_kernel_inst<false, false, true, false>(chunk) : res_kernel_inst<false, false, true, true>(chunk);
     if (mode == SWB_STRICT) return diff ? res_kernel_inst<true, true, false, true>(chunk) : res_kernel_inst<true, false, false, true>(chunk);
     if (mode == SWB_FAST) return diff ? res_kernel_inst<false, true, false, false>(chunk) : res_kernel_inst<false, false, false, false>(chunk);
@@ -250,7 +258,7 @@ ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk)
 }
 
 // Decide whether this context's grid runs resident (fp64, one band, latitude-only Coriolis,
-// flat topography, all blocks co-resident with marches of at most kResMaxChunk rows) and
+// flat topography, all blocks co-resident with marches of at most res_max_chunk() rows) and
 // size the launch.  SWB_RESIDENT=0 keeps the launch-per-step kernel, SWB_RES_CHUNK / SWB_KERNEL
 // (ldg | tma) override the choices below (tuning and tests).
 int setup_resident(swb_ctx *c)
@@ -268,33 +276,40 @@ int setup_resident(swb_ctx *c)
     int forced_chunk = 0;
     if (const char *e = getenv("SWB_RES_CHUNK")) forced_chunk = atoi(e);
     auto capacity = [&](bool tma, int *cap) -> int {
-        const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, kResMaxChunk);
-        CK(cudaFuncSetAttribute(rk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rk.smem));
-        int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk.fn, kWarpsPerBlock * 32, (size_t)rk.smem));
-        *cap = nb * c->sm_count;
+        // (the largest footprint of this kernel: at the longest march, or at the longest one that keeps two record sets)
+        // (every footprint this context may end up with must leave the same number of blocks per SM)
+        const int probe[3] = {kResPreSmemChunk, kResFourStageChunk, res_max_chunk(tma, cfg.use_diffusion)};
+        int nb_min = 1 << 30;
+        for (int k = 0; k < (tma ? 3 : 1); ++k) {
+            const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, probe[k]);
+            CK(cudaFuncSetAttribute(rk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rk.smem));
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk.fn, kWarpsPerBlock * 32, (size_t)rk.smem));
+            nb_min = nb < nb_min ? nb : nb_min;
+        }
+        *cap = nb_min * c->sm_count;
         return 0;
     };
-    auto chunk_for = [&](int cap, int mult) -> int {  // shortest march (a multiple of `mult`) with gx * ceil(rows / chunk) <= cap
+    auto chunk_for = [&](int cap, int mult, int max_chunk) -> int {  // shortest march (a multiple of `mult`) with gx * ceil(rows / chunk) <= cap
         const int ny = cap / gx;
         if (ny < 1) return 0;
         int ch = (rows + ny - 1) / ny;
         if (forced_chunk > 0) ch = forced_chunk;
         ch = (ch + mult - 1) / mult * mult;
-        if (ch > kResMaxChunk || (long long)gx * ((rows + ch - 1) / ch) > cap) return 0;
+        if (ch > max_chunk || (long long)gx * ((rows + ch - 1) / ch) > cap) return 0;
         return ch;
     };
     int cap = 0, chunk = 0;
     bool tma = false;
     int rc = capacity(false, &cap);
     if (rc) return rc;
-    chunk = chunk_for(cap, 1);
+    chunk = chunk_for(cap, 1, res_max_chunk(false, cfg.use_diffusion));
     // marches of 8 rows and more: the TMA ring with its unrolled four-row tiles (measured)
     if (tma_ok && (chunk >= 8 || chunk == 0 || (force && strcmp(force, "tma") == 0))) {
         int cap_t = 0;
         rc = capacity(true, &cap_t);
         if (rc) return rc;
-        const int ch_t = chunk_for(cap_t, 4);
+        const int ch_t = chunk_for(cap_t, 4, res_max_chunk(true, cfg.use_diffusion));
         if (ch_t > 0) { tma = true; chunk = ch_t; cap = cap_t; }
     }
     if (chunk <= 0) return 0;
@@ -303,6 +318,7 @@ int setup_resident(swb_ctx *c)
     c->res_smem = rk.smem;
     c->res_grid = dim3((unsigned)gx, (unsigned)((rows + chunk - 1) / chunk));
     p.chunk = chunk;
+    p.pre_smem = chunk <= kResPreSmemChunk ? 1 : 0;
     c->resident = true;
     return 0;
 }

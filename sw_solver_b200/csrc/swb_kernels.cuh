@@ -108,6 +108,7 @@ struct Params {
     int nstrips;            // warps needed along longitude
     int launch;             // launch index L (mod 3 cycle)
     int nsteps;             // resident_kernel: time steps run by this one launch
+    int pre_smem;           // resident_kernel: the dt-independent row records are kept in shared memory (short marches)
     long long *dbg;         // SWB_RES_TIMING builds: per block 8 clock64 stamps of one step (dev instrumentation)
     int fixed;              // 1: use fixed_dt, buffers 0 -> 1, no bookkeeping
     int force_rare;         // tuning / test knob (SWB_FORCE_RARE=1): every row takes the boundary-row body
@@ -910,7 +911,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     const size_t P = (size_t)p.pitch;
 
     // ---- TMA ring and the march's first two latitudes ----------------------------------
-    const int recb = rec_bytes(p.chunk, DIFF) * (RES ? 2 : 1);  // RES: the dt-independent records follow
+    const int recb = rec_bytes(p.chunk, DIFF) * ((RES && p.pre_smem) ? 2 : 1);  // RES, short marches: the dt-independent records follow
     unsigned char *wbase = smem_raw + recb + (size_t)warp * LY::kWarpBytes;
     const uint32_t ring_a = smem_u32(wbase), bar_a = ring_a + LY::kRing;
     const int ntiles = (jb - ja + R - 1) / R;  // tiles marched
@@ -1032,21 +1033,23 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         // the launch; stage 2 is one multiplication per slot (STRICT: the reference's own
         // quotients), spread over the block's threads.
         const int nrec = jb - ja + 2;
-        double *prec = reinterpret_cast<double *>(smem_raw + rec_bytes(p.chunk, DIFF));
-        double *pred = prec + (size_t)(p.chunk + 2) * kRowRec;
-        if (first) {
-            const double *src = p.pre + (size_t)(ja - 1) * kRowRec;
-            for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) prec[e] = src[e];
-            if (DIFF && !STRICT) {
-                const double *srcd = p.pred + (size_t)(ja - 1) * kRowDiff;
-                for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) pred[e] = srcd[e];
+        const double *src = p.pre + (size_t)(ja - 1) * kRowRec, *srcd = (DIFF && !STRICT) ? p.pred + (size_t)(ja - 1) * kRowDiff : nullptr;
+        if (p.pre_smem) {  // short marches: stage 1 stays in shared memory for the launch
+            double *prec = reinterpret_cast<double *>(smem_raw + rec_bytes(p.chunk, DIFF));
+            double *pred = prec + (size_t)(p.chunk + 2) * kRowRec;
+            if (first) {
+                for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) prec[e] = src[e];
+                if (DIFF && !STRICT)
+                    for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) pred[e] = srcd[e];
+                __syncthreads();
             }
-            __syncthreads();
+            src = prec;
+            srcd = pred;
         }
         const double dt64 = s_dt;
-        for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) rowc[e] = (T)scale_row_slot<STRICT>(e % kRowRec, prec[e], dt64);
+        for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) rowc[e] = (T)scale_row_slot<STRICT>(e % kRowRec, src[e], dt64);
         if (DIFF && !STRICT)
-            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == 6 ? dt64 * pred[e] : pred[e]);
+            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == 6 ? dt64 * srcd[e] : srcd[e]);
     } else {
         // one launch per step: both stages here, one latitude per thread (the same arithmetic; a
         // table look-up instead was tried and cost the hot loop registers)
