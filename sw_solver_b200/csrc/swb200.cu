@@ -145,7 +145,7 @@ cudaError_t launch_tma(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
         if (mode == SWB_FAST) return launch_inst<double, false, false, false, false, true, 4, 4, false, 2, kWarpsPerBlock, true>(c, g, st);
         return launch_inst<double, false, false, false, false, true, 4, 4, true, 2, kWarpsPerBlock, true>(c, g, st);
     }
-    if (c->cfg.use_diffusion) {  // the ring feeds the Lax-Wendroff stream; the diffusion star reads L2
+    if (c->cfg.use_diffusion) {  // three stages of 68-column boxes: the ring feeds the Lax-Wendroff stream and the diffusion star
         if (mode == SWB_STRICT) return launch_inst<double, true, true, false, false, true, 4, 3, true, 2>(c, g, st);
         if (mode == SWB_FAST) return launch_inst<double, false, true, false, false, true, 4, 3, false, 2>(c, g, st);
         return launch_inst<double, false, true, false, false, true, 4, 3, true, 2>(c, g, st);

@@ -1,7 +1,10 @@
 // swb_kernels.cuh -- device code of libswb200.so (sm_100a).
 //
-// The hot path is ONE kernel per time step (`march_kernel`) that replaces the body of the
-// loop at src/sw_solver/numpy.py:496-549 of the reference:
+// The hot path is one device function, `march_step`, that replaces the body of the loop at
+// src/sw_solver/numpy.py:496-549 of the reference.  Two kernels call it: `march_kernel` (one
+// launch per time step: any grid, any band decomposition) and `resident_kernel` (grids whose
+// blocks all fit the GPU at once: the whole batch of steps in one cooperative launch, a grid
+// barrier per step).  Per step:
 //   * prologue: dt from the device-resident CFL maxima + final-time clamp (numpy.py:524-532)
 //   * Lax-Wendroff half-step face values and full-step update      (numpy.py:185-354)
 //   * optional Laplacian diffusion increment on the OLD fields       (numpy.py:541-544, 66-133)
@@ -717,12 +720,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "DONE:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(dst), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
