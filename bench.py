@@ -55,6 +55,8 @@ def parse_args():
                     help="state type; f32 is the optional fp32 mode (24 algorithmic bytes per update)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="N > 1: split the ONE --grid globe over the GPUs (strong scaling; BASELINE configs 2 and 3) instead of one --grid band per GPU")
     ap.add_argument("--no-small", action="store_true", help="skip the L2-resident configurations (BASELINE.json configs 1 and 2)")
     return ap.parse_args()
 
@@ -265,7 +267,7 @@ def run_ours(args, M, N):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    N_glob = N * world
+    N_glob = N if args.strong else N * world
     ll = LatLonGrid(M, N_glob)
     cg = CartesianGrid(ll)
     f_lat = coriolis_latitude(ll)
@@ -371,10 +373,13 @@ def run_ours(args, M, N):
     if dist is not None:
         dist.barrier()
     if rank == 0:
-        per_gpu = f"{M}x{N} per GPU, {M}x{ll.N} globe in {world} latitude bands" if world > 1 else f"{M}x{ll.N}"
+        per_gpu = f"{M}x{ll.N}"
+        if world > 1:
+            per_gpu = (f"{M}x{ll.N} globe split into {world} latitude bands" if args.strong
+                       else f"{M}x{N} per GPU, {M}x{ll.N} globe in {world} latitude bands")
         line = {
             "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"Rossby-Haurwitz {per_gpu} {'fp64' if args.dtype == 'f64' else 'fp32'}, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
                        "mode": args.mode,
