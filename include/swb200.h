@@ -196,6 +196,14 @@ int64_t swb_launch_count(const swb_ctx *ctx);
  * swb_bind_state; the environment variable SWB_RESIDENT=0 keeps the launch-per-step kernel. */
 int swb_resident(const swb_ctx *ctx);
 
+/* Latitude bands (world > 1): allow the resident kernel for this band too -- the exchange with
+ * the other bands (CFL maxima, stamps) then runs inside the launch, between two steps.  Call
+ * after swb_link_peers and ONLY when every band of the globe runs on a GPU of its own (one
+ * process per GPU): resident kernels of several bands on one GPU would wait for each other
+ * without all being able to start.  A band that stays on the launch-per-step kernel (too large)
+ * and a resident neighbour interoperate: same slots, same stamps. */
+int swb_enable_resident_bands(swb_ctx *ctx);
+
 /* ---- multi-GPU (one process per GPU, latitude bands) ------------------------------ */
 
 #define SWB_IPC_HANDLE_BYTES 64

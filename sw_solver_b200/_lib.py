@@ -71,6 +71,7 @@ SYMBOLS = {
     "swb_read_log": (ctypes.c_int, [c_void_p, _dp, _dp, ctypes.c_int, c_void_p]),
     "swb_launch_count": (c_int64, [c_void_p]),
     "swb_resident": (ctypes.c_int, [c_void_p]),
+    "swb_enable_resident_bands": (ctypes.c_int, [c_void_p]),
     "swb_ipc_export": (ctypes.c_int, [c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint64)]),
     "swb_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(c_void_p)]),
     "swb_ipc_close": (ctypes.c_int, [c_void_p]),

@@ -18,6 +18,7 @@ used for set-up, barriers and the timing reduction only.
 """
 
 import ctypes
+import os
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -114,6 +115,14 @@ def link_distributed(stepper, group=None) -> None:
         return {"bufs": [base + k * stride for k in range(6)], "j_begin": d["j_begin"], "pitch": d["pitch"]}
 
     stepper.link(blocks, neighbour(plan["south"]), neighbour(plan["north"]))
+    # One process per GPU and no two bands on the same device: the bands may run the resident
+    # kernel, exchanging their CFL maxima inside the launch (include/swb200.h).
+    props = torch.cuda.get_device_properties(stepper.device)
+    ident = str(getattr(props, "uuid", "")) or f"{os.uname().nodename}:{dev}"
+    idents: List[Optional[str]] = [None] * world
+    dist.all_gather_object(idents, ident, group=group)
+    if len(set(idents)) == world and os.environ.get("SWB_RESIDENT", "1") != "0":
+        check(lib.swb_enable_resident_bands(stepper._ctx))
     dist.barrier(group=group)  # nobody steps before everybody is linked
 
 

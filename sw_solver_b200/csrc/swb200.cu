@@ -77,6 +77,7 @@ struct swb_ctx {
     // resident_kernel (grids that fit the GPU as one wave of blocks): the whole batch of steps in one launch
     int base_chunk = 2;  // marching length of march_kernel (the resident kernel picks its own)
     bool resident = false;
+    bool resident_bands = false;  // swb_enable_resident_bands: every band of this globe has a GPU of its own
     const void *res_fn = nullptr;
     int res_smem = 0;
     dim3 res_grid;
@@ -238,23 +239,31 @@ constexpr int kResFourStageChunk = 96;  // no diffusion: four ring stages up to 
 constexpr int res_max_chunk(bool tma, bool /*diff*/) { return !tma ? kResPreSmemChunk : 128; }
 
 struct ResKernel { const void *fn; int smem; };
-template <bool STRICT, bool DIFF, bool TMA, bool GUARD, int S = (DIFF ? 3 : 4)>  // (with diffusion: three stages of wider boxes, as in march_kernel)
+template <bool STRICT, bool DIFF, bool TMA, bool GUARD, int S = (DIFF ? 3 : 4), bool BANDS = false>  // (with diffusion: three stages of wider boxes, as in march_kernel)
 ResKernel res_kernel_inst(int chunk)
 {
     using LY = TmaLayout<4, S, double, box_cols<double, DIFF, TMA>()>;
-    auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? S : 1), GUARD, 2>;
+    auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? S : 1), GUARD, 2, BANDS>;
     return ResKernel{(const void *)fn, (chunk <= kResPreSmemChunk ? 2 : 1) * rec_bytes(chunk, DIFF) +
                                            (TMA ? kWarpsPerBlock * LY::kWarpBytes : kWarpsPerBlock * kFirstRowsBytes)};
 }
-ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk)
+template <bool BANDS>
+ResKernel res_kernel_sel(int mode, bool diff, bool tma, int chunk)
 {
-    if (tma && diff) return mode == SWB_FAST ? res_kernel_inst<false, true, true, false>(chunk) : res_kernel_inst<false, true, true, true>(chunk);
+    if (tma && diff)
+        return mode == SWB_FAST ? res_kernel_inst<false, true, true, false, 3, BANDS>(chunk) : res_kernel_inst<false, true, true, true, 3, BANDS>(chunk);
     if (tma && chunk > kResFourStageChunk)
-        return mode == SWB_FAST ? res_kernel_inst<false, false, true, false, 3>(chunk) : res_kernel_inst<false, false, true, true, 3>(chunk);
-    if (tma) return mode == SWB_FAST ? res_kernel_inst<false, false, true, false>(chunk) : res_kernel_inst<false, false, true, true>(chunk);
-    if (mode == SWB_STRICT) return diff ? res_kernel_inst<true, true, false, true>(chunk) : res_kernel_inst<true, false, false, true>(chunk);
-    if (mode == SWB_FAST) return diff ? res_kernel_inst<false, true, false, false>(chunk) : res_kernel_inst<false, false, false, false>(chunk);
-    return diff ? res_kernel_inst<false, true, false, true>(chunk) : res_kernel_inst<false, false, false, true>(chunk);
+        return mode == SWB_FAST ? res_kernel_inst<false, false, true, false, 3, BANDS>(chunk) : res_kernel_inst<false, false, true, true, 3, BANDS>(chunk);
+    if (tma) return mode == SWB_FAST ? res_kernel_inst<false, false, true, false, 4, BANDS>(chunk) : res_kernel_inst<false, false, true, true, 4, BANDS>(chunk);
+    if (mode == SWB_FAST) return diff ? res_kernel_inst<false, true, false, false, 3, BANDS>(chunk) : res_kernel_inst<false, false, false, false, 4, BANDS>(chunk);
+    return diff ? res_kernel_inst<false, true, false, true, 3, BANDS>(chunk) : res_kernel_inst<false, false, false, true, 4, BANDS>(chunk);
+}
+// (bands: the FAST modes; a STRICT band keeps one launch per step)
+ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk, bool bands)
+{
+    if (bands) return res_kernel_sel<true>(mode, diff, tma, chunk);
+    if (!tma && mode == SWB_STRICT) return diff ? res_kernel_inst<true, true, false, true>(chunk) : res_kernel_inst<true, false, false, true>(chunk);
+    return res_kernel_sel<false>(mode, diff, tma, chunk);
 }
 
 // Decide whether this context's grid runs resident (fp64, one band, latitude-only Coriolis,
@@ -266,7 +275,10 @@ int setup_resident(swb_ctx *c)
     c->resident = false;
     const swb_config &cfg = c->cfg;
     Params &p = c->prm;
-    if (cfg.world != 1 || cfg.dtype != SWB_F64 || cfg.f_is_2d || cfg.has_hs) return 0;
+    if (cfg.dtype != SWB_F64 || cfg.f_is_2d || cfg.has_hs) return 0;
+    // bands: only once the peers are linked AND the caller vouches that every band runs on a GPU of
+    // its own (several resident kernels waiting for each other on one GPU would never all start)
+    if (cfg.world != 1 && !(c->linked && c->resident_bands && cfg.mode != SWB_STRICT)) return 0;
     if (const char *e = getenv("SWB_RESIDENT"))
         if (atoi(e) == 0) return 0;
     const int rows = p.jl_last - p.jl_first + 1;
@@ -281,7 +293,7 @@ int setup_resident(swb_ctx *c)
         const int probe[3] = {kResPreSmemChunk, kResFourStageChunk, res_max_chunk(tma, cfg.use_diffusion)};
         int nb_min = 1 << 30;
         for (int k = 0; k < (tma ? 3 : 1); ++k) {
-            const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, probe[k]);
+            const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, probe[k], cfg.world > 1);
             CK(cudaFuncSetAttribute(rk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rk.smem));
             int nb = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk.fn, kWarpsPerBlock * 32, (size_t)rk.smem));
@@ -313,7 +325,7 @@ int setup_resident(swb_ctx *c)
         if (ch_t > 0) { tma = true; chunk = ch_t; cap = cap_t; }
     }
     if (chunk <= 0) return 0;
-    const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, chunk);
+    const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, chunk, cfg.world > 1);
     c->res_fn = rk.fn;
     c->res_smem = rk.smem;
     c->res_grid = dim3((unsigned)gx, (unsigned)((rows + chunk - 1) / chunk));
@@ -589,6 +601,17 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
 
 int swb_resident(const swb_ctx *c) { return (c && c->resident) ? 1 : 0; }
 
+int swb_enable_resident_bands(swb_ctx *c)
+{
+    if (!c) return fail(SWB_E_INVALID, "swb_enable_resident_bands: null context");
+    if (c->cfg.world < 2 || !c->linked) return fail(SWB_E_STATE, "swb_enable_resident_bands: link the peers first (world > 1)");
+    if (!c->state_bound) return fail(SWB_E_STATE, "swb_enable_resident_bands: no state bound");
+    CK(cudaSetDevice(c->cfg.device));
+    c->resident_bands = true;
+    c->prm.chunk = c->base_chunk;
+    return setup_resident(c);
+}
+
 int swb_to_device_layout(swb_ctx *c, const void *ref, int ref_pitch, void *dev, void *stream)
 {
     if (!c || !ref || !dev) return fail(SWB_E_INVALID, "swb_to_device_layout: null argument");
@@ -669,7 +692,8 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
             const int m = left < (1 << 20) ? left : (1 << 20);
             c->prm.launch = c->launch;
             c->prm.nsteps = m;
-            CK(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned int), st));
+            c->prm.stamp = c->seq;
+            CK(cudaMemsetAsync(c->d_done, 0, 2 * sizeof(unsigned int), st));  // arrival counter and admission flag
             void *args[2] = {(void *)&c->prm, (void *)&c->maps};
 #ifdef SWB_RES_TIMING
             const size_t nb = (size_t)c->res_grid.x * c->res_grid.y;
@@ -703,8 +727,9 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
                     fprintf(stderr, " %s %.0f/%.0f", names[k], sum / nb, mx);
                 }
                 fprintf(stderr, "\n");
-                if (const char *path = getenv("SWB_RES_TIMING_FILE")) {  // raw stamps: nb x 16 int64 (0..7 clock64 per phase, 8 = SM id) after a 3-int header
-                    if (FILE *f = fopen(path, "wb")) {
+                if (const char *path0 = getenv("SWB_RES_TIMING_FILE")) {  // raw stamps: nb x 16 int64 (0..7 clock64 per phase, 8 = SM id) after a 3-int header
+                    const std::string path = std::string(path0) + (c->cfg.world > 1 ? "." + std::to_string(c->cfg.rank) : "");
+                    if (FILE *f = fopen(path.c_str(), "wb")) {
                         const int hdr[4] = {(int)c->res_grid.x, (int)c->res_grid.y, c->prm.chunk, 0};
                         fwrite(hdr, sizeof(int), 4, f);
                         fwrite(hst.data(), sizeof(long long), nb * 16, f);

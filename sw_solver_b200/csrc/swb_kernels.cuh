@@ -874,7 +874,7 @@ __device__ __forceinline__ unsigned swb_smid() { unsigned r; asm volatile("mov.u
 // `par_io` (RES): buffer set holding the current state if the caller knows it (>= 0) -- the
 // first loads then start before dt is known -- and on return the set holding the new state.
 // Returns false when the loop has ended (time >= final_time) -- uniform over the grid.
-template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int W, bool CFLF, bool RES>
+template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int W, bool CFLF, bool RES, bool RESBANDS = false>
 __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, const int launch, const bool first, int &tbase,
                                            int &par_io, unsigned char *smem_raw, double &s_dt, int &s_flags, CflFilter &s_filter,
                                            unsigned long long *s_max)
@@ -1148,6 +1148,10 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     if (warp_wraps || p.force_rare) plain_hi = plain_lo - 1;  // strips that feed the periodic ghost columns: every row
     // resident kernel: only the pole rows (and degenerate grids) leave the fast body
     int res_lo = p.pole_s ? 2 : 0, res_hi = p.pole_n ? p.nrows - 3 : p.nrows;
+    if (RESBANDS) {  // rows a neighbour band reads as its halo are stored there too: boundary body
+        if (p.south[0][0] != nullptr) res_lo = max(res_lo, p.jl_first + p.halo);
+        if (p.north[0][0] != nullptr) res_hi = min(res_hi, p.jl_last - p.halo);
+    }
     if (p.force_rare || (warp_wraps && !res_wrap)) res_hi = res_lo - 1;
 
     // Resident kernel, ring-fed star, strips at the periodic seam: the two neighbours that lie
@@ -1530,6 +1534,72 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p)
     return v;
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void st_release_gpu(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Latitude bands inside the resident kernel: the exchange of publish_kernel / gather_kernel (below),
+// run by one warp of block (0,0) between two steps.  Same slots, same stamps: a band that runs
+// resident and a neighbour that launches per step understand each other.
+//   band_publish: lane r deposits this band's CFL maxima of the state after step `launch` in rank
+//   r's exchange block and releases the stamp (system scope: the halo rows this band stored into
+//   its neighbours' arrays are visible before it).
+__device__ __forceinline__ void band_publish(const Params &p, int launch, unsigned long long stamp, unsigned long long ex,
+                                             unsigned long long ey, int lane)
+{
+    if (lane < p.world) {
+        // (the release is cumulative: it covers the maxima stored just before it and, through the
+        // arrival counter this warp has acquired, the halo rows every block of the band stored)
+        XSlot *dst = &p.xpeer[lane]->slot[(launch + 1) % 3][p.rank];
+        dst->ex_bits = ex;
+        dst->ey_bits = ey;
+        st_release_sys(&dst->stamp, stamp + 1);
+    }
+}
+//   band_gather: lane r waits (on this GPU's own memory) for rank r's stamp of step `launch`; lane 0
+//   writes the maxima over all bands into the slot the step reads.  False after a time-out.
+__device__ __forceinline__ bool band_gather(const Params &p, int launch, unsigned long long stamp, int lane)
+{
+    unsigned long long ex = 0ULL, ey = 0ULL;
+    bool ok = true;
+    if (lane < p.world) {
+        const XSlot *xs = &p.xlocal->slot[launch % 3][lane];
+        const long long t0 = clock64();
+        while (ld_acquire_sys(&xs->stamp) != stamp) {
+            if (clock64() - t0 > p.spin_limit) {
+                atomicMin(p.err, -4);  // SWB_E_TIMEOUT
+                ok = false;
+                break;
+            }
+        }
+        ex = *reinterpret_cast<const volatile unsigned long long *>(&xs->ex_bits);
+        ey = *reinterpret_cast<const volatile unsigned long long *>(&xs->ey_bits);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        ex = umax64(ex, __shfl_xor_sync(0xffffffffu, ex, s));
+        ey = umax64(ey, __shfl_xor_sync(0xffffffffu, ey, s));
+    }
+    if (lane == 0) {
+        Ctrl *cur_slot = p.ctrl + (launch % 3);
+        cur_slot->ex_bits = ex;
+        cur_slot->ey_bits = ey;
+    }
+    return __all_sync(0xffffffffu, ok);
+}
+
 // Grids that fit the GPU as ONE wave of blocks (360 x 180, 1440 x 720 -- the
 // state lives in the L2, a step takes microseconds and a launch per step would cost as much
 // again): the whole time loop of numpy.py:496-549 in one cooperative launch.  Every block
@@ -1537,7 +1607,7 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p)
 // acquire at gpu scope), behind which the next step reads the CFL maxima -- accumulated by
 // the same atomics as in march_kernel -- and its neighbours' new rows and columns straight
 // from the L2.  Same step body, same arithmetic: bit-identical to a launch per step.
-template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock>
+template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, bool BANDS = false, int W = kWarpsPerBlock>
 __global__ void __launch_bounds__(W * 32, MINB)
 resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
 {
@@ -1547,16 +1617,45 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
     __shared__ CflFilter s_filter;
     __shared__ unsigned long long s_max[2];
     const unsigned int nblocks = gridDim.x * gridDim.y;
+    // latitude bands (world > 1): warp 0 of block (0,0) runs the exchange with the other GPUs; the
+    // blocks are admitted to a step through `go` (done_ctr[1]) once the maxima of ALL bands are in
+    constexpr bool bands = BANDS;  // (a template axis: the one-band kernels keep their register allocation)
+    const bool xwarp = bands && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 32;
+    unsigned int *const go = p.done_ctr + 1;
+    const int lane = threadIdx.x & 31;
     int tbase = 0, par = -1;
-    for (int s = 0; s < p.nsteps; ++s) {
+    int s = 0;
+    for (; s < p.nsteps; ++s) {
 #ifdef SWB_RES_TIMING
         constexpr bool RES = true;
         const int launch = p.launch + s;
         SWB_STAMP(0);
         SWB_STAMP(8);
 #endif
-        const bool active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true>(p, tm, p.launch + s, s == 0, tbase, par, smem_raw,
-                                                                                                     s_dt, s_flags, s_filter, s_max);
+        if (bands) {
+            if (xwarp) {
+                SWB_STAMP(13);
+                const bool ok = band_gather(p, p.launch + s, p.stamp + (unsigned long long)s, lane);
+                SWB_STAMP(14);
+                if (lane == 0) {
+                    __threadfence();
+                    st_release_gpu(go, ok ? (unsigned int)(s + 1) : 0x7fffffffu);  // (after a time-out: nobody waits any more)
+                }
+                SWB_STAMP(15);
+            }
+            if (threadIdx.x == 0) {
+                const long long t0 = clock64();
+                while ((int)(ld_acquire_gpu(go) - (unsigned int)(s + 1)) < 0) {
+                    if (clock64() - t0 > 2 * p.spin_limit) {
+                        atomicMin(p.err, -4);
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        const bool active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true, BANDS>(p, tm, p.launch + s, s == 0, tbase, par,
+                                                                                                            smem_raw, s_dt, s_flags, s_filter, s_max);
         if (!active) break;
         // Grid barrier: all stores and atomics of step s happen before any load of step s+1.
         // (TMA: every thread first orders its generic-proxy stores before the async-proxy reads
@@ -1564,14 +1663,14 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
         if (TMA) asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncthreads();
         SWB_STAMP(5);
+        Ctrl *const new_slot = p.ctrl + ((p.launch + s + 1) % 3);
+        const unsigned int target = (unsigned int)(s + 1) * nblocks;
         if (threadIdx.x == 0) {
-            Ctrl *const new_slot = p.ctrl + ((p.launch + s + 1) % 3);
             atomicMax(&new_slot->ex_bits, s_max[0]);
             atomicMax(&new_slot->ey_bits, s_max[1]);
-            if (s + 1 < p.nsteps) {
-                asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.done_ctr) : "memory");
-                SWB_STAMP(6);
-                const unsigned int target = (unsigned int)(s + 1) * nblocks;
+            if (bands || s + 1 < p.nsteps) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.done_ctr) : "memory");
+            SWB_STAMP(6);
+            if ((!bands && s + 1 < p.nsteps) || xwarp) {  // one band: every block waits here; bands: the exchange warp only
                 const long long t0 = clock64();
                 while ((int)(ld_acquire_gpu(p.done_ctr) - target) < 0) {
                     if (clock64() - t0 > p.spin_limit) {  // never in a healthy run: turn a lost block into an error, not a hang
@@ -1583,20 +1682,36 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
                 SWB_STAMP(7);
             }
         }
+        if (xwarp) {  // every block of this band is done with step s: tell the other bands
+            unsigned long long ex = 0ULL, ey = 0ULL;
+            if (lane == 0) {
+                ex = ld1<LD_CG>(&new_slot->ex_bits);
+                ey = ld1<LD_CG>(&new_slot->ey_bits);
+            }
+            ex = __shfl_sync(0xffffffffu, ex, 0);
+            ey = __shfl_sync(0xffffffffu, ey, 0);
+            band_publish(p, p.launch + s, p.stamp + (unsigned long long)s, ex, ey, lane);
+            SWB_STAMP(12);
+        }
         __syncthreads();
         if (s_flags == -1) break;
     }
-}
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    // Bands: a launch that ended early (time >= final_time at step s) still owes the other bands the
+    // stamps of its remaining steps -- they are no-ops everywhere, with the maxima carried forward
+    if (xwarp && s < p.nsteps && s_flags != -1) {
+        for (int k = s; k < p.nsteps; ++k) {
+            const Ctrl *carry = p.ctrl + ((p.launch + k + 1) % 3);
+            unsigned long long ex = 0ULL, ey = 0ULL;
+            if (lane == 0) {
+                ex = ld1<LD_CG>(&carry->ex_bits);
+                ey = ld1<LD_CG>(&carry->ey_bits);
+            }
+            ex = __shfl_sync(0xffffffffu, ex, 0);
+            ey = __shfl_sync(0xffffffffu, ey, 0);
+            band_publish(p, p.launch + k, p.stamp + (unsigned long long)k, ex, ey, lane);
+            if (k + 1 < p.nsteps && !band_gather(p, p.launch + k + 1, p.stamp + (unsigned long long)(k + 1), lane)) break;
+        }
+    }
 }
 
 // Multi-GPU step epilogue (one warp, after the step kernel in stream order): lane r deposits
