@@ -1,2 +1,2 @@
-bash scripts/gpu_multi.sh 8
-bash scripts/gpu_strong.sh 8
+python -m pytest tests -x -q -m gpu > gpurun_out/pytest_t.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_t.log
+tail -6 gpurun_out/pytest_t.log

@@ -491,6 +491,12 @@ def _run_batches(M, N, ic, diff, mode, batches, final_time, resident, monkeypatc
     (1440, 720, ICType.RossbyHaurwitzWave, True, "fast"),
     (1440, 720, ICType.RossbyHaurwitzWave, False, "fast"),          # TMA ring inside the resident loop
     (1440, 720, ICType.RossbyHaurwitzWave, False, "fast_guarded"),
+    # smallest grids: one strip holds both ends of the periodic seam; M < 4 keeps the boundary body
+    (2, 4, ICType.RossbyHaurwitzWave, False, "fast"),
+    (3, 4, ICType.RossbyHaurwitzWave, True, "fast"),
+    (4, 6, ICType.RossbyHaurwitzWave, True, "fast"),
+    (5, 6, ICType.RossbyHaurwitzWave, True, "strict"),
+    (6, 8, ICType.RossbyHaurwitzWave, True, "fast_guarded"),
 ])
 def test_resident_kernel_is_bit_identical_to_launch_per_step(M, N, ic, diff, mode, monkeypatch):
     """The same step body behind a grid barrier instead of a launch: every bit of the state,
@@ -525,6 +531,16 @@ def test_resident_kernel_marching_lengths_and_load_paths(monkeypatch):
         assert tr == tr_ref, env
         for name, a, b in zip("huv", res, ref):
             assert _bits(a, b), (env, name, _worst(a, b))
+
+
+def test_resident_kernel_long_run(monkeypatch):
+    """Thousands of steps in a handful of launches: still the same bits as a launch per step."""
+    batches = [1000, 1, 999]
+    ref, tr_ref, _, _ = _run_batches(180, 90, ICType.RossbyHaurwitzWave, True, "fast", batches, 1e12, False, monkeypatch)
+    res, tr_res, _, n_res = _run_batches(180, 90, ICType.RossbyHaurwitzWave, True, "fast", batches, 1e12, True, monkeypatch)
+    assert tr_res == tr_ref and tr_res[-1][0] == 2000
+    for name, a, b in zip("huv", res, ref):
+        assert _bits(a, b), name
 
 
 def test_resident_kernel_stops_at_final_time(monkeypatch):
