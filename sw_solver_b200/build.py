@@ -14,7 +14,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libswb200.so")
 SOURCES = [os.path.join(CSRC, "swb200.cu")]
-HEADERS = [os.path.join(CSRC, "swb_kernels.cuh"), os.path.join(ROOT, "include", "swb200.h")]
+HEADERS = [os.path.join(CSRC, h) for h in ("swb_types.cuh", "swb_scheme.cuh", "swb_step.cuh", "swb_kernels.cuh")] + [
+    os.path.join(ROOT, "include", "swb200.h")]
 
 
 def nvcc_path() -> str:

@@ -1,0 +1,979 @@
+// swb_step.cuh -- one time step of a block's tile (`march_step`): step prologue (dt from the
+// device-resident CFL maxima), row records, TMA ring plumbing, CFL filter, the march itself.
+// Called by march_kernel and resident_kernel (swb_kernels.cuh).
+#pragma once
+#include "swb_scheme.cuh"
+
+namespace swb {
+
+// ------------------------------------------------------------------------------------
+// step prologue: dt from the device-resident CFL maxima (numpy.py:524-532)
+// ------------------------------------------------------------------------------------
+// Executed by thread 0 of every block (every block needs dt); block (0,0) also advances
+// the loop state.  Returns through shared memory: dt and flags (bit 0 active, bit 1 parity).
+// With several latitude bands (world > 1) `gather_kernel` has replaced the slot's maxima by
+// the maxima over all bands before this kernel starts.
+// RES (resident_kernel): the launch stops at the first inactive step, so that step leaves
+// the carried-forward state in BOTH other slots -- whatever launch index comes next reads it.
+template <bool RES>
+__device__ __forceinline__ void step_prologue(const Params &p, int launch, double *s_dt, int *s_flags)
+{
+    Ctrl *const cur_slot = p.ctrl + (launch % 3);
+    Ctrl *const new_slot = p.ctrl + ((launch + 1) % 3);
+    if (p.fixed) {
+        *s_dt = p.fixed_dt;
+        *s_flags = 1;
+        return;
+    }
+    // (RES: written by other SMs earlier in this launch -- read at the L2)
+    const double time = ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->time);
+    const long long nsteps = ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->nsteps);
+    const unsigned long long exb = ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->ex_bits), eyb = ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->ey_bits);
+    const double tx = __ddiv_rn(p.dxmin, __longlong_as_double((long long)exb));
+    const double ty = __ddiv_rn(p.dymin, __longlong_as_double((long long)eyb));
+    const double dtmax = (tx != tx) ? tx : ((ty != ty) ? ty : (tx < ty ? tx : ty));  // np.minimum propagates NaN
+    double dt = __dmul_rn(p.courant, dtmax);
+    const bool active = time < p.final_time;  // numpy.py:496 (false for NaN)
+    double tnew = time;
+    if (active) {
+        if (__dadd_rn(time, dt) > p.final_time) {
+            dt = __dsub_rn(p.final_time, time);
+            tnew = p.final_time;
+        } else {
+            tnew = __dadd_rn(time, dt);
+        }
+    }
+    *s_dt = dt;
+    *s_flags = (active ? 1 : 0) | (int)((nsteps & 1) << 1);
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+        Ctrl *const clr_slot = p.ctrl + ((launch + 2) % 3);
+        clr_slot->ex_bits = 0ULL;
+        clr_slot->ey_bits = 0ULL;
+        clr_slot->reserved = 0;  // found-mask of the CFL filter (march_kernel<..., CFLF>)
+        new_slot->time = tnew;
+        new_slot->nsteps = nsteps + (active ? 1 : 0);
+        new_slot->current = (int)((nsteps + (active ? 1 : 0)) & 1);
+        new_slot->last_dt = active ? dt : ld1<(RES ? LD_CG : LD_PLAIN)>(&cur_slot->last_dt);
+        new_slot->done = !(tnew < p.final_time);
+        new_slot->error = 0;
+        if (!active) {  // nothing will be accumulated: carry the maxima forward
+            new_slot->ex_bits = exb;
+            new_slot->ey_bits = eyb;
+            new_slot->reserved = 3;
+            if (RES) *clr_slot = *new_slot;
+        } else if (p.log != nullptr && nsteps < (long long)p.log_cap) {
+            p.log[nsteps] = dt;
+            p.log[(size_t)p.log_cap + nsteps] = tnew;
+        }
+    }
+}
+
+// Row records are built in two stages so that a resident kernel can keep the first one:
+//   stage 1 (`build_row_pre`): everything that does not depend on dt -- table look-ups and,
+//            in FAST mode, the reciprocals of the metric spacings;
+//   stage 2 (`scale_row_record`): the record of this time step.  FAST: one multiplication by dt
+//            per slot; STRICT: the reference's own quotients hdt/dy1, hdt/dy, dt/dy1c, dt/dyc.
+// march_kernel runs both stages every step, resident_kernel stage 1 once per launch: the
+// arithmetic, and therefore every bit of the result, is the same.
+template <bool STRICT>
+__device__ __forceinline__ void build_row_pre(const Params &p, int jl, double *__restrict__ pre)
+{
+    using O = Op<STRICT>;
+    const int nr = p.nrows;
+    const int j = min(max(jl, 0), nr - 1), jp = min(j + 1, nr - 1), jm = max(j - 1, 0);
+    const double *tab = p.tab;
+    const double c = tab[(size_t)T_C * nr + j], tg = tab[(size_t)T_TG * nr + j], ac = tab[(size_t)T_AC * nr + j];
+    const double f_j = tab[(size_t)T_F * nr + j], f_jp = tab[(size_t)T_F * nr + jp];
+    const double tgm = tab[(size_t)T_TGMIDY * nr + j], cm = tab[(size_t)T_CMIDY * nr + j];
+    const double dy = tab[(size_t)T_DY * nr + j], dy1 = tab[(size_t)T_DY1 * nr + j];
+    const double dyc = tab[(size_t)T_DYC * nr + j], dy1c = tab[(size_t)T_DY1C * nr + j];
+    pre[RC_C] = c;
+    pre[RC_AC] = ac;
+    pre[RC_CM] = cm;
+    pre[RC_DY1S] = O::add(tab[(size_t)T_DY1 * nr + jm], dy1);
+    if (STRICT) {
+        pre[RC_KX] = tg;   // tgMidx == tan(theta_j): 0.5*(theta+theta) is exact (grid.py:107)
+        pre[RC_FKX] = f_j; // 0.5*(f+f) is exact
+        pre[RC_CDX] = 0.0;
+        pre[RC_CXU] = 0.0;
+        pre[RC_KY] = tgm;
+        pre[RC_FKY] = O::mul(0.5, O::add(f_jp, f_j));
+        pre[RC_CY1F] = dy1;
+        pre[RC_CYF] = dy;
+        pre[RC_CY1U] = dy1c;
+        pre[RC_CYU] = dyc;
+        pre[RC_KC] = tg;
+        pre[RC_FD] = f_j;
+    } else {
+        // (times dt in stage 2; hdt = dt/2 and the doubled face values are folded in here)
+        const double ra = 1.0 / p.a;
+        const double rdx = 1.0 / (ac * p.dphi);  // analytic dx_j (the reference's differs by roundoff only)
+        pre[RC_KX] = 0.25 * tg * ra;             // hdt * 0.5 * tan / a
+        pre[RC_FKX] = 0.5 * f_j;                 // hdt * f
+        pre[RC_CDX] = rdx;                       // dt / dx
+        pre[RC_CXU] = 0.5 * rdx;                 // 0.5 dt / dx
+        pre[RC_KY] = 0.25 * tgm * ra;
+        pre[RC_FKY] = 0.25 * (f_jp + f_j);       // hdt * 0.5 * (f_j + f_j+1)
+        pre[RC_CY1F] = 1.0 / dy1;
+        pre[RC_CYF] = 1.0 / dy;
+        pre[RC_CY1U] = 0.5 / dy1c;
+        pre[RC_CYU] = 0.5 / dyc;
+        pre[RC_KC] = 0.03125 * tg * ra;          // (dt*0.25) * 0.5[doubled sums] * 0.25 * tan/a
+        pre[RC_FD] = 0.125 * f_j;                // (dt*0.25) * 0.5 * f
+    }
+}
+
+// slot k of the record of time step dt from slot k of the dt-independent record
+template <bool STRICT>
+__device__ __forceinline__ double scale_row_slot(int k, double pre, double dt)
+{
+    using O = Op<STRICT>;
+    if (STRICT) {
+        if (k == RC_CY1F || k == RC_CYF) return O::div(O::mul(0.5, dt), pre);  // hdt / dy1, hdt / dy
+        if (k == RC_CY1U || k == RC_CYU) return O::div(dt, pre);               // dt / dy1c, dt / dyc
+        return pre;
+    }
+    constexpr unsigned kPlain = (1u << RC_C) | (1u << RC_AC) | (1u << RC_CM) | (1u << RC_DY1S);
+    return ((kPlain >> k) & 1u) ? pre : dt * pre;
+}
+
+// FAST diffusion record of local latitude jl: [0..4] combined latitude weights,
+// [5] = 1/(2 dx_j)^2 (both independent of dt), [6] = dt*nu (stage 2)
+__device__ __forceinline__ void build_diff_pre(const Params &p, int jl, double *__restrict__ rd)
+{
+    const int nr = p.nrows;
+    const int j = min(max(jl, 0), nr - 1);
+    const W3 w = y_weights(p.tab, nr, j);
+    rd[0] = w.C[1] * w.C[0];
+    rd[1] = w.A[1] * w.C[1] + w.C[1] * w.A[0];
+    rd[2] = w.A[1] * w.A[1] + w.B[1] * w.C[2] + w.C[1] * w.B[0];
+    rd[3] = w.A[1] * w.B[1] + w.B[1] * w.A[2];
+    rd[4] = w.B[1] * w.B[2];
+    const double dxa = p.tab[(size_t)T_AC * nr + j] * p.dphi;
+    rd[5] = 0.25 / (dxa * dxa);
+    rd[6] = p.nu;
+    rd[7] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------
+// TMA plumbing
+// ------------------------------------------------------------------------------------
+struct TmaMaps {
+    CUtensorMap in[2];  // per buffer set: box {64 longitudes, R latitudes, 3 fields} over (M+3, nrows, {h, u, v})
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+// 16 bytes global -> shared without passing through registers (LDGSTS, L2 only)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+constexpr int kFirstRowsBytes = 6 * 32 * 16;  // per warp: h, u, v pairs of the march's first two latitudes
+
+// Columns of a TMA box: the strip, plus two columns either side when the diffusion star is read
+// from the ring as well (fp64 with diffusion: SSTAR in march_step)
+template <typename T, bool DIFF, bool TMA>
+__host__ __device__ constexpr int box_cols() { return (DIFF && TMA && sizeof(T) == 8) ? kStripCols + 4 : kStripCols; }
+
+template <int R, int S, typename T = double, int COLS = kStripCols>
+struct TmaLayout {
+    static constexpr int kField = R * COLS * (int)sizeof(T);  // one field, one stage
+    static constexpr int kStage = 3 * kField;
+    static constexpr int kRing = S * kStage;
+    static constexpr int kBars = 128;
+    static constexpr int kWarpBytes = kRing + kBars;
+};
+
+// bytes of row records in front of the per-warp rings (multiple of 1024)
+__host__ __device__ constexpr int rec_bytes(int chunk, bool diff)
+{
+    return (((chunk + 2) * (kRowRec + (diff ? kRowDiff : 0)) * 8) + 1023) / 1024 * 1024;
+}
+
+
+// Store a lane's pair of values without branching: both (one 16-byte store), or only the
+// first / only the second (the strip's edge lanes and the right end of the grid).
+__device__ __forceinline__ void st_pair(double *addr, double a, double b, int both, int only_a, int only_b)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pb, pa, pc;\n\t"
+        "setp.ne.s32 pb, %3, 0;\n\t"
+        "setp.ne.s32 pa, %4, 0;\n\t"
+        "setp.ne.s32 pc, %5, 0;\n\t"
+        "@pb st.global.v2.f64 [%0], {%1, %2};\n\t"
+        "@pa st.global.f64 [%0], %1;\n\t"
+        "@pc st.global.f64 [%0+8], %2;\n\t"
+        "}" ::"l"(addr), "d"(a), "d"(b), "r"(both), "r"(only_a), "r"(only_b) : "memory");
+}
+__device__ __forceinline__ void st_pair(float *addr, float a, float b, int both, int only_a, int only_b)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pb, pa, pc;\n\t"
+        "setp.ne.s32 pb, %3, 0;\n\t"
+        "setp.ne.s32 pa, %4, 0;\n\t"
+        "setp.ne.s32 pc, %5, 0;\n\t"
+        "@pb st.global.v2.f32 [%0], {%1, %2};\n\t"
+        "@pa st.global.f32 [%0], %1;\n\t"
+        "@pc st.global.f32 [%0+4], %2;\n\t"
+        "}" ::"l"(addr), "f"(a), "f"(b), "r"(both), "r"(only_a), "r"(only_b) : "memory");
+}
+
+
+// one predicated scalar store (no branch: the unrolled tile stays one basic block)
+__device__ __forceinline__ void st_if(double *addr, double a, int pred)
+{
+    asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %2, 0;\n\t@pp st.global.f64 [%0], %1;\n\t}" ::"l"(addr), "d"(a), "r"(pred) : "memory");
+}
+__device__ __forceinline__ void st_if(float *addr, float a, int pred)
+{
+    asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.s32 pp, %2, 0;\n\t@pp st.global.f32 [%0], %1;\n\t}" ::"l"(addr), "f"(a), "r"(pred) : "memory");
+}
+
+// |u| + sqrt(g|h|) and |v| + sqrt(g|h|) of one cell as ordering keys (FAST arithmetic)
+template <typename T>
+__device__ __forceinline__ void cfl_keys_fast(T h, T u, T v, T g, bits_t<T> &kx, bits_t<T> &ky)
+{
+    const T cs = fast_sqrt(g * fabs(h));
+    kx = nonneg_bits(fabs(u) + cs);
+    ky = nonneg_bits(fabs(v) + cs);
+}
+
+// CFL filter (fp64 FAST, large grids).  The exact keys above cost 10 FP64-pipe instructions
+// per cell; all the step needs is their MAXIMUM, which moves by ~1e-5 per step.  So every
+// cell first forms a cheap estimate -- the MUFU.RSQ64H seed instead of the refined root, 4
+// instructions -- and only cells whose estimate reaches the trigger threshold (the band's
+// previous maximum less 2^-9) are evaluated exactly, from the values just stored.  A result
+// counts only if it reaches the validity threshold (previous maximum less 2^-10): every
+// cell at or above it is guaranteed to trigger (the seed errs by < 2^-20), so the maximum
+// found is the exact one.  If nothing valid was found -- the maximum fell by more than
+// 2^-10 within one step -- `cfl_fixup_kernel` recomputes it over the whole band.
+struct CflFilter {
+    int trig_x, trig_y;                  // hi words of the trigger thresholds
+    unsigned long long valid_x, valid_y; // validity thresholds (bit patterns)
+};
+__device__ __forceinline__ CflFilter make_cfl_filter(unsigned long long exb, unsigned long long eyb)
+{
+    CflFilter f;
+    const double ex = __longlong_as_double((long long)exb), ey = __longlong_as_double((long long)eyb);
+    auto trig = [](double m) {
+        const double t = m * (1.0 - 1.0 / 512.0);
+        return (t > 0.0 && t < 1e300) ? __double2hiint(t) : 0;  // unknown / non-finite: everything triggers
+    };
+    auto valid = [](double m) {
+        const double t = m * (1.0 - 1.0 / 1024.0);
+        return (t > 0.0 && t < 1e300) ? (unsigned long long)__double_as_longlong(t) : 0ULL;
+    };
+    f.trig_x = trig(ex); f.trig_y = trig(ey);
+    f.valid_x = valid(ex); f.valid_y = valid(ey);
+    return f;
+}
+__device__ __forceinline__ double rsqrt_seed(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+}
+
+// ------------------------------------------------------------------------------------
+// the fused step kernel
+// ------------------------------------------------------------------------------------
+// Template axes: arithmetic (STRICT / FAST), diffusion, 2-D Coriolis array, topography,
+// TMA ring (R latitudes per box, S stages) or direct loads, and whether FAST evaluates the
+// reference's hMid > 0 selects (GUARD) or assumes them true and raises SWB_E_DEPTH when a
+// half-step depth turns out non-positive.
+// SSTAR: where a lane finds its pair of latitudes jl-2, jl-1, jl and jl+2 in the ring (field 0;
+// latitude jl+1 is the row the march streams anyway)
+template <typename V2>
+struct StarRows {
+    const V2 *m2, *m1, *c0, *p2;
+};
+
+#ifdef SWB_RES_TIMING
+__device__ __forceinline__ unsigned swb_smid() { unsigned r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+#define SWB_STAMP(k)                                                                                       \
+    do {                                                                                                   \
+        if (RES && p.dbg != nullptr && threadIdx.x == 0 && launch == p.launch + p.nsteps - 2)              \
+            p.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + (k)] = ((k) == 8) ? (long long)swb_smid() : clock64();                     \
+    } while (0)
+#else
+#define SWB_STAMP(k) do { } while (0)
+#endif
+
+// One time step of the block's tile; the body of both step kernels below.  RES = called from
+// resident_kernel's loop: coherent (L2) loads of the state, dt-independent row records and
+// mbarriers kept across steps (`first` = the launch's first step sets them up; `tbase` counts
+// the TMA tiles this warp consumed so far, which fixes ring stage and mbarrier parity), ghost
+// columns and pole rows handled inside the unrolled tiles (in a single wave of blocks the
+// slowest warp sets the step time), the block's CFL maxima gathered in `s_max`.
+// `par_io` (RES): buffer set holding the current state if the caller knows it (>= 0) -- the
+// first loads then start before dt is known -- and on return the set holding the new state.
+// Returns false when the loop has ended (time >= final_time) -- uniform over the grid.
+template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int W, bool CFLF, bool RES, bool RESBANDS = false>
+__device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, const int launch, const bool first, int &tbase,
+                                           int &par_io, unsigned char *smem_raw, double &s_dt, int &s_flags, CflFilter &s_filter,
+                                           unsigned long long *s_max)
+{
+    static_assert(!STRICT || sizeof(T) == 8, "STRICT reproduces numpy's float64 arithmetic");
+    static_assert(!CFLF || (!STRICT && TMA && sizeof(T) == 8), "the CFL filter serves the fp64 FAST TMA kernel");
+    static_assert(!RES || (sizeof(T) == 8 && !F2D && !HS && !CFLF), "resident_kernel: fp64, latitude-only Coriolis, flat topography");
+    using O = Op<STRICT, T>;
+    // SSTAR: the diffusion star comes out of the ring too -- boxes two columns wider on either
+    // side, one tile more at either end of the march, tiles t-1, t, t+1 resident while tile t
+    // is marched (S >= 3)
+    constexpr bool SSTAR = DIFF && TMA && sizeof(T) == 8;
+    constexpr int kBoxCols = box_cols<T, DIFF, TMA>();
+    constexpr int kLead = SSTAR ? 1 : 0;  // ring tile u holds latitudes ja+1+(u-kLead)R ..; the march consumes u = kLead ..
+    static_assert(!SSTAR || (S >= 3 && R == 4), "the star needs three four-row tiles in the ring");
+    using LY = TmaLayout<R, S, T, kBoxCols>;
+    using V2 = vec2_t<T>;
+    constexpr int kValid = sizeof(T) == 8 ? kStripValid : kStripValidF32;
+    constexpr bool kGuard = STRICT || GUARD;
+    constexpr int kLdStar = RES ? LD_CA : LD_PLAIN;                   // diffusion star
+    constexpr int kLdRow = RES ? (DIFF ? LD_CA : LD_CG) : LD_PLAIN;   // the march's own rows
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int strip = blockIdx.x * W + warp;
+    const bool warp_on = strip < p.nstrips;
+    const int ja = p.jl_first + blockIdx.y * p.chunk;  // first latitude updated
+    const int jb = min(ja + p.chunk, p.jl_last + 1);   // one past the last
+    const int c0 = kValid * strip;
+    const int colA = c0 + 2 * lane;  // this lane's cells: (., colA) and (., colA + 1)
+    const size_t P = (size_t)p.pitch;
+
+    // ---- TMA ring and the march's first two latitudes ----------------------------------
+    const int recb = rec_bytes(p.chunk, DIFF) * ((RES && p.pre_smem) ? 2 : 1);  // RES, short marches: the dt-independent records follow
+    unsigned char *wbase = smem_raw + recb + (size_t)warp * LY::kWarpBytes;
+    const uint32_t ring_a = smem_u32(wbase), bar_a = ring_a + LY::kRing;
+    const int ntiles = (jb - ja + R - 1) / R;  // tiles marched
+    // tiles loaded: with SSTAR one before (latitudes ja-3 .. ja) and, when the last marched
+    // tile ends on jb, one after (the star of latitude jb-1 reaches jb+1)
+    const int nload = ntiles + (SSTAR ? 1 + ((ntiles * R < jb - ja + 1) ? 1 : 0) : 0);
+    const int tb = RES ? tbase : 0;  // ring tiles consumed before this step
+    int par = 0;
+    const T *__restrict__ H, *__restrict__ U, *__restrict__ V;
+    T *__restrict__ Hn, *__restrict__ Un, *__restrict__ Vn;
+    const CUtensorMap *maps;
+    auto bind = [&](int pr) {
+        par = pr;
+        H = (const T *)p.buf[pr][0]; U = (const T *)p.buf[pr][1]; V = (const T *)p.buf[pr][2];
+        Hn = (T *)p.buf[pr ^ 1][0]; Un = (T *)p.buf[pr ^ 1][1]; Vn = (T *)p.buf[pr ^ 1][2];
+        maps = &tm.in[pr];
+    };
+    auto stage_of = [&](int u) { return (tb + u) % S; };
+    auto wait_tile = [&](int u) { mbar_wait(bar_a + 8 * stage_of(u), (uint32_t)(((tb + u) / S) & 1)); };
+    auto issue_load = [&](int u) {  // lane 0 only: ring tile u -- h, u, v of R latitudes in one box (out-of-range parts read as zero)
+        const int s = stage_of(u);
+        const uint32_t bar = bar_a + 8 * s;
+        mbar_expect_tx(bar, LY::kStage);
+        tma_load_3d(ring_a + s * LY::kStage, maps, c0 - (SSTAR ? 2 : 0), ja + 1 + (u - kLead) * R, 0, bar);
+    };
+    constexpr int kFirstIssue = S - 1 + kLead;  // tiles requested before the march starts
+    auto start_ring = [&](int u_lo, int u_hi) {
+        if (TMA && warp_on) {
+            if (lane == 0) {
+                if ((!RES || first) && u_lo == 0) {
+#pragma unroll
+                    for (int s = 0; s < S; ++s) mbar_init(bar_a + 8 * s, 1);
+                    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                }
+#pragma unroll
+                for (int u = 0; u < kFirstIssue; ++u)
+                    if (u >= u_lo && u < u_hi && u < nload) issue_load(u);
+            }
+            __syncwarp();
+        }
+    };
+    V2 h0, u0, v0, h1, u1, v1;  // latitudes ja-1 and ja
+    auto load_first_rows = [&]() {
+        const size_t k0 = (size_t)(ja - 1) * P + colA, k1 = k0 + P;
+        h0 = ld2<kLdRow>(H + k0); u0 = ld2<kLdRow>(U + k0); v0 = ld2<kLdRow>(V + k0);
+        h1 = ld2<kLdRow>(H + k1); u1 = ld2<kLdRow>(U + k1); v1 = ld2<kLdRow>(V + k1);
+    };
+    // RES, early: the same twelve values parked in shared memory by asynchronous copies (each lane
+    // copies and later reads its own 6 x 16 bytes) -- in the ring stage that is not in flight yet
+    // (TMA), or in a staging area behind the records
+    unsigned char *stg = (TMA ? wbase + (size_t)((tb + S - 1) % S) * LY::kStage : smem_raw + recb + (size_t)warp * kFirstRowsBytes) + lane * 16;
+    constexpr int kEarly = 1 + kLead;  // tiles requested before dt is known (RES); SSTAR: its first tile holds the first rows
+    auto first_rows_async = [&]() {
+        const size_t k0 = (size_t)(ja - 1) * P + colA, k1 = k0 + P;
+        const uint32_t d = smem_u32(stg);
+        cp_async16(d, H + k0); cp_async16(d + 512, U + k0); cp_async16(d + 1024, V + k0);
+        cp_async16(d + 1536, H + k1); cp_async16(d + 2048, U + k1); cp_async16(d + 2560, V + k1);
+    };
+    auto first_rows_landed = [&]() {
+        cp_async_wait_all();
+        const V2 *q = reinterpret_cast<const V2 *>(stg);
+        h0 = q[0]; u0 = q[32]; v0 = q[64]; h1 = q[96]; u1 = q[128]; v1 = q[160];
+    };
+    // RES, second step onwards: the parity is known, so the first tile is requested while thread 0
+    // works out dt (only the first: the SM's whole share of the state arrives in microseconds anyway,
+    // and a deeper prefetch by every warp at once only queues up in front of the first tiles)
+    const bool early = RES && par_io >= 0;
+    if (early) {
+        bind(par_io);
+        if (warp != 0) {  // (warp 0: after the prologue -- its lane 0 is the prologue's thread)
+            start_ring(0, kEarly);
+            if (warp_on && !SSTAR) first_rows_async();
+        }
+    }
+    SWB_STAMP(9);
+
+    if (threadIdx.x == 0) {
+        step_prologue<RES>(p, launch, &s_dt, &s_flags);
+        if (RES) s_max[0] = s_max[1] = 0ULL;
+        if (CFLF) {
+            // thresholds from THIS band's maxima of the current state (with several bands the
+            // slot holds the global maxima; the band's own live in its exchange block)
+            const Ctrl *cur_slot = p.ctrl + (launch % 3);
+            unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
+            if (p.world > 1) {
+                exb = p.xlocal->slot[launch % 3][p.rank].ex_bits;
+                eyb = p.xlocal->slot[launch % 3][p.rank].ey_bits;
+            }
+            s_filter = p.fixed ? make_cfl_filter(0ULL, 0ULL) : make_cfl_filter(exb, eyb);
+        }
+    }
+    SWB_STAMP(10);
+    if (early && warp == 0) {
+        start_ring(0, kEarly);
+        if (!SSTAR) first_rows_async();
+    }
+    SWB_STAMP(11);
+    __syncthreads();
+    SWB_STAMP(1);
+    const int flags = s_flags;
+    if (!(flags & 1)) {
+        if (early && TMA && warp_on && lane == 0)  // the loads already under way must land before the block may exit
+            for (int u = 0; u < kEarly && u < nload; ++u) wait_tile(u);
+        return false;
+    }
+    if (!early) bind((flags >> 1) & 1);
+    start_ring(early ? kEarly : 0, kFirstIssue);
+    if (RES) par_io = par ^ 1;
+    const T dt = (T)s_dt;
+    const T g_ = (T)p.g;
+
+    // ---- row records of latitudes ja-1 .. jb ----------------------------------------
+    // (built in fp64 whatever T is -- SURVEY 7, hard part 6 -- and rounded once)
+    T *rowc = reinterpret_cast<T *>(smem_raw);
+    T *rowd = rowc + (size_t)(p.chunk + 2) * kRowRec;
+    if (RES) {
+        // stage 1 (everything that does not depend on dt: look-ups, reciprocals of the metric
+        // spacings) was computed once per context by prerec_kernel and is kept in shared memory for
+        // the launch; stage 2 is one multiplication per slot (STRICT: the reference's own
+        // quotients), spread over the block's threads.
+        const int nrec = jb - ja + 2;
+        const double *src = p.pre + (size_t)(ja - 1) * kRowRec, *srcd = (DIFF && !STRICT) ? p.pred + (size_t)(ja - 1) * kRowDiff : nullptr;
+        if (p.pre_smem) {  // short marches: stage 1 stays in shared memory for the launch
+            double *prec = reinterpret_cast<double *>(smem_raw + rec_bytes(p.chunk, DIFF));
+            double *pred = prec + (size_t)(p.chunk + 2) * kRowRec;
+            if (first) {
+                for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) prec[e] = src[e];
+                if (DIFF && !STRICT)
+                    for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) pred[e] = srcd[e];
+                __syncthreads();
+            }
+            src = prec;
+            srcd = pred;
+        }
+        const double dt64 = s_dt;
+        for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) rowc[e] = (T)scale_row_slot<STRICT>(e % kRowRec, src[e], dt64);
+        if (DIFF && !STRICT)
+            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == 6 ? dt64 * srcd[e] : srcd[e]);
+    } else {
+        // one launch per step: both stages here, one latitude per thread (the same arithmetic; a
+        // table look-up instead was tried and cost the hot loop registers)
+        for (int r = threadIdx.x; r < jb - ja + 2; r += blockDim.x) {
+            double pre[kRowRec];
+            build_row_pre<STRICT>(p, ja - 1 + r, pre);
+#pragma unroll
+            for (int k = 0; k < kRowRec; ++k) rowc[(size_t)r * kRowRec + k] = (T)scale_row_slot<STRICT>(k, pre[k], s_dt);
+            if (DIFF && !STRICT) {
+                double rd[kRowDiff];
+                build_diff_pre(p, ja - 1 + r, rd);
+#pragma unroll
+                for (int k = 0; k < kRowDiff; ++k) rowd[(size_t)r * kRowDiff + k] = (T)(k == 6 ? s_dt * rd[6] : rd[k]);
+            }
+        }
+    }
+    __syncthreads();
+    SWB_STAMP(2);
+    if (!warp_on) return true;
+    if (RES) tbase = tb + nload;
+    constexpr int kFieldV = LY::kField / (int)sizeof(V2), kRowV = kBoxCols / 2;  // ring strides in lane pairs
+    auto tile_of = [&](int u) {  // this lane's pair in row 0, field 0 of ring tile u
+        return reinterpret_cast<const V2 *>(wbase + (size_t)stage_of(u) * LY::kStage) + lane + (SSTAR ? 1 : 0);
+    };
+    if (SSTAR) {  // latitudes ja-1, ja: the last two rows of the leading tile
+        wait_tile(0);
+        const V2 *q = tile_of(0);
+        h0 = q[(R - 2) * kRowV]; u0 = q[kFieldV + (R - 2) * kRowV]; v0 = q[2 * kFieldV + (R - 2) * kRowV];
+        h1 = q[(R - 1) * kRowV]; u1 = q[kFieldV + (R - 1) * kRowV]; v1 = q[2 * kFieldV + (R - 1) * kRowV];
+    } else if (early) {
+        first_rows_landed();
+    } else {
+        load_first_rows();
+    }
+
+    // ---- per-lane set-up ------------------------------------------------------------
+    const bool vA = (lane >= 1) && (colA <= c0 + kValid) && (colA <= p.M + 1);
+    const bool vB = (colA + 1 <= c0 + kValid) && (colA + 1 <= p.M + 1);
+    const T hdt = O::mul(T(0.5), dt);
+    const T hgCell = O::mul(T(0.5), g_);               // numpy.py:203, 255: 0.5*g
+    const T hgK = STRICT ? hgCell : T(0.25) * g_;      // FAST faces are doubled
+    const T raK = STRICT ? (T)p.a : (T)(1.0 / p.a);
+    T ph_m = 0, ph_0 = 0, ph_1 = 0, ph_2 = 0;  // STRICT: phi at colA-1 .. colA+2
+    if (STRICT) {
+        ph_m = (T)p.phi[max(colA - 1, 0)];
+        ph_0 = (T)p.phi[colA];
+        ph_1 = (T)p.phi[colA + 1];
+        ph_2 = (T)p.phi[colA + 2];
+    }
+    // extra copies a cell owes: periodic ghost columns (numpy.py:402)
+    const bool wrapA = vA && (colA == p.M || colA == 2), wrapB = vB && (colA + 1 == p.M || colA + 1 == 2);
+    // with diffusion, column M+1 reaches across the periodic seam too (its i+2 is column 3)
+    const bool seam = DIFF && ((vA && colA == p.M + 1) || (vB && colA + 1 == p.M + 1));
+    const bool warp_wraps = __any_sync(0xffffffffu, wrapA || wrapB || seam);
+    const int st_both = (vA && vB) ? 1 : 0, st_onlyA = (vA && !vB) ? 1 : 0, st_onlyB = (vB && !vA) ? 1 : 0;
+    // resident kernel: the ghost-column copy of a wrapping cell as one predicated store per field
+    // (column M -> column 0, column 2 -> column M+2; M >= 4 so that no column is both)
+    const bool res_wrap = RES && p.M >= 4;
+    const int gpA = (res_wrap && wrapA) ? 1 : 0, gpB = (res_wrap && wrapB) ? 1 : 0;
+    const long long goA = (long long)((colA == p.M) ? 0 : p.M + 2) - colA;      // element offset from (jl, colA) to A's ghost column
+    const long long goB = (long long)((colA + 1 == p.M) ? 0 : p.M + 2) - colA;  // ... and to B's
+    bits_t<T> mxA = 0, myA = 0, mxB = 0, myB = 0;  // running CFL maxima (bit patterns)
+    const int trig_x = CFLF ? s_filter.trig_x : 0, trig_y = CFLF ? s_filter.trig_y : 0;
+    bool trig = false;  // CFLF: some cell of the current tile reached a trigger threshold
+    int negA = 0, negB = 0;  // sign watch of the half-step depths (FAST without GUARD)
+
+    auto rec_of = [&](int jl) { return rowc + (size_t)(jl - (ja - 1)) * kRowRec; };
+    auto load_f = [&](int jl) -> V2 {
+        if (F2D) return ldg2((const T *)p.f2d + (size_t)min(jl, p.nrows - 1) * P + colA);
+        return mk2(T(0), T(0));
+    };
+
+    Cell<T> curA, curB;
+    Face<T> y0A, y0B;
+    {
+        const V2 f0 = load_f(ja - 1), f1 = load_f(ja);
+        const T *r0 = rec_of(ja - 1), *r1 = rec_of(ja);
+        const Cell<T> pA = make_cell<STRICT>(h0.x, u0.x, v0.x, r0[RC_C], hgCell, f0.x);
+        const Cell<T> pB = make_cell<STRICT>(h0.y, u0.y, v0.y, r0[RC_C], hgCell, f0.y);
+        curA = make_cell<STRICT>(h1.x, u1.x, v1.x, r1[RC_C], hgCell, f1.x);
+        curB = make_cell<STRICT>(h1.y, u1.y, v1.y, r1[RC_C], hgCell, f1.y);
+        auto fy = [&](const Cell<T> &a, const Cell<T> &b) -> T {
+            if (!F2D) return r0[RC_FKY];
+            return STRICT ? O::mul(T(0.5), O::add(b.f, a.f)) : hdt * T(0.5) * (b.f + a.f);
+        };
+        y0A = y_face<STRICT, kGuard>(pA, curA, r0[RC_CY1F], r0[RC_CYF], r0[RC_KY], fy(pA, curA), r0[RC_CM], hdt, hgK, raK);
+        y0B = y_face<STRICT, kGuard>(pB, curB, r0[RC_CY1F], r0[RC_CYF], r0[RC_KY], fy(pB, curB), r0[RC_CM], hdt, hgK, raK);
+    }
+
+    // rows at which a cell owes more than its own store: zero-gradient pole rows
+    // (numpy.py:403-404) and the rows a neighbour band reads as its halo
+    int plain_lo = ja, plain_hi = jb - 1;  // rows in [plain_lo, plain_hi] need nothing special
+    if (p.pole_s) plain_lo = max(plain_lo, 2);
+    if (p.pole_n) plain_hi = min(plain_hi, p.nrows - 3);
+    if (p.world > 1) {
+        if (p.south[0][0] != nullptr) plain_lo = max(plain_lo, p.jl_first + p.halo);
+        if (p.north[0][0] != nullptr) plain_hi = min(plain_hi, p.jl_last - p.halo);
+    }
+    if (warp_wraps || p.force_rare) plain_hi = plain_lo - 1;  // strips that feed the periodic ghost columns: every row
+    // resident kernel: only the pole rows (and degenerate grids) leave the fast body
+    int res_lo = p.pole_s ? 2 : 0, res_hi = p.pole_n ? p.nrows - 3 : p.nrows;
+    if (RESBANDS) {  // rows a neighbour band reads as its halo are stored there too: boundary body
+        if (p.south[0][0] != nullptr) res_lo = max(res_lo, p.jl_first + p.halo);
+        if (p.north[0][0] != nullptr) res_hi = min(res_hi, p.jl_last - p.halo);
+    }
+    if (p.force_rare || (warp_wraps && !res_wrap)) res_hi = res_lo - 1;
+
+    // Resident kernel, ring-fed star, strips at the periodic seam: the two neighbours that lie
+    // across the seam (numpy.py:376-378: column 1 reaches back to column M-1, column M+1 forward
+    // to column 3) are written INTO the landed tile, in place of the out-of-range / padding
+    // columns the box brought -- once per tile, latencies overlapped -- so that these strips run
+    // the same branch-free body as all others.  The lane that writes a value is the lane that
+    // reads it (its pair to the left / right), hence no synchronisation.
+    const bool seam_b1 = vB && (colA + 1 == 1), seam_ae = vA && (colA == p.M + 1), seam_be = vB && (colA + 1 == p.M + 1);
+    auto patch_tile = [&](int u) {
+        if (!(RES && SSTAR) || !warp_wraps || !res_wrap) return;
+        if (seam_b1 || seam_ae || seam_be) {
+            T *base = reinterpret_cast<T *>(wbase + (size_t)stage_of(u) * LY::kStage) + (2 * lane + 2);  // box element of (row 0, colA)
+            const int src_col = seam_b1 ? p.M - 1 : 3;
+            const int dst_off = seam_b1 ? -1 : (seam_ae ? 2 : 3);  // column -1, or M+3, relative to colA
+            const int row0 = ja + 1 + (u - kLead) * R;
+            T val[3][R];
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const size_t k = (size_t)min(max(row0 + r, 0), p.nrows - 1) * P + src_col;
+                    val[f][r] = ld1<kLdStar>((f == 0 ? H : (f == 1 ? U : V)) + k);
+                }
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+#pragma unroll
+                for (int r = 0; r < R; ++r) base[(f * R + r) * kBoxCols + dst_off] = val[f][r];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes before the stage's next tensor load
+        }
+    };
+
+    // One latitude: cells (jl, colA), (jl, colA+1) from `cur`, the row above in (h2,u2,v2).
+    // `hot` (a compile-time tag) = a live row in [plain_lo, plain_hi]: own stores only.
+    size_t krow = (size_t)ja * P + colA;  // element index of (jl, colA), advanced row by row
+    auto do_row = [&](auto hot_tag, int jl, V2 h2, V2 u2, V2 v2, bool live, const StarRows<V2> &sr) {
+        constexpr bool HOT = decltype(hot_tag)::value;
+        // resident kernel: ghost columns and pole rows are served inside the fast (unrolled) body
+        constexpr bool EXTRA = RES && HOT;
+        const V2 *rc2 = reinterpret_cast<const V2 *>(rec_of(jl));
+        // the row record, read as 16-byte pairs (broadcast LDS.128)
+        const V2 r_c_ac = rc2[RC_C / 2], r_kx_fkx = rc2[RC_KX / 2], r_cdx_cxu = rc2[RC_CDX / 2], r_ky_fky = rc2[RC_KY / 2];
+        const V2 r_cm_cy1f = rc2[RC_CM / 2], r_cyf_cy1u = rc2[RC_CYF / 2], r_cyu_kc = rc2[RC_CYU / 2], r_fd_dy1s = rc2[RC_FD / 2];
+        const T cn = rec_of(jl)[kRowRec + RC_C];
+        const V2 f2 = load_f(jl + 1);
+        const Cell<T> nxtA = make_cell<STRICT>(h2.x, u2.x, v2.x, cn, hgCell, f2.x);
+        const Cell<T> nxtB = make_cell<STRICT>(h2.y, u2.y, v2.y, cn, hgCell, f2.y);
+
+        // y-faces (jl | jl+1)
+        T fyA = r_ky_fky.y, fyB = fyA;
+        if (F2D) {
+            fyA = STRICT ? O::mul(T(0.5), O::add(nxtA.f, curA.f)) : hdt * T(0.5) * (nxtA.f + curA.f);
+            fyB = STRICT ? O::mul(T(0.5), O::add(nxtB.f, curB.f)) : hdt * T(0.5) * (nxtB.f + curB.f);
+        }
+        const Face<T> y1A = y_face<STRICT, kGuard>(curA, nxtA, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyA, r_cm_cy1f.x, hdt, hgK, raK);
+        const Face<T> y1B = y_face<STRICT, kGuard>(curB, nxtB, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyB, r_cm_cy1f.x, hdt, hgK, raK);
+
+        // x-faces of this latitude: (A | B) and (B | next lane's A)
+        Cell<T> nA;
+        nA.h = shfl_down1(curA.h);   nA.u = shfl_down1(curA.u);
+        nA.hu = shfl_down1(curA.hu); nA.hv = shfl_down1(curA.hv);
+        nA.Ux = shfl_down1(curA.Ux); nA.Vx = shfl_down1(curA.Vx);
+        nA.f = F2D ? shfl_down1(curA.f) : T(0);
+        T cdxAB, cdxBN, cxA, cxB, dxsA = 0, dxsB = 0;
+        if (STRICT) {
+            const T ac = r_c_ac.y;
+            const T xm = O::mul(ac, ph_m), x0 = O::mul(ac, ph_0), x1 = O::mul(ac, ph_1), x2 = O::mul(ac, ph_2);
+            const T dxm = O::sub(x0, xm), dxA = O::sub(x1, x0), dxB = O::sub(x2, x1);
+            cdxAB = O::div(hdt, dxA);
+            cdxBN = O::div(hdt, dxB);
+            dxsA = O::add(dxm, dxA);
+            dxsB = O::add(dxA, dxB);
+            cxA = O::div(dt, O::mul(T(0.5), dxsA));
+            cxB = O::div(dt, O::mul(T(0.5), dxsB));
+        } else {
+            cdxAB = cdxBN = r_cdx_cxu.x;
+            cxA = cxB = r_cdx_cxu.y;
+            if (HS) dxsA = dxsB = T(2.0) * r_c_ac.y * (T)p.dphi;
+        }
+        T fxAB = r_kx_fkx.y, fxBN = fxAB;
+        if (F2D) {
+            fxAB = STRICT ? O::mul(T(0.5), O::add(curB.f, curA.f)) : hdt * T(0.5) * (curB.f + curA.f);
+            fxBN = STRICT ? O::mul(T(0.5), O::add(nA.f, curB.f)) : hdt * T(0.5) * (nA.f + curB.f);
+        }
+        const Face<T> xAB = x_face<STRICT, kGuard>(curA, curB, cdxAB, r_kx_fkx.x, fxAB, hdt, hgK, raK);
+        const Face<T> xBN = x_face<STRICT, kGuard>(curB, nA, cdxBN, r_kx_fkx.x, fxBN, hdt, hgK, raK);
+        Face<T> xL;  // (previous lane's B | A)
+        xL.huM = shfl_up1(xBN.huM); xL.hvM = shfl_up1(xBN.hvM); xL.q = shfl_up1(xBN.q);
+        xL.F1 = shfl_up1(xBN.F1);   xL.F2 = shfl_up1(xBN.F2);
+        xL.hM = HS ? shfl_up1(xBN.hM) : T(0);
+
+        // topography differences (numpy.py:310-317, 342-349)
+        T hsxA = 0, hsxB = 0, hsyA = 0, hsyB = 0;
+        if (HS) {
+            const T *hr = (const T *)p.hs + (size_t)jl * P + colA;
+            const T *hu_ = (const T *)p.hs + (size_t)min(jl + 1, p.nrows - 1) * P + colA;
+            const T *hd_ = (const T *)p.hs + (size_t)max(jl - 1, 0) * P + colA;
+            const T e0 = hr[colA > 0 ? -1 : 0], e1 = hr[0], e2 = hr[1], e3 = hr[2];
+            hsxA = O::sub(e2, e0);
+            hsxB = O::sub(e3, e1);
+            hsyA = O::sub(hu_[0], hd_[0]);
+            hsyB = O::sub(hu_[1], hd_[1]);
+        }
+
+        T hnA, unA, vnA, hnB, unB, vnB;
+        const T fcA = F2D ? (STRICT ? curA.f : dt * T(0.125) * curA.f) : r_fd_dy1s.x;
+        const T fcB = F2D ? (STRICT ? curB.f : dt * T(0.125) * curB.f) : r_fd_dy1s.x;
+        update_cell<STRICT, HS>(curA, xL, xAB, y0A, y1A, cxA, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcA, dt, g_, raK, hsxA, hsyA,
+                                dxsA, r_fd_dy1s.y, hnA, unA, vnA);
+        update_cell<STRICT, HS>(curB, xAB, xBN, y0B, y1B, cxB, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcB, dt, g_, raK, hsxB, hsyB,
+                                dxsB, r_fd_dy1s.y, hnB, unB, vnB);
+
+        if (DIFF) {  // numpy.py:541-544: Laplacian of the OLD fields; u, v (not hu, hv)
+            const int iA = min(max(colA, 1), p.M + 1), iB = min(max(colA + 1, 1), p.M + 1);  // keep invalid lanes in bounds
+            Star<T> shA, shB, suA, suB, svA, svB;
+            // HOT: no pole row, no periodic column within reach: plain neighbours (EXTRA: checked per row)
+            if (HOT && SSTAR) {
+                // out of the ring: per field the pairs left and right of the lane's own and the
+                // lane's pairs two and one latitudes below and two above (LDS.128, conflict-free)
+                auto star = [&](int fld, T q0A, T q0B, V2 p1, Star<T> &sA, Star<T> &sB) {
+                    const V2 L = sr.c0[fld * kFieldV - 1], Rr = sr.c0[fld * kFieldV + 1];
+                    const V2 m2 = sr.m2[fld * kFieldV], m1 = sr.m1[fld * kFieldV], p2 = sr.p2[fld * kFieldV];
+                    sA.q0 = q0A; sA.xmm = L.x; sA.xm = L.y; sA.xp = q0B;  sA.xpp = Rr.x;
+                    sB.q0 = q0B; sB.xmm = L.y; sB.xm = q0A; sB.xp = Rr.x; sB.xpp = Rr.y;
+                    sA.ymm = m2.x; sA.ym = m1.x; sA.yp = p1.x; sA.ypp = p2.x;
+                    sB.ymm = m2.y; sB.ym = m1.y; sB.yp = p1.y; sB.ypp = p2.y;
+                };
+                star(0, curA.h, curB.h, h2, shA, shB);
+                star(1, curA.u, curB.u, u2, suA, suB);
+                star(2, curA.v, curB.v, v2, svA, svB);
+            } else if (HOT && (!EXTRA || !warp_wraps)) {  // (direct loads: the seam strips keep the general star -- patching costs registers here)
+                load_star_pair<T, kLdStar>(H, p.pitch, jl, colA, curA.h, curB.h, shA, shB);
+                load_star_pair<T, kLdStar>(U, p.pitch, jl, colA, curA.u, curB.u, suA, suB);
+                load_star_pair<T, kLdStar>(V, p.pitch, jl, colA, curA.v, curB.v, svA, svB);
+            } else {
+                shA = load_star<T, kLdStar>(H, p.pitch, p.nrows, p.M, jl, iA); shB = load_star<T, kLdStar>(H, p.pitch, p.nrows, p.M, jl, iB);
+                suA = load_star<T, kLdStar>(U, p.pitch, p.nrows, p.M, jl, iA); suB = load_star<T, kLdStar>(U, p.pitch, p.nrows, p.M, jl, iB);
+                svA = load_star<T, kLdStar>(V, p.pitch, p.nrows, p.M, jl, iA); svB = load_star<T, kLdStar>(V, p.pitch, p.nrows, p.M, jl, iB);
+            }
+            if (STRICT) {
+                const T dnu = O::mul(dt, (T)p.nu);
+                const W3 wy = y_weights(p.tab, p.nrows, jl);
+                const W3 wxA = x_weights_strict(p.phi, r_c_ac.y, iA, p.M), wxB = x_weights_strict(p.phi, r_c_ac.y, iB, p.M);
+                auto lap = [&](const Star<T> &s, const W3 &wx) -> T {
+                    return O::add(second_diff_strict(wx, s.xmm, s.xm, s.q0, s.xp, s.xpp),
+                                  second_diff_strict(wy, s.ymm, s.ym, s.q0, s.yp, s.ypp));
+                };
+                hnA = O::add(hnA, O::mul(dnu, lap(shA, wxA))); hnB = O::add(hnB, O::mul(dnu, lap(shB, wxB)));
+                unA = O::add(unA, O::mul(dnu, lap(suA, wxA))); unB = O::add(unB, O::mul(dnu, lap(suB, wxB)));
+                vnA = O::add(vnA, O::mul(dnu, lap(svA, wxA))); vnB = O::add(vnB, O::mul(dnu, lap(svB, wxB)));
+            } else {
+                const T *rd = rowd + (size_t)(jl - (ja - 1)) * kRowDiff;
+                const T dnu = rd[6];
+                hnA = fma(dnu, laplacian_fast(shA, rd), hnA); hnB = fma(dnu, laplacian_fast(shB, rd), hnB);
+                unA = fma(dnu, laplacian_fast(suA, rd), unA); unB = fma(dnu, laplacian_fast(suB, rd), unB);
+                vnA = fma(dnu, laplacian_fast(svA, rd), vnA); vnB = fma(dnu, laplacian_fast(svB, rd), vnB);
+            }
+        }
+
+        // CFL maxima of the new state: max(|q-c|, |q|, |q+c|) == |q| + c for c >= 0
+        if (CFLF && HOT) {
+            // estimate only; tiles in which an estimate reaches the trigger threshold are
+            // re-evaluated exactly after their last row (see CflFilter)
+            const T xA = g_ * fabs(hnA), xB = g_ * fabs(hnB);
+            const T cA = xA * (T)rsqrt_seed((double)xA), cB = xB * (T)rsqrt_seed((double)xB);
+            // (bitwise | on purpose: no short-circuit branches inside the hot tile)
+            trig = trig | ((hi_word(fabs(unA) + cA) & 0x7fffffff) >= trig_x) | ((hi_word(fabs(vnA) + cA) & 0x7fffffff) >= trig_y) |
+                   ((hi_word(fabs(unB) + cB) & 0x7fffffff) >= trig_x) | ((hi_word(fabs(vnB) + cB) & 0x7fffffff) >= trig_y);
+        } else if (HOT || live) {
+            bits_t<T> kxA, kyA, kxB, kyB;
+            if (STRICT) {
+                const T csA = (T)__dsqrt_rn(O::mul(g_, fabs(hnA))), csB = (T)__dsqrt_rn(O::mul(g_, fabs(hnB)));
+                kxA = nonneg_bits(O::add(fabs(unA), csA)); kyA = nonneg_bits(O::add(fabs(vnA), csA));
+                kxB = nonneg_bits(O::add(fabs(unB), csB)); kyB = nonneg_bits(O::add(fabs(vnB), csB));
+            } else {
+                cfl_keys_fast(hnA, unA, vnA, g_, kxA, kyA);
+                cfl_keys_fast(hnB, unB, vnB, g_, kxB, kyB);
+            }
+            mxA = umax64(mxA, kxA); myA = umax64(myA, kyA);
+            mxB = umax64(mxB, kxB); myB = umax64(myB, kyB);
+        }
+        if (!kGuard && (HOT || live)) {
+            negA |= hi_word(xAB.hM) | hi_word(y1A.hM) | hi_word(hnA);
+            negB |= hi_word(xBN.hM) | hi_word(y1B.hM) | hi_word(hnB);
+        }
+
+        // stores: the pair is 16-byte aligned; the strip's first and last column are not ours
+        if (HOT || live) {
+            st_pair(Hn + krow, hnA, hnB, st_both, st_onlyA, st_onlyB);
+            st_pair(Un + krow, unA, unB, st_both, st_onlyA, st_onlyB);
+            st_pair(Vn + krow, vnA, vnB, st_both, st_onlyA, st_onlyB);
+        }
+        if (EXTRA) {  // periodic ghost columns (numpy.py:402), branch-free; pole rows never come here
+            st_if(Hn + krow + goA, hnA, gpA); st_if(Un + krow + goA, unA, gpA); st_if(Vn + krow + goA, vnA, gpA);
+            st_if(Hn + krow + goB, hnB, gpB); st_if(Un + krow + goB, unB, gpB); st_if(Vn + krow + goB, vnB, gpB);
+        }
+        if (!HOT && live) {
+            // boundary conditions (numpy.py:402-404): periodic ghost columns, zero-gradient
+            // pole rows (which also copy the ghost columns), halo rows of the neighbour bands
+            const bool south = p.pole_s && (jl == 1), north = p.pole_n && (jl == p.nrows - 2);
+            if (warp_wraps || south || north) {
+                auto put = [&](size_t kk, T hh, T uu, T vv) { Hn[kk] = hh; Un[kk] = uu; Vn[kk] = vv; };
+                auto dup = [&](bool valid, bool wraps, int col, T hh, T uu, T vv) {
+                    if (!valid) return;
+                    // a wrapping column is mirrored at column 0 (col == M) and / or M+2 (col == 2)
+                    const bool w0 = wraps && (col == p.M), w2 = wraps && (col == 2);
+                    auto row_put = [&](int row, bool centre) {
+                        if (centre) put((size_t)row * P + col, hh, uu, vv);
+                        if (w0) put((size_t)row * P, hh, uu, vv);
+                        if (w2) put((size_t)row * P + p.M + 2, hh, uu, vv);
+                    };
+                    row_put(jl, false);
+                    if (south) row_put(jl - 1, true);
+                    if (north) row_put(jl + 1, true);
+                };
+                dup(vA, wrapA, colA, hnA, unA, vnA);
+                dup(vB, wrapB, colA + 1, hnB, unB, vnB);
+            }
+            if (p.world > 1) {
+                // rows a neighbour band reads as its halo: store them into its arrays as well
+                const int ds = jl - p.jl_first, dn = p.jl_last - jl;
+                auto peer_put = [&](T *const *nb, int prow, int ppitch) {
+                    const size_t kb = (size_t)prow * ppitch + colA;
+                    auto one = [&](int col_off, bool valid, bool wraps, T hh, T uu, T vv) {
+                        if (!valid) return;
+                        nb[0][kb + col_off] = hh; nb[1][kb + col_off] = uu; nb[2][kb + col_off] = vv;
+                        const int col = colA + col_off;
+                        if (wraps && col == p.M) {
+                            const size_t kg = (size_t)prow * ppitch;
+                            nb[0][kg] = hh; nb[1][kg] = uu; nb[2][kg] = vv;
+                        }
+                        if (wraps && col == 2) {
+                            const size_t kg = (size_t)prow * ppitch + p.M + 2;
+                            nb[0][kg] = hh; nb[1][kg] = uu; nb[2][kg] = vv;
+                        }
+                    };
+                    one(0, vA, wrapA, hnA, unA, vnA);
+                    one(1, vB, wrapB, hnB, unB, vnB);
+                };
+                if (ds < p.halo && p.south[par ^ 1][0] != nullptr) peer_put(reinterpret_cast<T *const *>(p.south[par ^ 1]), p.south_row + ds, p.south_pitch);
+                if (dn < p.halo && p.north[par ^ 1][0] != nullptr) peer_put(reinterpret_cast<T *const *>(p.north[par ^ 1]), p.north_row - dn, p.north_pitch);
+            }
+        }
+        krow += P;
+        curA = nxtA; curB = nxtB;
+        y0A = y1A;   y0B = y1B;
+    };
+    using HotTag = std::integral_constant<bool, true>;
+    using RareTag = std::integral_constant<bool, false>;
+
+    // ---- the march ------------------------------------------------------------------
+    SWB_STAMP(3);
+    const StarRows<V2> no_star{nullptr, nullptr, nullptr, nullptr};
+    if (TMA) {
+        if (SSTAR) {
+            wait_tile(1);
+            patch_tile(0);
+            patch_tile(1);
+        }
+        for (int t = 0; t < ntiles; ++t) {
+            const int u = t + kLead;
+            if (!SSTAR) wait_tile(u);
+            const V2 *tile = tile_of(u);
+            const V2 *tprev = SSTAR ? tile_of(u - 1) : tile, *tnext = SSTAR ? tile_of(u + 1) : tile;
+            // row i of the marched tile, reaching into its neighbours in the ring (i is a constant after unrolling)
+            auto ring_row = [&](int i) { return i < 0 ? tprev + (i + R) * kRowV : (i >= R ? tnext + (i - R) * kRowV : tile + i * kRowV); };
+            // SSTAR ring protocol: tile u-1 is dead once row R-2 of tile u is done (the last row reaches
+            // into tiles u and u+1 only), so its stage is refilled THERE -- and tile u+1, requested at the
+            // same point of the previous tile, is awaited there: a whole tile of slack with three stages.
+            auto turn_ring = [&]() {
+                __syncwarp();
+                if (lane == 0 && u + S - 1 < nload) issue_load(u + S - 1);
+                if (u + 1 < nload) {
+                    wait_tile(u + 1);
+                    patch_tile(u + 1);
+                }
+            };
+            const int j0 = ja + t * R;
+            // warp-uniform; the resident kernel's fast body serves every complete tile
+            const bool hot_tile = RES ? (j0 + R <= jb && j0 >= res_lo && j0 + R - 1 <= res_hi) : (j0 >= plain_lo && j0 + R - 1 <= plain_hi);
+            if (hot_tile) {
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    if (SSTAR && rr == R - 1) turn_ring();
+                    // the streamed row rr is latitude jl+1: jl-2, jl-1, jl, jl+2 are rows rr-3, rr-2, rr-1, rr+1
+                    const StarRows<V2> sr{ring_row(rr - 3), ring_row(rr - 2), ring_row(rr - 1), ring_row(rr + 1)};
+                    do_row(HotTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true, SSTAR ? sr : no_star);
+                }
+                if (CFLF) {
+                    if (__any_sync(0xffffffffu, trig)) {  // rare: exact keys of the tile's cells, from the values just stored
+#pragma unroll 1
+                        for (int rr = 0; rr < R; ++rr) {
+                            const size_t k = (size_t)(j0 + rr) * P + colA;
+                            const V2 hh = ldg2(Hn + k), uu = ldg2(Un + k), vv = ldg2(Vn + k);
+                            bits_t<T> kxA, kyA, kxB, kyB;
+                            cfl_keys_fast(hh.x, uu.x, vv.x, g_, kxA, kyA);
+                            cfl_keys_fast(hh.y, uu.y, vv.y, g_, kxB, kyB);
+                            mxA = umax64(mxA, kxA); myA = umax64(myA, kyA);
+                            mxB = umax64(mxB, kxB); myB = umax64(myB, kyB);
+                        }
+                    }
+                    trig = false;
+                }
+            } else {
+#pragma unroll 1
+                for (int rr = 0; rr < R; ++rr)
+                    do_row(RareTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV],
+                           j0 + rr < jb, no_star);
+            }
+            if (SSTAR) {
+                if (!hot_tile) turn_ring();
+            } else {
+                __syncwarp();  // every lane is done with the stage that is refilled next
+                if (lane == 0 && u + S - 1 < nload) issue_load(u + S - 1);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int jl = ja; jl < jb; ++jl) {
+            const size_t k = (size_t)min(jl + 1, p.nrows - 1) * P + colA;
+            if (RES ? (jl >= res_lo && jl <= res_hi) : (jl >= plain_lo && jl <= plain_hi)) do_row(HotTag(), jl, ld2<kLdRow>(H + k), ld2<kLdRow>(U + k), ld2<kLdRow>(V + k), true, no_star);
+            else do_row(RareTag(), jl, ld2<kLdRow>(H + k), ld2<kLdRow>(U + k), ld2<kLdRow>(V + k), true, no_star);
+        }
+    }
+
+    // ---- epilogue: publish the CFL maxima and the depth watch -------------------------
+    SWB_STAMP(4);
+    if (!p.fixed) {
+        bits_t<T> mx = umax64(vA ? mxA : bits_t<T>(0), vB ? mxB : bits_t<T>(0));
+        bits_t<T> my = umax64(vA ? myA : bits_t<T>(0), vB ? myB : bits_t<T>(0));
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            mx = umax64(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+            my = umax64(my, __shfl_xor_sync(0xffffffffu, my, s));
+        }
+        if (lane == 0) {
+            Ctrl *const new_slot = p.ctrl + ((launch + 1) % 3);
+            if (RES) {  // per block first; resident_kernel forwards the block's maxima behind its barrier's __syncthreads
+                atomicMax(&s_max[0], widen_bits(mx));
+                atomicMax(&s_max[1], widen_bits(my));
+            } else if (CFLF) {
+                // most warps hold nothing: their cells stayed below the trigger threshold
+                const unsigned long long wx = widen_bits(mx), wy = widen_bits(my);
+                if (wx != 0ULL) atomicMax(&new_slot->ex_bits, wx);
+                if (wy != 0ULL) atomicMax(&new_slot->ey_bits, wy);
+                const int found = (wx >= s_filter.valid_x && wx != 0ULL ? 1 : 0) | (wy >= s_filter.valid_y && wy != 0ULL ? 2 : 0);
+                if (found) atomicOr(&new_slot->reserved, found);
+            } else {
+                atomicMax(&new_slot->ex_bits, widen_bits(mx));
+                atomicMax(&new_slot->ey_bits, widen_bits(my));
+            }
+        }
+    }
+    if (!kGuard) {
+        const bool bad = (vA && negA < 0) || (vB && negB < 0);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicMin(p.err, -6);  // SWB_E_DEPTH
+    }
+    return true;
+}
+
+}  // namespace swb
