@@ -368,7 +368,10 @@ def run_ours(args, M, N):
 
     small = None
     if world == 1 and not args.no_small:
-        small = small_configs(dev)
+        try:  # informational leg: never at the expense of the headline line
+            small = small_configs(dev)
+        except Exception as e:  # noqa: BLE001
+            small = [{"error": f"{type(e).__name__}: {e}"[:300]}]
 
     if dist is not None:
         dist.barrier()
