@@ -163,6 +163,10 @@ def run_reference_arm(args, M, N):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; this arm is one CPU job on rank 0 and takes
+    # every host thread (set before the oracle's OpenMP runtime is loaded)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or "TORCHELASTIC_RUN_ID" in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     ns = cpu_sample_rows(M)
     r = cpu_reference_run(M, ns, args.diffusion, max(1, args.steps), max(1, args.warmup))
     sample = (f"oracle port (oracle/sw_oracle.c, OpenMP) of numpy.py:503-549 on a {M}x{r['N_sample']} latitude band "
