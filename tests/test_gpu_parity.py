@@ -587,3 +587,24 @@ def test_diffusion_star_from_the_ring_is_bit_identical(M, N, mode, monkeypatch):
         assert tr == tr_ref, env
         for name, a, b in zip("huv", res, ref):
             assert _bits(a, b), (resident, env, name, _worst(a, b))
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+@pytest.mark.parametrize("M,N,diff", [(360, 180, False), (333, 97, True), (10, 10, True)])
+def test_guards_select_nothing_on_positive_depths(M, N, diff, dtype):
+    """`fast` assumes what `fast_guarded` checks (the reference's hMid > 0 selects): on a state
+    whose half-step depths stay positive the two modes are the same arithmetic, bit for bit."""
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    h, u, v, f = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+    out = {}
+    for mode in ("fast", "fast_guarded"):
+        st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=1e12, use_diffusion=diff, mode=mode, dtype=dtype)
+        st.enqueue(40)
+        s = st.status()
+        assert s.steps == 40 and s.error == 0
+        out[mode] = (st.to_numpy(), s.time)
+        st.close()
+    assert out["fast"][1] == out["fast_guarded"][1]
+    for name, a, b in zip("huv", out["fast"][0], out["fast_guarded"][0]):
+        assert _bits(a, b), (name, _worst(a, b))
