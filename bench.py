@@ -25,6 +25,7 @@ step a bounded sample.
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -58,6 +59,10 @@ def parse_args():
     ap.add_argument("--strong", action="store_true",
                     help="N > 1: split the ONE --grid globe over the GPUs (strong scaling; BASELINE configs 2 and 3) instead of one --grid band per GPU")
     ap.add_argument("--no-small", action="store_true", help="skip the L2-resident configurations (BASELINE.json configs 1 and 2)")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32 sub-record (N = 1)")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s sustained run")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the band-parity check in front of the timed region")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling sub-record (7200x3600 split into N bands)")
     return ap.parse_args()
 
 
@@ -159,6 +164,29 @@ def cpu_sample_rows(M):
     return int(max(8, min(512, (4_000_000 // (M + 1)) // 2 * 2)))
 
 
+def numpy_reference_leg(M, budget_s=25.0):
+    """The UNMODIFIED reference numpy solver (oracle/_ref, staged by __graft_entry__.build()) timed on
+    this box's host cores through its own `solve` (numpy.py:409-575): seconds per loop iteration from
+    two runs of different length, differenced.  One core: numpy's element-wise kernels are
+    single-threaded.  BASELINE configs 1 and 2 (360x180 x 20 steps, 1440x720 x 5 steps) and
+    a thin latitude band of the bench workload's own longitudes.  None when the copy is not staged."""
+    try:
+        from oracle import ref_numpy as rn
+
+        if not rn.available():
+            return None
+        runs = []
+        t0 = time.perf_counter()
+        for (m, n, k0, k1, diff) in ((360, 180, 2, 22, False), (1440, 720, 1, 6, True), (M, 64, 1, 5, False)):
+            if time.perf_counter() - t0 > budget_s:
+                break
+            runs.append(rn.time_loop_body(m, n, k0, k1, diff))
+        return {"kind": "_ref", "what": "unmodified reference src/sw_solver/numpy.py solve(), staged copy in oracle/_ref, numpy " + np.__version__,
+                "cores": 1, "unit": UNIT, "runs": runs}
+    except Exception as e:  # noqa: BLE001  (informational leg)
+        return {"kind": "_ref", "error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def run_reference_arm(args, M, N):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -176,12 +204,15 @@ def run_reference_arm(args, M, N):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"Rossby-Haurwitz {M}x{N} fp64, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
-                   "reference_kind": "the reference is pure Python/numpy and cannot run on the GPU box; "
-                                     "this arm is its C port (oracle), pinned bit-exact to the reference"},
+                   "cpu_sample": f"{M}x{r['N_sample']} latitude band ({r['pts_per_step']} updates per step)",
+                   "reference_kind": "value = the C/OpenMP port of the reference loop body (oracle, pinned bit-exact to the reference) on all "
+                                     "host threads -- the FASTER of the two CPU baselines, so ratios against it are conservative; "
+                                     "numpy_ref = the unmodified numpy reference itself on one core"},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    line["cpu_baseline"]["numpy_ref"] = numpy_reference_leg(M)
     print(json.dumps(line), flush=True)
 
 
@@ -234,6 +265,18 @@ def small_configs(dev):
     return out
 
 
+def _timed(st, steps, barrier, local_rank, torch):
+    """`steps` loop iterations timed with CUDA events on the launch stream between two barriers."""
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record()
+        st.enqueue(steps)
+        ev1.record()
+        barrier()
+    return ev0.elapsed_time(ev1), clk.summary()
+
+
 def run_ours(args, M, N):
     """One rank of the job.  N = 1: the whole M x N grid on cuda:0.  N > 1 (torchrun, one
     process per GPU): weak scaling -- every GPU owns an M x N latitude band of the
@@ -284,6 +327,26 @@ def run_ours(args, M, N):
               dtype={"f64": "float64", "f32": "float32"}[args.dtype])
     bytes_per_update = BYTES_PER_UPDATE_F64 if args.dtype == "f64" else BYTES_PER_UPDATE_F64 / 2
     metric = METRIC if args.dtype == "f64" else METRIC.replace("fp64", "fp32")
+    peak, peak_src = measured_peak_gbs()
+
+    # --- N > 1, before anything is timed: the band path against ONE GPU, bit for bit ---------------
+    # (real CUDA-IPC peers: BASELINE configs 2 and 3 and a few steps of the benched globe itself)
+    band_parity = None
+    if world > 1 and not args.no_parity:
+        cases = [(1440, 720, True, "fast", 40), (7200, 3600, False, "fast", 30)]
+        if args.dtype == "f64" and (M + 3) * ll.N * 8 * 7 < 120e9:  # the whole globe must fit rank 0's GPU next to its band
+            cases.append((M, ll.N, args.diffusion, args.mode, 4))
+        recs = [bands.parity_check(m, n, d, md, k, dev) for (m, n, d, md, k) in cases]
+        flag = torch.tensor([1 if (rank != 0 or all(r["bit_identical"] for r in recs)) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            band_parity = {"bit_identical": bool(flag.item()), "against": "the same globe stepped on one GPU (rank 0), compared on the device",
+                           "cases": recs}
+        if not bool(flag.item()):
+            if rank == 0:
+                print(json.dumps({"error": "band parity FAILED: the banded result differs from one GPU", "band_parity": band_parity}), file=sys.stderr, flush=True)
+            dist.destroy_process_group()
+            raise SystemExit(3)
 
     # --- device-resident leg: the state is assembled on the GPU, in the device layout -----
     hd, ud, vd, _ = bands.rossby_haurwitz_band(ll, j_begin, n_local, dev)
@@ -295,27 +358,59 @@ def run_ours(args, M, N):
     st.enqueue(args.warmup)
     barrier()
     launches0 = st.launch_count
-
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        barrier()
-        ev0.record()
-        st.enqueue(args.steps)
-        ev1.record()
-        barrier()
-    ms_local = ev0.elapsed_time(ev1)
+    ms_local, clocks = _timed(st, args.steps, barrier, local_rank, torch)
     ms = max_over_ranks(ms_local)
     if os.environ.get("SWB_BENCH_VERBOSE"):
-        print(f"[bench] rank {rank}: {ms_local / args.steps:.4f} ms/step locally, clocks {clk.summary()}", file=sys.stderr, flush=True)
+        print(f"[bench] rank {rank}: {ms_local / args.steps:.4f} ms/step locally, clocks {clocks}", file=sys.stderr, flush=True)
     launches = st.launch_count - launches0
     s = st.status()
     assert s.steps == args.warmup + args.steps and not s.done and s.error == 0, (s.steps, s.done, s.error)
     hcur = st.state()[0]
     assert bool(torch.isfinite(hcur).all()), "non-finite state after the timed region"
+    del hcur
     value = pts * args.steps / (ms * 1e-3)
     resident = st.resident
+    kernel_ms = ms / args.steps
+
+    # --- fp32 mode on the same workload (N = 1): step time, roofline at 24 B/update, and the distance
+    # from the fp64 state after the same warm-up + timed steps (north-star tolerance 1e-5) ----------
+    fp32 = None
+    if world == 1 and args.dtype == "f64" and not args.no_fp32:
+        try:
+            hd, ud, vd, _ = bands.rossby_haurwitz_band(ll, 0, ll.N, dev)
+            st32 = Stepper(ll, cg, hd, ud, vd, f_lat, None, layout="device", **dict(kw, dtype="float32"))
+            del hd, ud, vd
+            st32.enqueue(args.warmup)
+            ms32, clk32 = _timed(st32, args.steps, barrier, local_rank, torch)
+            s32 = st32.status()
+            assert s32.steps == s.steps and s32.error == 0
+            q64, q32 = st._raw[s.current, :, :, : M + 3], st32._raw[s32.current, :, :, : M + 3]
+            err = [float((q32[k].double() - q64[k]).abs().max()) / float(q64[k].abs().max()) for k in range(3)]
+            a32 = 0.5 * BYTES_PER_UPDATE_F64 * pts / (ms32 / args.steps * 1e-3) / 1e9
+            fp32 = {"ms_per_step": ms32 / args.steps, "value": pts * args.steps / (ms32 * 1e-3), "unit": UNIT, "bytes_per_update": 24,
+                    "roofline": {"bound": "hbm", "achieved": a32, "peak": peak, "unit": "GB/s", "frac": a32 / peak},
+                    "normwise_error_vs_fp64": {"h": err[0], "u": err[1], "v": err[2], "after_steps": int(s.steps), "tolerance": 1e-5},
+                    "clocks": clk32}
+            st32.close()
+            del st32, q32, q64
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001  (informational leg)
+            fp32 = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # --- sustained: the same loop for >= 2 s (the real workload is ~340 k steps per simulated day;
+    # past ~100 ms the 1000 W power cap sets the clock) -- its own clock record ----------------------
+    sustained = None
+    if not args.no_sustained:
+        nsus = int(min(200000, max(args.steps, math.ceil(2200.0 / max(kernel_ms, 1e-3)))))
+        ms_s, clk_s = _timed(st, nsus, barrier, local_rank, torch)
+        ms_s = max_over_ranks(ms_s)
+        ss = st.status()
+        assert ss.error == 0 and ss.steps == s.steps + nsus, (ss.error, ss.steps)
+        a_s = bytes_per_update * pts_rank / (ms_s / nsus * 1e-3) / 1e9
+        sustained = {"steps": nsus, "seconds": ms_s * 1e-3, "ms_per_step": ms_s / nsus, "achieved": a_s, "frac": a_s / peak,
+                     "value": pts * nsus / (ms_s * 1e-3), "clocks": clk_s}
     st.close()
-    del st, hcur
+    del st
     torch.cuda.empty_cache()
 
     # --- end to end through the public host API, HOST buffers in and out -----------------
@@ -327,32 +422,73 @@ def run_ours(args, M, N):
         barrier()
         t0 = time.perf_counter()
         st2 = Stepper(ll, cg, host[0], host[1], host[2], f_lat, None, band=band, world=world, **kw)  # H2D of h, u, v
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
         if world > 1:
             bands.link_distributed(st2)
         st2.enqueue(args.steps)
         cur = st2.status().current                                                  # blocks until done
-        snap = st2.snapshot(cur)                                                    # K4: back to the reference layout
-        for k in range(3):
-            out[k].copy_(snap[k], non_blocking=True)                                # D2H of h, u, v
-        torch.cuda.synchronize(dev)
-        el = max_over_ranks(time.perf_counter() - t0)
+        t2 = time.perf_counter()
+        st2.download(cur, out)                                                      # K4 + D2H of h, u, v
+        t3 = time.perf_counter()
+        el = max_over_ranks(t3 - t0)
         st2.close()
         e2e = {"value": pts * args.steps / el, "unit": UNIT,
                "h2d_bytes_per_step": world * state_bytes / args.steps, "d2h_bytes_per_step": world * state_bytes / args.steps,
-               "call": f"per rank: Stepper(host h,u,v) + enqueue({args.steps}) + snapshot + D2H of h,u,v; "
+               "call": f"per rank: Stepper(host h,u,v) + enqueue({args.steps}) + download (K4 + D2H of h,u,v); "
                        f"{state_bytes} B each way per rank per call",
-               "seconds": el}
-        del host, out, snap
+               "seconds": el,
+               "phases_rank0": {"h2d_s": t1 - t0, "steps_s": t2 - t1, "d2h_s": t3 - t2,
+                                "h2d_gbs": state_bytes / (t1 - t0) / 1e9, "d2h_gbs": state_bytes / (t3 - t2) / 1e9}}
+        del host, out
 
-    peak, peak_src = measured_peak_gbs()
-    kernel_ms = ms / args.steps
+    # --- N > 1: strong scaling of BASELINE config 4 (7200 x 3600 split into N bands) ---------------
+    strong = None
+    if world > 1 and not args.strong and not args.no_strong:
+        try:
+            sM, sN, ssteps = 7200, 3600, 400
+            sll = LatLonGrid(sM, sN)
+            scg = CartesianGrid(sll)
+            sf = coriolis_latitude(sll)
+            skw = dict(courant=0.5, final_time=1e12, use_diffusion=False, mode="fast", device=dev, layout="device")
+            sband = band_layout(sll.N, world, 1)[rank]
+            hd, ud, vd, _ = bands.rossby_haurwitz_band(sll, sband["j_begin"], sband["n_local"], dev)
+            sst = Stepper(sll, scg, hd, ud, vd, sf, None, band=sband, world=world, **skw)
+            del hd, ud, vd
+            bands.link_distributed(sst)
+            sst.enqueue(20)
+            ms_b, _ = _timed(sst, ssteps, barrier, local_rank, torch)
+            ms_b = max_over_ranks(ms_b)
+            kern = "swb::resident_kernel" if sst.resident else "swb::march_kernel"
+            assert sst.status().error == 0
+            sst.close()
+            ms_1 = None
+            if rank == 0:  # the same globe on ONE GPU, same steps
+                hd, ud, vd, _ = bands.rossby_haurwitz_band(sll, 0, sll.N, dev)
+                one = Stepper(sll, scg, hd, ud, vd, sf, None, **skw)
+                del hd, ud, vd
+                one.enqueue(20)
+                ms_1, _ = _timed(one, ssteps, lambda: torch.cuda.synchronize(dev), local_rank, torch)
+                kern1 = "swb::resident_kernel" if one.resident else "swb::march_kernel"
+                one.close()
+            dist.barrier()
+            if rank == 0:
+                spts = (sM + 1) * (sll.N - 2)
+                strong = {"workload": f"Rossby-Haurwitz {sM}x{sll.N} fp64 globe split into {world} latitude bands, diffusion off", "steps": ssteps,
+                          "us_per_step": 1e3 * ms_b / ssteps, "value": spts * ssteps / (ms_b * 1e-3), "unit": UNIT, "kernel": kern,
+                          "one_gpu_us_per_step": 1e3 * ms_1 / ssteps, "one_gpu_kernel": kern1, "speedup": ms_1 / ms_b,
+                          "one_gpu_frac_of_hbm": 48.0 * spts / (ms_1 / ssteps * 1e-3) / 1e9 / peak}
+        except Exception as e:  # noqa: BLE001  (informational leg)
+            strong = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     achieved = bytes_per_update * pts_rank / (kernel_ms * 1e-3) / 1e9  # per GPU
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "kernel": "swb::resident_kernel" if resident else "swb::march_kernel", "kernel_ms": kernel_ms,
                 "bytes_per_launch": bytes_per_update * pts_rank, "peak_source": peak_src,
                 "note": ("per GPU; one resident_kernel launch for all timed steps (kernel_ms = step time, CUDA events on the launch stream)"
                          if resident else
-                         "per GPU; one march_kernel launch per step (kernel_ms = step time, CUDA events on the launch stream)")}
+                         "per GPU; one march_kernel launch per step (kernel_ms = step time, CUDA events on the launch stream)"),
+                "sustained": sustained}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof):
         try:
@@ -361,14 +497,17 @@ def run_ours(args, M, N):
             pass
 
     cpu = None
+    cpu_sample = None
     if not args.no_cpu_baseline and world == 1:
         ns = cpu_sample_rows(M)
         probe = cpu_reference_run(M, ns, args.diffusion, 1, 1)
         nsteps = int(max(2, min(200, 12.0 / max(probe["seconds"], 1e-3))))
         r = cpu_reference_run(M, ns, args.diffusion, nsteps, 1)
+        cpu_sample = f"{M}x{r['N_sample']} latitude band ({r['pts_per_step']} updates per step)"
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                "sample": f"oracle port of numpy.py:503-549 (C, OpenMP) on a {M}x{r['N_sample']} latitude band of the "
-                         f"workload, {nsteps} steps, {r['seconds']:.1f} s"}
+                         f"workload, {nsteps} steps, {r['seconds']:.1f} s",
+               "numpy_ref": numpy_reference_leg(M)}
 
     small = None
     if world == 1 and not args.no_small:
@@ -393,9 +532,9 @@ def run_ours(args, M, N):
                        "l2": (f"state ({2 * bytes_per_update / 2 * pts_rank / 1e9:.2f} GB touched per GPU per step) is larger than the 126 MB L2; no flush needed"
                               if bytes_per_update * pts_rank > 4 * 126e6 else
                               "state fits the L2: this grid is L2-resident by nature (no flush; the roofline fraction is not an HBM figure)"),
-                       "pts_per_step": pts, "parallelism": f"lat-bands x{world}"},
+                       "pts_per_step": pts, "parallelism": f"lat-bands x{world}", "cpu_sample": cpu_sample},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
-            "clocks": clk.summary(), "l2_resident_configs": small,
+            "clocks": clocks, "fp32": fp32, "band_parity": band_parity, "strong_7200x3600": strong, "l2_resident_configs": small,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -5,6 +5,7 @@ nvcc, and if that is impossible the import of the solver fails loudly."""
 
 import ctypes
 import os
+import warnings
 
 from . import build as _build
 
@@ -100,9 +101,13 @@ def load():
         elif _build.needs_build():
             try:
                 path = _build.build()
-            except RuntimeError:
+            except _build.NvccMissing:
+                # no toolkit on this box: a prebuilt library is acceptable, but say that it is older
+                # than the sources (a compile ERROR is never swallowed -- stale kernels must not run
+                # silently after an edit)
                 if not os.path.exists(path):
                     raise
+                warnings.warn(f"{path} is older than its sources and nvcc is not available to rebuild it", RuntimeWarning)
         if not os.path.exists(path):
             raise ImportError(f"{path} is missing and cannot be built: the CUDA path is the only path")
         L = ctypes.CDLL(path)

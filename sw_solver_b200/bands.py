@@ -166,3 +166,71 @@ def rossby_haurwitz_band(latlon_grid: LatLonGrid, j_begin: int, n_local: int, de
     u = col("uA") + u
     v = col("vB") * sR
     return h, u, v, coriolis_latitude(latlon_grid)
+
+
+# --------------------------------------------------------------------------------------
+# self-check of the decomposition (G bands must be BIT-IDENTICAL to one band)
+# --------------------------------------------------------------------------------------
+def parity_check(M: int, N: int, use_diffusion: bool, mode: str, nsteps: int, device, group=None) -> Optional[Dict[str, Any]]:
+    """Run under torchrun (one rank per GPU).  Every rank steps its latitude band of the M x N
+    Rossby-Haurwitz globe for ``nsteps`` steps over the real peer mappings (``link_distributed``);
+    rank 0 also steps the WHOLE globe on its own GPU and compares each band's window -- halo, ghost
+    and pole rows included -- bit for bit, together with step count, time and error flag.  All
+    comparisons happen on the device.  Returns the record on rank 0, None elsewhere."""
+    import torch.distributed as dist
+
+    from .grid import CartesianGrid
+    from .ic import coriolis_latitude
+    from .solver import Stepper, band_layout
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = torch.device(device)
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    f_lat = coriolis_latitude(ll)
+    kw = dict(courant=0.5, final_time=1e12, use_diffusion=use_diffusion, mode=mode, device=dev, layout="device")
+    band = band_layout(ll.N, world, 2 if use_diffusion else 1)[rank]
+    hd, ud, vd, _ = rossby_haurwitz_band(ll, band["j_begin"], band["n_local"], dev)
+    st = Stepper(ll, cg, hd, ud, vd, f_lat, None, band=band, world=world, **kw)
+    del hd, ud, vd
+    link_distributed(st, group)
+    st.enqueue(nsteps)
+    s = st.status()
+    resident = st.resident
+    mine = st._raw[s.current, :, :, : M + 3].contiguous()  # (3, n_local, M+3), device layout
+    st.close()
+    del st
+    metas: List[Any] = [None] * world
+    dist.all_gather_object(metas, (band["j_begin"], band["n_local"], int(s.steps), float(s.time), int(s.error)), group=group)
+    rec = None
+    if rank == 0:
+        hf, uf, vf, _ = rossby_haurwitz_band(ll, 0, ll.N, dev)
+        one = Stepper(ll, cg, hf, uf, vf, f_lat, None, **kw)
+        del hf, uf, vf
+        one.enqueue(nsteps)
+        s1 = one.status()
+        full = one._raw[s1.current]  # (3, N, pitch)
+        ok, bad = True, []
+        for r in range(world):
+            jb, nl, steps_r, time_r, err_r = metas[r]
+            part = mine
+            if r > 0:
+                part = torch.empty((3, nl, M + 3), dtype=mine.dtype, device=dev)
+                dist.recv(part, src=r, group=group)
+            same = bool(torch.equal(part, full[:, jb:jb + nl, : M + 3])) and steps_r == s1.steps == nsteps and time_r == s1.time and err_r == 0 == s1.error
+            if not same:
+                bad.append(r)
+            ok = ok and same
+            del part
+        rec = {"grid": f"{M}x{ll.N}", "diffusion": bool(use_diffusion), "mode": mode, "steps": int(nsteps), "bands": world,
+               "bit_identical": bool(ok), "time": float(s1.time), "kernel": "resident" if resident else "launch-per-step"}
+        if bad:
+            rec["mismatching_ranks"] = bad
+        one.close()
+        del one, full
+    else:
+        dist.send(mine, dst=0, group=group)
+    del mine
+    torch.cuda.empty_cache()
+    dist.barrier(group=group)
+    return rec

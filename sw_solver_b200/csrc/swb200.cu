@@ -489,6 +489,10 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     p.halo = cfg->halo;
     p.xlocal = c->d_xblock;
     p.spin_limit = 20000000000LL;  // ~10 s of SM clock ticks
+#ifdef SWB_BAND_TIMING
+    CK(cudaMalloc(&p.tlog, sizeof(unsigned long long) * kTlogCap * kTlogRow));
+    CK(cudaMemset(p.tlog, 0, sizeof(unsigned long long) * kTlogCap * kTlogRow));
+#endif
     *out = c;
     return 0;
 }
@@ -497,6 +501,24 @@ int swb_destroy(swb_ctx *c)
 {
     if (!c) return 0;
     cudaSetDevice(c->cfg.device);
+#ifdef SWB_BAND_TIMING
+    if (const char *path0 = getenv("SWB_BAND_TIMING_FILE")) {  // header {world, rank, cap, row, last stamp} + the raw ring
+        if (c->prm.tlog && c->seq > 64) {
+            std::vector<unsigned long long> h((size_t)kTlogCap * kTlogRow);
+            cudaDeviceSynchronize();
+            cudaMemcpy(h.data(), c->prm.tlog, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+            const std::string path = std::string(path0) + "." + std::to_string(c->cfg.M) + "x" + std::to_string(c->cfg.N) + ".r" + std::to_string(c->cfg.rank);
+            if (FILE *f = fopen(path.c_str(), "wb")) {
+                const unsigned long long hdr[8] = {(unsigned long long)c->cfg.world, (unsigned long long)c->cfg.rank, (unsigned long long)kTlogCap,
+                                                   (unsigned long long)kTlogRow, c->seq, (unsigned long long)c->resident, 0, 0};
+                fwrite(hdr, sizeof(unsigned long long), 8, f);
+                fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+                fclose(f);
+            }
+        }
+    }
+    cudaFree(c->prm.tlog);
+#endif
     cudaFree(c->d_phi);
     cudaFree(c->d_tab);
     cudaFree(c->d_pre);

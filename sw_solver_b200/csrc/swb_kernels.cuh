@@ -32,6 +32,20 @@
 
 namespace swb {
 
+#ifdef SWB_BAND_TIMING
+__device__ __forceinline__ unsigned long long swb_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define SWB_TLOG(p, k) do { if ((p).tlog != nullptr) (p).tlog[((p).stamp % kTlogCap) * kTlogRow + (k)] = swb_globaltimer(); } while (0)
+#define SWB_TLOG_MAX(p, k) do { if ((p).tlog != nullptr) atomicMax(&(p).tlog[((p).stamp % kTlogCap) * kTlogRow + (k)], swb_globaltimer()); } while (0)
+#else
+#define SWB_TLOG(p, k) do { } while (0)
+#define SWB_TLOG_MAX(p, k) do { } while (0)
+#endif
+
 // One launch per time step (any grid size, any band decomposition).
 template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
           bool CFLF = false>
@@ -43,8 +57,13 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     __shared__ int s_flags;
     __shared__ CflFilter s_filter;
     int tbase = 0, par = -1;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) SWB_TLOG(p, 2);
     march_step<T, STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, W, CFLF, false>(p, tm, p.launch, true, tbase, par, smem_raw, s_dt, s_flags, s_filter,
                                                                            nullptr);
+#ifdef SWB_BAND_TIMING
+    __syncthreads();
+    if (threadIdx.x == 0) SWB_TLOG_MAX(p, 3);
+#endif
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p)
@@ -107,6 +126,9 @@ __device__ __forceinline__ bool band_gather(const Params &p, int launch, unsigne
         ex = *reinterpret_cast<const volatile unsigned long long *>(&xs->ex_bits);
         ey = *reinterpret_cast<const volatile unsigned long long *>(&xs->ey_bits);
     }
+    // every lane's acquire happens before anything lane 0 releases afterwards (the shuffles below
+    // exchange values but order no memory accesses)
+    __syncwarp();
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) {
         ex = umax64(ex, __shfl_xor_sync(0xffffffffu, ex, s));
@@ -242,7 +264,12 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
 __global__ void publish_kernel(const __grid_constant__ Params p)
 {
     const Ctrl *new_slot = p.ctrl + ((p.launch + 1) % 3);
+    if (threadIdx.x == 0) SWB_TLOG(p, 5);
     band_publish(p, p.launch, p.stamp, new_slot->ex_bits, new_slot->ey_bits, (int)threadIdx.x);
+#ifdef SWB_BAND_TIMING
+    __syncwarp();
+    if (threadIdx.x == 0) SWB_TLOG(p, 6);
+#endif
 }
 
 // Multi-GPU step prologue (one warp, before the step kernel in stream order): lane r waits
@@ -254,6 +281,7 @@ __global__ void gather_kernel(const __grid_constant__ Params p)
 {
     const int r = threadIdx.x;
     unsigned long long ex = 0ULL, ey = 0ULL;
+    if (r == 0) SWB_TLOG(p, 0);
     if (r < p.world) {
         const XSlot *xs = &p.xlocal->slot[p.launch % 3][r];
         const long long t0 = clock64();
@@ -264,6 +292,7 @@ __global__ void gather_kernel(const __grid_constant__ Params p)
             }
             __nanosleep(100);
         }
+        SWB_TLOG(p, 8 + r);
         ex = *reinterpret_cast<const volatile unsigned long long *>(&xs->ex_bits);
         ey = *reinterpret_cast<const volatile unsigned long long *>(&xs->ey_bits);
     }
@@ -276,6 +305,7 @@ __global__ void gather_kernel(const __grid_constant__ Params p)
         Ctrl *cur_slot = p.ctrl + (p.launch % 3);
         cur_slot->ex_bits = ex;
         cur_slot->ey_bits = ey;
+        SWB_TLOG(p, 1);
     }
 }
 
@@ -286,6 +316,7 @@ __global__ void gather_kernel(const __grid_constant__ Params p)
 __global__ void __launch_bounds__(256) cfl_fixup_kernel(const __grid_constant__ Params p)
 {
     Ctrl *new_slot = p.ctrl + ((p.launch + 1) % 3);
+    if (blockIdx.x == 0 && threadIdx.x == 0) SWB_TLOG(p, 4);
     if ((new_slot->reserved & 3) == 3) return;
     const int cur = new_slot->current;
     const double *__restrict__ H = (const double *)p.buf[cur][0];

@@ -103,6 +103,14 @@ struct Params {
     int south_pitch, north_pitch;
     int halo;                       // rows exchanged per side (1, or 2 with diffusion)
     long long spin_limit;           // clock64 ticks to wait for peers before flagging SWB_E_TIMEOUT
+    unsigned long long *tlog;       // SWB_BAND_TIMING builds: kTlogCap x kTlogRow globaltimer stamps, indexed by stamp % kTlogCap
 };
+
+// SWB_BAND_TIMING (dev instrumentation of the launch-per-step band path): per step one row of
+// nanosecond stamps -- [0] gather enter, [1] gather exit, [2] first block of the step kernel starts,
+// [3] its last block ends, [4] fix-up kernel starts, [5] publish enters, [6] publish done (stamp
+// released), [8 + r] the stamp of rank r was seen by the gather.  scripts/band_timing.py reads the dump.
+constexpr int kTlogCap = 4096;
+constexpr int kTlogRow = 16;
 
 }  // namespace swb

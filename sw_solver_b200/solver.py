@@ -229,11 +229,11 @@ class Stepper:
             setattr(ct, name, arr.ctypes.data_as(_lib._dp) if arr is not None else None)
         check(self.lib.swb_set_tables(self._ctx, ctypes.byref(ct)))
 
-        # set 0 receives the initial state
-        for k, q in enumerate((h, u, v)):
-            self._load(q, self._raw[0, k])
-        self._f2d = self._load(f, None) if f_lat is None else None
-        self._hs = None if hs_flat else self._load(hs, None)
+        # set 0 receives the initial state (H2D copies and K4 transposes pipelined over two streams)
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._upload((h, u, v), [self._raw[0, k] for k in range(3)])
+        self._f2d = self._upload((f,), [None])[0] if f_lat is None else None
+        self._hs = None if hs_flat else self._upload((hs,), [None])[0]
 
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
         check(self.lib.swb_bind_state(self._ctx, *(ptr(self._raw[s, k]) for s in (0, 1) for k in range(3)),
@@ -242,29 +242,85 @@ class Stepper:
         self._staging: Optional[torch.Tensor] = None
 
     # -- plumbing ------------------------------------------------------------------
-    def _load(self, q, dst: Optional[torch.Tensor]) -> torch.Tensor:
-        """Bring one field into the device layout (``dst`` or a fresh (n_local, pitch) array)."""
+    def _side_stream(self) -> torch.cuda.Stream:
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        return self._copy_stream
+
+    def _upload(self, fields, dsts: List[Optional[torch.Tensor]]) -> List[torch.Tensor]:
+        """Bring fields into the device layout (``dsts[k]`` or a fresh (n_local, pitch) array each).
+
+        Host arrays: the H2D copy of field k+1 (copy stream, two staging buffers) overlaps the K4
+        transpose of field k (current stream); pinned sources are copied asynchronously.  CUDA
+        tensors in the reference layout are transposed in place of the copy; ``layout="device"``
+        tensors are copied (and rounded to the state type in the fp32 mode)."""
         M, nl = self.M, self.n_local
-        if dst is None:
-            dst = torch.zeros((nl, self.pitch), dtype=self._tdtype, device=self.device)
-        if self._layout == "device":
-            if not (isinstance(q, torch.Tensor) and q.is_cuda and tuple(q.shape) == (nl, M + 3) and q.dtype == torch.float64):
-                raise ValueError(f"layout='device' expects float64 CUDA tensors of shape {(nl, M + 3)}")
-            dst[:, : M + 3].copy_(q)  # rounds to the state type in the fp32 mode
-            return dst
-        t = q if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64))
-        if t.dtype != torch.float64 or t.ndim != 2 or t.shape[0] != M + 3 or t.shape[1] not in (self.N, nl):
-            raise ValueError(f"expected a float64 array of shape {(M + 3, self.N)} (or the band window {(M + 3, nl)}), "
-                             f"got {tuple(t.shape)} {t.dtype}")
-        if t.shape[1] != nl:  # the full grid was given: take this band's rows
-            t = t[:, self.j_begin:self.j_begin + nl]
-        t = t.to(self.device, non_blocking=False)  # H2D (or a no-op for a CUDA tensor): plumbing
-        if t.stride(1) != 1:
-            t = t.contiguous()
-        check(self.lib.swb_to_device_layout(self._ctx, ctypes.c_void_p(t.data_ptr()), int(t.stride(0)),
-                                            ctypes.c_void_p(dst.data_ptr()), _stream(self.device)))
-        torch.cuda.current_stream(self.device).synchronize()  # `t` may be a temporary
-        return dst
+        out: List[torch.Tensor] = []
+        main = torch.cuda.current_stream(self.device)
+        staging: List[Optional[torch.Tensor]] = [None, None]
+        freed: List[Optional[torch.cuda.Event]] = [None, None]  # staging buffer k is free again (its transpose ran)
+        nhost = 0
+        for q, dst in zip(fields, dsts):
+            if dst is None:
+                dst = torch.zeros((nl, self.pitch), dtype=self._tdtype, device=self.device)
+            out.append(dst)
+            if self._layout == "device":
+                if not (isinstance(q, torch.Tensor) and q.is_cuda and tuple(q.shape) == (nl, M + 3) and q.dtype == torch.float64):
+                    raise ValueError(f"layout='device' expects float64 CUDA tensors of shape {(nl, M + 3)}")
+                dst[:, : M + 3].copy_(q)  # rounds to the state type in the fp32 mode
+                continue
+            t = q if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64))
+            if t.dtype != torch.float64 or t.ndim != 2 or t.shape[0] != M + 3 or t.shape[1] not in (self.N, nl):
+                raise ValueError(f"expected a float64 array of shape {(M + 3, self.N)} (or the band window {(M + 3, nl)}), "
+                                 f"got {tuple(t.shape)} {t.dtype}")
+            if t.shape[1] != nl:  # the full grid was given: take this band's rows
+                t = t[:, self.j_begin:self.j_begin + nl]
+            if t.is_cuda:
+                src = t if t.stride(1) == 1 else t.contiguous()
+                check(self.lib.swb_to_device_layout(self._ctx, ctypes.c_void_p(src.data_ptr()), int(src.stride(0)),
+                                                    ctypes.c_void_p(dst.data_ptr()), _stream(self.device)))
+                continue
+            k = nhost & 1
+            nhost += 1
+            side = self._side_stream()
+            if staging[k] is None:
+                staging[k] = torch.empty((M + 3, nl), dtype=torch.float64, device=self.device)
+                side.wait_stream(main)  # the allocation is ordered on the current stream
+            if freed[k] is not None:
+                side.wait_event(freed[k])
+            with torch.cuda.stream(side):
+                staging[k].copy_(t, non_blocking=True)  # H2D: plumbing
+                landed = torch.cuda.Event()
+                landed.record(side)
+            main.wait_event(landed)
+            check(self.lib.swb_to_device_layout(self._ctx, ctypes.c_void_p(staging[k].data_ptr()), int(staging[k].stride(0)),
+                                                ctypes.c_void_p(dst.data_ptr()), _stream(self.device)))
+            freed[k] = torch.cuda.Event()
+            freed[k].record(main)
+        if nhost:
+            main.synchronize()  # the sources may be temporaries; the staging buffers go back to the allocator
+        return out
+
+    def _load(self, q, dst: Optional[torch.Tensor]) -> torch.Tensor:
+        return self._upload((q,), [dst])[0]
+
+    def download(self, current: int, out) -> None:
+        """K4 + D2H of the buffer set ``current`` into three host tensors of shape (M+3, n_local)
+        (pinned ones are filled asynchronously): the transpose of field k+1 overlaps the copy of
+        field k.  Returns when all three have landed."""
+        M, nl = self.M, self.n_local
+        main, side = torch.cuda.current_stream(self.device), self._side_stream()
+        stage = torch.empty((3, M + 3, nl), dtype=torch.float64, device=self.device)
+        side.wait_stream(main)
+        for k in range(3):
+            self.export(self._raw[current, k], stage[k])
+            ready = torch.cuda.Event()
+            ready.record(main)
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                out[k].copy_(stage[k], non_blocking=True)
+        side.synchronize()
+        stage.record_stream(side)
 
     def export(self, src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Device-layout (n_local, pitch) array -> (M+3, n_local) CUDA tensor in the reference layout."""

@@ -163,7 +163,7 @@ def test_reference_known_answer_files(golden_ref10, mode):
 @pytest.mark.parametrize("M,N,ic,diff,nsteps", [
     (360, 180, 0, False, 100),   # BASELINE configs[1]
     (360, 180, 1, True, 40),
-    (1440, 720, 0, True, 20),    # BASELINE configs[2]
+    (1440, 720, 0, True, 100),   # BASELINE configs[2] at the horizon SURVEY 8(d) names (1 / 10 / 100 steps)
     (333, 97, 0, False, 25),     # ragged: odd N -> 98, widths not multiples of the 30-lane strips
     (2, 4, 0, True, 5),          # smallest legal grid
 ])
@@ -374,6 +374,57 @@ def test_headline_grid_properties():
 
 
 TOL_FP32 = 1e-5  # north-star tolerance of the optional fp32 mode
+
+
+@pytest.mark.parametrize("M,N,nsteps,checks", [
+    (7200, 3600, 200, (1, 10, 100, 200)),    # BASELINE configs[3]: SURVEY 8(d) names 200 steps
+    (16384, 8192, 110, (1, 10, 110)),        # BASELINE configs[4]: bench.py's warm-up + timed steps
+])
+def test_bench_horizon_fast_and_fp32_against_strict(M, N, nsteps, checks):
+    """The arithmetic every bench number uses (FAST fp64; fp32) over the WHOLE bench horizon on
+    the benched grids, against STRICT -- which is bit-exact to numpy on every grid the oracle
+    reaches (test_config3_grid_against_oracle, test_headline_grid_properties).  FAST replaces the
+    reference's roundoff-noisy dx[i,j] = x[i+1,j]-x[i,j] (grid.py:35-40) by the analytic
+    ac_j*dphi, ~5e-12 relative off at M = 16384: this test shows the state (and the dt history,
+    i.e. every CFL maximum on the way) still stays within 1e-12 of the reference after 110 / 200
+    steps, and the fp32 state within 1e-5.  Compared on the device."""
+    from sw_solver_b200.bands import rossby_haurwitz_band
+
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+
+    def make(mode, dtype):
+        hd, ud, vd, f_lat = rossby_haurwitz_band(ll, 0, ll.N, "cuda")
+        return Stepper(ll, cg, hd, ud, vd, f_lat, None, courant=0.5, final_time=1e12, use_diffusion=False, mode=mode,
+                       layout="device", log_capacity=nsteps, dtype=dtype)
+
+    ref = make("strict", "float64")
+    arms = {"fast": (make("fast", "float64"), TOL_FAST), "fp32": (make("fast", "float32"), TOL_FP32)}
+    done, worst = 0, {}
+    for cp in checks:
+        for st in (ref, arms["fast"][0], arms["fp32"][0]):
+            st.enqueue(cp - done)
+        done = cp
+        s = ref.status()
+        assert s.steps == cp and s.error == 0 and not s.done
+        rq = ref._raw[s.current, :, :, : M + 3]
+        rdt = ref.read_log(cp)[0]
+        for name, (st, tol) in arms.items():
+            sa = st.status()
+            assert sa.steps == cp and sa.error == 0, (name, cp, sa.steps, sa.error)
+            q = st._raw[sa.current, :, :, : M + 3]
+            for k, fld in enumerate("huv"):
+                err = float((q[k].double() - rq[k]).abs().max()) / float(rq[k].abs().max())
+                worst[(name, fld)] = max(worst.get((name, fld), 0.0), err)
+                assert err < tol, (name, fld, cp, err)
+            edt = normwise(st.read_log(cp)[0], rdt)
+            assert edt < (1e-13 if name == "fast" else tol), (name, "dt", cp, edt)
+            assert abs(sa.time - s.time) <= (1e-13 if name == "fast" else tol) * s.time
+    print("bench-horizon parity", f"{M}x{ll.N}", {f"{a}:{f}": f"{e:.2e}" for (a, f), e in worst.items()})
+    for st in (ref, arms["fast"][0], arms["fp32"][0]):
+        st.close()
+    del ref, arms
+    torch.cuda.empty_cache()
 
 
 @pytest.mark.parametrize("M,N,diff,nsteps", [(360, 180, False, 100), (1440, 720, True, 20), (333, 97, True, 30)])

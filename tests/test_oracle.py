@@ -101,3 +101,22 @@ def test_driver_semantics():
     og = so.OracleGrid(6, 6)
     h0, u0, v0, _ = so.initial_conditions(0, og)
     assert _bits(h, h0) and _bits(u, u0) and _bits(v, v0)
+
+
+def test_oracle_matches_the_staged_reference_live():
+    """oracle/_ref holds the UNMODIFIED reference numpy modules (staged by __graft_entry__.build()
+    where /root/reference exists; it travels to the GPU box like the built shared objects).  When
+    present, the C oracle must reproduce the reference's own `solve` bit for bit, live: both ICs,
+    with and without diffusion, odd N, the final-time clamp."""
+    from oracle import ref_numpy as rn
+
+    if not rn.available():
+        pytest.skip("oracle/_ref is not staged on this machine")
+    for (M, N, ic, diff, nsteps) in ((10, 10, 0, True, 25), (12, 9, 1, False, 12), (33, 20, 0, False, 8), (16, 12, 1, True, 6)):
+        sd = {}
+        so.solve(M, N, ic, 1e9, 0.5, diff, save_data=sd, max_steps=nsteps)
+        h, u, v, final_time, _ = rn.solve_steps(M, N, ic, nsteps, 0.5, diff, sd["_dts"])
+        sd2 = {}
+        ho, uo, vo = so.solve(M, N, ic, final_time / 86400.0, 0.5, diff, save_data=sd2)
+        assert len(sd2["_dts"]) == nsteps
+        assert _bits(h, ho) and _bits(u, uo) and _bits(v, vo), (M, N, ic, diff)
