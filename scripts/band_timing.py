@@ -34,6 +34,7 @@ def main():
     ap.add_argument("prefix")
     ap.add_argument("--last", type=int, default=80)
     ap.add_argument("--skip-tail", type=int, default=4)
+    ap.add_argument("--first", type=int, default=0, help="analyse stamps [first, first + last) instead of the last ones (burst regime)")
     a = ap.parse_args()
     files = sorted(glob.glob(a.prefix + ".r*"))
     if not files:
@@ -46,6 +47,8 @@ def main():
         cap = t.shape[0]
         hi = seq - 1 - a.skip_tail          # last stamp used is seq-1
         lo = hi - a.last
+        if a.first > 0:
+            lo, hi = a.first, a.first + a.last
         idx = np.arange(lo, hi) % cap
         nxt = np.arange(lo + 1, hi + 1) % cap
         T, Tn = t[idx], t[nxt]

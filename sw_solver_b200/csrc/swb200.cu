@@ -57,7 +57,8 @@ struct swb_ctx {
     swb_config cfg;
     Params prm;
     bool tables_set = false, state_bound = false, cfl_ready = false, linked = false;
-    double *d_phi = nullptr, *d_tab = nullptr, *d_log = nullptr, *d_pre = nullptr, *d_pred = nullptr;
+    double *d_phi = nullptr, *d_tab = nullptr, *d_log = nullptr, *d_pre = nullptr, *d_pred = nullptr, *d_prec = nullptr;
+    cudaStream_t setup_stream = nullptr;  // table upload + prerec_kernel (never the caller's or the default stream)
     Ctrl *d_ctrl = nullptr;
     int *d_err = nullptr;
     unsigned int *d_done = nullptr;
@@ -77,6 +78,7 @@ struct swb_ctx {
     // resident_kernel (grids that fit the GPU as one wave of blocks): the whole batch of steps in one launch
     int base_chunk = 2;  // marching length of march_kernel (the resident kernel picks its own)
     bool resident = false;
+    bool streaming = false;       // resident_kernel<..., STREAM>: one contiguous range of rows per block
     bool resident_bands = false;  // swb_enable_resident_bands: every band of this globe has a GPU of its own
     const void *res_fn = nullptr;
     int res_smem = 0;
@@ -258,6 +260,26 @@ ResKernel res_kernel_sel(int mode, bool diff, bool tma, int chunk)
     if (mode == SWB_FAST) return diff ? res_kernel_inst<false, true, false, false, 3, BANDS>(chunk) : res_kernel_inst<false, false, false, false, 4, BANDS>(chunk);
     return diff ? res_kernel_inst<false, true, false, true, 3, BANDS>(chunk) : res_kernel_inst<false, false, false, true, 4, BANDS>(chunk);
 }
+// streaming variant (FAST modes, TMA ring; the rings carry the row records: no block-shared records)
+template <bool DIFF, bool GUARD, bool BANDS>
+ResKernel stream_kernel_inst()
+{
+    constexpr int S = DIFF ? 3 : 4;
+    using LY = TmaLayout<4, S, double, box_cols<double, DIFF, true>(), stage_rec_bytes<4>(true, DIFF)>;
+    auto fn = resident_kernel<double, false, DIFF, true, 4, S, GUARD, 2, BANDS, kWarpsPerBlock, true>;
+    return ResKernel{(const void *)fn, kWarpsPerBlock * LY::kWarpBytes};
+}
+ResKernel stream_kernel_of(int mode, bool diff, bool bands)
+{
+    const bool guard = mode != SWB_FAST;
+    if (bands) {
+        if (diff) return guard ? stream_kernel_inst<true, true, true>() : stream_kernel_inst<true, false, true>();
+        return guard ? stream_kernel_inst<false, true, true>() : stream_kernel_inst<false, false, true>();
+    }
+    if (diff) return guard ? stream_kernel_inst<true, true, false>() : stream_kernel_inst<true, false, false>();
+    return guard ? stream_kernel_inst<false, true, false>() : stream_kernel_inst<false, false, false>();
+}
+
 // (bands: the FAST modes; a STRICT band keeps one launch per step)
 ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk, bool bands)
 {
@@ -273,6 +295,7 @@ ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk, bool bands)
 int setup_resident(swb_ctx *c)
 {
     c->resident = false;
+    c->streaming = false;
     const swb_config &cfg = c->cfg;
     Params &p = c->prm;
     if (cfg.dtype != SWB_F64 || cfg.f_is_2d || cfg.has_hs) return 0;
@@ -323,6 +346,35 @@ int setup_resident(swb_ctx *c)
         if (rc) return rc;
         const int ch_t = chunk_for(cap_t, 4, res_max_chunk(true, cfg.use_diffusion));
         if (ch_t > 0) { tma = true; chunk = ch_t; cap = cap_t; }
+    }
+    // Streaming: whenever the one-tile-per-block layout does not exist (more blocks than the GPU holds at
+    // once) or would march more than kResPreSmemChunk rows per block (few long tiles balance badly over
+    // the SMs).  SWB_STREAM=0 / 1 overrides.
+    bool stream = c->tma_ready && cfg.mode != SWB_STRICT && c->d_prec != nullptr && (chunk <= 0 || (tma && chunk > kResPreSmemChunk));
+    if (const char *e = getenv("SWB_STREAM")) stream = c->tma_ready && cfg.mode != SWB_STRICT && c->d_prec != nullptr && atoi(e) != 0;
+    if (stream) {
+        const ResKernel rk = stream_kernel_of(cfg.mode, cfg.use_diffusion, cfg.world > 1);
+        CK(cudaFuncSetAttribute(rk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rk.smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk.fn, kWarpsPerBlock * 32, (size_t)rk.smem));
+        const long long capb = (long long)nb * c->sm_count;
+        if (capb < 1) return 0;
+        const long long total = (long long)gx * rows;
+        long long unit = (total + capb - 1) / capb;
+        if (const char *e = getenv("SWB_STREAM_UNIT")) unit = atoll(e) > 0 ? atoll(e) : unit;
+        unit = (unit + 3) / 4 * 4;  // whole four-row tiles
+        const long long nblk = (total + unit - 1) / unit;
+        if (nblk > capb || unit > (1 << 30)) return 0;
+        p.stream_total = total;
+        p.stream_unit = (int)unit;
+        p.stream_rows = rows;
+        p.pre_smem = 0;
+        c->res_fn = rk.fn;
+        c->res_smem = rk.smem;
+        c->res_grid = dim3((unsigned)nblk, 1);
+        c->resident = true;
+        c->streaming = true;
+        return 0;
     }
     if (chunk <= 0) return 0;
     const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, chunk, cfg.world > 1);
@@ -434,6 +486,9 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     CK(cudaMemset(c->d_tab, 0, sizeof(double) * (size_t)T_COUNT * nloc));
     CK(cudaMalloc(&c->d_pre, sizeof(double) * (size_t)kRowRec * nloc));
     if (cfg->use_diffusion && cfg->mode != SWB_STRICT) CK(cudaMalloc(&c->d_pred, sizeof(double) * (size_t)kRowDiff * nloc));
+    if (cfg->mode != SWB_STRICT && cfg->dtype == SWB_F64)  // the streaming kernel's padded table: row record + diffusion record per latitude
+        CK(cudaMalloc(&c->d_prec, sizeof(double) * (size_t)rec_stride(cfg->use_diffusion != 0) * (nloc + 2 * kRecPad)));
+    CK(cudaStreamCreateWithFlags(&c->setup_stream, cudaStreamNonBlocking));
     CK(cudaMalloc(&c->d_ctrl, sizeof(Ctrl) * 3));
     CK(cudaMemset(c->d_ctrl, 0, sizeof(Ctrl) * 3));
     CK(cudaMalloc(&c->d_err, sizeof(int)));
@@ -456,6 +511,7 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     p.tab = c->d_tab;
     p.pre = c->d_pre;
     p.pred = c->d_pred;
+    p.prec = c->d_prec ? c->d_prec + (size_t)kRecPad * rec_stride(cfg->use_diffusion != 0) : nullptr;
     p.ctrl = c->d_ctrl;
     p.err = c->d_err;
     p.done_ctr = c->d_done;
@@ -523,6 +579,8 @@ int swb_destroy(swb_ctx *c)
     cudaFree(c->d_tab);
     cudaFree(c->d_pre);
     cudaFree(c->d_pred);
+    cudaFree(c->d_prec);
+    if (c->setup_stream) cudaStreamDestroy(c->setup_stream);
     cudaFree(c->d_ctrl);
     cudaFree(c->d_err);
     cudaFree(c->d_done);
@@ -548,15 +606,18 @@ int swb_set_tables(swb_ctx *c, const swb_tables *t)
     const double *src[T_COUNT] = {t->c, t->tg, t->ac, t->f_lat, t->tgMidy, t->cMidy, t->dy, t->dy1, t->dyc, t->dy1c, t->Ay, t->By, t->Cy};
     for (int k = 0; k < T_COUNT; ++k)
         if (src[k]) memcpy(&host[(size_t)k * nloc], src[k], sizeof(double) * nloc);
-    CK(cudaMemcpy(c->d_tab, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_phi, t->phi, sizeof(double) * (size_t)(c->cfg.M + 3), cudaMemcpyHostToDevice));
+    // (on the context's own non-blocking stream: neither the default stream nor a device-wide
+    // synchronisation is involved; the host waits for this stream only)
+    cudaStream_t ss = c->setup_stream;
+    CK(cudaMemcpyAsync(c->d_tab, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice, ss));
+    CK(cudaMemcpyAsync(c->d_phi, t->phi, sizeof(double) * (size_t)(c->cfg.M + 3), cudaMemcpyHostToDevice, ss));
     // the dt-independent stage of the row records, once
-    const int nb = (c->cfg.n_local + 127) / 128;
-    if (c->cfg.mode == SWB_STRICT) prerec_kernel<true><<<nb, 128>>>(c->prm, c->d_pre, nullptr);
-    else prerec_kernel<false><<<nb, 128>>>(c->prm, c->d_pre, c->d_pred);
+    const int nb = (c->cfg.n_local + 2 * kRecPad + 127) / 128;
+    if (c->cfg.mode == SWB_STRICT) prerec_kernel<true><<<nb, 128, 0, ss>>>(c->prm, c->d_pre, nullptr, nullptr);
+    else prerec_kernel<false><<<nb, 128, 0, ss>>>(c->prm, c->d_pre, c->d_pred, c->d_prec);
     c->launches++;
     CK(cudaGetLastError());
-    CK(cudaDeviceSynchronize());
+    CK(cudaStreamSynchronize(ss));
     c->tables_set = true;
     return 0;
 }
@@ -621,7 +682,7 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     return setup_resident(c);
 }
 
-int swb_resident(const swb_ctx *c) { return (c && c->resident) ? 1 : 0; }
+int swb_resident(const swb_ctx *c) { return (c && c->resident) ? (c->streaming ? 2 : 1) : 0; }
 
 int swb_enable_resident_bands(swb_ctx *c)
 {
@@ -728,6 +789,7 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
                 // slice, ...): this context goes back to one launch per step, for good
                 (void)cudaGetLastError();
                 c->resident = false;
+                c->streaming = false;
                 c->prm.chunk = c->base_chunk;
                 break;
             }

@@ -58,8 +58,10 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     __shared__ CflFilter s_filter;
     int tbase = 0, par = -1;
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) SWB_TLOG(p, 2);
+    const int ja = p.jl_first + blockIdx.y * p.chunk;
+    const Tile tl{(int)blockIdx.x * W, ja, min(ja + p.chunk, p.jl_last + 1), blockIdx.x == 0 && blockIdx.y == 0, true};
     march_step<T, STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, W, CFLF, false>(p, tm, p.launch, true, tbase, par, smem_raw, s_dt, s_flags, s_filter,
-                                                                           nullptr);
+                                                                           nullptr, tl);
 #ifdef SWB_BAND_TIMING
     __syncthreads();
     if (threadIdx.x == 0) SWB_TLOG_MAX(p, 3);
@@ -149,7 +151,14 @@ __device__ __forceinline__ bool band_gather(const Params &p, int launch, unsigne
 // acquire at gpu scope), behind which the next step reads the CFL maxima -- accumulated by
 // the same atomics as in march_kernel -- and its neighbours' new rows and columns straight
 // from the L2.  Same step body, same arithmetic: bit-identical to a launch per step.
-template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, bool BANDS = false, int W = kWarpsPerBlock>
+//
+// STREAM: grids beyond one wave of blocks (7200 x 3600, 16384 x 8192, latitude bands of any size).  The
+// (block column, latitude) space is cut into one contiguous range of `stream_unit` rows per block --
+// equal work for every block, whatever the grid -- which the block's warps march in one go (two, when
+// the range crosses into the next block column), each warp on its own: the row records arrive with the
+// tiles (see march_step).  No launch per step, no wave tail, no march start-up per 64 rows.
+template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, bool BANDS = false, int W = kWarpsPerBlock,
+          bool STREAM = false>
 __global__ void __launch_bounds__(W * 32, MINB)
 resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
 {
@@ -159,6 +168,9 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
     __shared__ CflFilter s_filter;
     __shared__ unsigned long long s_max[2];
     const unsigned int nblocks = gridDim.x * gridDim.y;
+    // STREAM: this block's range of the linearised (block column, row) space
+    const long long lin0 = STREAM ? (long long)blockIdx.x * p.stream_unit : 0;
+    const long long lin1 = STREAM ? min(lin0 + p.stream_unit, p.stream_total) : 0;
     // latitude bands (world > 1): warp 0 of block (0,0) runs the exchange with the other GPUs; the
     // blocks are admitted to a step through `go` (done_ctr[1]) once the maxima of ALL bands are in
     constexpr bool bands = BANDS;  // (a template axis: the one-band kernels keep their register allocation)
@@ -196,8 +208,29 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
             }
             __syncthreads();
         }
-        const bool active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true, BANDS>(p, tm, p.launch + s, s == 0, tbase, par,
-                                                                                                            smem_raw, s_dt, s_flags, s_filter, s_max);
+        bool active = true;
+        if constexpr (STREAM) {
+            int par_in = par;  // buffer set holding the current state (-1: not known yet), the same for every piece of the step
+            bool head = true;
+            for (long long lin = lin0; lin < lin1;) {
+                const int col = (int)(lin / p.stream_rows), r0 = (int)(lin % p.stream_rows);
+                const int len = (int)min((long long)(p.stream_rows - r0), lin1 - lin);
+                const Tile tl{col * W, p.jl_first + r0, p.jl_first + r0 + len, blockIdx.x == 0, head};
+                int pio = par_in;
+                active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true, BANDS, true>(p, tm, p.launch + s, s == 0 && head, tbase, pio,
+                                                                                                                 smem_raw, s_dt, s_flags, s_filter, s_max, tl);
+                if (!active) break;
+                par = pio;          // the set holding the NEW state: the next step's current one
+                par_in = pio ^ 1;
+                head = false;
+                lin += len;
+            }
+        } else {
+            const int ja = p.jl_first + blockIdx.y * p.chunk;
+            const Tile tl{(int)blockIdx.x * W, ja, min(ja + p.chunk, p.jl_last + 1), blockIdx.x == 0 && blockIdx.y == 0, true};
+            active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true, BANDS>(p, tm, p.launch + s, s == 0, tbase, par, smem_raw,
+                                                                                                      s_dt, s_flags, s_filter, s_max, tl);
+        }
         if (!active) break;
         // Grid barrier: all stores and atomics of step s happen before any load of step s+1.
         // (TMA: every thread first orders its generic-proxy stores before the async-proxy reads
@@ -345,10 +378,26 @@ __global__ void __launch_bounds__(256) cfl_fixup_kernel(const __grid_constant__ 
 }
 
 // Stage 1 of the row records for every local latitude, once per context (swb_set_tables).
+// `prec` (FAST): the same records once more as ONE table of (nrows + 2 kRecPad) rows -- row record, then
+// diffusion record -- for the streaming kernel's bulk copies; the padding rows repeat the end rows.
 template <bool STRICT>
-__global__ void __launch_bounds__(128) prerec_kernel(const __grid_constant__ Params p, double *__restrict__ pre, double *__restrict__ pred)
+__global__ void __launch_bounds__(128) prerec_kernel(const __grid_constant__ Params p, double *__restrict__ pre, double *__restrict__ pred,
+                                                     double *__restrict__ prec)
 {
     const int jl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (prec != nullptr && jl < p.nrows + 2 * kRecPad) {  // padded row jl holds local latitude jl - kRecPad (clamped by the builders)
+        const int stride = rec_stride(pred != nullptr);
+        double rec[kRowRec];
+        build_row_pre<STRICT>(p, jl - kRecPad, rec);
+#pragma unroll
+        for (int k = 0; k < kRowRec; ++k) prec[(size_t)jl * stride + k] = rec[k];
+        if (pred != nullptr) {
+            double rd[kRowDiff];
+            build_diff_pre(p, jl - kRecPad, rd);
+#pragma unroll
+            for (int k = 0; k < kRowDiff; ++k) prec[(size_t)jl * stride + kRowRec + k] = rd[k];
+        }
+    }
     if (jl >= p.nrows) return;
     double rec[kRowRec];
     build_row_pre<STRICT>(p, jl, rec);

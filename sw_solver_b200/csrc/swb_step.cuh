@@ -16,7 +16,7 @@ namespace swb {
 // RES (resident_kernel): the launch stops at the first inactive step, so that step leaves
 // the carried-forward state in BOTH other slots -- whatever launch index comes next reads it.
 template <bool RES>
-__device__ __forceinline__ void step_prologue(const Params &p, int launch, double *s_dt, int *s_flags)
+__device__ __forceinline__ void step_prologue(const Params &p, int launch, bool lead, double *s_dt, int *s_flags)
 {
     Ctrl *const cur_slot = p.ctrl + (launch % 3);
     Ctrl *const new_slot = p.ctrl + ((launch + 1) % 3);
@@ -45,7 +45,7 @@ __device__ __forceinline__ void step_prologue(const Params &p, int launch, doubl
     }
     *s_dt = dt;
     *s_flags = (active ? 1 : 0) | (int)((nsteps & 1) << 1);
-    if (blockIdx.x == 0 && blockIdx.y == 0) {
+    if (lead) {
         Ctrl *const clr_slot = p.ctrl + ((launch + 2) % 3);
         clr_slot->ex_bits = 0ULL;
         clr_slot->ey_bits = 0ULL;
@@ -190,6 +190,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
                  ::"r"(dst), "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
 }
 
+// contiguous bytes global -> shared by the TMA unit (size a multiple of 16, both addresses 16-byte aligned)
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // 16 bytes global -> shared without passing through registers (LDGSTS, L2 only)
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src)
 {
@@ -203,10 +210,16 @@ constexpr int kFirstRowsBytes = 6 * 32 * 16;  // per warp: h, u, v pairs of the 
 template <typename T, bool DIFF, bool TMA>
 __host__ __device__ constexpr int box_cols() { return (DIFF && TMA && sizeof(T) == 8) ? kStripCols + 4 : kStripCols; }
 
-template <int R, int S, typename T = double, int COLS = kStripCols>
+// doubles per row of the streamed record table: the row record, then the diffusion record
+__host__ __device__ constexpr int rec_stride(bool diff) { return kRowRec + (diff ? kRowDiff : 0); }
+// bytes of row records a stage of the streaming kernel carries behind its h, u, v tile: latitudes j0-1 .. j0+R
+template <int R>
+__host__ __device__ constexpr int stage_rec_bytes(bool stream, bool diff) { return stream ? (R + 2) * rec_stride(diff) * 8 : 0; }
+
+template <int R, int S, typename T = double, int COLS = kStripCols, int EXTRA = 0>
 struct TmaLayout {
     static constexpr int kField = R * COLS * (int)sizeof(T);  // one field, one stage
-    static constexpr int kStage = 3 * kField;
+    static constexpr int kStage = 3 * kField + EXTRA;         // (EXTRA: the streamed row records)
     static constexpr int kRing = S * kStage;
     static constexpr int kBars = 128;
     static constexpr int kWarpBytes = kRing + kBars;
@@ -338,11 +351,17 @@ __device__ __forceinline__ unsigned swb_smid() { unsigned r; asm volatile("mov.u
 // `par_io` (RES): buffer set holding the current state if the caller knows it (>= 0) -- the
 // first loads then start before dt is known -- and on return the set holding the new state.
 // Returns false when the loop has ended (time >= final_time) -- uniform over the grid.
-template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int W, bool CFLF, bool RES, bool RESBANDS = false>
+// STREAM (resident_kernel only): the call covers `tl`, any range of latitudes of one block column; nothing
+// is shared between the warps of the block but dt -- the dt-independent row records of latitudes
+// j0-1 .. j0+R arrive with every tile (one more bulk copy on the tile's mbarrier, from Params::prec)
+// and are scaled by dt in place once the tile has landed.
+template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int W, bool CFLF, bool RES, bool RESBANDS = false,
+          bool STREAM = false>
 __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, const int launch, const bool first, int &tbase,
                                            int &par_io, unsigned char *smem_raw, double &s_dt, int &s_flags, CflFilter &s_filter,
-                                           unsigned long long *s_max)
+                                           unsigned long long *s_max, const Tile tl)
 {
+    static_assert(!STREAM || (RES && TMA && !STRICT && sizeof(T) == 8), "the streaming kernel: resident, TMA ring, FAST fp64");
     static_assert(!STRICT || sizeof(T) == 8, "STRICT reproduces numpy's float64 arithmetic");
     static_assert(!CFLF || (!STRICT && TMA && sizeof(T) == 8), "the CFL filter serves the fp64 FAST TMA kernel");
     static_assert(!RES || (sizeof(T) == 8 && !F2D && !HS && !CFLF), "resident_kernel: fp64, latitude-only Coriolis, flat topography");
@@ -354,7 +373,9 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     constexpr int kBoxCols = box_cols<T, DIFF, TMA>();
     constexpr int kLead = SSTAR ? 1 : 0;  // ring tile u holds latitudes ja+1+(u-kLead)R ..; the march consumes u = kLead ..
     static_assert(!SSTAR || (S >= 3 && R == 4), "the star needs three four-row tiles in the ring");
-    using LY = TmaLayout<R, S, T, kBoxCols>;
+    constexpr int kRecStride = rec_stride(DIFF);                    // STREAM: doubles per row of the streamed records
+    constexpr int kRecBytes = stage_rec_bytes<R>(STREAM, DIFF);
+    using LY = TmaLayout<R, S, T, kBoxCols, kRecBytes>;
     using V2 = vec2_t<T>;
     constexpr int kValid = sizeof(T) == 8 ? kStripValid : kStripValidF32;
     constexpr bool kGuard = STRICT || GUARD;
@@ -363,16 +384,16 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int strip = blockIdx.x * W + warp;
+    const int strip = tl.strip0 + warp;
     const bool warp_on = strip < p.nstrips;
-    const int ja = p.jl_first + blockIdx.y * p.chunk;  // first latitude updated
-    const int jb = min(ja + p.chunk, p.jl_last + 1);   // one past the last
+    const int ja = tl.ja;  // first latitude updated
+    const int jb = tl.jb;  // one past the last
     const int c0 = kValid * strip;
     const int colA = c0 + 2 * lane;  // this lane's cells: (., colA) and (., colA + 1)
     const size_t P = (size_t)p.pitch;
 
     // ---- TMA ring and the march's first two latitudes ----------------------------------
-    const int recb = rec_bytes(p.chunk, DIFF) * ((RES && p.pre_smem) ? 2 : 1);  // RES, short marches: the dt-independent records follow
+    const int recb = STREAM ? 0 : rec_bytes(p.chunk, DIFF) * ((RES && p.pre_smem) ? 2 : 1);  // RES, short marches: the dt-independent records follow
     unsigned char *wbase = smem_raw + recb + (size_t)warp * LY::kWarpBytes;
     const uint32_t ring_a = smem_u32(wbase), bar_a = ring_a + LY::kRing;
     const int ntiles = (jb - ja + R - 1) / R;  // tiles marched
@@ -397,12 +418,22 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         const uint32_t bar = bar_a + 8 * s;
         mbar_expect_tx(bar, LY::kStage);
         tma_load_3d(ring_a + s * LY::kStage, maps, c0 - (SSTAR ? 2 : 0), ja + 1 + (u - kLead) * R, 0, bar);
+        if (STREAM)  // records of latitudes j0-1 .. j0+R of the tile's marched rows j0 = ja + (u - kLead) R ..  (the table is padded)
+            tma_load_1d(ring_a + s * LY::kStage + 3 * LY::kField, p.prec + (ptrdiff_t)(ja - 1 + (u - kLead) * R) * kRecStride, kRecBytes, bar);
     };
     constexpr int kFirstIssue = S - 1 + kLead;  // tiles requested before the march starts
+    if (STREAM) {  // every warp, also one whose strip lies outside this block column: a later piece may need its ring
+        if (first && lane == 0) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) mbar_init(bar_a + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     auto start_ring = [&](int u_lo, int u_hi) {
         if (TMA && warp_on) {
             if (lane == 0) {
-                if ((!RES || first) && u_lo == 0) {
+                if (!STREAM && (!RES || first) && u_lo == 0) {
 #pragma unroll
                     for (int s = 0; s < S; ++s) mbar_init(bar_a + 8 * s, 1);
                     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -449,8 +480,8 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     }
     SWB_STAMP(9);
 
-    if (threadIdx.x == 0) {
-        step_prologue<RES>(p, launch, &s_dt, &s_flags);
+    if (threadIdx.x == 0 && (!STREAM || tl.prologue)) {
+        step_prologue<RES>(p, launch, tl.lead, &s_dt, &s_flags);
         if (RES) s_max[0] = s_max[1] = 0ULL;
         if (CFLF) {
             // thresholds from THIS band's maxima of the current state (with several bands the
@@ -470,7 +501,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         if (!SSTAR) first_rows_async();
     }
     SWB_STAMP(11);
-    __syncthreads();
+    if (!STREAM || tl.prologue) __syncthreads();  // (STREAM: later pieces of a step find dt and the flags in place)
     SWB_STAMP(1);
     const int flags = s_flags;
     if (!(flags & 1)) {
@@ -488,7 +519,9 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     // (built in fp64 whatever T is -- SURVEY 7, hard part 6 -- and rounded once)
     T *rowc = reinterpret_cast<T *>(smem_raw);
     T *rowd = rowc + (size_t)(p.chunk + 2) * kRowRec;
-    if (RES) {
+    if (STREAM) {
+        // nothing here: the records travel with the tiles
+    } else if (RES) {
         // stage 1 (everything that does not depend on dt: look-ups, reciprocals of the metric
         // spacings) was computed once per context by prerec_kernel and is kept in shared memory for
         // the launch; stage 2 is one multiplication per slot (STRICT: the reference's own
@@ -527,7 +560,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             }
         }
     }
-    __syncthreads();
+    if (!STREAM) __syncthreads();
     SWB_STAMP(2);
     if (!warp_on) return true;
     if (RES) tbase = tb + nload;
@@ -577,12 +610,49 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     bool trig = false;  // CFLF: some cell of the current tile reached a trigger threshold
     int negA = 0, negB = 0;  // sign watch of the half-step depths (FAST without GUARD)
 
-    auto rec_of = [&](int jl) { return rowc + (size_t)(jl - (ja - 1)) * kRowRec; };
+    // STREAM: the records of the tile being marched (latitudes rec_j0 ..) sit behind its h, u, v in the ring
+    const T *rec_tile = rowc;
+    int rec_j0 = ja - 1;
+    constexpr int kRecStep = STREAM ? kRecStride : kRowRec;  // elements between the records of consecutive latitudes
+    auto rec_of = [&](int jl) { return STREAM ? rec_tile + (jl - rec_j0) * kRecStep : rowc + (size_t)(jl - (ja - 1)) * kRowRec; };
+    auto set_rec_tile = [&](int u) {
+        rec_tile = reinterpret_cast<const T *>(wbase + (size_t)stage_of(u) * LY::kStage + 3 * LY::kField);
+        rec_j0 = ja - 1 + (u - kLead) * R;
+    };
+    // STREAM: a landed tile's records times dt, in place (slot k of a row: scale_row_slot; the diffusion
+    // part: slot 6).  The same products as the block-shared records of the other kernels.
+    auto scale_tile = [&](int u) {
+        double2 *rec = reinterpret_cast<double2 *>(wbase + (size_t)stage_of(u) * LY::kStage + 3 * LY::kField);
+        constexpr int kPairs = (R + 2) * kRecStride / 2;
+        const double dt64 = s_dt;
+#pragma unroll
+        for (int e0 = 0; e0 < kPairs; e0 += 32) {
+            const int e = e0 + lane;
+            if (e < kPairs) {
+                const int k = (2 * e) % kRecStride;  // slot of the pair's first element (kRecStride is even)
+                double2 v = rec[e];
+                if (k < kRowRec) {
+                    v.x = scale_row_slot<false>(k, v.x, dt64);
+                    v.y = scale_row_slot<false>(k + 1, v.y, dt64);
+                } else if (k - kRowRec == 6) {
+                    v.x = dt64 * v.x;
+                }
+                rec[e] = v;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes before the stage's next tensor load
+        __syncwarp();
+    };
     auto load_f = [&](int jl) -> V2 {
         if (F2D) return ldg2((const T *)p.f2d + (size_t)min(jl, p.nrows - 1) * P + colA);
         return mk2(T(0), T(0));
     };
 
+    if (STREAM) {  // the first marched tile's records serve the first y-face
+        wait_tile(kLead);
+        scale_tile(kLead);
+        set_rec_tile(kLead);
+    }
     Cell<T> curA, curB;
     Face<T> y0A, y0B;
     {
@@ -659,7 +729,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         // the row record, read as 16-byte pairs (broadcast LDS.128)
         const V2 r_c_ac = rc2[RC_C / 2], r_kx_fkx = rc2[RC_KX / 2], r_cdx_cxu = rc2[RC_CDX / 2], r_ky_fky = rc2[RC_KY / 2];
         const V2 r_cm_cy1f = rc2[RC_CM / 2], r_cyf_cy1u = rc2[RC_CYF / 2], r_cyu_kc = rc2[RC_CYU / 2], r_fd_dy1s = rc2[RC_FD / 2];
-        const T cn = rec_of(jl)[kRowRec + RC_C];
+        const T cn = rec_of(jl)[kRecStep + RC_C];
         const V2 f2 = load_f(jl + 1);
         const Cell<T> nxtA = make_cell<STRICT>(h2.x, u2.x, v2.x, cn, hgCell, f2.x);
         const Cell<T> nxtB = make_cell<STRICT>(h2.y, u2.y, v2.y, cn, hgCell, f2.y);
@@ -767,7 +837,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                 unA = O::add(unA, O::mul(dnu, lap(suA, wxA))); unB = O::add(unB, O::mul(dnu, lap(suB, wxB)));
                 vnA = O::add(vnA, O::mul(dnu, lap(svA, wxA))); vnB = O::add(vnB, O::mul(dnu, lap(svB, wxB)));
             } else {
-                const T *rd = rowd + (size_t)(jl - (ja - 1)) * kRowDiff;
+                const T *rd = STREAM ? rec_of(jl) + kRowRec : rowd + (size_t)(jl - (ja - 1)) * kRowDiff;
                 const T dnu = rd[6];
                 hnA = fma(dnu, laplacian_fast(shA, rd), hnA); hnB = fma(dnu, laplacian_fast(shB, rd), hnB);
                 unA = fma(dnu, laplacian_fast(suA, rd), unA); unB = fma(dnu, laplacian_fast(suB, rd), unB);
@@ -878,6 +948,10 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         for (int t = 0; t < ntiles; ++t) {
             const int u = t + kLead;
             if (!SSTAR) wait_tile(u);
+            if (STREAM) {
+                if (!SSTAR && t > 0) scale_tile(u);
+                set_rec_tile(u);
+            }
             const V2 *tile = tile_of(u);
             const V2 *tprev = SSTAR ? tile_of(u - 1) : tile, *tnext = SSTAR ? tile_of(u + 1) : tile;
             // row i of the marched tile, reaching into its neighbours in the ring (i is a constant after unrolling)
@@ -891,6 +965,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                 if (u + 1 < nload) {
                     wait_tile(u + 1);
                     patch_tile(u + 1);
+                    if (STREAM && u + 1 < kLead + ntiles) scale_tile(u + 1);
                 }
             };
             const int j0 = ja + t * R;

@@ -16,6 +16,7 @@ constexpr int kMaxChunk = 128;   // latitudes marched by one warp, at most
 constexpr int kRowRec = 16;      // doubles per row record
 constexpr int kRowDiff = 8;      // doubles per diffusion row record
 constexpr int kMaxRanks = 8;
+constexpr int kRecPad = 8;       // rows of padding either side of the streamed record table (Params::prec)
 
 // row indices of the packed latitude table (each row `nrows` long, indexed by local latitude)
 enum Tab { T_C = 0, T_TG, T_AC, T_F, T_TGMIDY, T_CMIDY, T_DY, T_DY1, T_DYC, T_DY1C, T_AY, T_BY, T_CY, T_COUNT };
@@ -66,6 +67,14 @@ struct XBlock {
     XSlot slot[3][kMaxRanks];
 };
 
+// What one call of `march_step` covers: warps strip0 .. strip0+W-1, latitudes [ja, jb).  `lead`: the
+// block that advances the loop state (time, step count); `prologue`: this call starts a time step
+// (the streaming kernel marches several pieces per step).
+struct Tile {
+    int strip0, ja, jb;
+    bool lead, prologue;
+};
+
 struct Params {
     void *buf[2][3];    // two buffer sets {h,u,v} (fp64 or fp32); set (nsteps & 1) holds the current state
     const void *f2d;    // (nrows, pitch) or null
@@ -103,6 +112,12 @@ struct Params {
     int south_pitch, north_pitch;
     int halo;                       // rows exchanged per side (1, or 2 with diffusion)
     long long spin_limit;           // clock64 ticks to wait for peers before flagging SWB_E_TIMEOUT
+    // streaming resident kernel (resident_kernel<..., STREAM>): every block marches a contiguous range of
+    // `stream_unit` rows of the (block column, latitude) space, its row records arriving with the tiles
+    const double *prec;             // (nrows + 2 kRecPad) x (kRowRec [+ kRowDiff]) dt-independent records; points at local row 0
+    long long stream_total;         // block columns x updated rows
+    int stream_unit;                // rows per block (a multiple of 4)
+    int stream_rows;                // updated rows of this context (jl_last - jl_first + 1)
     unsigned long long *tlog;       // SWB_BAND_TIMING builds: kTlogCap x kTlogRow globaltimer stamps, indexed by stamp % kTlogCap
 };
 

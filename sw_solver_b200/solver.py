@@ -419,6 +419,12 @@ class Stepper:
         GPU as one wave of blocks) instead of one launch per step."""
         return bool(self.lib.swb_resident(self._ctx))
 
+    @property
+    def streaming(self) -> bool:
+        """True when the resident kernel runs its streaming variant (grids beyond one wave of blocks:
+        one contiguous range of rows per block, row records travelling with the TMA tiles)."""
+        return int(self.lib.swb_resident(self._ctx)) == 2
+
     # -- latitude bands (multi-GPU) ---------------------------------------------------
     def exchange_block(self) -> Tuple[int, int]:
         """Device address and size of the block peers deposit their CFL maxima in."""

@@ -514,7 +514,7 @@ def test_cfl_filter_is_exact(monkeypatch):
 
 
 # ---- resident kernel: one cooperative launch per batch of steps --------
-def _run_batches(M, N, ic, diff, mode, batches, final_time, resident, monkeypatch, extra_env=None):
+def _run_batches(M, N, ic, diff, mode, batches, final_time, resident, monkeypatch, extra_env=None, streaming=False):
     monkeypatch.setenv("SWB_RESIDENT", "1" if resident else "0")
     for k, v in (extra_env or {}).items():
         monkeypatch.setenv(k, v)
@@ -522,7 +522,7 @@ def _run_batches(M, N, ic, diff, mode, batches, final_time, resident, monkeypatc
     cg = CartesianGrid(ll)
     h, u, v, f = get_initial_conditions(ic, ll)
     st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=final_time, use_diffusion=diff, mode=mode, log_capacity=256)
-    assert st.resident == resident
+    assert st.resident == resident and st.streaming == streaming
     trace = []
     for n in batches:
         st.enqueue(n)
@@ -614,7 +614,9 @@ def test_resident_kernel_stops_at_final_time(monkeypatch):
         assert _bits(a, b), name
 
 
-def test_large_grids_keep_the_launch_per_step_kernel():
+def test_large_grids_run_the_streaming_resident_kernel():
+    """Grids beyond one wave of blocks (BASELINE configs 3 and 4) run resident as well: the streaming
+    variant, one contiguous range of rows per block, one launch per batch of steps."""
     ll = LatLonGrid(7200, 3600)
     cg = CartesianGrid(ll)
     from sw_solver_b200 import bands
@@ -623,8 +625,62 @@ def test_large_grids_keep_the_launch_per_step_kernel():
     hd, ud, vd, _ = bands.rossby_haurwitz_band(ll, 0, ll.N, torch.device("cuda", 0))
     st = Stepper(ll, cg, hd, ud, vd, coriolis_latitude(ll), None, courant=0.5, final_time=1e12, use_diffusion=False,
                  mode="fast", layout="device")
-    assert not st.resident
+    assert st.resident and st.streaming
+    n0 = st.launch_count
+    st.enqueue(7)
+    assert st.status().steps == 7 and st.launch_count == n0 + 1
     st.close()
+
+
+@pytest.mark.parametrize("M,N,ic,diff,mode,units", [
+    (360, 180, ICType.RossbyHaurwitzWave, False, "fast", ("4", "8", "20", "100", "")),
+    (360, 180, ICType.RossbyHaurwitzWave, True, "fast", ("4", "12", "")),
+    (1440, 720, ICType.RossbyHaurwitzWave, True, "fast", ("", "60")),
+    (1440, 720, ICType.RossbyHaurwitzWave, False, "fast_guarded", ("", "36")),
+    (333, 97, ICType.RossbyHaurwitzWave, True, "fast_guarded", ("4", "28", "")),       # ragged: odd N, last strip nearly empty
+    (500, 100, ICType.RossbyHaurwitzWave, False, "fast", ("16", "44", "300")),         # ranges that cross into the next block column
+    (62, 40, ICType.RossbyHaurwitzWave, True, "fast", ("4", "")),                      # one strip holds both ends of the periodic seam
+    (125, 34, ICType.RossbyHaurwitzWave, False, "fast", ("8",)),
+    (2000, 1000, ICType.RossbyHaurwitzWave, False, "fast", ("",)),
+    (2000, 1000, ICType.RossbyHaurwitzWave, True, "fast", ("",)),
+])
+def test_streaming_kernel_is_bit_identical_to_launch_per_step(M, N, ic, diff, mode, units, monkeypatch):
+    """resident_kernel<..., STREAM>: every block marches one contiguous range of rows of the (block
+    column, latitude) space, its row records arriving with the tiles through the TMA ring.  Same step
+    body, same arithmetic: every bit of state, time, dt history and step count equals a launch per
+    step, for any range length (forced: a few rows ... more than a column) and any batching."""
+    batches = [1, 2, 7, 13, 1]
+    ref, tr_ref, log_ref, n_ref = _run_batches(M, N, ic, diff, mode, batches, 1e12, False, monkeypatch)
+    for unit in units:
+        env = {"SWB_STREAM": "1"}
+        if unit:
+            env["SWB_STREAM_UNIT"] = unit
+        res, tr_res, log_res, n_res = _run_batches(M, N, ic, diff, mode, batches, 1e12, True, monkeypatch, env, streaming=True)
+        assert tr_res == tr_ref, unit
+        for a, b in zip(log_res, log_ref):
+            assert _bits(a, b), unit
+        for name, a, b in zip("huv", res, ref):
+            assert _bits(a, b), (unit, name, _worst(a, b))
+        assert n_res < n_ref
+
+
+def test_streaming_kernel_stops_at_final_time_and_runs_long(monkeypatch):
+    M, N = 96, 64
+    final_time = 3600.0
+    batches = [40, 40, 5, 1]
+    ref, tr_ref, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, "fast", batches, final_time, False, monkeypatch)
+    res, tr_res, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, "fast", batches, final_time, True, monkeypatch,
+                                     {"SWB_STREAM": "1", "SWB_STREAM_UNIT": "8"}, streaming=True)
+    assert tr_ref[1][2] == 1 and tr_res == tr_ref
+    for name, a, b in zip("huv", res, ref):
+        assert _bits(a, b), name
+    batches = [1000, 1, 999]
+    ref, tr_ref, _, _ = _run_batches(180, 90, ICType.RossbyHaurwitzWave, False, "fast", batches, 1e12, False, monkeypatch)
+    res, tr_res, _, _ = _run_batches(180, 90, ICType.RossbyHaurwitzWave, False, "fast", batches, 1e12, True, monkeypatch,
+                                     {"SWB_STREAM": "1", "SWB_STREAM_UNIT": "12"}, streaming=True)
+    assert tr_res == tr_ref and tr_res[-1][0] == 2000
+    for name, a, b in zip("huv", res, ref):
+        assert _bits(a, b), name
 
 
 @pytest.mark.parametrize("M,N,mode", [(500, 100, "fast"), (333, 97, "strict"), (700, 260, "fast_guarded"), (62, 40, "fast"), (125, 34, "fast")])
