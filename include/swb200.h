@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SWB_ABI_VERSION 2
+#define SWB_ABI_VERSION 3
 
 enum {
     SWB_E_INVALID = -1,  /* bad argument / configuration                    */
@@ -170,10 +170,20 @@ int swb_step_fixed_dt(swb_ctx *ctx, double dt, void *stream);
 /* Laplacian of one field (numpy.py:359-382 `compute_diffusion`): q is an (n_local, pitch)
  * device array, out receives the same shape with the interior filled. */
 int swb_laplacian(swb_ctx *ctx, const void *q, void *out, void *stream);
+/* Laplacian of an ALREADY EXTENDED field (numpy.py:66-133 `compute_laplacian`): the reference's
+ * (M+5, N+2) argument, here latitude-major -- `qext` is an (N+2, pitch_ext) device array of
+ * doubles, pitch_ext >= M+5, element (j+1, i+2) holding q[i, j] of the unextended field.  No
+ * periodic wrap or row duplication is applied: whatever extension the caller built is used as is.
+ * `out` as for swb_laplacian.  One band (world == 1) only. */
+int swb_laplacian_ext(swb_ctx *ctx, const void *qext, int pitch_ext, void *out, void *stream);
 
 /* max sqrt(u^2+v^2) over the full current state (numpy.py:553-554); result (double)
  * is written to *out_host after an internal stream synchronisation. */
 int swb_max_speed(swb_ctx *ctx, double *out_host, void *stream);
+/* The same reduction over buffer set `current` (0 or 1), enqueued only: the result, a double,
+ * arrives in `out` (8 bytes of pinned host or device memory) in stream order.  With
+ * swb_status_async in front of it a print (numpy.py:552-557) costs ONE synchronisation. */
+int swb_max_speed_async(swb_ctx *ctx, int current, void *out, void *stream);
 
 /* Enqueue an asynchronous copy of the status record as of all steps enqueued so far into
  * `host_out` (ideally pinned memory; it must stay valid until the stream reaches the
@@ -187,13 +197,20 @@ int swb_get_status(swb_ctx *ctx, swb_status *out, void *stream);
 /* Copy the first `count` (dt, time) pairs of the step history to host arrays. */
 int swb_read_log(swb_ctx *ctx, double *dt_out, double *time_out, int count, void *stream);
 
+/* How long (seconds, ~2 GHz SM clock) a kernel waits for a peer band's stamp or for the grid barrier
+ * before it raises SWB_E_TIMEOUT and ends the time loop (later steps become no-ops).  Default 10 s;
+ * the environment variable SWB_SPIN_SECONDS sets the default of new contexts. */
+int swb_set_spin_limit(swb_ctx *ctx, double seconds);
+
 /* Number of kernels this context has launched so far (for bench.py's gpu_launches). */
 int64_t swb_launch_count(const swb_ctx *ctx);
 
-/* 1 if swb_enqueue_steps runs each batch of steps as ONE cooperative launch of the resident
- * kernel (grids whose blocks all fit the GPU at once: the loop of numpy.py:496-549 then never
- * leaves the device, a grid barrier replaces the launch per step), else 0.  Decided by
- * swb_bind_state; the environment variable SWB_RESIDENT=0 keeps the launch-per-step kernel. */
+/* Non-zero if swb_enqueue_steps runs each batch of steps as ONE cooperative launch of the resident
+ * kernel (the loop of numpy.py:496-549 then never leaves the device, a grid barrier replaces the
+ * launch per step), else 0: 1 = one tile per block (grids whose blocks all fit the GPU at once),
+ * 2 = the streaming variant (larger grids: every block marches several tiles per step, its row
+ * records travelling with the tiles).  Decided by swb_bind_state; the environment variable
+ * SWB_RESIDENT=0 keeps the launch-per-step kernel, SWB_STREAM=0 / 1 overrides the variant. */
 int swb_resident(const swb_ctx *ctx);
 
 /* Latitude bands (world > 1): allow the resident kernel for this band too -- the exchange with

@@ -66,6 +66,9 @@ SYMBOLS = {
     "swb_step_fixed_dt": (ctypes.c_int, [c_void_p, c_double, c_void_p]),
     "swb_laplacian": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "swb_max_speed": (ctypes.c_int, [c_void_p, _dp, c_void_p]),
+    "swb_max_speed_async": (ctypes.c_int, [c_void_p, ctypes.c_int, c_void_p, c_void_p]),
+    "swb_laplacian_ext": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, c_void_p, c_void_p]),
+    "swb_set_spin_limit": (ctypes.c_int, [c_void_p, c_double]),
     "swb_status_async": (ctypes.c_int, [c_void_p, c_void_p, c_void_p]),
     "swb_status_peek": (ctypes.c_int, [c_void_p, ctypes.POINTER(SwbStatus)]),
     "swb_get_status": (ctypes.c_int, [c_void_p, ctypes.POINTER(SwbStatus), c_void_p]),
@@ -114,7 +117,7 @@ def load():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError here means header and library disagree
             fn.restype, fn.argtypes = res, args
-        if L.swb_abi_version() != 2:
+        if L.swb_abi_version() != 3:
             raise ImportError("libswb200.so ABI version mismatch")
         _lib = L
     return _lib

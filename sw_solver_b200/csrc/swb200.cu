@@ -41,6 +41,26 @@ int cuda_fail(cudaError_t e, const char *where)
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
+// Every ABI call works on the context's device and leaves the caller's current device as it found it
+// (constructing a Stepper on cuda:1 must not move torch's current device).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+        else if (err == cudaSuccess) prev = -1;  // nothing to restore
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define ON_DEVICE(c)                      \
+    DeviceGuard guard__((c)->cfg.device); \
+    CK(guard__.err)
+
 int valid_cols(int dtype) { return dtype == SWB_F32 ? kStripValidF32 : kStripValid; }
 int nstrips_of(int M, int dtype) { return (M + 1 + valid_cols(dtype) - 1) / valid_cols(dtype); }
 
@@ -261,23 +281,24 @@ ResKernel res_kernel_sel(int mode, bool diff, bool tma, int chunk)
     return diff ? res_kernel_inst<false, true, false, true, 3, BANDS>(chunk) : res_kernel_inst<false, false, false, true, 4, BANDS>(chunk);
 }
 // streaming variant (FAST modes, TMA ring; the rings carry the row records: no block-shared records)
-template <bool DIFF, bool GUARD, bool BANDS>
+template <bool DIFF, bool GUARD, bool BANDS, bool CFLF>
 ResKernel stream_kernel_inst()
 {
     constexpr int S = DIFF ? 3 : 4;
     using LY = TmaLayout<4, S, double, box_cols<double, DIFF, true>(), stage_rec_bytes<4>(true, DIFF)>;
-    auto fn = resident_kernel<double, false, DIFF, true, 4, S, GUARD, 2, BANDS, kWarpsPerBlock, true>;
+    auto fn = stream_kernel<DIFF, S, GUARD, BANDS, CFLF>;
     return ResKernel{(const void *)fn, kWarpsPerBlock * LY::kWarpBytes};
 }
-ResKernel stream_kernel_of(int mode, bool diff, bool bands)
+template <bool BANDS>
+ResKernel stream_kernel_sel(bool guard, bool diff, bool cflf)
 {
-    const bool guard = mode != SWB_FAST;
-    if (bands) {
-        if (diff) return guard ? stream_kernel_inst<true, true, true>() : stream_kernel_inst<true, false, true>();
-        return guard ? stream_kernel_inst<false, true, true>() : stream_kernel_inst<false, false, true>();
-    }
-    if (diff) return guard ? stream_kernel_inst<true, true, false>() : stream_kernel_inst<true, false, false>();
-    return guard ? stream_kernel_inst<false, true, false>() : stream_kernel_inst<false, false, false>();
+    if (diff) return guard ? stream_kernel_inst<true, true, BANDS, false>() : stream_kernel_inst<true, false, BANDS, false>();
+    if (cflf) return guard ? stream_kernel_inst<false, true, BANDS, true>() : stream_kernel_inst<false, false, BANDS, true>();
+    return guard ? stream_kernel_inst<false, true, BANDS, false>() : stream_kernel_inst<false, false, BANDS, false>();
+}
+ResKernel stream_kernel_of(int mode, bool diff, bool bands, bool cflf)
+{
+    return bands ? stream_kernel_sel<true>(mode != SWB_FAST, diff, cflf) : stream_kernel_sel<false>(mode != SWB_FAST, diff, cflf);
 }
 
 // (bands: the FAST modes; a STRICT band keeps one launch per step)
@@ -347,33 +368,64 @@ int setup_resident(swb_ctx *c)
         const int ch_t = chunk_for(cap_t, 4, res_max_chunk(true, cfg.use_diffusion));
         if (ch_t > 0) { tma = true; chunk = ch_t; cap = cap_t; }
     }
-    // Streaming: whenever the one-tile-per-block layout does not exist (more blocks than the GPU holds at
-    // once) or would march more than kResPreSmemChunk rows per block (few long tiles balance badly over
-    // the SMs).  SWB_STREAM=0 / 1 overrides.
-    bool stream = c->tma_ready && cfg.mode != SWB_STRICT && c->d_prec != nullptr && (chunk <= 0 || (tma && chunk > kResPreSmemChunk));
+    // Streaming variant (stream_kernel): any grid, also beyond one wave of blocks.
+    // Opt-in (SWB_STREAM=1): measured on B200 the streaming kernel is bit-identical but 15-25 % slower per row than
+    // march_kernel / the one-tile resident kernel (register pressure: its tile loop spills loop-control values, see
+    // profiles/r2_stream_kernel.md), which outweighs the launch chain and the wave tail it removes.
+    bool stream = false;
     if (const char *e = getenv("SWB_STREAM")) stream = c->tma_ready && cfg.mode != SWB_STRICT && c->d_prec != nullptr && atoi(e) != 0;
     if (stream) {
-        const ResKernel rk = stream_kernel_of(cfg.mode, cfg.use_diffusion, cfg.world > 1);
+        // the CFL filter (estimate per cell, exact evaluation near the previous maximum, fix-up inside the launch):
+        // as for march_kernel on grids whose step takes far longer than the barrier; SWB_CFL_FILTER=0 / 1 overrides
+        bool cflf = !cfg.use_diffusion && (long long)(p.M + 1) * rows >= 4000000LL;
+        if (const char *e = getenv("SWB_CFL_FILTER")) cflf = !cfg.use_diffusion && atoi(e) != 0;
+        const ResKernel rk = stream_kernel_of(cfg.mode, cfg.use_diffusion, cfg.world > 1, cflf);
         CK(cudaFuncSetAttribute(rk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rk.smem));
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk.fn, kWarpsPerBlock * 32, (size_t)rk.smem));
         const long long capb = (long long)nb * c->sm_count;
         if (capb < 1) return 0;
-        const long long total = (long long)gx * rows;
-        long long unit = (total + capb - 1) / capb;
-        if (const char *e = getenv("SWB_STREAM_UNIT")) unit = atoll(e) > 0 ? atoll(e) : unit;
-        unit = (unit + 3) / 4 * 4;  // whole four-row tiles
-        const long long nblk = (total + unit - 1) / unit;
-        if (nblk > capb || unit > (1 << 30)) return 0;
+        int map = 1;
+        if (const char *e = getenv("SWB_STREAM_MAP")) map = atoi(e) != 0;
+        long long forced_unit = 0;
+        if (const char *e = getenv("SWB_STREAM_UNIT")) forced_unit = atoll(e);
+        long long unit = 0, nblk = 0, total = 0;
+        if (map == 0) {  // one contiguous range per block
+            total = (long long)gx * rows;
+            unit = forced_unit > 0 ? forced_unit : (total + capb - 1) / capb;
+            unit = (unit + 3) / 4 * 4;  // whole four-row tiles
+            nblk = (total + unit - 1) / unit;
+        } else {
+            // tiles of `unit` rows dealt round-robin: the tile height with the fewest row-times per block,
+            // rounds x (unit + the rows a march start costs); ties go to the longer march
+            auto cost = [&](long long u) {
+                const long long ntile = (long long)gx * ((rows + u - 1) / u);
+                const long long rounds = (ntile + capb - 1) / capb;
+                return rounds * (u + 6);
+            };
+            unit = 4;
+            for (long long u = 4; u <= 2048 && u <= ((rows + 3) / 4 * 4); u += 4)
+                if (cost(u) <= cost(unit)) unit = u;
+            if (forced_unit > 0) unit = (forced_unit + 3) / 4 * 4;
+            total = (long long)gx * ((rows + unit - 1) / unit);
+            nblk = total < capb ? total : capb;
+        }
+        if (nblk > capb || nblk < 1 || unit > (1 << 30)) return 0;
         p.stream_total = total;
         p.stream_unit = (int)unit;
         p.stream_rows = rows;
+        p.stream_gx = gx;
+        p.stream_map = map;
         p.pre_smem = 0;
         c->res_fn = rk.fn;
         c->res_smem = rk.smem;
         c->res_grid = dim3((unsigned)nblk, 1);
         c->resident = true;
         c->streaming = true;
+        if (getenv("SWB_VERBOSE"))
+            fprintf(stderr, "[swb] streaming resident kernel: %d x %d rows, %d block columns, map %d, unit %lld rows, %lld tiles/rows, %lld blocks "
+                            "(%d per SM x %d SMs), %d B of shared memory per block, CFL filter %d\n",
+                    cfg.M, rows, gx, map, unit, total, nblk, nb, c->sm_count, rk.smem, (int)cflf);
         return 0;
     }
     if (chunk <= 0) return 0;
@@ -435,6 +487,8 @@ int pick_chunk(int rows, int nstrips, int sm_count)
 
 extern "C" {
 
+static int create_resources(swb_ctx *c);
+
 int swb_abi_version(void) { return SWB_ABI_VERSION; }
 const char *swb_last_error(void) { return g_err.c_str(); }
 int swb_required_pitch(int M, int dtype) { return (M >= 2 && (dtype == SWB_F64 || dtype == SWB_F32)) ? required_pitch(M, dtype) : SWB_E_INVALID; }
@@ -469,7 +523,8 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return fail(SWB_E_NODEVICE, "swb_create: no CUDA device (this library has no CPU fallback)");
     if (cfg->device < 0 || cfg->device >= ndev) return fail(SWB_E_INVALID, "swb_create: bad device ordinal");
-    CK(cudaSetDevice(cfg->device));
+    DeviceGuard guard(cfg->device);
+    CK(guard.err);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, cfg->device));
     if (prop.major != 10) return fail(SWB_E_NODEVICE, "swb_create: kernels are built for sm_100a (Blackwell B200) only");
@@ -478,6 +533,20 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     if (!c) return fail(SWB_E_INVALID, "swb_create: out of host memory");
     c->cfg = *cfg;
     c->sm_count = prop.multiProcessorCount;
+    int rc = create_resources(c);
+    if (rc) {  // nothing allocated so far outlives a failed create
+        const std::string msg = g_err;
+        swb_destroy(c);
+        g_err = msg;
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+static int create_resources(swb_ctx *c)
+{
+    const swb_config *cfg = &c->cfg;
     const size_t nloc = (size_t)cfg->n_local;
     const size_t nphi = (size_t)cfg->pitch + 8;  // lanes of the last strip look past M+2
     CK(cudaMalloc(&c->d_phi, sizeof(double) * nphi));
@@ -544,19 +613,22 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     p.world = 1;  // becomes cfg->world once the peers are linked
     p.halo = cfg->halo;
     p.xlocal = c->d_xblock;
-    p.spin_limit = 20000000000LL;  // ~10 s of SM clock ticks
+    p.spin_limit = 20000000000LL;  // ~10 s of SM clock ticks; SWB_SPIN_SECONDS / swb_set_spin_limit change it
+    if (const char *e = getenv("SWB_SPIN_SECONDS")) {
+        const double sec = atof(e);
+        if (sec > 0.0) p.spin_limit = (long long)(sec * 2.0e9);
+    }
 #ifdef SWB_BAND_TIMING
     CK(cudaMalloc(&p.tlog, sizeof(unsigned long long) * kTlogCap * kTlogRow));
     CK(cudaMemset(p.tlog, 0, sizeof(unsigned long long) * kTlogCap * kTlogRow));
 #endif
-    *out = c;
     return 0;
 }
 
 int swb_destroy(swb_ctx *c)
 {
     if (!c) return 0;
-    cudaSetDevice(c->cfg.device);
+    DeviceGuard guard(c->cfg.device);
 #ifdef SWB_BAND_TIMING
     if (const char *path0 = getenv("SWB_BAND_TIMING_FILE")) {  // header {world, rank, cap, row, last stamp} + the raw ring
         if (c->prm.tlog && c->seq > 64) {
@@ -600,7 +672,7 @@ int swb_set_tables(swb_ctx *c, const swb_tables *t)
         return fail(SWB_E_INVALID, "swb_set_tables: a required table is null");
     if (!c->cfg.f_is_2d && !t->f_lat) return fail(SWB_E_INVALID, "swb_set_tables: f_lat required when f_is_2d == 0");
     if (c->cfg.use_diffusion && (!t->Ay || !t->By || !t->Cy)) return fail(SWB_E_INVALID, "swb_set_tables: Ay/By/Cy required with diffusion");
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     const size_t nloc = (size_t)c->cfg.n_local;
     std::vector<double> host((size_t)T_COUNT * nloc, 0.0);
     const double *src[T_COUNT] = {t->c, t->tg, t->ac, t->f_lat, t->tgMidy, t->cMidy, t->dy, t->dy1, t->dyc, t->dy1c, t->Ay, t->By, t->Cy};
@@ -670,7 +742,7 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
         const long long cells = (long long)(p.M + 1) * (p.jl_last - p.jl_first + 1);
         c->cfl_filter = !f32 && !c->cfg.use_diffusion && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && cells >= 4000000LL;
         if (const char *e = getenv("SWB_CFL_FILTER")) c->cfl_filter = !f32 && !c->cfg.use_diffusion && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && atoi(e) != 0;
-        CK(cudaSetDevice(c->cfg.device));
+        ON_DEVICE(c);
         for (int s = 0; s < 2; ++s) {
             // (fp64 with diffusion: the box also carries the star's two columns either side)
             int rc = make_map(&c->maps.in[s], p.buf[s][0], (uint64_t)(p.M + 3), (uint64_t)p.nrows, (uint64_t)p.pitch, (uint64_t)(s ? fs1 : fs0),
@@ -689,7 +761,7 @@ int swb_enable_resident_bands(swb_ctx *c)
     if (!c) return fail(SWB_E_INVALID, "swb_enable_resident_bands: null context");
     if (c->cfg.world < 2 || !c->linked) return fail(SWB_E_STATE, "swb_enable_resident_bands: link the peers first (world > 1)");
     if (!c->state_bound) return fail(SWB_E_STATE, "swb_enable_resident_bands: no state bound");
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     c->resident_bands = true;
     c->prm.chunk = c->base_chunk;
     return setup_resident(c);
@@ -699,7 +771,7 @@ int swb_to_device_layout(swb_ctx *c, const void *ref, int ref_pitch, void *dev, 
 {
     if (!c || !ref || !dev) return fail(SWB_E_INVALID, "swb_to_device_layout: null argument");
     if (ref_pitch < c->cfg.n_local) return fail(SWB_E_INVALID, "swb_to_device_layout: ref_pitch < n_local");
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     const int rows = c->cfg.n_local, cols = c->cfg.M + 3;
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
     if (c->cfg.dtype == SWB_F32)
@@ -715,7 +787,7 @@ int swb_from_device_layout(swb_ctx *c, const void *dev, void *ref, int ref_pitch
 {
     if (!c || !ref || !dev) return fail(SWB_E_INVALID, "swb_from_device_layout: null argument");
     if (ref_pitch < c->cfg.n_local) return fail(SWB_E_INVALID, "swb_from_device_layout: ref_pitch < n_local");
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     const int rows = c->cfg.M + 3, cols = c->cfg.n_local;
     dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
     if (c->cfg.dtype == SWB_F32)
@@ -732,11 +804,12 @@ int swb_cfl_init(swb_ctx *c, void *stream)
     if (!c) return fail(SWB_E_INVALID, "swb_cfl_init: null context");
     if (!c->state_bound) return fail(SWB_E_STATE, "swb_cfl_init: no state bound");
     if (c->cfg.world > 1 && !c->linked) return fail(SWB_E_STATE, "swb_cfl_init: call swb_link_peers first (world > 1)");
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     cudaStream_t st = (cudaStream_t)stream;
     Params &p = c->prm;
     CK(cudaMemsetAsync(c->d_ctrl, 0, sizeof(Ctrl) * 3, st));
     CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), st));
+    CK(cudaMemsetAsync(c->d_done, 0, sizeof(unsigned int) * 4, st));  // barrier counter, admission token, halt flag
     // every local row this band owns or mirrors takes part at step 1 (ghosts hold real
     // initial values); rows that are another band's interior are scanned by that band.
     const int jl0 = p.pole_s ? 0 : p.jl_first, jl1 = p.pole_n ? p.nrows : p.jl_last + 1;
@@ -766,7 +839,7 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
     if (!c) return fail(SWB_E_INVALID, "swb_enqueue_steps: null context");
     if (!c->tables_set || !c->state_bound) return fail(SWB_E_STATE, "swb_enqueue_steps: tables / state not set");
     if (!c->cfl_ready) return fail(SWB_E_STATE, "swb_enqueue_steps: call swb_cfl_init first");
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     cudaStream_t st = (cudaStream_t)stream;
     c->prm.fixed = 0;
     if (c->resident) {  // the whole batch in one cooperative launch
@@ -845,7 +918,7 @@ int swb_step_fixed_dt(swb_ctx *c, double dt, void *stream)
 {
     if (!c) return fail(SWB_E_INVALID, "swb_step_fixed_dt: null context");
     if (!c->tables_set || !c->state_bound) return fail(SWB_E_STATE, "swb_step_fixed_dt: tables / state not set");
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     c->prm.fixed = 1;
     c->prm.fixed_dt = dt;
     c->prm.launch = 0;
@@ -859,10 +932,28 @@ int swb_laplacian(swb_ctx *c, const void *q, void *out, void *stream)
     if (!c || !q || !out) return fail(SWB_E_INVALID, "swb_laplacian: null argument");
     if (!c->tables_set || !c->cfg.use_diffusion) return fail(SWB_E_STATE, "swb_laplacian: needs tables with diffusion weights");
     if (c->cfg.dtype != SWB_F64) return fail(SWB_E_STATE, "swb_laplacian: the operator-level Laplacian is fp64 (strict)");
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     const Params &p = c->prm;
-    dim3 grid((unsigned)((p.M + 1 + 127) / 128), (unsigned)(p.jl_last - p.jl_first + 1));
+    const int rows = p.jl_last - p.jl_first + 1;
+    dim3 grid((unsigned)((p.M + 1 + 127) / 128), (unsigned)(rows < 32768 ? rows : 32768));
     laplacian_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const double *)q, (double *)out, p);
+    c->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int swb_laplacian_ext(swb_ctx *c, const void *qext, int pitch_ext, void *out, void *stream)
+{
+    if (!c || !qext || !out) return fail(SWB_E_INVALID, "swb_laplacian_ext: null argument");
+    if (!c->tables_set || !c->cfg.use_diffusion) return fail(SWB_E_STATE, "swb_laplacian_ext: needs tables with diffusion weights");
+    if (c->cfg.dtype != SWB_F64) return fail(SWB_E_STATE, "swb_laplacian_ext: the operator-level Laplacian is fp64 (strict)");
+    if (c->cfg.world != 1 || c->cfg.n_local != c->cfg.N) return fail(SWB_E_STATE, "swb_laplacian_ext: one band holding the whole grid only");
+    if (pitch_ext < c->cfg.M + 5) return fail(SWB_E_INVALID, "swb_laplacian_ext: pitch_ext < M + 5");
+    ON_DEVICE(c);
+    const Params &p = c->prm;
+    const int rows = p.jl_last - p.jl_first + 1;
+    dim3 grid((unsigned)((p.M + 1 + 127) / 128), (unsigned)(rows < 32768 ? rows : 32768));
+    laplacian_ext_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>((const double *)qext, pitch_ext, (double *)out, p);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -872,7 +963,7 @@ int swb_status_async(swb_ctx *c, swb_status *host_out, void *stream)
 {
     if (!c) return fail(SWB_E_INVALID, "swb_status_async: null context");
     static_assert(sizeof(Ctrl) == sizeof(swb_status), "Ctrl mirrors swb_status");
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     swb_status *dst = host_out ? host_out : c->h_status;
     CK(cudaMemcpyAsync(dst, c->d_ctrl + (c->launch % 3), sizeof(Ctrl), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaMemcpyAsync(&dst->error, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
@@ -894,29 +985,46 @@ int swb_get_status(swb_ctx *c, swb_status *out, void *stream)
     return swb_status_peek(c, out);
 }
 
+int swb_max_speed_async(swb_ctx *c, int current, void *out, void *stream)
+{
+    if (!c || !out) return fail(SWB_E_INVALID, "swb_max_speed_async: null argument");
+    if (!c->state_bound) return fail(SWB_E_STATE, "swb_max_speed_async: no state bound");
+    if (current != 0 && current != 1) return fail(SWB_E_INVALID, "swb_max_speed_async: current must be 0 or 1");
+    ON_DEVICE(c);
+    cudaStream_t st = (cudaStream_t)stream;
+    const Params &p = c->prm;
+    CK(cudaMemsetAsync(c->d_scratch, 0, sizeof(unsigned long long), st));
+    const int jl0 = p.pole_s ? 0 : p.jl_first, jl1 = p.pole_n ? p.nrows : p.jl_last + 1;
+    if (c->cfg.dtype == SWB_F32)
+        max_speed_kernel<float><<<c->sm_count * 8, 256, 0, st>>>((const float *)p.buf[current][1], (const float *)p.buf[current][2], p.M + 3, jl0, jl1, p.pitch, c->d_scratch);
+    else
+        max_speed_kernel<double><<<c->sm_count * 8, 256, 0, st>>>((const double *)p.buf[current][1], (const double *)p.buf[current][2], p.M + 3, jl0, jl1, p.pitch, c->d_scratch);
+    c->launches++;
+    CK(cudaGetLastError());
+    // (the bit pattern of a non-negative double IS that double)
+    CK(cudaMemcpyAsync(out, c->d_scratch, sizeof(unsigned long long), cudaMemcpyDefault, st));
+    return 0;
+}
+
 int swb_max_speed(swb_ctx *c, double *out_host, void *stream)
 {
     if (!c || !out_host) return fail(SWB_E_INVALID, "swb_max_speed: null argument");
     if (!c->state_bound) return fail(SWB_E_STATE, "swb_max_speed: no state bound");
-    CK(cudaSetDevice(c->cfg.device));
-    cudaStream_t st = (cudaStream_t)stream;
     swb_status s;
     int rc = swb_get_status(c, &s, stream);
     if (rc) return rc;
-    const Params &p = c->prm;
-    const int cur = s.current;
-    CK(cudaMemsetAsync(c->d_scratch, 0, sizeof(unsigned long long), st));
-    const int jl0 = p.pole_s ? 0 : p.jl_first, jl1 = p.pole_n ? p.nrows : p.jl_last + 1;
-    if (c->cfg.dtype == SWB_F32)
-        max_speed_kernel<float><<<c->sm_count * 8, 256, 0, st>>>((const float *)p.buf[cur][1], (const float *)p.buf[cur][2], p.M + 3, jl0, jl1, p.pitch, c->d_scratch);
-    else
-        max_speed_kernel<double><<<c->sm_count * 8, 256, 0, st>>>((const double *)p.buf[cur][1], (const double *)p.buf[cur][2], p.M + 3, jl0, jl1, p.pitch, c->d_scratch);
-    c->launches++;
-    CK(cudaGetLastError());
     unsigned long long bits = 0;
-    CK(cudaMemcpyAsync(&bits, c->d_scratch, sizeof bits, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    rc = swb_max_speed_async(c, s.current, &bits, stream);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
     memcpy(out_host, &bits, 8);
+    return 0;
+}
+
+int swb_set_spin_limit(swb_ctx *c, double seconds)
+{
+    if (!c || !(seconds > 0.0)) return fail(SWB_E_INVALID, "swb_set_spin_limit: need a context and a positive time");
+    c->prm.spin_limit = (long long)(seconds * 2.0e9);  // SM clock ticks at ~2 GHz
     return 0;
 }
 
@@ -925,7 +1033,7 @@ int swb_read_log(swb_ctx *c, double *dt_out, double *time_out, int count, void *
     if (!c) return fail(SWB_E_INVALID, "swb_read_log: null context");
     if (count < 0 || count > c->cfg.log_capacity) return fail(SWB_E_INVALID, "swb_read_log: count exceeds log_capacity");
     if (count == 0) return 0;
-    CK(cudaSetDevice(c->cfg.device));
+    ON_DEVICE(c);
     cudaStream_t st = (cudaStream_t)stream;
     if (dt_out) CK(cudaMemcpyAsync(dt_out, c->d_log, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, st));
     if (time_out) CK(cudaMemcpyAsync(time_out, c->d_log + c->cfg.log_capacity, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, st));
@@ -963,7 +1071,8 @@ int swb_ipc_export(const void *dptr, unsigned char handle[SWB_IPC_HANDLE_BYTES],
 int swb_ipc_open(const unsigned char handle[SWB_IPC_HANDLE_BYTES], int device, void **base)
 {
     if (!handle || !base) return fail(SWB_E_INVALID, "swb_ipc_open: null argument");
-    CK(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CK(guard.err);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle, sizeof h);
     CK(cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess));

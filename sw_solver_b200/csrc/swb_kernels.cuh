@@ -120,7 +120,8 @@ __device__ __forceinline__ bool band_gather(const Params &p, int launch, unsigne
         const long long t0 = clock64();
         while (ld_acquire_sys(&xs->stamp) != stamp) {
             if (clock64() - t0 > p.spin_limit) {
-                atomicMin(p.err, -4);  // SWB_E_TIMEOUT
+                atomicMin(p.err, -4);            // SWB_E_TIMEOUT
+                atomicExch(p.done_ctr + 2, 1u);  // ... and the loop ends here (step_prologue)
                 ok = false;
                 break;
             }
@@ -151,14 +152,7 @@ __device__ __forceinline__ bool band_gather(const Params &p, int launch, unsigne
 // acquire at gpu scope), behind which the next step reads the CFL maxima -- accumulated by
 // the same atomics as in march_kernel -- and its neighbours' new rows and columns straight
 // from the L2.  Same step body, same arithmetic: bit-identical to a launch per step.
-//
-// STREAM: grids beyond one wave of blocks (7200 x 3600, 16384 x 8192, latitude bands of any size).  The
-// (block column, latitude) space is cut into one contiguous range of `stream_unit` rows per block --
-// equal work for every block, whatever the grid -- which the block's warps march in one go (two, when
-// the range crosses into the next block column), each warp on its own: the row records arrive with the
-// tiles (see march_step).  No launch per step, no wave tail, no march start-up per 64 rows.
-template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, bool BANDS = false, int W = kWarpsPerBlock,
-          bool STREAM = false>
+template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, bool BANDS = false, int W = kWarpsPerBlock>
 __global__ void __launch_bounds__(W * 32, MINB)
 resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
 {
@@ -168,9 +162,6 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
     __shared__ CflFilter s_filter;
     __shared__ unsigned long long s_max[2];
     const unsigned int nblocks = gridDim.x * gridDim.y;
-    // STREAM: this block's range of the linearised (block column, row) space
-    const long long lin0 = STREAM ? (long long)blockIdx.x * p.stream_unit : 0;
-    const long long lin1 = STREAM ? min(lin0 + p.stream_unit, p.stream_total) : 0;
     // latitude bands (world > 1): warp 0 of block (0,0) runs the exchange with the other GPUs; the
     // blocks are admitted to a step through `go` (done_ctr[1]) once the maxima of ALL bands are in
     constexpr bool bands = BANDS;  // (a template axis: the one-band kernels keep their register allocation)
@@ -202,35 +193,17 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
                 while ((int)(ld_acquire_gpu(go) - (unsigned int)(s + 1)) < 0) {
                     if (clock64() - t0 > 2 * p.spin_limit) {
                         atomicMin(p.err, -4);
+                        atomicExch(p.done_ctr + 2, 1u);
                         break;
                     }
                 }
             }
             __syncthreads();
         }
-        bool active = true;
-        if constexpr (STREAM) {
-            int par_in = par;  // buffer set holding the current state (-1: not known yet), the same for every piece of the step
-            bool head = true;
-            for (long long lin = lin0; lin < lin1;) {
-                const int col = (int)(lin / p.stream_rows), r0 = (int)(lin % p.stream_rows);
-                const int len = (int)min((long long)(p.stream_rows - r0), lin1 - lin);
-                const Tile tl{col * W, p.jl_first + r0, p.jl_first + r0 + len, blockIdx.x == 0, head};
-                int pio = par_in;
-                active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true, BANDS, true>(p, tm, p.launch + s, s == 0 && head, tbase, pio,
-                                                                                                                 smem_raw, s_dt, s_flags, s_filter, s_max, tl);
-                if (!active) break;
-                par = pio;          // the set holding the NEW state: the next step's current one
-                par_in = pio ^ 1;
-                head = false;
-                lin += len;
-            }
-        } else {
-            const int ja = p.jl_first + blockIdx.y * p.chunk;
-            const Tile tl{(int)blockIdx.x * W, ja, min(ja + p.chunk, p.jl_last + 1), blockIdx.x == 0 && blockIdx.y == 0, true};
-            active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true, BANDS>(p, tm, p.launch + s, s == 0, tbase, par, smem_raw,
-                                                                                                      s_dt, s_flags, s_filter, s_max, tl);
-        }
+        const int ja = p.jl_first + blockIdx.y * p.chunk;
+        const Tile tl{(int)blockIdx.x * W, ja, min(ja + p.chunk, p.jl_last + 1), blockIdx.x == 0 && blockIdx.y == 0, true};
+        const bool active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true, BANDS>(p, tm, p.launch + s, s == 0, tbase, par, smem_raw,
+                                                                                                            s_dt, s_flags, s_filter, s_max, tl);
         if (!active) break;
         // Grid barrier: all stores and atomics of step s happen before any load of step s+1.
         // (TMA: every thread first orders its generic-proxy stores before the async-proxy reads
@@ -250,6 +223,7 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
                 while ((int)(ld_acquire_gpu(p.done_ctr) - target) < 0) {
                     if (clock64() - t0 > p.spin_limit) {  // never in a healthy run: turn a lost block into an error, not a hang
                         atomicMin(p.err, -4);             // SWB_E_TIMEOUT
+                        atomicExch(p.done_ctr + 2, 1u);
                         s_flags = -1;
                         break;
                     }
@@ -273,6 +247,283 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
     }
     // Bands: a launch that ended early (time >= final_time at step s) still owes the other bands the
     // stamps of its remaining steps -- they are no-ops everywhere, with the maxima carried forward
+    if (xwarp && s < p.nsteps && s_flags != -1) {
+        for (int k = s; k < p.nsteps; ++k) {
+            const Ctrl *carry = p.ctrl + ((p.launch + k + 1) % 3);
+            unsigned long long ex = 0ULL, ey = 0ULL;
+            if (lane == 0) {
+                ex = ld1<LD_CG>(&carry->ex_bits);
+                ey = ld1<LD_CG>(&carry->ey_bits);
+            }
+            ex = __shfl_sync(0xffffffffu, ex, 0);
+            ey = __shfl_sync(0xffffffffu, ey, 0);
+            band_publish(p, p.launch + k, p.stamp + (unsigned long long)k, ex, ey, lane);
+            if (k + 1 < p.nsteps && !band_gather(p, p.launch + k + 1, p.stamp + (unsigned long long)(k + 1), lane)) break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// stream_kernel: the resident loop for grids BEYOND one wave of blocks (7200 x 3600, 16384 x 8192,
+// latitude bands of any height).  One cooperative launch runs a whole batch of time steps; per step
+// every block marches several tiles -- map 1: tiles of `stream_unit` rows dealt round-robin in the
+// row-major (tile row, block column) order, so that the blocks sweep the grid together like the
+// blocks of a launch per step (DRAM-page / TLB locality); map 0: one contiguous range of the
+// column-major space per block (equal work whatever the grid, but 296 scattered streams) -- with its
+// row records arriving through the TMA ring next to the tiles (march_step<..., STREAM>): no launch per
+// step, no block-shared records, no __syncthreads inside a step but the one behind the prologue.
+// CFLF: the CFL filter of march_kernel (estimate per cell, exact evaluation near the previous
+// maximum) with its fix-up INSIDE the launch: behind the grid barrier every block reads the
+// found-mask; in the rare step in which a maximum fell by more than 2^-10 all blocks re-evaluate
+// their tiles exactly (one more barrier).  BANDS: the exchange with the other GPUs as in
+// resident_kernel, by warp 0 of block 0; admission tokens on `go`: 2s+2 = step s of this launch may
+// start, 2s+1 = first recompute the maxima of the state step s reads (fix-up round).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool stream_next_piece(const Params &p, long long &it, const long long it_end, const long long lin1, int &col, int &r0,
+                                                  int &len)
+{
+    if (it >= it_end) return false;
+    if (p.stream_map != 0) {  // tile `it` of the row-major (tile row, block column) order
+        col = (int)(it % p.stream_gx);
+        r0 = (int)(it / p.stream_gx) * p.stream_unit;
+        len = min(p.stream_unit, p.stream_rows - r0);
+        it += gridDim.x;
+    } else {                  // the part of this block's range that lies in block column `col`
+        col = (int)(it / p.stream_rows);
+        r0 = (int)(it % p.stream_rows);
+        len = (int)min((long long)(p.stream_rows - r0), lin1 - it);
+        it += len;
+    }
+    return true;
+}
+
+template <bool DIFF, int S, bool GUARD, bool BANDS, bool CFLF>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 2)
+stream_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
+{
+    constexpr int W = kWarpsPerBlock, R = 4;
+    static_assert(!CFLF || !DIFF, "the CFL filter serves the kernels without diffusion");
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ double s_dt;
+    __shared__ int s_flags;
+    __shared__ CflFilter s_filter;
+    __shared__ unsigned long long s_max[3];  // block maxima (x, y) and, CFLF, which of them the filter validated
+    __shared__ int s_fix;
+    const unsigned int nblocks = gridDim.x;
+    const bool lead = blockIdx.x == 0;
+    const bool xwarp = BANDS && lead && threadIdx.x < 32;
+    unsigned int *const go = p.done_ctr + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long it0 = p.stream_map != 0 ? (long long)blockIdx.x : (long long)blockIdx.x * p.stream_unit;
+    const long long lin1 = min((long long)(blockIdx.x + 1) * p.stream_unit, p.stream_total);
+    const long long it_end = p.stream_map != 0 ? p.stream_total : lin1;
+    unsigned int epoch = 0;  // arrival rounds of this launch so far (the same in every block)
+    int tbase = 0, par = -1;
+
+    auto arrive = [&]() {  // thread 0
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.done_ctr) : "memory");
+    };
+    auto wait_all = [&]() {  // thread 0: every block has arrived `epoch` times
+        const unsigned int target = epoch * nblocks;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_gpu(p.done_ctr) - target) < 0) {
+            if (clock64() - t0 > p.spin_limit) {  // never in a healthy run: turn a lost block into an error, not a hang
+                atomicMin(p.err, -4);             // SWB_E_TIMEOUT
+                atomicExch(p.done_ctr + 2, 1u);   // ... and into the end of the loop (step_prologue)
+                s_flags = -1;
+                break;
+            }
+        }
+    };
+    // thread 0: the block's maxima (CFLF: only what the filter let through, and its found-mask) -> the slot the next step reads
+    auto flush = [&](Ctrl *slot, bool with_mask) {
+        if (!CFLF || s_max[0] != 0ULL) atomicMax(&slot->ex_bits, s_max[0]);
+        if (!CFLF || s_max[1] != 0ULL) atomicMax(&slot->ey_bits, s_max[1]);
+        if (CFLF && with_mask && s_max[2] != 0ULL) atomicOr(&slot->reserved, (int)s_max[2]);
+    };
+    // CFLF fix-up round: the exact CFL keys of every cell this block updated, from the new state (set `cur`)
+    auto fixup = [&](int cur) {
+        if (threadIdx.x == 0) s_max[0] = s_max[1] = 0ULL;
+        __syncthreads();
+        const double *__restrict__ Hq = (const double *)p.buf[cur][0], *__restrict__ Uq = (const double *)p.buf[cur][1],
+                     *__restrict__ Vq = (const double *)p.buf[cur][2];
+        unsigned long long mx = 0ULL, my = 0ULL;
+        long long it = it0;
+        int col, r0, len;
+        while (stream_next_piece(p, it, it_end, lin1, col, r0, len)) {
+            const int strip = col * W + warp;
+            if (strip >= p.nstrips) continue;
+            const int c0 = kStripValid * strip, colA = c0 + 2 * lane;
+            const bool vA = (lane >= 1) && (colA <= c0 + kStripValid) && (colA <= p.M + 1);
+            const bool vB = (colA + 1 <= c0 + kStripValid) && (colA + 1 <= p.M + 1);
+            if (!vA && !vB) continue;
+            for (int jl = p.jl_first + r0; jl < p.jl_first + r0 + len; ++jl) {
+                const size_t k = (size_t)jl * p.pitch + colA;
+                const double2 hh = __ldcg(reinterpret_cast<const double2 *>(Hq + k)), uu = __ldcg(reinterpret_cast<const double2 *>(Uq + k)),
+                              vv = __ldcg(reinterpret_cast<const double2 *>(Vq + k));
+                unsigned long long kxA, kyA, kxB, kyB;
+                cfl_keys_fast(hh.x, uu.x, vv.x, p.g, kxA, kyA);
+                cfl_keys_fast(hh.y, uu.y, vv.y, p.g, kxB, kyB);
+                if (vA) { mx = umax64(mx, kxA); my = umax64(my, kyA); }
+                if (vB) { mx = umax64(mx, kxB); my = umax64(my, kyB); }
+            }
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) {
+            mx = umax64(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
+            my = umax64(my, __shfl_xor_sync(0xffffffffu, my, sft));
+        }
+        if (lane == 0) {
+            atomicMax(&s_max[0], mx);
+            atomicMax(&s_max[1], my);
+        }
+        __syncthreads();
+    };
+    // BANDS, blocks other than block 0: wait for the token that admits them to step k of this launch (2k+2);
+    // CFLF: a fix-up round (token 2k+1) for the state that step reads may come first
+    auto wait_go = [&](int k, Ctrl *slot) {
+        bool fixed = false;
+        for (;;) {
+            if (threadIdx.x == 0) {
+                const unsigned int need = (CFLF && !fixed) ? (unsigned int)(2 * k + 1) : (unsigned int)(2 * k + 2);
+                unsigned int v = 0;
+                const long long t0 = clock64();
+                while ((int)((v = ld_acquire_gpu(go)) - need) < 0) {
+                    if (clock64() - t0 > 2 * p.spin_limit) {
+                        atomicMin(p.err, -4);
+                        atomicExch(p.done_ctr + 2, 1u);
+                        v = 0x7fffffffu;
+                        break;
+                    }
+                }
+                s_fix = (CFLF && v == (unsigned int)(2 * k + 1)) ? 1 : 0;
+            }
+            __syncthreads();
+            if (!CFLF || !s_fix) break;
+            fixup(par);
+            if (threadIdx.x == 0) {
+                flush(slot, false);
+                arrive();
+            }
+            ++epoch;
+            fixed = true;
+            __syncthreads();
+        }
+    };
+
+    int s = 0;
+    for (; s < p.nsteps; ++s) {
+        Ctrl *const cur_slot = p.ctrl + ((p.launch + s) % 3);
+        if (BANDS) {
+            if (xwarp) {
+                const bool ok = band_gather(p, p.launch + s, p.stamp + (unsigned long long)s, lane);
+                if (lane == 0) {
+                    __threadfence();
+                    st_release_gpu(go, ok ? (unsigned int)(2 * s + 2) : 0x7fffffffu);  // (after a time-out: nobody waits any more)
+                }
+            }
+            if (lead) __syncthreads();
+            else wait_go(s, cur_slot);
+        }
+        // ---- the step: this block's tiles ----
+        bool active = true;
+        {
+            int par_in = par;  // buffer set holding the current state (-1: not known yet), the same for every piece of the step
+            bool head = true;
+            long long it = it0;
+            int col, r0, len;
+            while (stream_next_piece(p, it, it_end, lin1, col, r0, len)) {
+                const Tile tl{col * W, p.jl_first + r0, p.jl_first + r0 + len, lead, head};
+                int pio = par_in;
+                active = march_step<double, false, DIFF, false, false, true, R, S, GUARD, W, CFLF, true, BANDS, true>(p, tm, p.launch + s, s == 0 && head, tbase, pio,
+                                                                                                                    smem_raw, s_dt, s_flags, s_filter, s_max, tl);
+                if (!active) break;
+                par = pio;  // the set holding the NEW state: the next step's current one
+                par_in = pio ^ 1;
+                head = false;
+            }
+        }
+        if (!active) break;
+        // ---- grid barrier: all stores and atomics of step s happen before any load of step s+1.  (Every thread
+        // first orders its generic-proxy stores before the async-proxy reads the next step's tensor loads are.)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __syncthreads();
+        Ctrl *const new_slot = p.ctrl + ((p.launch + s + 1) % 3);
+        const bool last = s + 1 == p.nsteps;
+        if (!BANDS) {
+            if (CFLF || !last) {
+                if (threadIdx.x == 0) {
+                    flush(new_slot, true);
+                    arrive();
+                }
+                ++epoch;
+                if (threadIdx.x == 0) {
+                    wait_all();
+                    if (CFLF) s_fix = ((ld1<LD_CG>(&new_slot->reserved) & 3) != 3) ? 1 : 0;
+                }
+                if (CFLF) {
+                    __syncthreads();
+                    if (s_fix) {  // uniform over the grid: every block reads the same word behind the barrier
+                        fixup(par);
+                        if (threadIdx.x == 0) {
+                            flush(new_slot, false);
+                            arrive();
+                        }
+                        ++epoch;
+                        if (threadIdx.x == 0) wait_all();
+                    }
+                }
+            } else if (threadIdx.x == 0) {
+                flush(new_slot, true);
+            }
+            __syncthreads();
+        } else {
+            if (threadIdx.x == 0) {
+                flush(new_slot, true);
+                arrive();
+            }
+            ++epoch;
+            if (lead) {
+                if (threadIdx.x == 0) {
+                    wait_all();  // every block of this band is done with step s
+                    if (CFLF) {
+                        s_fix = ((ld1<LD_CG>(&new_slot->reserved) & 3) != 3) ? 1 : 0;
+                        if (s_fix) st_release_gpu(go, (unsigned int)(2 * (s + 1) + 1));  // the other blocks: fix-up round
+                    }
+                }
+                if (CFLF) {
+                    __syncthreads();
+                    if (s_fix) {
+                        fixup(par);
+                        if (threadIdx.x == 0) {
+                            flush(new_slot, false);
+                            arrive();
+                        }
+                        ++epoch;
+                        if (threadIdx.x == 0) wait_all();
+                        __syncthreads();
+                    }
+                }
+                if (xwarp) {  // tell the other bands
+                    unsigned long long ex = 0ULL, ey = 0ULL;
+                    if (lane == 0) {
+                        ex = ld1<LD_CG>(&new_slot->ex_bits);
+                        ey = ld1<LD_CG>(&new_slot->ey_bits);
+                    }
+                    ex = __shfl_sync(0xffffffffu, ex, 0);
+                    ey = __shfl_sync(0xffffffffu, ey, 0);
+                    band_publish(p, p.launch + s, p.stamp + (unsigned long long)s, ex, ey, lane);
+                    if (CFLF && last && lane == 0) st_release_gpu(go, (unsigned int)(2 * (s + 1) + 2));  // the launch's final token
+                }
+                __syncthreads();
+            } else if (CFLF && last) {
+                wait_go(s + 1, new_slot);  // the state of the last step may still need its fix-up round
+            }
+        }
+        if (s_flags == -1) break;
+    }
+    // Bands: a launch that ended early (time >= final_time at step s) still owes the other bands the stamps of its
+    // remaining steps -- they are no-ops everywhere, with the maxima carried forward
     if (xwarp && s < p.nsteps && s_flags != -1) {
         for (int k = s; k < p.nsteps; ++k) {
             const Ctrl *carry = p.ctrl + ((p.launch + k + 1) % 3);
@@ -320,7 +571,8 @@ __global__ void gather_kernel(const __grid_constant__ Params p)
         const long long t0 = clock64();
         while (ld_acquire_sys(&xs->stamp) != p.stamp) {
             if (clock64() - t0 > p.spin_limit) {
-                atomicMin(p.err, -4);  // SWB_E_TIMEOUT
+                atomicMin(p.err, -4);            // SWB_E_TIMEOUT
+                atomicExch(p.done_ctr + 2, 1u);  // ... and the loop ends here (step_prologue)
                 break;
             }
             __nanosleep(100);
@@ -462,18 +714,41 @@ __global__ void __launch_bounds__(256) max_speed_kernel(const T *__restrict__ U,
     if ((threadIdx.x & 31) == 0) atomicMax(out, m);
 }
 
-// Operator-level Laplacian (numpy.py:359-382 `compute_diffusion`), strict arithmetic.
+// Operator-level Laplacian (numpy.py:359-382 `compute_diffusion`), strict arithmetic.  Rows are
+// folded over blockIdx.y (any number of latitudes).
 __global__ void __launch_bounds__(128) laplacian_kernel(const double *__restrict__ q, double *__restrict__ out, Params p)
 {
     const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int jl = p.jl_first + blockIdx.y;
-    if (jl > p.jl_last || i > p.M + 1) return;
+    if (i > p.M + 1) return;
     using O = Op<true>;
-    const Star<double> s = load_star(q, p.pitch, p.nrows, p.M, jl, i);
-    const W3 wy = y_weights(p.tab, p.nrows, jl);
-    const W3 wx = x_weights_strict(p.phi, p.tab[(size_t)T_AC * p.nrows + jl], i, p.M);
-    out[(size_t)jl * p.pitch + i] = O::add(second_diff_strict(wx, s.xmm, s.xm, s.q0, s.xp, s.xpp),
-                                           second_diff_strict(wy, s.ymm, s.ym, s.q0, s.yp, s.ypp));
+    for (int jl = p.jl_first + blockIdx.y; jl <= p.jl_last; jl += gridDim.y) {
+        const Star<double> s = load_star(q, p.pitch, p.nrows, p.M, jl, i);
+        const W3 wy = y_weights(p.tab, p.nrows, jl);
+        const W3 wx = x_weights_strict(p.phi, p.tab[(size_t)T_AC * p.nrows + jl], i, p.M);
+        out[(size_t)jl * p.pitch + i] = O::add(second_diff_strict(wx, s.xmm, s.xm, s.q0, s.xp, s.xpp),
+                                               second_diff_strict(wy, s.ymm, s.ym, s.q0, s.yp, s.ypp));
+    }
+}
+
+// The reference's `compute_laplacian` itself (numpy.py:66-133): the same weights applied to a field the
+// CALLER has extended -- (N+2, pitch_ext) latitude-major, element (j+1, i+2) = q[i, j] -- with no wrap
+// or clamp logic: q[2:-2, 2:-2] is the centre, q[1:-3], q[3:-1], q[:-4], q[4:] its neighbours.
+__global__ void __launch_bounds__(128) laplacian_ext_kernel(const double *__restrict__ qe, int pe, double *__restrict__ out, Params p)
+{
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > p.M + 1) return;
+    using O = Op<true>;
+    for (int jl = p.jl_first + blockIdx.y; jl <= p.jl_last; jl += gridDim.y) {
+        const double *c = qe + (size_t)(jl + 1) * pe + (i + 2);
+        Star<double> s;
+        s.q0 = c[0];
+        s.xm = c[-1]; s.xp = c[1]; s.xmm = c[-2]; s.xpp = c[2];
+        s.ym = c[-(ptrdiff_t)pe]; s.yp = c[pe]; s.ymm = c[-2 * (ptrdiff_t)pe]; s.ypp = c[2 * (ptrdiff_t)pe];
+        const W3 wy = y_weights(p.tab, p.nrows, jl);
+        const W3 wx = x_weights_strict(p.phi, p.tab[(size_t)T_AC * p.nrows + jl], i, p.M);
+        out[(size_t)jl * p.pitch + i] = O::add(second_diff_strict(wx, s.xmm, s.xm, s.q0, s.xp, s.xpp),
+                                               second_diff_strict(wy, s.ymm, s.ym, s.q0, s.yp, s.ypp));
+    }
 }
 
 // K4: layout conversion between the reference's (M+3, n) array (latitude contiguous) and

@@ -33,7 +33,10 @@ __device__ __forceinline__ void step_prologue(const Params &p, int launch, bool 
     const double ty = __ddiv_rn(p.dymin, __longlong_as_double((long long)eyb));
     const double dtmax = (tx != tx) ? tx : ((ty != ty) ? ty : (tx < ty ? tx : ty));  // np.minimum propagates NaN
     double dt = __dmul_rn(p.courant, dtmax);
-    const bool active = time < p.final_time;  // numpy.py:496 (false for NaN)
+    // (a kernel that timed out waiting for a peer band or for the grid barrier raises done_ctr[2]: the loop ends there
+    // instead of running on with unsynchronised halo rows and CFL maxima)
+    const bool halted = ld1<(RES ? LD_CG : LD_PLAIN)>(p.done_ctr + 2) != 0u;
+    const bool active = time < p.final_time && !halted;  // numpy.py:496 (false for NaN)
     double tnew = time;
     if (active) {
         if (__dadd_rn(time, dt) > p.final_time) {
@@ -364,7 +367,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     static_assert(!STREAM || (RES && TMA && !STRICT && sizeof(T) == 8), "the streaming kernel: resident, TMA ring, FAST fp64");
     static_assert(!STRICT || sizeof(T) == 8, "STRICT reproduces numpy's float64 arithmetic");
     static_assert(!CFLF || (!STRICT && TMA && sizeof(T) == 8), "the CFL filter serves the fp64 FAST TMA kernel");
-    static_assert(!RES || (sizeof(T) == 8 && !F2D && !HS && !CFLF), "resident_kernel: fp64, latitude-only Coriolis, flat topography");
+    static_assert(!RES || (sizeof(T) == 8 && !F2D && !HS && (!CFLF || STREAM)), "resident kernels: fp64, latitude-only Coriolis, flat topography");
     using O = Op<STRICT, T>;
     // SSTAR: the diffusion star comes out of the ring too -- boxes two columns wider on either
     // side, one tile more at either end of the march, tiles t-1, t, t+1 resident while tile t
@@ -483,14 +486,17 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     if (threadIdx.x == 0 && (!STREAM || tl.prologue)) {
         step_prologue<RES>(p, launch, tl.lead, &s_dt, &s_flags);
         if (RES) s_max[0] = s_max[1] = 0ULL;
+        if (RES && CFLF) s_max[2] = 0ULL;
         if (CFLF) {
             // thresholds from THIS band's maxima of the current state (with several bands the
             // slot holds the global maxima; the band's own live in its exchange block)
+            // (RES: written by other SMs earlier in this launch -- read at the L2)
+            constexpr int kLd = RES ? LD_CG : LD_PLAIN;
             const Ctrl *cur_slot = p.ctrl + (launch % 3);
-            unsigned long long exb = cur_slot->ex_bits, eyb = cur_slot->ey_bits;
+            unsigned long long exb = ld1<kLd>(&cur_slot->ex_bits), eyb = ld1<kLd>(&cur_slot->ey_bits);
             if (p.world > 1) {
-                exb = p.xlocal->slot[launch % 3][p.rank].ex_bits;
-                eyb = p.xlocal->slot[launch % 3][p.rank].ey_bits;
+                exb = ld1<kLd>(&p.xlocal->slot[launch % 3][p.rank].ex_bits);
+                eyb = ld1<kLd>(&p.xlocal->slot[launch % 3][p.rank].ey_bits);
             }
             s_filter = p.fixed ? make_cfl_filter(0ULL, 0ULL) : make_cfl_filter(exb, eyb);
         }
@@ -696,7 +702,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     // reads it (its pair to the left / right), hence no synchronisation.
     const bool seam_b1 = vB && (colA + 1 == 1), seam_ae = vA && (colA == p.M + 1), seam_be = vB && (colA + 1 == p.M + 1);
     auto patch_tile = [&](int u) {
-        if (!(RES && SSTAR) || !warp_wraps || !res_wrap) return;
+        if (STREAM || !(RES && SSTAR) || !warp_wraps || !res_wrap) return;
         if (seam_b1 || seam_ae || seam_be) {
             T *base = reinterpret_cast<T *>(wbase + (size_t)stage_of(u) * LY::kStage) + (2 * lane + 2);  // box element of (row 0, colA)
             const int src_col = seam_b1 ? p.M - 1 : 3;
@@ -724,7 +730,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     auto do_row = [&](auto hot_tag, int jl, V2 h2, V2 u2, V2 v2, bool live, const StarRows<V2> &sr) {
         constexpr bool HOT = decltype(hot_tag)::value;
         // resident kernel: ghost columns and pole rows are served inside the fast (unrolled) body
-        constexpr bool EXTRA = RES && HOT;
+        constexpr bool EXTRA = RES && HOT && !STREAM;  // (the streaming kernel deals many tiles per block: its few seam strips take the boundary body)
         const V2 *rc2 = reinterpret_cast<const V2 *>(rec_of(jl));
         // the row record, read as 16-byte pairs (broadcast LDS.128)
         const V2 r_c_ac = rc2[RC_C / 2], r_kx_fkx = rc2[RC_KX / 2], r_cdx_cxu = rc2[RC_CDX / 2], r_ky_fky = rc2[RC_KY / 2];
@@ -970,7 +976,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             };
             const int j0 = ja + t * R;
             // warp-uniform; the resident kernel's fast body serves every complete tile
-            const bool hot_tile = RES ? (j0 + R <= jb && j0 >= res_lo && j0 + R - 1 <= res_hi) : (j0 >= plain_lo && j0 + R - 1 <= plain_hi);
+            const bool hot_tile = (RES && !STREAM) ? (j0 + R <= jb && j0 >= res_lo && j0 + R - 1 <= res_hi) : (j0 >= plain_lo && j0 + R - 1 <= plain_hi);
             if (hot_tile) {
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) {
@@ -1028,7 +1034,13 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         }
         if (lane == 0) {
             Ctrl *const new_slot = p.ctrl + ((launch + 1) % 3);
-            if (RES) {  // per block first; resident_kernel forwards the block's maxima behind its barrier's __syncthreads
+            if (RES && CFLF) {  // stream_kernel: per block first, with the found-mask of the filter
+                const unsigned long long wx = widen_bits(mx), wy = widen_bits(my);
+                if (wx != 0ULL) atomicMax(&s_max[0], wx);
+                if (wy != 0ULL) atomicMax(&s_max[1], wy);
+                const unsigned long long found = (wx >= s_filter.valid_x && wx != 0ULL ? 1ULL : 0ULL) | (wy >= s_filter.valid_y && wy != 0ULL ? 2ULL : 0ULL);
+                if (found) atomicOr(&s_max[2], found);
+            } else if (RES) {  // per block first; the resident kernels forward the block's maxima behind their barrier's __syncthreads
                 atomicMax(&s_max[0], widen_bits(mx));
                 atomicMax(&s_max[1], widen_bits(my));
             } else if (CFLF) {

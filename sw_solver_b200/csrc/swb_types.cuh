@@ -115,9 +115,13 @@ struct Params {
     // streaming resident kernel (resident_kernel<..., STREAM>): every block marches a contiguous range of
     // `stream_unit` rows of the (block column, latitude) space, its row records arriving with the tiles
     const double *prec;             // (nrows + 2 kRecPad) x (kRowRec [+ kRowDiff]) dt-independent records; points at local row 0
-    long long stream_total;         // block columns x updated rows
-    int stream_unit;                // rows per block (a multiple of 4)
+    long long stream_total;         // map 0: block columns x updated rows; map 1: number of tiles
+    int stream_unit;                // rows per block range (map 0) / per tile (map 1), a multiple of 4
     int stream_rows;                // updated rows of this context (jl_last - jl_first + 1)
+    int stream_gx;                  // block columns
+    int stream_map;                 // 0: one contiguous range of the column-major (column, row) space per block
+                                    // 1: tiles of stream_unit rows dealt round-robin, row-major over the columns (the
+                                    //    blocks sweep the grid together: DRAM-page / TLB locality of a launch per step)
     unsigned long long *tlog;       // SWB_BAND_TIMING builds: kTlogCap x kTlogRow globaltimer stamps, indexed by stamp % kTlogCap
 };
 

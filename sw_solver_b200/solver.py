@@ -231,6 +231,7 @@ class Stepper:
 
         # set 0 receives the initial state (H2D copies and K4 transposes pipelined over two streams)
         self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._stage_pair: List[Optional[torch.Tensor]] = [None, None]
         self._upload((h, u, v), [self._raw[0, k] for k in range(3)])
         self._f2d = self._upload((f,), [None])[0] if f_lat is None else None
         self._hs = None if hs_flat else self._upload((hs,), [None])[0]
@@ -257,7 +258,7 @@ class Stepper:
         M, nl = self.M, self.n_local
         out: List[torch.Tensor] = []
         main = torch.cuda.current_stream(self.device)
-        staging: List[Optional[torch.Tensor]] = [None, None]
+        staging = self._stage_pair  # two (M+3, n_local) device buffers, kept for the download of the result
         freed: List[Optional[torch.cuda.Event]] = [None, None]  # staging buffer k is free again (its transpose ran)
         nhost = 0
         for q, dst in zip(fields, dsts):
@@ -298,29 +299,40 @@ class Stepper:
             freed[k] = torch.cuda.Event()
             freed[k].record(main)
         if nhost:
-            main.synchronize()  # the sources may be temporaries; the staging buffers go back to the allocator
+            main.synchronize()  # the sources may be temporaries
         return out
+
+    def release_staging(self):
+        """Give the two (M+3, n_local) staging buffers of ``_upload`` / ``download`` back to the allocator."""
+        torch.cuda.current_stream(self.device).synchronize()
+        self._stage_pair = [None, None]
 
     def _load(self, q, dst: Optional[torch.Tensor]) -> torch.Tensor:
         return self._upload((q,), [dst])[0]
 
     def download(self, current: int, out) -> None:
         """K4 + D2H of the buffer set ``current`` into three host tensors of shape (M+3, n_local)
-        (pinned ones are filled asynchronously): the transpose of field k+1 overlaps the copy of
-        field k.  Returns when all three have landed."""
+        (pinned ones are filled asynchronously): the transpose of field k+1 (current stream) overlaps
+        the copy of field k (copy stream), through the same two staging buffers the upload used.
+        Returns when all three have landed."""
         M, nl = self.M, self.n_local
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
-        stage = torch.empty((3, M + 3, nl), dtype=torch.float64, device=self.device)
-        side.wait_stream(main)
+        copied: List[Optional[torch.cuda.Event]] = [None, None]
         for k in range(3):
-            self.export(self._raw[current, k], stage[k])
+            b = k & 1
+            if self._stage_pair[b] is None:
+                self._stage_pair[b] = torch.empty((M + 3, nl), dtype=torch.float64, device=self.device)
+            if copied[b] is not None:
+                main.wait_event(copied[b])  # the copy out of this buffer has finished
+            self.export(self._raw[current, k], self._stage_pair[b])
             ready = torch.cuda.Event()
             ready.record(main)
             side.wait_event(ready)
             with torch.cuda.stream(side):
-                out[k].copy_(stage[k], non_blocking=True)
+                out[k].copy_(self._stage_pair[b], non_blocking=True)
+                copied[b] = torch.cuda.Event()
+                copied[b].record(side)
         side.synchronize()
-        stage.record_stream(side)
 
     def export(self, src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Device-layout (n_local, pitch) array -> (M+3, n_local) CUDA tensor in the reference layout."""
@@ -395,6 +407,11 @@ class Stepper:
         check(self.lib.swb_max_speed(self._ctx, ctypes.byref(out), _stream(self.device)))
         return out.value
 
+    def max_speed_async(self, current: int, out: torch.Tensor):
+        """Enqueue K5 on buffer set ``current``; the result (a float64) lands in ``out`` -- 8 bytes of
+        pinned host or device memory -- in stream order.  No synchronisation."""
+        check(self.lib.swb_max_speed_async(self._ctx, int(current), ctypes.c_void_p(out.data_ptr()), _stream(self.device)))
+
     def read_log(self, count: int) -> Tuple[np.ndarray, np.ndarray]:
         dts, ts = np.empty(count), np.empty(count)
         check(self.lib.swb_read_log(self._ctx, dts.ctypes.data_as(_lib._dp), ts.ctypes.data_as(_lib._dp),
@@ -408,6 +425,28 @@ class Stepper:
         check(self.lib.swb_laplacian(self._ctx, ctypes.c_void_p(qd.data_ptr()), ctypes.c_void_p(out.data_ptr()),
                                      _stream(self.device)))
         return out[1:-1, 1:self.M + 2].transpose(0, 1)
+
+    def laplacian_ext(self, q_ext) -> torch.Tensor:
+        """The reference's ``compute_laplacian`` (numpy.py:66-133) on an ALREADY extended (M+5, N+2)
+        array -- whatever extension the caller built is used as it is -- as (M+1, N-2)."""
+        M, N = self.M, self.N
+        t = q_ext if isinstance(q_ext, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q_ext, dtype=np.float64))
+        if t.dtype != torch.float64 or tuple(t.shape) != (M + 5, N + 2):
+            raise ValueError(f"expected a float64 array of shape {(M + 5, N + 2)}, got {tuple(t.shape)} {t.dtype}")
+        qe = t.to(self.device).t().contiguous()  # (N+2, M+5): latitude-major like the state (plumbing)
+        out = torch.zeros((self.n_local, self.pitch), dtype=torch.float64, device=self.device)
+        check(self.lib.swb_laplacian_ext(self._ctx, ctypes.c_void_p(qe.data_ptr()), int(qe.stride(0)), ctypes.c_void_p(out.data_ptr()),
+                                         _stream(self.device)))
+        return out[1:-1, 1:M + 2].transpose(0, 1)
+
+    def reload(self, h, u, v, f=None, hs=None):
+        """Replace the state of buffer set 0 (and a 2-D ``f`` / ``hs`` of a context created with them) by
+        new arrays of the same kind -- the operator-level entry points reuse one context per grid."""
+        self._upload((h, u, v), [self._raw[0, k] for k in range(3)])
+        if self._f2d is not None and f is not None:
+            self._upload((f,), [self._f2d])
+        if self._hs is not None and hs is not None:
+            self._upload((hs,), [self._hs])
 
     @property
     def launch_count(self) -> int:
@@ -512,6 +551,39 @@ def _match(result: torch.Tensor, like):
     return result.cpu().numpy()
 
 
+# One context per (grid, arithmetic mode, device, kind of Coriolis / topography input) is kept alive for
+# the operator-level entry points: a caller that drives its own loop -- the reason these exist -- pays
+# the context set-up (a dozen allocations, table upload, tensor maps) once, not per call.
+_OPERATOR_CONTEXTS: "Dict[tuple, Stepper]" = {}
+_OPERATOR_CONTEXT_LIMIT = 6
+_OPERATOR_CONTEXT_CELLS = 1 << 24  # larger grids (> 0.8 GB of state per context) are not kept
+
+
+def _release_operator_contexts():
+    while _OPERATOR_CONTEXTS:
+        try:
+            _OPERATOR_CONTEXTS.popitem()[1].close()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+
+import atexit  # noqa: E402
+
+atexit.register(_release_operator_contexts)
+
+
+def _operator_key(latlon_grid, f, hs, use_diffusion, mode, dev):
+    f_lat = None
+    if f is not None:
+        f_lat = np.ascontiguousarray(f, dtype=np.float64) if (isinstance(f, np.ndarray) and f.ndim == 1) else _latitude_only(f)
+    if isinstance(hs, torch.Tensor):
+        hs_flat = not bool((hs != 0).any())
+    else:
+        hs_flat = hs is None or not np.any(np.asarray(hs))
+    return (latlon_grid.M, latlon_grid.N, mode, dev.index, bool(use_diffusion), f_lat is None and f is not None, not hs_flat,
+            None if f_lat is None else f_lat.tobytes())
+
+
 def lax_wendroff_update(latlon_grid: LatLonGrid, cart_grid: CartesianGrid, dt: FloatT, f: FloatArray2D,
                         hs: FloatArray2D, h: FloatArray2D, u: FloatArray2D, v: FloatArray2D, *,
                         mode: Optional[str] = "strict", device=None):
@@ -520,48 +592,66 @@ def lax_wendroff_update(latlon_grid: LatLonGrid, cart_grid: CartesianGrid, dt: F
     Takes (M+3, N) arrays (numpy or torch), returns ``hnew, unew, vnew`` of shape
     (M+1, N-2) in the same kind of array; inputs are not modified
     (reference tests/numpy_test.py:33-80).  Defaults to the bit-exact arithmetic mode.
+    The context of the grid is kept for the next call (see ``_OPERATOR_CONTEXTS``).
     """
-    st = Stepper(latlon_grid, cart_grid, h, u, v, f, hs, courant=0.0, final_time=0.0, use_diffusion=False,
-                 mode=mode, device=device)
+    mode = DEFAULT_MODE if mode is None else mode
+    dev = _require_cuda(device)
+    key = _operator_key(latlon_grid, f, hs, False, mode, dev)
+    st = _OPERATOR_CONTEXTS.pop(key, None)
+    if st is None:
+        while len(_OPERATOR_CONTEXTS) >= _OPERATOR_CONTEXT_LIMIT:
+            _OPERATOR_CONTEXTS.pop(next(iter(_OPERATOR_CONTEXTS))).close()
+        st = Stepper(latlon_grid, cart_grid, h, u, v, f, hs, courant=0.0, final_time=0.0, use_diffusion=False,
+                     mode=mode, device=dev)
+    else:
+        st.reload(h, u, v, f, hs)
+    keep = (latlon_grid.M + 3) * latlon_grid.N <= _OPERATOR_CONTEXT_CELLS
+    if keep:
+        _OPERATOR_CONTEXTS[key] = st  # most recently used last
     try:
         st.step_fixed_dt(dt)
         out = tuple(_match(st.buf[1, k, 1:-1, 1:-1], h) for k in range(3))
-        torch.cuda.synchronize(st.device)
+        torch.cuda.current_stream(st.device).synchronize()
     finally:
-        st.close()
+        if not keep:
+            st.close()
     return out
+
+
+def _diffusion_context(diffusion: "DiffusionCoefficients", device) -> Stepper:
+    cart = diffusion.cart_grid
+    dev = _require_cuda(device)
+    key = (cart.M, cart.N, "laplacian", dev.index)
+    st = _OPERATOR_CONTEXTS.pop(key, None)
+    if st is None:
+        while len(_OPERATOR_CONTEXTS) >= _OPERATOR_CONTEXT_LIMIT:
+            _OPERATOR_CONTEXTS.pop(next(iter(_OPERATOR_CONTEXTS))).close()
+        zeros = torch.zeros((cart.M + 3, cart.N), dtype=torch.float64, device=dev)
+        st = Stepper(_grids_of(cart), cart, zeros, zeros, zeros, np.zeros(cart.N), None, courant=0.0, final_time=0.0,
+                     use_diffusion=True, mode="strict", device=dev)
+    _OPERATOR_CONTEXTS[key] = st
+    return st
 
 
 def compute_diffusion(quantity: FloatArray2D, diffusion: DiffusionCoefficients, *, device=None):
     """Laplacian of a (M+3, N) quantity at the interior cells, shape (M+1, N-2)
     (numpy.py:359-382: periodic extension in longitude, duplicated rows in latitude)."""
-    cart = diffusion.cart_grid
-    ll = _grids_of(cart)
-    zeros = np.zeros((cart.M + 3, cart.N))
-    st = Stepper(ll, cart, zeros, zeros, zeros, np.zeros(cart.N), None, courant=0.0, final_time=0.0,
-                 use_diffusion=True, mode="strict", device=device)
-    try:
-        out = _match(st.laplacian(quantity), quantity)
-        torch.cuda.synchronize(st.device)
-    finally:
-        st.close()
+    st = _diffusion_context(diffusion, device)
+    out = _match(st.laplacian(quantity), quantity)
+    torch.cuda.current_stream(st.device).synchronize()
     return out
 
 
 def compute_laplacian(coeff: DiffusionCoefficients, q: FloatArray2D, *, device=None):
-    """Laplacian of an already-extended (M+5, N+2) array (numpy.py:66-133).
+    """Laplacian of an already-extended (M+5, N+2) array (numpy.py:66-133), shape (M+1, N-2).
 
-    The kernel applies the reference's extension (numpy.py:376-381) itself, so the
-    argument must be such an extension; anything else is rejected rather than silently
-    computed differently.
-    """
-    qa = q.detach().cpu().numpy() if isinstance(q, torch.Tensor) else np.asarray(q)
-    core = qa[1:-1, 1:-1]
-    ext = np.concatenate((core[-4:-3, :], core, core[3:4, :]), axis=0)
-    ext = np.concatenate((ext[:, 0:1], ext, ext[:, -1:]), axis=1)
-    if ext.shape != qa.shape or not np.array_equal(ext, qa, equal_nan=True):
-        raise NotImplementedError("compute_laplacian expects the extension built by compute_diffusion")
-    return compute_diffusion(q[1:-1, 1:-1], coeff, device=device)
+    Like the reference it applies the difference weights to ``q`` as given -- ``q[2:-2, 2:-2]`` is the
+    centre, the outer two rows / columns are whatever the caller put there (``compute_diffusion``
+    builds the reference's own extension, numpy.py:376-381)."""
+    st = _diffusion_context(coeff, device)
+    out = _match(st.laplacian_ext(q), q)
+    torch.cuda.current_stream(st.device).synchronize()
+    return out
 
 
 def _apply_bcs(q, qnew):
@@ -580,10 +670,43 @@ def _apply_bcs(q, qnew):
 # the driver
 # --------------------------------------------------------------------------------------
 _STATUS_BYTES = ctypes.sizeof(SwbStatus)
+_STATUS_SLOT = 64  # bytes per status slot (a swb_status record and the K5 result behind it)
 
 
 def _read_status(pinned: torch.Tensor) -> SwbStatus:
     return SwbStatus.from_buffer_copy(pinned.numpy().tobytes()[:_STATUS_BYTES])
+
+
+class _PinnedArena:
+    """Page-locked host memory handed out in slices: ONE ``cudaHostAlloc`` per chunk instead of one per
+    snapshot / status record (numpy.py:488-492, 559-563 append to arrays; a pinned allocation per save
+    point would cost more than the step it saves).  Chunks grow geometrically, so a run with
+    ``save_data["interval"] = 1`` over thousands of steps makes a handful of allocations."""
+
+    def __init__(self, first_bytes: int, max_chunk_bytes: int = 1 << 30):
+        self._next = max(int(first_bytes), 1 << 16)
+        self._max = max(int(max_chunk_bytes), self._next)
+        self._chunk: Optional[torch.Tensor] = None
+        self._used = 0
+        self.allocations = 0
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        """A pinned uint8 tensor of ``nbytes`` bytes (64-byte aligned inside its chunk)."""
+        nbytes = int(nbytes)
+        need = (nbytes + 63) // 64 * 64
+        if self._chunk is None or self._used + need > self._chunk.numel():
+            size = max(self._next, need)
+            self._chunk = torch.empty(size, dtype=torch.uint8).pin_memory()
+            self._used = 0
+            self.allocations += 1
+            self._next = min(self._max, 2 * size)
+        out = self._chunk[self._used:self._used + nbytes]
+        self._used += need
+        return out
+
+    def take_f64(self, shape) -> torch.Tensor:
+        n = int(np.prod(shape))
+        return self.take(8 * n).view(torch.float64).view(*shape)
 
 
 def _dist_world(distributed: Optional[bool]):
@@ -663,6 +786,11 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
 
             link_distributed(st)
         st.cfl_init()
+        # Output pipeline: snapshots and status records land in slices of a few
+        # large pinned chunks; the loop below never allocates page-locked memory per step.
+        snap_bytes = 3 * (M + 1) * n_local * 8
+        arena = _PinnedArena(min(max(4 * snap_bytes, 1 << 20), 1 << 28)) if save_interval > 0 else None
+        status_pool = _PinnedArena(256 * _STATUS_SLOT, 1 << 20)
         snaps: List[torch.Tensor] = []   # pinned (3, M+1, n_local) host copies, one per save point
         snap_status: List[torch.Tensor] = []
         stage = None  # device staging of one snapshot in the reference layout (K4)
@@ -670,7 +798,7 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
         def take_snapshot(current: int) -> torch.Tensor:
             nonlocal stage
             stage = st.snapshot(current, stage)
-            pinned = torch.empty((3, M + 1, n_local), dtype=torch.float64).pin_memory()
+            pinned = arena.take_f64((3, M + 1, n_local))
             for k in range(3):
                 pinned[k].copy_(stage[k, 1:-1, :], non_blocking=True)  # numpy.py:488-492: h[1:-1, :]
             return pinned
@@ -689,25 +817,28 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
                 yield nxt
                 n = nxt
 
-        def max_speed() -> float:
-            m = st.max_speed()
-            if dist is not None:  # numpy's max propagates NaN: so does this one
-                t = torch.tensor([float("inf") if m != m else m], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                m = float("nan") if t.item() == float("inf") else t.item()
-            return m
-
         # Every rank sees the same time / step count / termination flag (identical dt on all
         # bands), so the control flow below is the same on every rank.
+        batch_slots = [status_pool.take(_STATUS_SLOT) for _ in range(4)]  # reused round-robin: at most two are in flight
         ring: List[Tuple[int, torch.Tensor, torch.cuda.Event]] = []
-        enq = 0
+        enq, nbatch = 0, 0
         for target in stops():
             st.enqueue(target - enq)
             enq = target
             if print_interval > 0 and enq % print_interval == 0:
-                s = st.status()
+                # status and K5 (max |velocity| of the buffer set that holds step `enq` if the loop
+                # is still running) are enqueued together: ONE synchronisation per print
+                slot = status_pool.take(_STATUS_SLOT)
+                st.status_async(slot)
+                st.max_speed_async(enq & 1, slot[_STATUS_BYTES:_STATUS_BYTES + 8])
+                torch.cuda.current_stream(dev).synchronize()
+                s = _read_status(slot)
                 if s.steps == enq:  # the loop was still running at this step
-                    speed = max_speed()
+                    speed = float(slot[_STATUS_BYTES:_STATUS_BYTES + 8].view(torch.float64)[0])
+                    if dist is not None:  # numpy's max propagates NaN: so does this one
+                        t = torch.tensor([float("inf") if speed != speed else speed], dtype=torch.float64, device=dev)
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                        speed = float("nan") if t.item() == float("inf") else t.item()
                     if rank == 0:
                         print(
                             f"Time = {s.time / 3600.0:6.2f} hours (max {int(final_time / 3600.0)}); "
@@ -716,10 +847,11 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
             if save_interval > 0 and enq % save_interval == 0:
                 # valid only if all `enq` steps ran, in which case the parity is known
                 snaps.append(take_snapshot(enq & 1))
-                pin = torch.zeros(_STATUS_BYTES, dtype=torch.uint8).pin_memory()
+                pin = status_pool.take(_STATUS_SLOT)
                 st.status_async(pin)
                 snap_status.append(pin)
-            pin = torch.zeros(_STATUS_BYTES, dtype=torch.uint8).pin_memory()
+            pin = batch_slots[nbatch % len(batch_slots)]
+            nbatch += 1
             st.status_async(pin)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(dev))
@@ -728,7 +860,8 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
             if len(ring) >= 2:
                 _, pin0, ev0 = ring.pop(0)
                 ev0.synchronize()
-                if _read_status(pin0).done:
+                s0 = _read_status(pin0)
+                if s0.done or s0.error:  # (a device-side error ends the loop on the device too)
                     break
         final = st.status()
         if final.error:

@@ -118,6 +118,73 @@ def test_operator_api_matches_reference_shapes_and_values(golden_single_step):
     assert all(isinstance(o, torch.Tensor) and o.is_cuda and o.shape == (M + 1, N - 2) for o in out)
 
 
+def test_compute_laplacian_takes_any_extension(golden_single_step):
+    """The reference's ``compute_laplacian(coeff, q)`` (numpy.py:66-133) applies its weights to ANY
+    (M+5, N+2) array.  Checked against the reference formula evaluated in numpy with the reference's
+    coefficient arrays (bit for bit): the extension ``compute_diffusion`` builds, and arbitrary ones."""
+    from sw_solver_b200.solver import compute_laplacian
+
+    rng = np.random.default_rng(3)
+    for M, N in ((5, 6), (37, 24), (130, 70)):
+        ll = LatLonGrid(M, N)
+        cg = CartesianGrid(ll)
+        dc = DiffusionCoefficients(cg)
+        c = dc
+
+        def ref(q):  # numpy.py:87-133, verbatim structure
+            qxx = (c.Ax[1:-1, :] * (c.Ax[1:-1, :] * q[2:-2, 2:-2] + c.Bx[1:-1, :] * q[3:-1, 2:-2] + c.Cx[1:-1, :] * q[1:-3, 2:-2])
+                   + c.Bx[1:-1, :] * (c.Ax[2:, :] * q[3:-1, 2:-2] + c.Bx[2:, :] * q[4:, 2:-2] + c.Cx[2:, :] * q[2:-2, 2:-2])
+                   + c.Cx[1:-1, :] * (c.Ax[:-2, :] * q[1:-3, 2:-2] + c.Bx[:-2, :] * q[2:-2, 2:-2] + c.Cx[:-2, :] * q[:-4, 2:-2]))
+            qyy = (c.Ay[:, 1:-1] * (c.Ay[:, 1:-1] * q[2:-2, 2:-2] + c.By[:, 1:-1] * q[2:-2, 3:-1] + c.Cy[:, 1:-1] * q[2:-2, 1:-3])
+                   + c.By[:, 1:-1] * (c.Ay[:, 2:] * q[2:-2, 3:-1] + c.By[:, 2:] * q[2:-2, 4:] + c.Cy[:, 2:] * q[2:-2, 2:-2])
+                   + c.Cy[:, 1:-1] * (c.Ay[:, :-2] * q[2:-2, 1:-3] + c.By[:, :-2] * q[2:-2, 2:-2] + c.Cy[:, :-2] * q[2:-2, :-4]))
+            return qxx + qyy
+
+        h = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)[0]
+        ext = np.concatenate((h[-4:-3, :], h, h[3:4, :]), axis=0)
+        ext = np.concatenate((ext[:, 0:1], ext, ext[:, -1:]), axis=1)
+        arbitrary = 8000.0 + 500.0 * rng.uniform(-1, 1, (M + 5, ll.N + 2))
+        for q in (ext, arbitrary):
+            before = q.copy()
+            got = compute_laplacian(dc, q)
+            assert got.shape == (M + 1, ll.N - 2) and _bits(got, ref(q)), (M, N, _worst(got, ref(q)))
+            assert _bits(q, before)
+        assert _bits(compute_laplacian(dc, ext), compute_diffusion(h, dc))
+
+
+def test_operator_calls_reuse_one_context():
+    """A caller driving its own loop through ``lax_wendroff_update`` / ``compute_diffusion`` pays the
+    context set-up once per grid: repeat calls reuse it (same bits, far less wall time)."""
+    import time
+
+    from sw_solver_b200 import solver as sv
+
+    ll = LatLonGrid(96, 64)
+    cg = CartesianGrid(ll)
+    h, u, v, f = get_initial_conditions(ICType.ZonalGeostrophicFlow, ll)  # 2-D Coriolis
+    hs = np.zeros(ll.shape)
+    sv._release_operator_contexts()
+    t0 = time.perf_counter()
+    first = lax_wendroff_update(ll, cg, 30.0, f, hs, h, u, v)
+    t1 = time.perf_counter()
+    n0 = len(sv._OPERATOR_CONTEXTS)
+    times = []
+    for k in range(5):
+        ta = time.perf_counter()
+        again = lax_wendroff_update(ll, cg, 30.0, f, hs, h, u, v)
+        times.append(time.perf_counter() - ta)
+    assert len(sv._OPERATOR_CONTEXTS) == n0 == 1
+    assert all(_bits(a, b) for a, b in zip(first, again))
+    # another state through the same context: equals a fresh context's result
+    h2 = h + 1.0
+    got = lax_wendroff_update(ll, cg, 30.0, f, hs, h2, u, v)
+    sv._release_operator_contexts()
+    fresh = lax_wendroff_update(ll, cg, 30.0, f, hs, h2, u, v)
+    assert all(_bits(a, b) for a, b in zip(got, fresh))
+    print(f"lax_wendroff_update 96x64: first call {1e3 * (t1 - t0):.2f} ms, repeat calls {1e6 * min(times):.0f} us")
+    assert min(times) < 0.5 * (t1 - t0) and min(times) < 5e-3
+
+
 def test_multi_step_driver_strict_is_bit_exact(golden_multi_step):
     """Full `solve` runs saved every step: t, phi, theta, h, u, v and the returned state."""
     g = golden_multi_step
@@ -513,6 +580,49 @@ def test_cfl_filter_is_exact(monkeypatch):
             assert np.ptp(log0[0]) > 1e-3 * log0[0].mean()  # dt really moved: the maxima were not static
 
 
+def test_cfl_filter_inside_the_streaming_kernel_is_exact(monkeypatch):
+    """The same filter inside stream_kernel, where the fix-up is a round INSIDE the launch (every block
+    reads the found-mask behind the grid barrier; when a maximum fell by more than 2^-10 all blocks
+    re-evaluate their tiles exactly, one more barrier): dt history, time and state equal the
+    launch-per-step run without the filter, bit for bit -- rough state (trigger, validity and fix-up
+    paths all run, several fix-up rounds per launch), smooth wave, both tile mappings, steps batched
+    unevenly so that fix-up rounds also fall on the last step of a launch."""
+    rng = np.random.default_rng(11)
+    for M, N, rough, batches in ((200, 96, True, [1, 9, 20]), (500, 260, False, [5, 35]), (333, 97, True, [7, 7, 7])):
+        ll = LatLonGrid(M, N)
+        cg = CartesianGrid(ll)
+        h, u, v, f = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+        if rough:
+            h = h + 300.0 * rng.uniform(-1, 1, h.shape)
+            u = u + 30.0 * rng.standard_normal(u.shape)
+            v = v + 30.0 * rng.standard_normal(v.shape)
+        nsteps = sum(batches)
+        runs = {}
+        for tag, env in (("march", {"SWB_RESIDENT": "0", "SWB_CFL_FILTER": "0"}),
+                         ("stream-tiles", {"SWB_RESIDENT": "1", "SWB_STREAM": "1", "SWB_STREAM_MAP": "1", "SWB_STREAM_UNIT": "8", "SWB_CFL_FILTER": "1"}),
+                         ("stream-ranges", {"SWB_RESIDENT": "1", "SWB_STREAM": "1", "SWB_STREAM_MAP": "0", "SWB_STREAM_UNIT": "20", "SWB_CFL_FILTER": "1"}),
+                         ("stream-nofilter", {"SWB_RESIDENT": "1", "SWB_STREAM": "1", "SWB_CFL_FILTER": "0"})):
+            for k, val in env.items():
+                monkeypatch.setenv(k, val)
+            st = Stepper(ll, cg, h, u, v, f, None, courant=0.4, final_time=1e9, use_diffusion=False, mode="fast", log_capacity=nsteps)
+            assert st.streaming == (tag != "march")
+            for n in batches:
+                st.enqueue(n)
+            s = st.status()
+            assert s.steps == nsteps and s.error == 0, (tag, s.steps, s.error)
+            runs[tag] = (st.to_numpy(), st.read_log(nsteps), s.time)
+            st.close()
+            for k in env:
+                monkeypatch.delenv(k)
+        q0, log0, t0 = runs["march"]
+        for tag in ("stream-tiles", "stream-ranges", "stream-nofilter"):
+            q1, log1, t1 = runs[tag]
+            assert _bits(log0[0], log1[0]) and _bits(log0[1], log1[1]) and t0 == t1, tag
+            assert all(_bits(a, b) for a, b in zip(q0, q1)), tag
+        if rough:
+            assert np.ptp(log0[0]) > 1e-3 * log0[0].mean()
+
+
 # ---- resident kernel (SURVEY 8f rank 4): one cooperative launch per batch of steps --------
 def _run_batches(M, N, ic, diff, mode, batches, final_time, resident, monkeypatch, extra_env=None, streaming=False):
     monkeypatch.setenv("SWB_RESIDENT", "1" if resident else "0")
@@ -614,22 +724,27 @@ def test_resident_kernel_stops_at_final_time(monkeypatch):
         assert _bits(a, b), name
 
 
-def test_large_grids_run_the_streaming_resident_kernel():
-    """Grids beyond one wave of blocks (BASELINE configs 3 and 4) run resident as well: the streaming
-    variant, one contiguous range of rows per block, one launch per batch of steps."""
+def test_large_grids_keep_the_launch_per_step_kernel_unless_streaming_is_asked_for(monkeypatch):
+    """Grids beyond one wave of blocks (BASELINE configs 3 and 4) run one launch per step by default;
+    SWB_STREAM=1 runs them resident through the streaming kernel (one launch per batch of steps)."""
     ll = LatLonGrid(7200, 3600)
     cg = CartesianGrid(ll)
     from sw_solver_b200 import bands
     from sw_solver_b200.ic import coriolis_latitude
 
-    hd, ud, vd, _ = bands.rossby_haurwitz_band(ll, 0, ll.N, torch.device("cuda", 0))
-    st = Stepper(ll, cg, hd, ud, vd, coriolis_latitude(ll), None, courant=0.5, final_time=1e12, use_diffusion=False,
-                 mode="fast", layout="device")
-    assert st.resident and st.streaming
-    n0 = st.launch_count
-    st.enqueue(7)
-    assert st.status().steps == 7 and st.launch_count == n0 + 1
-    st.close()
+    for env, streaming in ((None, False), ("1", True)):
+        if env is not None:
+            monkeypatch.setenv("SWB_STREAM", env)
+        hd, ud, vd, _ = bands.rossby_haurwitz_band(ll, 0, ll.N, torch.device("cuda", 0))
+        st = Stepper(ll, cg, hd, ud, vd, coriolis_latitude(ll), None, courant=0.5, final_time=1e12, use_diffusion=False,
+                     mode="fast", layout="device")
+        assert st.resident == streaming and st.streaming == streaming
+        st.cfl_init()
+        n0 = st.launch_count
+        st.enqueue(7)
+        assert st.status().steps == 7 and (st.launch_count == n0 + 1) == streaming
+        st.close()
+    monkeypatch.delenv("SWB_STREAM")
 
 
 @pytest.mark.parametrize("M,N,ic,diff,mode,units", [
@@ -652,21 +767,22 @@ def test_streaming_kernel_is_bit_identical_to_launch_per_step(M, N, ic, diff, mo
     batches = [1, 2, 7, 13, 1]
     ref, tr_ref, log_ref, n_ref = _run_batches(M, N, ic, diff, mode, batches, 1e12, False, monkeypatch)
     for unit in units:
-        env = {"SWB_STREAM": "1"}
-        if unit:
-            env["SWB_STREAM_UNIT"] = unit
-        res, tr_res, log_res, n_res = _run_batches(M, N, ic, diff, mode, batches, 1e12, True, monkeypatch, env, streaming=True)
-        assert tr_res == tr_ref, unit
-        for a, b in zip(log_res, log_ref):
-            assert _bits(a, b), unit
-        for name, a, b in zip("huv", res, ref):
-            assert _bits(a, b), (unit, name, _worst(a, b))
-        assert n_res < n_ref
+        for mapping in ("1", "0"):  # tiles dealt round-robin / one contiguous range of the column-major space per block
+            env = {"SWB_STREAM": "1", "SWB_STREAM_MAP": mapping}
+            if unit:
+                env["SWB_STREAM_UNIT"] = unit
+            res, tr_res, log_res, n_res = _run_batches(M, N, ic, diff, mode, batches, 1e12, True, monkeypatch, env, streaming=True)
+            assert tr_res == tr_ref, (unit, mapping)
+            for a, b in zip(log_res, log_ref):
+                assert _bits(a, b), (unit, mapping)
+            for name, a, b in zip("huv", res, ref):
+                assert _bits(a, b), (unit, mapping, name, _worst(a, b))
+            assert n_res < n_ref
 
 
 def test_streaming_kernel_stops_at_final_time_and_runs_long(monkeypatch):
     M, N = 96, 64
-    final_time = 3600.0
+    final_time = 2700.0  # ~59 steps
     batches = [40, 40, 5, 1]
     ref, tr_ref, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, "fast", batches, final_time, False, monkeypatch)
     res, tr_res, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, "fast", batches, final_time, True, monkeypatch,

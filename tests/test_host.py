@@ -137,7 +137,7 @@ def test_c_abi_exports_every_declared_symbol():
     L = _lib.load()  # dlopen + prototype declaration (raises if a symbol is missing)
     for name in declared:
         assert hasattr(L, name)
-    assert L.swb_abi_version() == 2
+    assert L.swb_abi_version() == 3
     assert ctypes.sizeof(_lib.SwbStatus) == 56 and ctypes.sizeof(_lib.SwbConfig) == 18 * 4 + 8 * 8
 
 
