@@ -260,8 +260,23 @@ def small_configs(dev):
     sd = {"interval": 10 ** 9}
     solve(360, 180, ICType.RossbyHaurwitzWave, 1.0, 0.5, False, save_data=sd)
     wall = time.perf_counter() - t0
+    # the same run with a snapshot every 10 steps (~750 snapshots of h, u, v: K4 transposes + async D2H into slices of a
+    # few pinned chunks) and with a print every 100 steps (one synchronisation each)
+    t0 = time.perf_counter()
+    sd10 = {"interval": 10}
+    solve(360, 180, ICType.RossbyHaurwitzWave, 1.0, 0.5, False, save_data=sd10)
+    wall10 = time.perf_counter() - t0
+    import contextlib
+    import io
+
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        solve(360, 180, ICType.RossbyHaurwitzWave, 1.0, 0.5, False, print_interval=100)
+    wallp = time.perf_counter() - t0
     out.append({"workload": "solve(360, 180, RossbyHaurwitzWave, sim_days=1, courant=0.5, use_diffusion=False) -- the reference's call",
-                "wall_seconds": wall, "note": "about 7.5 k adaptive steps; the numpy reference runs 21 ms per step on this grid (SURVEY 6)"})
+                "wall_seconds": wall, "wall_seconds_save_interval_10": wall10, "snapshots": int(len(sd10["t"])),
+                "wall_seconds_print_interval_100": wallp,
+                "note": "about 7.5 k adaptive steps; the numpy reference runs 8-15 ms per step on this grid (cpu_baseline.numpy_ref)"})
     return out
 
 

@@ -81,11 +81,19 @@ typedef struct swb_config {
     int32_t world;        /* number of latitude bands / GPUs (1 on one GPU)           */
     int32_t halo;         /* rows exchanged with each neighbour band (1; 2 with
                              diffusion); ignored when world == 1                      */
+    int32_t f_sep;        /* 1: the Coriolis parameter is SEPARABLE,
+                             f[i,j] = fsep_scale * ((fsep_lon[i] * fsep_lat_b[j]) * fsep_sa + fsep_lat_d[j])
+                             evaluated in exactly this order -- Williamson case 2 of the reference
+                             (ic.py:126-133) from 1-D tables: no (M+3, N) array, and the TMA / resident
+                             kernels apply.  fp64, flat topography, f_is_2d == 0.                  */
+    int32_t reserved0;
     double courant;       /* CFL number (numpy.py:413)                                */
     double final_time;    /* seconds (numpy.py:470-472)                               */
     double dxmin, dymin;  /* CartesianGrid.dxmin / dymin (grid.py:46-47)              */
     double g, a, nu;      /* EARTH_CONSTANTS (utils.py:28-33)                         */
     double dphi;          /* 2 pi / M (grid.py:86)                                    */
+    double fsep_scale;    /* f_sep: the outer factor (2 Omega)                        */
+    double fsep_sa;       /* f_sep: the factor of the product term (sin(alpha))       */
 } swb_config;
 
 /* Latitude tables of the local band (host pointers, each n_local long, indexed by local
@@ -106,6 +114,9 @@ typedef struct swb_tables {
     const double *dy1c;   /* 0.5*(dy1[j-1]+dy1[j])                 CartesianGrid.dy1c */
     const double *Ay, *By, *Cy; /* DiffusionCoefficients.Ay/By/Cy of row j (may be NULL
                                    when use_diffusion == 0)                           */
+    const double *fsep_lon;   /* f_sep: M+3 longitude factors   (-cos(phi_i), ic.py:128)          */
+    const double *fsep_lat_b; /* f_sep: n_local latitude factors (cos(theta_j))                   */
+    const double *fsep_lat_d; /* f_sep: n_local latitude addends (sin(theta_j) * cos(alpha))      */
 } swb_tables;
 
 /* Small status record mirrored from the device (see swb_get_status). */
@@ -172,7 +183,7 @@ int swb_step_fixed_dt(swb_ctx *ctx, double dt, void *stream);
 int swb_laplacian(swb_ctx *ctx, const void *q, void *out, void *stream);
 /* Laplacian of an ALREADY EXTENDED field (numpy.py:66-133 `compute_laplacian`): the reference's
  * (M+5, N+2) argument, here latitude-major -- `qext` is an (N+2, pitch_ext) device array of
- * doubles, pitch_ext >= M+5, element (j+1, i+2) holding q[i, j] of the unextended field.  No
+ * doubles, pitch_ext >= M+5, element (j+1, i+1) holding q[i, j] of the unextended field.  No
  * periodic wrap or row duplication is applied: whatever extension the caller built is used as is.
  * `out` as for swb_laplacian.  One band (world == 1) only. */
 int swb_laplacian_ext(swb_ctx *ctx, const void *qext, int pitch_ext, void *out, void *stream);

@@ -25,7 +25,9 @@ def child(a):
     dev = torch.device("cuda", 0)
     ll = LatLonGrid(M, N)
     cg = CartesianGrid(ll)
-    hd, ud, vd, f = bands.rossby_haurwitz_band(ll, 0, ll.N, dev)
+    hd, ud, vd, f = (bands.zonal_flow_band if a.ic == "zgf" else bands.rossby_haurwitz_band)(ll, 0, ll.N, dev)
+    if a.ic == "zgf" and os.environ.get("SWB_FSEP", "1") == "0":  # the 2-D array kernels: materialise f in the device layout
+        f = torch.from_numpy(f.array().T.copy()).to(dev)
     st = Stepper(ll, cg, hd, ud, vd, f, None, courant=0.5, final_time=1e12, use_diffusion=a.diffusion, mode=a.mode, layout="device", dtype=a.dtype)
     del hd, ud, vd
     st.enqueue(a.warmup)
@@ -67,6 +69,7 @@ def main():
     ap.add_argument("--diffusion", action="store_true")
     ap.add_argument("--mode", default="fast")
     ap.add_argument("--dtype", default="float64")
+    ap.add_argument("--ic", default="rh", choices=["rh", "zgf"])
     ap.add_argument("--grid", default=None)
     ap.add_argument("--tag", default="")
     a = ap.parse_args()
@@ -80,7 +83,7 @@ def main():
                     k, v = kv.split("=", 1)
                     e[k] = v
             cmd = [sys.executable, __file__, "--grid", g, "--tag", env, "--steps", str(a.steps), "--warmup", str(a.warmup), "--sustain", str(a.sustain),
-                   "--mode", a.mode, "--dtype", a.dtype] + (["--diffusion"] if a.diffusion else [])
+                   "--mode", a.mode, "--dtype", a.dtype, "--ic", a.ic] + (["--diffusion"] if a.diffusion else [])
             r = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=600)
             sys.stderr.write(r.stderr[-600:] if os.environ.get("SWB_VERBOSE") else ""); line = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else json.dumps({"grid": g, "env": env, "failed": r.stderr[-400:]})
             print(line, flush=True)

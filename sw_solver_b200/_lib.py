@@ -31,13 +31,14 @@ class SwbError(RuntimeError):
 class SwbConfig(ctypes.Structure):
     _fields_ = [(n, c_int32) for n in (
         "struct_bytes", "M", "N", "j_begin", "n_local", "j_first", "j_last", "pitch", "dtype", "mode",
-        "use_diffusion", "f_is_2d", "has_hs", "device", "log_capacity", "rank", "world", "halo",
+        "use_diffusion", "f_is_2d", "has_hs", "device", "log_capacity", "rank", "world", "halo", "f_sep", "reserved0",
     )] + [(n, c_double) for n in (
-        "courant", "final_time", "dxmin", "dymin", "g", "a", "nu", "dphi",
+        "courant", "final_time", "dxmin", "dymin", "g", "a", "nu", "dphi", "fsep_scale", "fsep_sa",
     )]
 
 
-TABLE_FIELDS = ("phi", "c", "tg", "ac", "f_lat", "tgMidy", "cMidy", "dy", "dy1", "dyc", "dy1c", "Ay", "By", "Cy")
+TABLE_FIELDS = ("phi", "c", "tg", "ac", "f_lat", "tgMidy", "cMidy", "dy", "dy1", "dyc", "dy1c", "Ay", "By", "Cy",
+                "fsep_lon", "fsep_lat_b", "fsep_lat_d")
 
 
 class SwbTables(ctypes.Structure):

@@ -27,7 +27,7 @@ import torch
 from . import _lib
 from ._lib import check
 from .grid import LatLonGrid
-from .ic import separable_rossby_haurwitz
+from .ic import separable_rossby_haurwitz, separable_zonal_flow, zonal_flow_coriolis
 
 
 # --------------------------------------------------------------------------------------
@@ -166,6 +166,45 @@ def rossby_haurwitz_band(latlon_grid: LatLonGrid, j_begin: int, n_local: int, de
     u = col("uA") + u
     v = col("vB") * sR
     return h, u, v, coriolis_latitude(latlon_grid)
+
+
+def zonal_flow_band(latlon_grid: LatLonGrid, j_begin: int, n_local: int, device) -> Tuple[Any, ...]:
+    """h, u, v of the zonal geostrophic flow (reference ic.py:119-154) for latitudes
+    ``j_begin .. j_begin+n_local-1`` as (n_local, M+3) float64 CUDA tensors in the device layout, plus
+    the Coriolis parameter of the WHOLE grid in separable form (``ic.SeparableCoriolis``: no 2-D
+    array anywhere).  As in ``rossby_haurwitz_band`` numpy evaluates the transcendental factors on
+    O(M + N) points and the device forms the final products and sums one IEEE operation per torch
+    call in the reference's order: bit-identical to slicing ``get_initial_conditions``."""
+    s = separable_zonal_flow(latlon_grid)
+    sl = slice(j_begin, j_begin + n_local)
+    dev = torch.device(device)
+    M3 = latlon_grid.M + 3
+
+    def col(name):  # latitude factor -> column vector
+        return torch.from_numpy(np.ascontiguousarray(s[name][sl])).to(dev)[:, None]
+
+    def row(name):  # longitude factor -> row vector
+        return torch.from_numpy(np.ascontiguousarray(s[name])).to(dev)[None, :]
+
+    def scalar(name):  # a DEVICE scalar: torch folds python-scalar divisors into reciprocals
+        return torch.tensor(float(s[name]), dtype=torch.float64, device=dev)
+
+    sa = scalar("sa")
+    rot = col("ct") * row("ncp")      # (-cos(phi) * cos(theta)): the product commutes exactly
+    rot = rot * sa
+    rot = rot + col("sca")
+    t = rot * rot                      # numpy evaluates ** 2.0 as a square
+    del rot
+    t = scalar("K") * t
+    t = t / scalar("g")
+    h = scalar("h0") - t
+    del t
+    u = col("st") * row("cp")
+    u = u * sa
+    u = col("cca") + u
+    u = scalar("u0") * u
+    v = (row("sp_nu0") * sa).expand(n_local, M3).contiguous()
+    return h, u, v, zonal_flow_coriolis(latlon_grid)
 
 
 # --------------------------------------------------------------------------------------

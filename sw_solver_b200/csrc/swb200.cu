@@ -11,6 +11,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "swb200.h"
@@ -114,45 +115,81 @@ constexpr TmaVariant kTmaVariants[] = {{4, 4, 2, 4}, {4, 3, 2, 4}, {2, 4, 2, 4},
 constexpr int kNumTmaVariants = (int)(sizeof(kTmaVariants) / sizeof(kTmaVariants[0]));
 constexpr int kDefaultTmaVariant = 0;  // R = 4, S = 4, two blocks per SM: no spills (1.26 ms/step at 16384 x 8192)
 
-template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
+// Launch with programmatic stream serialisation (see pdl_enter in swb_kernels.cuh); SWB_PDL=0 launches plainly.
+bool pdl_enabled()
+{
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("SWB_PDL");
+        on = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    return on != 0;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = grid;
+    lc.blockDim = block;
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);
+}
+
+template <typename T, bool STRICT, bool DIFF, int FM, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
           bool CFLF = false>
 cudaError_t launch_inst(const swb_ctx *c, dim3 grid, cudaStream_t st)
 {
     using LY = TmaLayout<R, S, T, box_cols<T, DIFF, TMA>()>;
     const int smem = rec_bytes(c->prm.chunk, DIFF) + (TMA ? W * LY::kWarpBytes : 0);
     static int configured[64] = {0};  // per instantiation and device: largest size opted in so far
-    auto fn = march_kernel<T, STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, MINB, W, CFLF>;
+    auto fn = march_kernel<T, STRICT, DIFF, FM, HS, TMA, R, S, GUARD, MINB, W, CFLF>;
     const int dev = c->cfg.device & 63;
     if (configured[dev] < smem) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured[dev] = smem;
     }
-    fn<<<grid, W * 32, smem, st>>>(c->prm, c->maps);
-    return cudaSuccess;
+    return launch_chain(fn, grid, dim3(W * 32), (size_t)smem, st, c->prm, c->maps);
 }
 
-// mode: SWB_STRICT, SWB_FAST, SWB_FAST_GUARDED
-template <bool DIFF, bool F2D, bool HS>
+// mode: SWB_STRICT, SWB_FAST, SWB_FAST_GUARDED;  fm: 0 latitude-only Coriolis, 1 a 2-D array, 2 separable (tables)
+template <bool DIFF, int FM, bool HS>
 cudaError_t launch_ldg_m(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
-    if (mode == SWB_STRICT) return launch_inst<double, true, DIFF, F2D, HS, false, 1, 1, true, 2>(c, g, st);
-    if (mode == SWB_FAST) return launch_inst<double, false, DIFF, F2D, HS, false, 1, 1, false, 2>(c, g, st);
-    return launch_inst<double, false, DIFF, F2D, HS, false, 1, 1, true, 2>(c, g, st);
+    if (mode == SWB_STRICT) return launch_inst<double, true, DIFF, FM, HS, false, 1, 1, true, 2>(c, g, st);
+    if (mode == SWB_FAST) return launch_inst<double, false, DIFF, FM, HS, false, 1, 1, false, 2>(c, g, st);
+    return launch_inst<double, false, DIFF, FM, HS, false, 1, 1, true, 2>(c, g, st);
 }
-template <bool DIFF, bool F2D>
+template <bool DIFF, int FM>
 cudaError_t launch_ldg_h(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool hs)
 {
-    return hs ? launch_ldg_m<DIFF, F2D, true>(c, mode, g, st) : launch_ldg_m<DIFF, F2D, false>(c, mode, g, st);
+    return hs ? launch_ldg_m<DIFF, FM, true>(c, mode, g, st) : launch_ldg_m<DIFF, FM, false>(c, mode, g, st);
 }
 template <bool DIFF>
-cudaError_t launch_ldg_f(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool f2d, bool hs)
+cudaError_t launch_ldg_f(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, int fm, bool hs)
 {
-    return f2d ? launch_ldg_h<DIFF, true>(c, mode, g, st, hs) : launch_ldg_h<DIFF, false>(c, mode, g, st, hs);
+    if (fm == 2) return launch_ldg_m<DIFF, 2, false>(c, mode, g, st);  // (separable Coriolis: flat topography only, swb_create)
+    return fm == 1 ? launch_ldg_h<DIFF, 1>(c, mode, g, st, hs) : launch_ldg_h<DIFF, 0>(c, mode, g, st, hs);
 }
-cudaError_t launch_ldg(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool diff, bool f2d, bool hs)
+cudaError_t launch_ldg(const swb_ctx *c, int mode, dim3 g, cudaStream_t st, bool diff, int fm, bool hs)
 {
-    return diff ? launch_ldg_f<true>(c, mode, g, st, f2d, hs) : launch_ldg_f<false>(c, mode, g, st, f2d, hs);
+    return diff ? launch_ldg_f<true>(c, mode, g, st, fm, hs) : launch_ldg_f<false>(c, mode, g, st, fm, hs);
+}
+
+// separable Coriolis through the TMA ring (default ring shapes only)
+template <bool DIFF>
+cudaError_t launch_tma_sep(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
+{
+    constexpr int S = DIFF ? 3 : 4;
+    if (mode == SWB_STRICT) return launch_inst<double, true, DIFF, 2, false, true, 4, S, true, 2>(c, g, st);
+    if (mode == SWB_FAST) return launch_inst<double, false, DIFF, 2, false, true, 4, S, false, 2>(c, g, st);
+    return launch_inst<double, false, DIFF, 2, false, true, 4, S, true, 2>(c, g, st);
 }
 
 template <int R, int S, int MINB, int W = kWarpsPerBlock>
@@ -164,6 +201,7 @@ cudaError_t launch_tma_rs(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 }
 cudaError_t launch_tma(const swb_ctx *c, int mode, dim3 g, cudaStream_t st)
 {
+    if (c->cfg.f_sep) return c->cfg.use_diffusion ? launch_tma_sep<true>(c, mode, g, st) : launch_tma_sep<false>(c, mode, g, st);
     if (c->cfl_filter) {  // default ring shape only
         if (mode == SWB_FAST) return launch_inst<double, false, false, false, false, true, 4, 4, false, 2, kWarpsPerBlock, true>(c, g, st);
         return launch_inst<double, false, false, false, false, true, 4, 4, true, 2, kWarpsPerBlock, true>(c, g, st);
@@ -221,10 +259,10 @@ int launch_one(swb_ctx *c, cudaStream_t st)
     const Params &p = c->prm;
     const int rows = p.jl_last - p.jl_first + 1;
     const bool f32 = cfg.dtype == SWB_F32;
-    const int W = (c->use_tma && !f32 && !cfg.use_diffusion) ? kTmaVariants[c->tma_variant].W : kWarpsPerBlock;
+    const int W = (c->use_tma && !f32 && !cfg.use_diffusion && !cfg.f_sep) ? kTmaVariants[c->tma_variant].W : kWarpsPerBlock;
     dim3 grid((unsigned)((p.nstrips + W - 1) / W), (unsigned)((rows + p.chunk - 1) / p.chunk));
     if (c->linked && !p.fixed) {  // the maxima of all bands' previous step -> this step's slot
-        gather_kernel<<<1, 32, 0, st>>>(p);
+        CK(launch_chain(gather_kernel, dim3(1), dim3(32), 0, st, p));
         c->launches++;
         CK(cudaGetLastError());
     }
@@ -234,17 +272,17 @@ int launch_one(swb_ctx *c, cudaStream_t st)
     } else if (c->use_tma) {
         CK(launch_tma(c, cfg.mode, grid, st));
     } else {
-        CK(launch_ldg(c, cfg.mode, grid, st, cfg.use_diffusion, cfg.f_is_2d, cfg.has_hs));
+        CK(launch_ldg(c, cfg.mode, grid, st, cfg.use_diffusion, cfg.f_sep ? 2 : (cfg.f_is_2d ? 1 : 0), cfg.has_hs));
     }
     c->launches++;
     CK(cudaGetLastError());
     if (c->cfl_filter && !p.fixed) {  // returns at once unless the filter found no valid maximum
-        cfl_fixup_kernel<<<c->sm_count * 4, 256, 0, st>>>(p);
+        CK(launch_chain(cfl_fixup_kernel, dim3(c->sm_count * 4), dim3(256), 0, st, p));
         c->launches++;
         CK(cudaGetLastError());
     }
     if (c->linked && !p.fixed) {
-        publish_kernel<<<1, 32, 0, st>>>(p);
+        CK(launch_chain(publish_kernel, dim3(1), dim3(32), 0, st, p));
         c->launches++;
         CK(cudaGetLastError());
     }
@@ -261,11 +299,11 @@ constexpr int kResFourStageChunk = 96;  // no diffusion: four ring stages up to 
 constexpr int res_max_chunk(bool tma, bool /*diff*/) { return !tma ? kResPreSmemChunk : 128; }
 
 struct ResKernel { const void *fn; int smem; };
-template <bool STRICT, bool DIFF, bool TMA, bool GUARD, int S = (DIFF ? 3 : 4), bool BANDS = false>  // (with diffusion: three stages of wider boxes, as in march_kernel)
+template <bool STRICT, bool DIFF, bool TMA, bool GUARD, int S = (DIFF ? 3 : 4), bool BANDS = false, int FM = 0>  // (with diffusion: three stages of wider boxes, as in march_kernel)
 ResKernel res_kernel_inst(int chunk)
 {
     using LY = TmaLayout<4, S, double, box_cols<double, DIFF, TMA>()>;
-    auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? S : 1), GUARD, 2, BANDS>;
+    auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? S : 1), GUARD, 2, BANDS, kWarpsPerBlock, FM>;
     return ResKernel{(const void *)fn, (chunk <= kResPreSmemChunk ? 2 : 1) * rec_bytes(chunk, DIFF) +
                                            (TMA ? kWarpsPerBlock * LY::kWarpBytes : kWarpsPerBlock * kFirstRowsBytes)};
 }
@@ -301,9 +339,23 @@ ResKernel stream_kernel_of(int mode, bool diff, bool bands, bool cflf)
     return bands ? stream_kernel_sel<true>(mode != SWB_FAST, diff, cflf) : stream_kernel_sel<false>(mode != SWB_FAST, diff, cflf);
 }
 
-// (bands: the FAST modes; a STRICT band keeps one launch per step)
-ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk, bool bands)
+// separable Coriolis (one band): the same shapes with FM = 2
+ResKernel res_kernel_sep(int mode, bool diff, bool tma, int chunk)
 {
+    if (mode == SWB_STRICT) return diff ? res_kernel_inst<true, true, false, true, 3, false, 2>(chunk) : res_kernel_inst<true, false, false, true, 4, false, 2>(chunk);
+    const bool guard = mode != SWB_FAST;
+    if (tma && diff) return guard ? res_kernel_inst<false, true, true, true, 3, false, 2>(chunk) : res_kernel_inst<false, true, true, false, 3, false, 2>(chunk);
+    if (tma && chunk > kResFourStageChunk)
+        return guard ? res_kernel_inst<false, false, true, true, 3, false, 2>(chunk) : res_kernel_inst<false, false, true, false, 3, false, 2>(chunk);
+    if (tma) return guard ? res_kernel_inst<false, false, true, true, 4, false, 2>(chunk) : res_kernel_inst<false, false, true, false, 4, false, 2>(chunk);
+    if (diff) return guard ? res_kernel_inst<false, true, false, true, 3, false, 2>(chunk) : res_kernel_inst<false, true, false, false, 3, false, 2>(chunk);
+    return guard ? res_kernel_inst<false, false, false, true, 4, false, 2>(chunk) : res_kernel_inst<false, false, false, false, 4, false, 2>(chunk);
+}
+
+// (bands: the FAST modes; a STRICT band keeps one launch per step)
+ResKernel res_kernel_of(int mode, bool diff, bool tma, int chunk, bool bands, bool sep = false)
+{
+    if (sep) return res_kernel_sep(mode, diff, tma, chunk);
     if (bands) return res_kernel_sel<true>(mode, diff, tma, chunk);
     if (!tma && mode == SWB_STRICT) return diff ? res_kernel_inst<true, true, false, true>(chunk) : res_kernel_inst<true, false, false, true>(chunk);
     return res_kernel_sel<false>(mode, diff, tma, chunk);
@@ -320,6 +372,8 @@ int setup_resident(swb_ctx *c)
     const swb_config &cfg = c->cfg;
     Params &p = c->prm;
     if (cfg.dtype != SWB_F64 || cfg.f_is_2d || cfg.has_hs) return 0;
+    if (cfg.f_sep && cfg.world != 1) return 0;  // (separable Coriolis: the resident kernels serve one band)
+    const bool sep = cfg.f_sep != 0;
     // bands: only once the peers are linked AND the caller vouches that every band runs on a GPU of
     // its own (several resident kernels waiting for each other on one GPU would never all start)
     if (cfg.world != 1 && !(c->linked && c->resident_bands && cfg.mode != SWB_STRICT)) return 0;
@@ -337,7 +391,7 @@ int setup_resident(swb_ctx *c)
         const int probe[3] = {kResPreSmemChunk, kResFourStageChunk, res_max_chunk(tma, cfg.use_diffusion)};
         int nb_min = 1 << 30;
         for (int k = 0; k < (tma ? 3 : 1); ++k) {
-            const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, probe[k], cfg.world > 1);
+            const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, probe[k], cfg.world > 1, sep);
             CK(cudaFuncSetAttribute(rk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rk.smem));
             int nb = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk.fn, kWarpsPerBlock * 32, (size_t)rk.smem));
@@ -373,7 +427,7 @@ int setup_resident(swb_ctx *c)
     // march_kernel / the one-tile resident kernel (register pressure: its tile loop spills loop-control values, see
     // profiles/r2_stream_kernel.md), which outweighs the launch chain and the wave tail it removes.
     bool stream = false;
-    if (const char *e = getenv("SWB_STREAM")) stream = c->tma_ready && cfg.mode != SWB_STRICT && c->d_prec != nullptr && atoi(e) != 0;
+    if (const char *e = getenv("SWB_STREAM")) stream = c->tma_ready && cfg.mode != SWB_STRICT && c->d_prec != nullptr && !sep && atoi(e) != 0;
     if (stream) {
         // the CFL filter (estimate per cell, exact evaluation near the previous maximum, fix-up inside the launch):
         // as for march_kernel on grids whose step takes far longer than the barrier; SWB_CFL_FILTER=0 / 1 overrides
@@ -429,7 +483,7 @@ int setup_resident(swb_ctx *c)
         return 0;
     }
     if (chunk <= 0) return 0;
-    const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, chunk, cfg.world > 1);
+    const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, chunk, cfg.world > 1, sep);
     c->res_fn = rk.fn;
     c->res_smem = rk.smem;
     c->res_grid = dim3((unsigned)gx, (unsigned)((rows + chunk - 1) / chunk));
@@ -476,6 +530,10 @@ int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_
 // up with 2-row marches, large ones with 64 (measured).
 int pick_chunk(int rows, int nstrips, int sm_count)
 {
+    // (A wave-quantisation model -- waves x (rows + start-up) -- was tried for grids of several waves and
+    // dropped: measured at 7200 x 3600, 56 / 64 / 72 / 76 / 96-row marches take 267.9 / 272.1 / 271.9 / 275.1 /
+    // 281.9 us per step; at 16384 x 8192, 64 / 72 / 96 rows 1243 / 1248 / 1240 us.  Shorter marches drain
+    // better than fuller last waves pay; 64 stays.)
     const long long want_blocks = (long long)sm_count * 2 * 9 / 10;
     const int gx = (nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock;
     int chunk = 64;
@@ -500,6 +558,8 @@ int swb_create(swb_ctx **out, const swb_config *cfg)
     if (cfg->struct_bytes != (int32_t)sizeof(swb_config)) return fail(SWB_E_INVALID, "swb_create: swb_config size mismatch (ABI)");
     if (cfg->M < 2 || cfg->N < 2 || (cfg->N & 1)) return fail(SWB_E_INVALID, "swb_create: need M >= 2 and an even N >= 2");
     if (cfg->dtype != SWB_F64 && cfg->dtype != SWB_F32) return fail(SWB_E_INVALID, "swb_create: bad dtype");
+    if (cfg->f_sep && (cfg->f_is_2d || cfg->has_hs || cfg->dtype != SWB_F64))
+        return fail(SWB_E_INVALID, "swb_create: a separable Coriolis parameter serves fp64 with flat topography (pass the 2-D array otherwise)");
     if (cfg->dtype == SWB_F32 && (cfg->mode == SWB_STRICT || cfg->f_is_2d || cfg->has_hs))
         return fail(SWB_E_INVALID, "swb_create: the fp32 mode serves FAST arithmetic with latitude-only Coriolis and flat topography");
     if (cfg->mode != SWB_STRICT && cfg->mode != SWB_FAST && cfg->mode != SWB_FAST_GUARDED) return fail(SWB_E_INVALID, "swb_create: bad mode");
@@ -549,8 +609,8 @@ static int create_resources(swb_ctx *c)
     const swb_config *cfg = &c->cfg;
     const size_t nloc = (size_t)cfg->n_local;
     const size_t nphi = (size_t)cfg->pitch + 8;  // lanes of the last strip look past M+2
-    CK(cudaMalloc(&c->d_phi, sizeof(double) * nphi));
-    CK(cudaMemset(c->d_phi, 0, sizeof(double) * nphi));
+    CK(cudaMalloc(&c->d_phi, sizeof(double) * 2 * nphi));  // phi, then the longitude factor of a separable Coriolis parameter
+    CK(cudaMemset(c->d_phi, 0, sizeof(double) * 2 * nphi));
     CK(cudaMalloc(&c->d_tab, sizeof(double) * (size_t)T_COUNT * nloc));
     CK(cudaMemset(c->d_tab, 0, sizeof(double) * (size_t)T_COUNT * nloc));
     CK(cudaMalloc(&c->d_pre, sizeof(double) * (size_t)kRowRec * nloc));
@@ -577,6 +637,9 @@ static int create_resources(swb_ctx *c)
     Params &p = c->prm;
     memset(&p, 0, sizeof p);
     p.phi = c->d_phi;
+    p.fa = c->d_phi + nphi;
+    p.fs_scale = cfg->fsep_scale;
+    p.fs_sa = cfg->fsep_sa;
     p.tab = c->d_tab;
     p.pre = c->d_pre;
     p.pred = c->d_pred;
@@ -670,12 +733,14 @@ int swb_set_tables(swb_ctx *c, const swb_tables *t)
     if (!c || !t) return fail(SWB_E_INVALID, "swb_set_tables: null argument");
     if (!t->phi || !t->c || !t->tg || !t->ac || !t->tgMidy || !t->cMidy || !t->dy || !t->dy1 || !t->dyc || !t->dy1c)
         return fail(SWB_E_INVALID, "swb_set_tables: a required table is null");
-    if (!c->cfg.f_is_2d && !t->f_lat) return fail(SWB_E_INVALID, "swb_set_tables: f_lat required when f_is_2d == 0");
+    if (!c->cfg.f_is_2d && !c->cfg.f_sep && !t->f_lat) return fail(SWB_E_INVALID, "swb_set_tables: f_lat required when f_is_2d == 0");
+    if (c->cfg.f_sep && (!t->fsep_lon || !t->fsep_lat_b || !t->fsep_lat_d)) return fail(SWB_E_INVALID, "swb_set_tables: fsep_lon / fsep_lat_b / fsep_lat_d required with f_sep");
     if (c->cfg.use_diffusion && (!t->Ay || !t->By || !t->Cy)) return fail(SWB_E_INVALID, "swb_set_tables: Ay/By/Cy required with diffusion");
     ON_DEVICE(c);
     const size_t nloc = (size_t)c->cfg.n_local;
     std::vector<double> host((size_t)T_COUNT * nloc, 0.0);
-    const double *src[T_COUNT] = {t->c, t->tg, t->ac, t->f_lat, t->tgMidy, t->cMidy, t->dy, t->dy1, t->dyc, t->dy1c, t->Ay, t->By, t->Cy};
+    const double *src[T_COUNT] = {t->c, t->tg, t->ac, t->f_lat, t->tgMidy, t->cMidy, t->dy, t->dy1, t->dyc, t->dy1c, t->Ay, t->By, t->Cy,
+                                  t->fsep_lat_b, t->fsep_lat_d};
     for (int k = 0; k < T_COUNT; ++k)
         if (src[k]) memcpy(&host[(size_t)k * nloc], src[k], sizeof(double) * nloc);
     // (on the context's own non-blocking stream: neither the default stream nor a device-wide
@@ -683,6 +748,8 @@ int swb_set_tables(swb_ctx *c, const swb_tables *t)
     cudaStream_t ss = c->setup_stream;
     CK(cudaMemcpyAsync(c->d_tab, host.data(), sizeof(double) * host.size(), cudaMemcpyHostToDevice, ss));
     CK(cudaMemcpyAsync(c->d_phi, t->phi, sizeof(double) * (size_t)(c->cfg.M + 3), cudaMemcpyHostToDevice, ss));
+    if (c->cfg.f_sep)
+        CK(cudaMemcpyAsync(c->d_phi + ((size_t)c->cfg.pitch + 8), t->fsep_lon, sizeof(double) * (size_t)(c->cfg.M + 3), cudaMemcpyHostToDevice, ss));
     // the dt-independent stage of the row records, once
     const int nb = (c->cfg.n_local + 2 * kRecPad + 127) / 128;
     if (c->cfg.mode == SWB_STRICT) prerec_kernel<true><<<nb, 128, 0, ss>>>(c->prm, c->d_pre, nullptr, nullptr);
@@ -740,8 +807,9 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
         // CFL filter: worth its extra (normally empty) launch per step on grids whose step takes
         // far longer than a launch; SWB_CFL_FILTER=0/1 overrides
         const long long cells = (long long)(p.M + 1) * (p.jl_last - p.jl_first + 1);
-        c->cfl_filter = !f32 && !c->cfg.use_diffusion && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && cells >= 4000000LL;
-        if (const char *e = getenv("SWB_CFL_FILTER")) c->cfl_filter = !f32 && !c->cfg.use_diffusion && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant && atoi(e) != 0;
+        const bool filter_ok = !f32 && !c->cfg.use_diffusion && !c->cfg.f_sep && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant;
+        c->cfl_filter = filter_ok && cells >= 4000000LL;
+        if (const char *e = getenv("SWB_CFL_FILTER")) c->cfl_filter = filter_ok && atoi(e) != 0;
         ON_DEVICE(c);
         for (int s = 0; s < 2; ++s) {
             // (fp64 with diffusion: the box also carries the star's two columns either side)

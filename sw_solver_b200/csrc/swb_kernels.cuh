@@ -46,8 +46,19 @@ __device__ __forceinline__ unsigned long long swb_globaltimer()
 #define SWB_TLOG_MAX(p, k) do { } while (0)
 #endif
 
+// Programmatic dependent launch: the kernels of the per-step chain (gather -> march -> cfl_fixup -> publish) are
+// launched with programmatic stream serialisation, so the next kernel's blocks are scheduled while the previous
+// kernel drains; `pdl_wait` holds them until the previous grid has completed and flushed its memory operations.
+// Every kernel of the chain triggers its dependents at once and waits before it touches global memory.  (Both
+// are no-ops in a kernel launched without the attribute.)
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // One launch per time step (any grid size, any band decomposition).
-template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
+template <typename T, bool STRICT, bool DIFF, int FM, bool HS, bool TMA, int R, int S, bool GUARD, int MINB, int W = kWarpsPerBlock,
           bool CFLF = false>
 __global__ void __launch_bounds__(W * 32, MINB)
 march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
@@ -57,11 +68,12 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     __shared__ int s_flags;
     __shared__ CflFilter s_filter;
     int tbase = 0, par = -1;
+    pdl_enter();
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) SWB_TLOG(p, 2);
     const int ja = p.jl_first + blockIdx.y * p.chunk;
     const Tile tl{(int)blockIdx.x * W, ja, min(ja + p.chunk, p.jl_last + 1), blockIdx.x == 0 && blockIdx.y == 0, true};
-    march_step<T, STRICT, DIFF, F2D, HS, TMA, R, S, GUARD, W, CFLF, false>(p, tm, p.launch, true, tbase, par, smem_raw, s_dt, s_flags, s_filter,
-                                                                           nullptr, tl);
+    march_step<T, STRICT, DIFF, FM, HS, TMA, R, S, GUARD, W, CFLF, false>(p, tm, p.launch, true, tbase, par, smem_raw, s_dt, s_flags, s_filter,
+                                                                          nullptr, tl);
 #ifdef SWB_BAND_TIMING
     __syncthreads();
     if (threadIdx.x == 0) SWB_TLOG_MAX(p, 3);
@@ -152,7 +164,7 @@ __device__ __forceinline__ bool band_gather(const Params &p, int launch, unsigne
 // acquire at gpu scope), behind which the next step reads the CFL maxima -- accumulated by
 // the same atomics as in march_kernel -- and its neighbours' new rows and columns straight
 // from the L2.  Same step body, same arithmetic: bit-identical to a launch per step.
-template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, bool BANDS = false, int W = kWarpsPerBlock>
+template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, bool BANDS = false, int W = kWarpsPerBlock, int FM = 0>
 __global__ void __launch_bounds__(W * 32, MINB)
 resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
 {
@@ -202,8 +214,8 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
         }
         const int ja = p.jl_first + blockIdx.y * p.chunk;
         const Tile tl{(int)blockIdx.x * W, ja, min(ja + p.chunk, p.jl_last + 1), blockIdx.x == 0 && blockIdx.y == 0, true};
-        const bool active = march_step<T, STRICT, DIFF, false, false, TMA, R, S, GUARD, W, false, true, BANDS>(p, tm, p.launch + s, s == 0, tbase, par, smem_raw,
-                                                                                                            s_dt, s_flags, s_filter, s_max, tl);
+        const bool active = march_step<T, STRICT, DIFF, FM, false, TMA, R, S, GUARD, W, false, true, BANDS>(p, tm, p.launch + s, s == 0, tbase, par, smem_raw,
+                                                                                                         s_dt, s_flags, s_filter, s_max, tl);
         if (!active) break;
         // Grid barrier: all stores and atomics of step s happen before any load of step s+1.
         // (TMA: every thread first orders its generic-proxy stores before the async-proxy reads
@@ -435,7 +447,7 @@ stream_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps 
             while (stream_next_piece(p, it, it_end, lin1, col, r0, len)) {
                 const Tile tl{col * W, p.jl_first + r0, p.jl_first + r0 + len, lead, head};
                 int pio = par_in;
-                active = march_step<double, false, DIFF, false, false, true, R, S, GUARD, W, CFLF, true, BANDS, true>(p, tm, p.launch + s, s == 0 && head, tbase, pio,
+                active = march_step<double, false, DIFF, 0, false, true, R, S, GUARD, W, CFLF, true, BANDS, true>(p, tm, p.launch + s, s == 0 && head, tbase, pio,
                                                                                                                     smem_raw, s_dt, s_flags, s_filter, s_max, tl);
                 if (!active) break;
                 par = pio;  // the set holding the NEW state: the next step's current one
@@ -548,6 +560,7 @@ stream_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps 
 __global__ void publish_kernel(const __grid_constant__ Params p)
 {
     const Ctrl *new_slot = p.ctrl + ((p.launch + 1) % 3);
+    pdl_enter();
     if (threadIdx.x == 0) SWB_TLOG(p, 5);
     band_publish(p, p.launch, p.stamp, new_slot->ex_bits, new_slot->ey_bits, (int)threadIdx.x);
 #ifdef SWB_BAND_TIMING
@@ -565,6 +578,7 @@ __global__ void gather_kernel(const __grid_constant__ Params p)
 {
     const int r = threadIdx.x;
     unsigned long long ex = 0ULL, ey = 0ULL;
+    pdl_enter();
     if (r == 0) SWB_TLOG(p, 0);
     if (r < p.world) {
         const XSlot *xs = &p.xlocal->slot[p.launch % 3][r];
@@ -601,6 +615,7 @@ __global__ void gather_kernel(const __grid_constant__ Params p)
 __global__ void __launch_bounds__(256) cfl_fixup_kernel(const __grid_constant__ Params p)
 {
     Ctrl *new_slot = p.ctrl + ((p.launch + 1) % 3);
+    pdl_enter();
     if (blockIdx.x == 0 && threadIdx.x == 0) SWB_TLOG(p, 4);
     if ((new_slot->reserved & 3) == 3) return;
     const int cur = new_slot->current;
@@ -731,7 +746,7 @@ __global__ void __launch_bounds__(128) laplacian_kernel(const double *__restrict
 }
 
 // The reference's `compute_laplacian` itself (numpy.py:66-133): the same weights applied to a field the
-// CALLER has extended -- (N+2, pitch_ext) latitude-major, element (j+1, i+2) = q[i, j] -- with no wrap
+// CALLER has extended -- (N+2, pitch_ext) latitude-major, element (j+1, i+1) = q[i, j] -- with no wrap
 // or clamp logic: q[2:-2, 2:-2] is the centre, q[1:-3], q[3:-1], q[:-4], q[4:] its neighbours.
 __global__ void __launch_bounds__(128) laplacian_ext_kernel(const double *__restrict__ qe, int pe, double *__restrict__ out, Params p)
 {
@@ -739,7 +754,7 @@ __global__ void __launch_bounds__(128) laplacian_ext_kernel(const double *__rest
     if (i > p.M + 1) return;
     using O = Op<true>;
     for (int jl = p.jl_first + blockIdx.y; jl <= p.jl_last; jl += gridDim.y) {
-        const double *c = qe + (size_t)(jl + 1) * pe + (i + 2);
+        const double *c = qe + (size_t)(jl + 1) * pe + (i + 1);
         Star<double> s;
         s.q0 = c[0];
         s.xm = c[-1]; s.xp = c[1]; s.xmm = c[-2]; s.xpp = c[2];

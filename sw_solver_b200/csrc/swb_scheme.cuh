@@ -410,6 +410,11 @@ __device__ __forceinline__ void load_star_pair(const T *__restrict__ q, int pitc
 }
 
 // FAST diffusion row record: w[0..4] combined latitude weights, [5] = 1/(2 dx_j)^2, [6] = dt*nu
+// (Tried in round 2 and reverted: dt nu folded into the six weights and the update written as FMA chains --
+// 8 FP64 instructions per cell and field when the chains start from the Lax-Wendroff result, 9 when only the
+// last addition waits for it, against 10 here.  Neither was faster: 7200 x 3600 with diffusion 456 -> 449 / 456 us
+// per step, and the resident 1440 x 720 step went from 25.9 to 27.6 / 27.9 us -- the kernel is bound by latency at
+// 255 registers, not by its instruction count.)
 template <typename T>
 __device__ __forceinline__ T laplacian_fast(const Star<T> &s, const T *__restrict__ rd)
 {

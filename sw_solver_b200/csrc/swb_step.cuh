@@ -142,6 +142,7 @@ __device__ __forceinline__ double scale_row_slot(int k, double pre, double dt)
 
 // FAST diffusion record of local latitude jl: [0..4] combined latitude weights,
 // [5] = 1/(2 dx_j)^2 (both independent of dt), [6] = dt*nu (stage 2)
+constexpr int kDiffDtSlot = 6;  // the slot of the diffusion record that carries the factor dt
 __device__ __forceinline__ void build_diff_pre(const Params &p, int jl, double *__restrict__ rd)
 {
     const int nr = p.nrows;
@@ -358,16 +359,20 @@ __device__ __forceinline__ unsigned swb_smid() { unsigned r; asm volatile("mov.u
 // is shared between the warps of the block but dt -- the dt-independent row records of latitudes
 // j0-1 .. j0+R arrive with every tile (one more bulk copy on the tile's mbarrier, from Params::prec)
 // and are scaled by dt in place once the tile has landed.
-template <typename T, bool STRICT, bool DIFF, bool F2D, bool HS, bool TMA, int R, int S, bool GUARD, int W, bool CFLF, bool RES, bool RESBANDS = false,
+// FM: how the Coriolis parameter reaches a cell -- 0 latitude-only (folded into the row records), 1 a 2-D array, 2 separable
+// (rebuilt per cell from a longitude and two latitude tables in the reference's operation order, see Params::fa).
+template <typename T, bool STRICT, bool DIFF, int FM, bool HS, bool TMA, int R, int S, bool GUARD, int W, bool CFLF, bool RES, bool RESBANDS = false,
           bool STREAM = false>
 __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, const int launch, const bool first, int &tbase,
                                            int &par_io, unsigned char *smem_raw, double &s_dt, int &s_flags, CflFilter &s_filter,
                                            unsigned long long *s_max, const Tile tl)
 {
     static_assert(!STREAM || (RES && TMA && !STRICT && sizeof(T) == 8), "the streaming kernel: resident, TMA ring, FAST fp64");
+    constexpr bool F2D = FM != 0;  // the Coriolis parameter varies along a latitude: it travels with the cells
+    static_assert(FM == 0 || sizeof(T) == 8, "2-D Coriolis parameters serve the fp64 kernels");
     static_assert(!STRICT || sizeof(T) == 8, "STRICT reproduces numpy's float64 arithmetic");
     static_assert(!CFLF || (!STRICT && TMA && sizeof(T) == 8), "the CFL filter serves the fp64 FAST TMA kernel");
-    static_assert(!RES || (sizeof(T) == 8 && !F2D && !HS && (!CFLF || STREAM)), "resident kernels: fp64, latitude-only Coriolis, flat topography");
+    static_assert(!RES || (sizeof(T) == 8 && FM != 1 && !HS && (!CFLF || STREAM)), "resident kernels: fp64, Coriolis from tables, flat topography");
     using O = Op<STRICT, T>;
     // SSTAR: the diffusion star comes out of the ring too -- boxes two columns wider on either
     // side, one tile more at either end of the march, tiles t-1, t, t+1 resident while tile t
@@ -549,7 +554,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         const double dt64 = s_dt;
         for (int e = threadIdx.x; e < nrec * kRowRec; e += blockDim.x) rowc[e] = (T)scale_row_slot<STRICT>(e % kRowRec, src[e], dt64);
         if (DIFF && !STRICT)
-            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == 6 ? dt64 * srcd[e] : srcd[e]);
+            for (int e = threadIdx.x; e < nrec * kRowDiff; e += blockDim.x) rowd[e] = (T)((e % kRowDiff) == kDiffDtSlot ? dt64 * srcd[e] : srcd[e]);
     } else {
         // one launch per step: both stages here, one latitude per thread (the same arithmetic; a
         // table look-up instead was tried and cost the hot loop registers)
@@ -562,7 +567,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                 double rd[kRowDiff];
                 build_diff_pre(p, ja - 1 + r, rd);
 #pragma unroll
-                for (int k = 0; k < kRowDiff; ++k) rowd[(size_t)r * kRowDiff + k] = (T)(k == 6 ? s_dt * rd[6] : rd[k]);
+                for (int k = 0; k < kRowDiff; ++k) rowd[(size_t)r * kRowDiff + k] = (T)(k == kDiffDtSlot ? s_dt * rd[k] : rd[k]);
             }
         }
     }
@@ -640,7 +645,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                 if (k < kRowRec) {
                     v.x = scale_row_slot<false>(k, v.x, dt64);
                     v.y = scale_row_slot<false>(k + 1, v.y, dt64);
-                } else if (k - kRowRec == 6) {
+                } else if (k - kRowRec == kDiffDtSlot) {
                     v.x = dt64 * v.x;
                 }
                 rec[e] = v;
@@ -650,7 +655,15 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         __syncwarp();
     };
     auto load_f = [&](int jl) -> V2 {
-        if (F2D) return ldg2((const T *)p.f2d + (size_t)min(jl, p.nrows - 1) * P + colA);
+        if (FM == 1) return ldg2((const T *)p.f2d + (size_t)min(jl, p.nrows - 1) * P + colA);
+        if (FM == 2) {  // ic.py:126-133 of the reference, IEEE operation by operation (the tables are constant: read-only path)
+            const int j = min(jl, p.nrows - 1);
+            const double b = __ldg(p.tab + (size_t)T_FB * p.nrows + j), d = __ldg(p.tab + (size_t)T_FD * p.nrows + j);
+            const double2 a = __ldg(reinterpret_cast<const double2 *>(p.fa + colA));
+            const double fA = __dmul_rn(p.fs_scale, __dadd_rn(__dmul_rn(__dmul_rn(a.x, b), p.fs_sa), d));
+            const double fB = __dmul_rn(p.fs_scale, __dadd_rn(__dmul_rn(__dmul_rn(a.y, b), p.fs_sa), d));
+            return mk2((T)fA, (T)fB);
+        }
         return mk2(T(0), T(0));
     };
 
@@ -844,7 +857,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                 vnA = O::add(vnA, O::mul(dnu, lap(svA, wxA))); vnB = O::add(vnB, O::mul(dnu, lap(svB, wxB)));
             } else {
                 const T *rd = STREAM ? rec_of(jl) + kRowRec : rowd + (size_t)(jl - (ja - 1)) * kRowDiff;
-                const T dnu = rd[6];
+                const T dnu = rd[kDiffDtSlot];
                 hnA = fma(dnu, laplacian_fast(shA, rd), hnA); hnB = fma(dnu, laplacian_fast(shB, rd), hnB);
                 unA = fma(dnu, laplacian_fast(suA, rd), unA); unB = fma(dnu, laplacian_fast(suB, rd), unB);
                 vnA = fma(dnu, laplacian_fast(svA, rd), vnA); vnB = fma(dnu, laplacian_fast(svB, rd), vnB);

@@ -19,7 +19,8 @@ constexpr int kMaxRanks = 8;
 constexpr int kRecPad = 8;       // rows of padding either side of the streamed record table (Params::prec)
 
 // row indices of the packed latitude table (each row `nrows` long, indexed by local latitude)
-enum Tab { T_C = 0, T_TG, T_AC, T_F, T_TGMIDY, T_CMIDY, T_DY, T_DY1, T_DYC, T_DY1C, T_AY, T_BY, T_CY, T_COUNT };
+enum Tab { T_C = 0, T_TG, T_AC, T_F, T_TGMIDY, T_CMIDY, T_DY, T_DY1, T_DYC, T_DY1C, T_AY, T_BY, T_CY, T_FB, T_FD, T_COUNT };
+// (T_FB, T_FD: latitude factor and addend of a separable Coriolis parameter, see Params::fa)
 
 // slots of a row record (shared memory, one record per latitude of the block's chunk)
 enum Rec {
@@ -80,6 +81,11 @@ struct Params {
     const void *f2d;    // (nrows, pitch) or null
     const void *hs;     // (nrows, pitch) or null
     const double *phi;  // M+3 (+ padding)
+    // separable Coriolis parameter (FM == 2), f[i, j] = fs_scale * ((fa[i] * tab[T_FB][j]) * fs_sa + tab[T_FD][j]) in exactly
+    // this order: Williamson case 2 (ic.py:126-133 of the reference: 2 Omega (-cos(phi) cos(theta) sin(alpha) + sin(theta) cos(alpha)))
+    // from two 1-D tables instead of an (M+3, N) array
+    const double *fa;   // M+3 (+ padding): the longitude factor
+    double fs_scale, fs_sa;
     const double *tab;  // T_COUNT x nrows
     const double *pre;  // nrows x kRowRec: dt-independent stage of the row records (prerec_kernel)
     const double *pred; // nrows x kRowDiff: the same for the FAST diffusion records, or null

@@ -74,6 +74,57 @@ def separable_rossby_haurwitz(latlon_grid: LatLonGrid) -> Dict[str, np.ndarray]:
     }
 
 
+class SeparableCoriolis:
+    """A Coriolis parameter of the form ``f[i, j] = scale * ((lon[i] * lat_b[j]) * sa + lat_d[j])``, evaluated in
+    exactly this order (every operation rounded): what the reference's Williamson case 2 builds as an (M+3, N)
+    array (ic.py:126-133: ``2 Omega (-cos(phi) cos(theta) sin(alpha) + sin(theta) cos(alpha))``).  The kernels
+    rebuild it per cell from the three 1-D tables, so such a state needs no 2-D Coriolis array on the device and
+    runs through the TMA-ring and resident kernels like a latitude-only one."""
+
+    def __init__(self, lon: np.ndarray, lat_b: np.ndarray, lat_d: np.ndarray, scale: float, sa: float):
+        self.lon = np.ascontiguousarray(lon, dtype=np.float64)
+        self.lat_b = np.ascontiguousarray(lat_b, dtype=np.float64)
+        self.lat_d = np.ascontiguousarray(lat_d, dtype=np.float64)
+        self.scale, self.sa = float(scale), float(sa)
+
+    def array(self) -> np.ndarray:
+        """The (M+3, N) array, formed as the reference forms it."""
+        return self.scale * ((self.lon[:, None] * self.lat_b[None, :]) * self.sa + self.lat_d[None, :])
+
+    def matches(self, f) -> bool:
+        f = np.asarray(f)
+        return f.shape == (len(self.lon), len(self.lat_b)) and bool(np.array_equal(f, self.array()))
+
+
+_ZGF_ALPHA = math.pi / 2  # ic.py:118
+
+
+def zonal_flow_coriolis(latlon_grid: LatLonGrid) -> SeparableCoriolis:
+    """The Coriolis parameter of the zonal geostrophic flow (reference ic.py:126-133) in separable form."""
+    th, ph = latlon_grid.theta1d, latlon_grid.phi1d
+    return SeparableCoriolis(-np.cos(ph), np.cos(th), np.sin(th) * np.cos(_ZGF_ALPHA), 2.0 * EARTH_CONSTANTS.omega, np.sin(_ZGF_ALPHA))
+
+
+def separable_zonal_flow(latlon_grid: LatLonGrid) -> Dict[str, np.ndarray]:
+    """Longitude / latitude factors of the zonal geostrophic flow (reference ic.py:119-154).  With
+    ``rot[i, j] = (ncp[i] * ct[j]) * sa + sca[j]`` (the rotated sine of latitude):
+
+        h[i, j] = h0 - (K * (rot * rot)) / g
+        u[i, j] = u0 * (cca[j] + (cp[i] * st[j]) * sa)
+        v[i, j] = (nu0 * sp[i]) * sa
+    """
+    a, om, g = EARTH_CONSTANTS.a, EARTH_CONSTANTS.omega, EARTH_CONSTANTS.g
+    alpha = _ZGF_ALPHA
+    u0 = 2.0 * math.pi * a / (12.0 * 24.0 * 3600.0)
+    th, ph = latlon_grid.theta1d, latlon_grid.phi1d
+    return {
+        "h0": np.float64(2.94e4 / g), "g": np.float64(g), "K": np.float64(a * om * u0 + 0.5 * (u0 ** 2.0)),
+        "u0": np.float64(u0), "sa": np.float64(np.sin(alpha)),
+        "ncp": -np.cos(ph), "cp": np.cos(ph), "sp_nu0": -u0 * np.sin(ph),
+        "ct": np.cos(th), "st": np.sin(th), "sca": np.sin(th) * np.cos(alpha), "cca": np.cos(th) * np.cos(alpha),
+    }
+
+
 def rossby_haurwitz_window(latlon_grid: LatLonGrid, j_begin: int, n_local: int):
     """h, u, v of the Rossby-Haurwitz wave on latitudes ``j_begin .. j_begin+n_local-1`` only,
     shape (M+3, n_local): bit-identical to the same columns of ``get_initial_conditions``

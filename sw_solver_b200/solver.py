@@ -18,6 +18,7 @@ fallback: without a CUDA device every entry point raises.
 
 import ctypes
 import math
+import os
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -26,8 +27,11 @@ import torch
 from . import _lib
 from ._lib import DTYPES, MODES, SwbConfig, SwbError, SwbStatus, SwbTables, check
 from .grid import CartesianGrid, LatLonGrid
-from .ic import ICType, coriolis_latitude, get_initial_conditions
+from .ic import ICType, SeparableCoriolis, coriolis_latitude, get_initial_conditions, zonal_flow_coriolis
 from .utils import EARTH_CONSTANTS, FloatArray2D, FloatT
+
+#: grids with more cells than this get their initial state assembled on the device (nothing M x N on the host)
+_DEVICE_IC_CELLS = 1 << 24
 
 #: arithmetic mode used when a caller does not choose: "fast" (FMA contraction, shared
 #: reciprocals; <= 1e-12 from numpy) or "strict" (bit-identical to numpy, slower)
@@ -81,7 +85,8 @@ def diffusion_weights_lat(cart_grid: CartesianGrid) -> Tuple[np.ndarray, np.ndar
 
 
 def latitude_tables(latlon_grid: LatLonGrid, cart_grid: CartesianGrid, f_lat: Optional[np.ndarray],
-                    use_diffusion: bool, j_begin: int = 0, n_local: Optional[int] = None) -> Dict[str, np.ndarray]:
+                    use_diffusion: bool, j_begin: int = 0, n_local: Optional[int] = None,
+                    f_sep: Optional[SeparableCoriolis] = None) -> Dict[str, np.ndarray]:
     """The 1-D tables ``swb_set_tables`` takes, sliced to a band (include/swb200.h)."""
     N = latlon_grid.N
     n_local = N if n_local is None else n_local
@@ -101,8 +106,12 @@ def latitude_tables(latlon_grid: LatLonGrid, cart_grid: CartesianGrid, f_lat: Op
         full["f_lat"] = np.asarray(f_lat, dtype=np.float64)
     if use_diffusion:
         full["Ay"], full["By"], full["Cy"] = diffusion_weights_lat(cart_grid)
+    if f_sep is not None:
+        full["fsep_lat_b"], full["fsep_lat_d"] = f_sep.lat_b, f_sep.lat_d
     out = {k: np.ascontiguousarray(v[sl], dtype=np.float64) for k, v in full.items()}
     out["phi"] = np.ascontiguousarray(latlon_grid.phi1d, dtype=np.float64)
+    if f_sep is not None:
+        out["fsep_lon"] = f_sep.lon
     return out
 
 
@@ -188,19 +197,30 @@ class Stepper:
         #: (2, 3, M+3, n_local) view of the two buffer sets in the reference's index order
         self.buf = self._raw[..., : M + 3].transpose(-1, -2)
 
-        # Coriolis: a latitude vector (length N, or the band's window) or a genuinely 2-D field
-        if isinstance(f, (np.ndarray, torch.Tensor)) and f.ndim == 1:
-            f_lat = np.ascontiguousarray(f.detach().cpu().numpy() if isinstance(f, torch.Tensor) else f, dtype=np.float64)
-        else:
-            f_lat = _latitude_only(f) if layout == "reference" else None
-        if f_lat is not None and len(f_lat) == self.n_local != N:  # the band's window: place it
-            full = np.zeros(N)
-            full[self.j_begin:self.j_begin + self.n_local] = f_lat
-            f_lat = full
         if isinstance(hs, torch.Tensor):
             hs_flat = not bool((hs != 0).any())  # flat topography only subtracts an exact zero
         else:
             hs_flat = hs is None or not np.any(np.asarray(hs))
+        # Coriolis: a latitude vector (length N, or the band's window), a separable parameter (tables), or a
+        # genuinely 2-D field
+        f_sep: Optional[SeparableCoriolis] = None
+        if isinstance(f, SeparableCoriolis):
+            f_sep, f_lat = f, None
+        elif isinstance(f, (np.ndarray, torch.Tensor)) and f.ndim == 1:
+            f_lat = np.ascontiguousarray(f.detach().cpu().numpy() if isinstance(f, torch.Tensor) else f, dtype=np.float64)
+        else:
+            f_lat = _latitude_only(f) if layout == "reference" else None
+            if f_lat is None and layout == "reference" and isinstance(f, np.ndarray) and os.environ.get("SWB_FSEP", "1") != "0":
+                # the reference's zonal-flow Coriolis array (ic.py:126-133), recognised bit for bit: rebuilt in-kernel
+                cand = zonal_flow_coriolis(latlon_grid)
+                if cand.matches(f):
+                    f_sep = cand
+        if f_sep is not None and (not hs_flat or dtype != "float64"):
+            f, f_sep = f_sep.array(), None  # topography / fp32: the array kernels (fp32 then refuses, as for any 2-D f)
+        if f_lat is not None and len(f_lat) == self.n_local != N:  # the band's window: place it
+            full = np.zeros(N)
+            full[self.j_begin:self.j_begin + self.n_local] = f_lat
+            f_lat = full
 
         cfg = SwbConfig()
         cfg.struct_bytes = ctypes.sizeof(SwbConfig)
@@ -209,7 +229,10 @@ class Stepper:
         cfg.j_first, cfg.j_last, cfg.pitch = int(band["j_first"]), int(band["j_last"]), self.pitch
         cfg.dtype, cfg.mode = DTYPES[dtype], MODES[mode]
         cfg.use_diffusion = int(self.use_diffusion)
-        cfg.f_is_2d = int(f_lat is None)
+        cfg.f_is_2d = int(f_lat is None and f_sep is None)
+        cfg.f_sep = int(f_sep is not None)
+        if f_sep is not None:
+            cfg.fsep_scale, cfg.fsep_sa = f_sep.scale, f_sep.sa
         cfg.has_hs = int(not hs_flat)
         cfg.device = self.device.index
         cfg.log_capacity = int(log_capacity)
@@ -222,7 +245,7 @@ class Stepper:
         self._ctx = ctypes.c_void_p()
         check(self.lib.swb_create(ctypes.byref(self._ctx), ctypes.byref(cfg)))
 
-        tabs = latitude_tables(latlon_grid, cart_grid, f_lat, self.use_diffusion, self.j_begin, self.n_local)
+        tabs = latitude_tables(latlon_grid, cart_grid, f_lat, self.use_diffusion, self.j_begin, self.n_local, f_sep)
         ct = SwbTables()
         for name in _lib.TABLE_FIELDS:
             arr = tabs.get(name)
@@ -233,7 +256,7 @@ class Stepper:
         self._copy_stream: Optional[torch.cuda.Stream] = None
         self._stage_pair: List[Optional[torch.Tensor]] = [None, None]
         self._upload((h, u, v), [self._raw[0, k] for k in range(3)])
-        self._f2d = self._upload((f,), [None])[0] if f_lat is None else None
+        self._f2d = self._upload((f,), [None])[0] if (f_lat is None and f_sep is None) else None
         self._hs = None if hs_flat else self._upload((hs,), [None])[0]
 
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
@@ -580,8 +603,10 @@ def _operator_key(latlon_grid, f, hs, use_diffusion, mode, dev):
         hs_flat = not bool((hs != 0).any())
     else:
         hs_flat = hs is None or not np.any(np.asarray(hs))
+    sep = f_lat is None and isinstance(f, np.ndarray) and f.ndim == 2 and hs_flat and os.environ.get("SWB_FSEP", "1") != "0" \
+        and zonal_flow_coriolis(latlon_grid).matches(f)
     return (latlon_grid.M, latlon_grid.N, mode, dev.index, bool(use_diffusion), f_lat is None and f is not None, not hs_flat,
-            None if f_lat is None else f_lat.tobytes())
+            None if f_lat is None else f_lat.tobytes(), bool(sep))
 
 
 def lax_wendroff_update(latlon_grid: LatLonGrid, cart_grid: CartesianGrid, dt: FloatT, f: FloatArray2D,
@@ -764,12 +789,15 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
     j_begin, n_local = (band["j_begin"], band["n_local"]) if band else (0, N)
 
     layout = "reference"
-    if ic_type == ICType.RossbyHaurwitzWave and (world > 1 or (M + 3) * N > (1 << 24)):
+    if world > 1 or (M + 3) * N > _DEVICE_IC_CELLS:
         # large grids / bands: assemble the state on the device from the 1-D factors
         # (bit-identical to get_initial_conditions; nothing of size M x N on the host)
-        from .bands import rossby_haurwitz_band
+        from .bands import rossby_haurwitz_band, zonal_flow_band
 
-        h, u, v, f = rossby_haurwitz_band(latlon_grid, j_begin, n_local, dev)
+        if ic_type == ICType.RossbyHaurwitzWave:
+            h, u, v, f = rossby_haurwitz_band(latlon_grid, j_begin, n_local, dev)
+        else:
+            h, u, v, f = zonal_flow_band(latlon_grid, j_begin, n_local, dev)
         layout = "device"
     else:
         h, u, v, f = get_initial_conditions(ic_type, latlon_grid)
@@ -887,8 +915,10 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
             for idx, name in enumerate(("h", "u", "v")):
                 save_data[name] = np.stack([np.asarray(s[idx]) for s in keep], axis=2)
             save_data["t"] = np.asarray(tsave)
-            save_data["phi"] = latlon_grid.phi
-            save_data["theta"] = latlon_grid.theta
+            # real, writable (M+3, N) arrays like the reference's (numpy.py:570-571), also on grids whose
+            # LatLonGrid keeps its 2-D attributes as broadcast views
+            save_data["phi"] = np.array(latlon_grid.phi)
+            save_data["theta"] = np.array(latlon_grid.theta)
     finally:
         st.close()
     return hh, uu, vv

@@ -161,3 +161,13 @@ def test_device_side_initial_state_is_bit_identical():
         for a, b in ((hd, h), (ud, u), (vd, v)):
             assert np.array_equal(a.cpu().numpy().T, b[:, jb:jb + nl])
         assert f.shape == (ll.N,)
+    # the zonal geostrophic flow (reference ic.py:119-154): state on the device, Coriolis parameter as tables
+    from sw_solver_b200.bands import zonal_flow_band
+
+    for M, N, jb, nl in ((96, 64, 0, 64), (333, 98, 17, 40), (1440, 720, 700, 20)):
+        ll = LatLonGrid(M, N)
+        h, u, v, f2d = get_initial_conditions(ICType.ZonalGeostrophicFlow, ll)
+        hd, ud, vd, fs = zonal_flow_band(ll, jb, nl, "cuda")
+        for a, b in ((hd, h), (ud, u), (vd, v)):
+            assert np.array_equal(a.cpu().numpy().T, b[:, jb:jb + nl])
+        assert fs.matches(f2d)

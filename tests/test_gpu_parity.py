@@ -185,6 +185,66 @@ def test_operator_calls_reuse_one_context():
     assert min(times) < 0.5 * (t1 - t0) and min(times) < 5e-3
 
 
+@pytest.mark.parametrize("M,N,diff,mode,nsteps", [
+    (5, 6, True, "strict", 4), (37, 24, False, "strict", 12), (64, 48, True, "fast", 20), (360, 180, False, "fast", 30),
+    (333, 97, True, "fast_guarded", 15), (360, 180, True, "strict", 10), (1440, 720, False, "fast", 12), (1440, 720, True, "fast", 12),
+])
+def test_separable_coriolis_equals_the_array_path(M, N, diff, mode, nsteps, monkeypatch):
+    """Williamson case 2: the reference builds its Coriolis parameter as an (M+3, N) array (ic.py:126-133).  The
+    library recognises that array bit for bit and rebuilds it per cell from three 1-D tables in the reference's
+    operation order (FM = 2: TMA ring and resident kernels apply).  Every kernel family must then give the SAME
+    bits as the 2-D-array kernels (SWB_FSEP=0), state and dt history, and STRICT must equal the oracle."""
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    h, u, v, f = get_initial_conditions(ICType.ZonalGeostrophicFlow, ll)
+    runs = {}
+    for tag, env in (("array", {"SWB_FSEP": "0"}), ("tables-launch", {"SWB_RESIDENT": "0"}), ("tables-launch-ldg", {"SWB_RESIDENT": "0", "SWB_KERNEL": "ldg"}),
+                     ("tables-resident", {"SWB_RESIDENT": "1"})):
+        for k, val in env.items():
+            monkeypatch.setenv(k, val)
+        st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=1e12, use_diffusion=diff, mode=mode, log_capacity=nsteps)
+        assert bool(st.cfg.f_sep) == (tag != "array") and bool(st.cfg.f_is_2d) == (tag == "array")
+        if tag == "tables-resident":
+            assert st.resident
+        st.enqueue(nsteps)
+        s = st.status()
+        assert s.steps == nsteps and s.error == 0
+        runs[tag] = (st.to_numpy(), st.read_log(nsteps), s.time)
+        st.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    q0, log0, t0 = runs["array"]
+    for tag in runs:
+        q1, log1, t1 = runs[tag]
+        assert _bits(log0[0], log1[0]) and t0 == t1, tag
+        assert all(_bits(a, b) for a, b in zip(q0, q1)), (tag, [_worst(a, b) for a, b in zip(q0, q1)])
+    if mode == "strict":
+        og = so.OracleGrid(M, N)
+        ho, uo, vo, fo = so.initial_conditions(1, og)
+        ho, uo, vo = (np.ascontiguousarray(x) for x in (ho, uo, vo))
+        stp = so.Stepper(og, fo, None, diff)
+        t = 0.0
+        for _ in range(nsteps):
+            _, t = stp.step(ho, uo, vo, 0.5, t, 1e12)
+        assert t == t0 and _bits(q0[0], ho) and _bits(q0[1], uo) and _bits(q0[2], vo)
+
+
+def test_solve_zonal_flow_on_a_large_grid_uses_tables():
+    """solve() with the zonal flow beyond the host-array limit: state assembled on the device, Coriolis
+    parameter as tables -- equal, bit for bit, to the host-array route on the same grid."""
+    from sw_solver_b200 import solver as sv
+
+    M, N = 2000, 1000
+    h1, u1, v1 = solve(M, N, ICType.ZonalGeostrophicFlow, 0.0005, 0.5, False, mode="fast")
+    limit = sv._DEVICE_IC_CELLS
+    try:
+        sv._DEVICE_IC_CELLS = 1000  # force the device-side route
+        h2, u2, v2 = solve(M, N, ICType.ZonalGeostrophicFlow, 0.0005, 0.5, False, mode="fast")
+    finally:
+        sv._DEVICE_IC_CELLS = limit
+    assert _bits(h1, h2) and _bits(u1, u2) and _bits(v1, v2)
+
+
 def test_multi_step_driver_strict_is_bit_exact(golden_multi_step):
     """Full `solve` runs saved every step: t, phi, theta, h, u, v and the returned state."""
     g = golden_multi_step

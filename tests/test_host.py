@@ -138,7 +138,7 @@ def test_c_abi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name)
     assert L.swb_abi_version() == 3
-    assert ctypes.sizeof(_lib.SwbStatus) == 56 and ctypes.sizeof(_lib.SwbConfig) == 18 * 4 + 8 * 8
+    assert ctypes.sizeof(_lib.SwbStatus) == 56 and ctypes.sizeof(_lib.SwbConfig) == 20 * 4 + 10 * 8
 
 
 def test_no_cpu_fallback():
