@@ -1,8 +1,8 @@
-"""Regenerates profiles/r1_step_kernel_ncu.md, profiles/r1_launches.md and profiles/traffic.json
-from the artefacts scripts/gpu_prof.sh leaves in gpurun_out/ (run here, where ncu reads reports
-without a GPU):
+"""Regenerates profiles/r<N>_step_kernel_ncu.md, profiles/r<N>_launches.md and profiles/traffic.json
+from the artefacts scripts/gpu_prof.sh (round 1) / scripts/r2_final1.sh (round 2) leave in gpurun_out/
+(run here, where ncu reads reports without a GPU):
 
-    python scripts/summarize_profiles.py
+    python scripts/summarize_profiles.py [--round 2]
 """
 import collections
 import csv
@@ -14,7 +14,13 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
-CMD = "python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-small"
+import sys
+
+ROUND = int(sys.argv[sys.argv.index("--round") + 1]) if "--round" in sys.argv else 1
+CMD = "python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-small" + (" --no-fp32 --no-sustained" if ROUND >= 2 else "")
+REP = "prof3.ncu-rep" if ROUND == 1 else f"r{ROUND}_prof_headline.ncu-rep"
+PLAIN = "plain2.log" if ROUND == 1 else f"r{ROUND}_plain2.log"
+LAUNCHES = f"launches_r{ROUND}.csv"
 
 WANT = [
     "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -37,13 +43,13 @@ def raw_page(rep):
 
 
 def step_kernel():
-    hdr, units, launches = raw_page(os.path.join(OUT, "prof3.ncu-rep"))
+    hdr, units, launches = raw_page(os.path.join(OUT, REP))
     unit = dict(zip(hdr, units))
-    out = ["# ncu --set full, fused step kernel (round 1, final build)", "",
-           "Command (on a B200 via gpurun, `scripts/gpu_prof.sh`; the same command exited 0 without ncu",
+    out = [f"# ncu --set full, fused step kernel (round {ROUND}, final build)", "",
+           f"Command (on a B200 via gpurun, `{'scripts/gpu_prof.sh' if ROUND == 1 else 'scripts/r2_final1.sh'}`; the same command exited 0 without ncu",
            "immediately before); regenerate this file with `python scripts/summarize_profiles.py`:", "",
            "    ncu --set full --clock-control none --import-source on -k regex:march_kernel -s 3 -c 2 \\",
-           f"        -o gpurun_out/prof3 {CMD}", "",
+           f"        -o gpurun_out/{REP[:-8]} {CMD}", "",
            "Workload: Rossby-Haurwitz 16384 x 8192 fp64, diffusion off, mode fast.",
            "Algorithmic bytes per launch: 48 B x 134,193,150 updates = 6.441 GB."]
     traffic = None
@@ -66,21 +72,21 @@ def step_kernel():
                 except ValueError:
                     pass
         body.append(f"| dram traffic (read + write) / algorithmic bytes | {tr / 6441271200.0:.4f} | |")
-    plain = json.loads(open(os.path.join(OUT, "plain2.log")).read().strip().splitlines()[-1])
+    plain = json.loads(open(os.path.join(OUT, PLAIN)).read().strip().splitlines()[-1])
     out += [f"Measured DRAM traffic (read + write) of launch 0: {traffic / 1e9:.3f} GB = {traffic / 6441271200.0:.3f} x algorithmic.",
             f"CUDA-event time of the same command without ncu (bench.py, {plain['steps']} steps): {plain['ms_per_step']:.3f} ms/step,",
             f"roofline fraction {plain['roofline']['frac']:.3f} of the measured {plain['roofline']['peak']} GB/s (burst; sustained runs of 100+ steps under",
             "`sw_power_cap` are 4-8 % slower, see DESIGN.md).", "",
             "SASS of this kernel: `UTMALDG.3D` (one TMA box per tile for h, u, v), `SYNCS.ARRIVE.TRANS64` /",
             "`SYNCS.PHASECHK.TRANS64.TRYWAIT` (mbarrier), `LDS.128`, `STG.E.128`, `SHFL`, `DFMA/DADD/DMUL`, `MUFU.RCP64H/RSQ64H`."]
-    open(os.path.join(PROF, "r1_step_kernel_ncu.md"), "w").write("\n".join(out + body) + "\n")
+    open(os.path.join(PROF, f"r{ROUND}_step_kernel_ncu.md"), "w").write("\n".join(out + body) + "\n")
     tj = {"16384x8192:fast": traffic,
-          "source": "profiles/r1_step_kernel_ncu.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"}
+          "source": f"profiles/r{ROUND}_step_kernel_ncu.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"}
     json.dump(tj, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
 
 
 def launch_list():
-    rows = [r for r in csv.reader(open(os.path.join(OUT, "launches_r1.csv"))) if r and not r[0].startswith("==")]
+    rows = [r for r in csv.reader(open(os.path.join(OUT, LAUNCHES))) if r and not r[0].startswith("==")]
     hdr = rows[0]
     ix = {h: i for i, h in enumerate(hdr)}
     data = [r for r in rows[1:] if len(r) == len(hdr) and r[ix["Metric Name"]] == "gpu__time_duration.sum"]
@@ -99,7 +105,7 @@ def launch_list():
     total = sum(ns)
     march = sum(v for n, v in zip(names, ns) if "march_kernel" in n)
     fix = sum(v for n, v in zip(names, ns) if "cfl_fixup" in n)
-    out = ["# ncu launch list (round 1, final build)", "",
+    out = [f"# ncu launch list (round {ROUND}, final build)", "",
            f"    ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv {CMD}", "",
            "Per time step ONE `march_kernel` launch followed by ONE `cfl_fixup_kernel` launch (the CFL filter's fix-up: every block",
            "reads a mask and returns).  Everything before the first `march_kernel` is set-up (device-side assembly of the initial",
@@ -111,7 +117,7 @@ def launch_list():
     out += ["", "| id | kernel | ns |", "|---|---|---|"]
     for k, (n, v) in enumerate(zip(names, ns)):
         out.append(f"| {k} | `{n}` | {v:.0f} |")
-    open(os.path.join(PROF, "r1_launches.md"), "w").write("\n".join(out) + "\n")
+    open(os.path.join(PROF, f"r{ROUND}_launches.md"), "w").write("\n".join(out) + "\n")
 
 
 if __name__ == "__main__":

@@ -33,6 +33,9 @@ from .utils import EARTH_CONSTANTS, FloatArray2D, FloatT
 #: grids with more cells than this get their initial state assembled on the device (nothing M x N on the host)
 _DEVICE_IC_CELLS = 1 << 24
 
+#: save_data snapshots are kept on the device up to this many bytes (and a quarter of the free memory), then on the host
+_SNAPSHOT_DEVICE_BUDGET = 16 << 30
+
 #: arithmetic mode used when a caller does not choose: "fast" (FMA contraction, shared
 #: reciprocals; <= 1e-12 from numpy) or "strict" (bit-identical to numpy, slower)
 DEFAULT_MODE = "fast"
@@ -823,12 +826,24 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
         snap_status: List[torch.Tensor] = []
         stage = None  # device staging of one snapshot in the reference layout (K4)
 
+        # One band: snapshots stay ON THE DEVICE while they fit a budget (a quarter of the free memory, at most
+        # 16 GB) and are assembled into the reference's (M+1, N, nsave+1) arrays there -- one strided gather
+        # kernel and one D2H per field at the end instead of a host-side np.stack (which, on 742 snapshots of the
+        # 1-degree grid, took 30 times as long as the time loop).  Beyond the budget, and for bands (rank 0 gathers
+        # host copies), every snapshot goes to pinned host memory as it is taken.
+        free_bytes = torch.cuda.mem_get_info(dev)[0]
+        dev_budget = min(free_bytes // 4, _SNAPSHOT_DEVICE_BUDGET) if world == 1 else 0
+        dev_bytes = 0
+
         def take_snapshot(current: int) -> torch.Tensor:
-            nonlocal stage
+            nonlocal stage, dev_bytes
+            if dev_bytes + snap_bytes <= dev_budget:
+                dev_bytes += snap_bytes
+                return st.snapshot(current, None)[:, 1:-1, :]  # numpy.py:488-492: h[1:-1, :]
             stage = st.snapshot(current, stage)
             pinned = arena.take_f64((3, M + 1, n_local))
             for k in range(3):
-                pinned[k].copy_(stage[k, 1:-1, :], non_blocking=True)  # numpy.py:488-492: h[1:-1, :]
+                pinned[k].copy_(stage[k, 1:-1, :], non_blocking=True)
             return pinned
 
         if save_interval > 0:
@@ -912,8 +927,15 @@ def solve(num_lon_pts: int, num_lat_pts: int, ic_type: ICType, sim_days: float, 
             hh, uu, vv, keep = _gather_bands(dist, dev, band, world, N, (hh, uu, vv), keep)
 
         if save_interval > 0 and rank == 0:
+            on_dev = [s for s in keep if isinstance(s, torch.Tensor) and s.is_cuda]
             for idx, name in enumerate(("h", "u", "v")):
-                save_data[name] = np.stack([np.asarray(s[idx]) for s in keep], axis=2)
+                parts = []
+                if on_dev:  # (M+1, N, k) assembled on the device, one D2H
+                    parts.append(torch.stack([s[idx] for s in on_dev], dim=2).cpu().numpy())
+                rest = [np.asarray(s[idx]) for s in keep[len(on_dev):]]
+                if rest:
+                    parts.append(np.stack(rest, axis=2))
+                save_data[name] = parts[0] if len(parts) == 1 else np.concatenate(parts, axis=2)
             save_data["t"] = np.asarray(tsave)
             # real, writable (M+3, N) arrays like the reference's (numpy.py:570-571), also on grids whose
             # LatLonGrid keeps its 2-D attributes as broadcast views

@@ -371,6 +371,29 @@ def test_driver_semantics_match_reference():
     assert _bits(sd["t"], ref["t"]) and _bits(sd["h"], ref["h"]) and _bits(sd["v"], ref["v"])
 
 
+def test_save_data_is_the_same_wherever_the_snapshots_wait(monkeypatch):
+    """Snapshots are kept on the device while they fit a budget and assembled there, else copied to pinned host
+    memory as they are taken: `save_data` must not depend on it (all on the device, all on the host, mixed)."""
+    from sw_solver_b200 import solver as sv
+
+    outs = []
+    for budget in (16 << 30, 0, 5 * 3 * 65 * 48 * 8):
+        monkeypatch.setattr(sv, "_SNAPSHOT_DEVICE_BUDGET", budget)
+        sd = {"interval": 3}
+        h, u, v = solve(64, 48, ICType.RossbyHaurwitzWave, 0.02, 0.5, True, save_data=sd, mode="strict")
+        outs.append((h, u, v, sd))
+    ref = outs[0][3]
+    assert ref["h"].shape[:2] == (65, 48) and ref["h"].shape[2] == len(ref["t"]) > 8
+    ho, uo, vo = so.solve(64, 48, 0, 0.02, 0.5, True, save_data=(sdo := {"interval": 3}))
+    for name in ("h", "u", "v", "t"):
+        assert _bits(ref[name], sdo[name]), name
+    for h, u, v, sd in outs[1:]:
+        assert _bits(h, outs[0][0]) and _bits(u, outs[0][1]) and _bits(v, outs[0][2])
+        for name in ("h", "u", "v", "t", "phi", "theta"):
+            assert _bits(sd[name], ref[name]), name
+        assert sd["h"].flags.c_contiguous and sd["phi"].flags.writeable
+
+
 def test_print_interval_output(capsys):
     solve(10, 10, ICType.RossbyHaurwitzWave, 0.02, 0.5, True, print_interval=3, mode="strict")
     ours = capsys.readouterr().out
