@@ -260,7 +260,9 @@ int launch_one(swb_ctx *c, cudaStream_t st)
     const int rows = p.jl_last - p.jl_first + 1;
     const bool f32 = cfg.dtype == SWB_F32;
     const int W = (c->use_tma && !f32 && !cfg.use_diffusion && !cfg.f_sep) ? kTmaVariants[c->tma_variant].W : kWarpsPerBlock;
-    dim3 grid((unsigned)((p.nstrips + W - 1) / W), (unsigned)((rows + p.chunk - 1) / p.chunk));
+    unsigned gy = (unsigned)((rows + p.chunk - 1) / p.chunk);
+    if (p.n_big > 0) gy = (unsigned)(p.n_big + (rows - p.n_big * p.chunk + p.chunk_small - 1) / p.chunk_small);
+    dim3 grid((unsigned)((p.nstrips + W - 1) / W), gy);
     if (c->linked && !p.fixed) {  // the maxima of all bands' previous step -> this step's slot
         CK(launch_chain(gather_kernel, dim3(1), dim3(32), 0, st, p));
         c->launches++;
@@ -766,6 +768,7 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
     if (!c || !h0 || !u0 || !v0 || !h1 || !u1 || !v1) return fail(SWB_E_INVALID, "swb_bind_state: null state pointer");
     if (c->cfg.f_is_2d && !f2d) return fail(SWB_E_INVALID, "swb_bind_state: f_is_2d set but no f array");
     if (c->cfg.has_hs && !hs) return fail(SWB_E_INVALID, "swb_bind_state: has_hs set but no hs array");
+    ON_DEVICE(c);  // tensor maps, function attributes and the occupancy query below belong to the context's device
     Params &p = c->prm;
     void *all[8] = {h0, u0, v0, h1, u1, v1, const_cast<void *>(f2d), const_cast<void *>(hs)};
     for (void *q : all)
@@ -810,7 +813,6 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
         const bool filter_ok = !f32 && !c->cfg.use_diffusion && !c->cfg.f_sep && c->cfg.mode != SWB_STRICT && c->tma_variant == kDefaultTmaVariant;
         c->cfl_filter = filter_ok && cells >= 4000000LL;
         if (const char *e = getenv("SWB_CFL_FILTER")) c->cfl_filter = filter_ok && atoi(e) != 0;
-        ON_DEVICE(c);
         for (int s = 0; s < 2; ++s) {
             // (fp64 with diffusion: the box also carries the star's two columns either side)
             int rc = make_map(&c->maps.in[s], p.buf[s][0], (uint64_t)(p.M + 3), (uint64_t)p.nrows, (uint64_t)p.pitch, (uint64_t)(s ? fs1 : fs0),
@@ -819,6 +821,26 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
         }
     }
     p.chunk = c->base_chunk;
+    // Guided tail (grids of several waves of blocks): the last block rows march 16 latitudes instead of 64.  The
+    // hardware dispatches blocks in order, so the short marches run last and the launch drains in a quarter of the
+    // time a wave of long marches takes.  SWB_TAIL_ROWS (0 = off) / SWB_TAIL_CHUNK override.
+    p.n_big = 0;
+    p.chunk_small = 16;
+    {
+        const int rows = p.jl_last - p.jl_first + 1;
+        const int gx = (p.nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock;
+        const long long slots = (long long)c->sm_count * 2;
+        long long tail_rows = 0;
+        // (about one wave of long marches: measured at 7200 x 3600, 0 / 192 / 320 / 640 tail rows give 274.1 / 266.4 / 260.3 /
+        // 256.3 us per step; at 16384 x 8192, 0 / 128 / 256 rows 1263 / 1247 / 1246 us; 8- or 32-row tails are no better)
+        if (p.chunk == 64 && (long long)gx * ((rows + 63) / 64) >= 3 * slots) tail_rows = 64 * ((2 * slots + gx) / (2 * gx));
+        if (const char *e = getenv("SWB_TAIL_ROWS")) tail_rows = atoll(e);
+        if (const char *e = getenv("SWB_TAIL_CHUNK")) p.chunk_small = atoi(e) > 0 ? atoi(e) : 16;
+        if (tail_rows > 0 && tail_rows < rows && p.chunk_small < p.chunk) {
+            p.n_big = (int)((rows - tail_rows) / p.chunk);
+            if (p.n_big < 1) p.n_big = 0;
+        }
+    }
     return setup_resident(c);
 }
 

@@ -991,31 +991,18 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             // warp-uniform; the resident kernel's fast body serves every complete tile
             const bool hot_tile = (RES && !STREAM) ? (j0 + R <= jb && j0 >= res_lo && j0 + R - 1 <= res_hi) : (j0 >= plain_lo && j0 + R - 1 <= plain_hi);
             if (hot_tile) {
-                // One row of the tile with a COMPILE-TIME row index: with the ring-fed star `#pragma unroll` alone left
-                // the loop rolled (ncu, round 1: the `rr == R-1` test and the ring_row selects executed per row, 20 % of
-                // all instructions were IMAD address arithmetic) -- the rows are spelled out instead.
-                auto hot_row = [&](auto rr_c) {
-                    constexpr int rr = decltype(rr_c)::value;
+                // (With the ring-fed star the compiler leaves this loop rolled -- ncu, round 1: the `rr == R-1` test and the
+                // ring_row selects execute per row, 20 % of that kernel's instructions are IMAD address arithmetic.  Spelling the
+                // four rows out (compile-time row index) was tried in round 2: the spills grow from 16 / 52 to 144 / 212 bytes
+                // and every diffusion grid gets SLOWER -- 7200 x 3600 454 -> 470 us, 1440 x 720 resident 25.9 -> 27.9 us.)
+                // (Unrolling by two instead of four: 234 instead of 248 registers for the headline kernel, and slower --
+                // 16384 x 8192 1333 -> 1356 us, 7200 x 3600 274 -> 281 us, fp32 740 -> 762 us per step.)
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
                     if (SSTAR && rr == R - 1) turn_ring();
                     // the streamed row rr is latitude jl+1: jl-2, jl-1, jl, jl+2 are rows rr-3, rr-2, rr-1, rr+1
                     const StarRows<V2> sr{ring_row(rr - 3), ring_row(rr - 2), ring_row(rr - 1), ring_row(rr + 1)};
                     do_row(HotTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true, SSTAR ? sr : no_star);
-                };
-#ifdef SWB_SSTAR_SPELLED
-                if constexpr (SSTAR) {  // (R == 4)
-                    hot_row(std::integral_constant<int, 0>());
-                    hot_row(std::integral_constant<int, 1>());
-                    hot_row(std::integral_constant<int, 2>());
-                    hot_row(std::integral_constant<int, 3>());
-                } else
-#endif
-                {
-#pragma unroll
-                    for (int rr = 0; rr < R; ++rr) {
-                        if (SSTAR && rr == R - 1) turn_ring();
-                        const StarRows<V2> sr{ring_row(rr - 3), ring_row(rr - 2), ring_row(rr - 1), ring_row(rr + 1)};
-                        do_row(HotTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true, SSTAR ? sr : no_star);
-                    }
                 }
                 if (CFLF) {
                     if (__any_sync(0xffffffffu, trig)) {  // rare: exact keys of the tile's cells, from the values just stored

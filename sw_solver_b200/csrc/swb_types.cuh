@@ -98,6 +98,8 @@ struct Params {
     int jl_first, jl_last;  // local latitude rows updated by this context (inclusive)
     int pole_s, pole_n;     // local row 0 / nrows-1 is the global copy row 0 / N-1
     int chunk;              // latitudes marched by one warp
+    int n_big, chunk_small; // march_kernel: block rows 0 .. n_big-1 march `chunk` latitudes, the rest `chunk_small` (the short
+                            // marches are dispatched last and shorten the tail of the launch); n_big == 0: every block row `chunk`
     int nstrips;            // warps needed along longitude
     int launch;             // launch index L (mod 3 cycle)
     int nsteps;             // resident_kernel: time steps run by this one launch

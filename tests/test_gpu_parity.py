@@ -394,6 +394,29 @@ def test_save_data_is_the_same_wherever_the_snapshots_wait(monkeypatch):
         assert sd["h"].flags.c_contiguous and sd["phi"].flags.writeable
 
 
+def test_contexts_leave_the_current_device_alone():
+    """Every ABI call works on its context's device and restores the caller's: a Stepper on cuda:1 must not move
+    torch's (and the runtime's) current device, and gives the same bits as on cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.cuda.set_device(0)
+    ll = LatLonGrid(96, 64)
+    cg = CartesianGrid(ll)
+    h, u, v, f = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+    out = []
+    for dev in ("cuda:0", "cuda:1"):
+        st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=1e9, use_diffusion=True, mode="fast", device=dev)
+        assert torch.cuda.current_device() == 0
+        st.enqueue(12)
+        s = st.status()
+        out.append(st.to_numpy())
+        st.close()
+        assert torch.cuda.current_device() == 0 and s.steps == 12
+        x = torch.ones(4, device="cuda")  # lands on the current device
+        assert x.device.index == 0
+    assert all(_bits(a, b) for a, b in zip(out[0], out[1]))
+
+
 def test_print_interval_output(capsys):
     solve(10, 10, ICType.RossbyHaurwitzWave, 0.02, 0.5, True, print_interval=3, mode="strict")
     ours = capsys.readouterr().out
@@ -661,6 +684,21 @@ def test_cfl_filter_is_exact(monkeypatch):
         assert all(_bits(a, b) for a, b in zip(q0, q1))
         if rough:
             assert np.ptp(log0[0]) > 1e-3 * log0[0].mean()  # dt really moved: the maxima were not static
+
+
+def test_guided_tail_is_bit_identical(monkeypatch):
+    """march_kernel's last block rows may march fewer latitudes than the others (they are dispatched last and
+    shorten the tail of the launch).  Any such split is the same arithmetic: same bits, state and dt history."""
+    for M, N, diff, mode in ((1440, 720, False, "fast"), (500, 260, True, "fast_guarded"), (333, 97, False, "strict")):
+        ref, tr_ref, log_ref, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, diff, mode, [4, 9], 1e12, False, monkeypatch,
+                                               {"SWB_CHUNK": "16", "SWB_TAIL_ROWS": "0"})
+        for env in ({"SWB_CHUNK": "16", "SWB_TAIL_ROWS": "50", "SWB_TAIL_CHUNK": "4"}, {"SWB_CHUNK": "16", "SWB_TAIL_ROWS": "23", "SWB_TAIL_CHUNK": "8"},
+                    {"SWB_CHUNK": "32", "SWB_TAIL_ROWS": "40", "SWB_TAIL_CHUNK": "12"}):
+            res, tr, log, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, diff, mode, [4, 9], 1e12, False, monkeypatch, env)
+            assert tr == tr_ref, env
+            assert all(_bits(a, b) for a, b in zip(log, log_ref)), env
+            for name, a, b in zip("huv", res, ref):
+                assert _bits(a, b), (env, name, _worst(a, b))
 
 
 def test_cfl_filter_inside_the_streaming_kernel_is_exact(monkeypatch):
