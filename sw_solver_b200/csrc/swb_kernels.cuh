@@ -71,9 +71,12 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     pdl_enter();
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) SWB_TLOG(p, 2);
     const int by = (int)blockIdx.y;
-    const bool tail = p.n_big > 0 && by >= p.n_big;
-    const int ja = p.jl_first + (tail ? p.n_big * p.chunk + (by - p.n_big) * p.chunk_small : by * p.chunk);
-    const Tile tl{(int)blockIdx.x * W, ja, min(ja + (tail ? p.chunk_small : p.chunk), p.jl_last + 1), blockIdx.x == 0 && blockIdx.y == 0, true};
+    int ja = p.jl_first + by * p.chunk, len = p.chunk;
+    if (p.n_big > 0 && by >= p.n_big) {  // guided tail: shorter marches in the block rows dispatched last
+        ja = p.jl_first + p.n_big * p.chunk + (by - p.n_big) * p.chunk_small;
+        len = p.chunk_small;
+    }
+    const Tile tl{(int)blockIdx.x * W, ja, min(ja + len, p.jl_last + 1), blockIdx.x == 0 && blockIdx.y == 0, true};
     march_step<T, STRICT, DIFF, FM, HS, TMA, R, S, GUARD, W, CFLF, false>(p, tm, p.launch, true, tbase, par, smem_raw, s_dt, s_flags, s_filter,
                                                                           nullptr, tl);
 #ifdef SWB_BAND_TIMING

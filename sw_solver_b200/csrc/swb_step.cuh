@@ -1019,6 +1019,15 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                     }
                     trig = false;
                 }
+            } else if (RES && !STREAM && j0 + R > jb && j0 >= res_lo && jb - 1 <= res_hi) {
+                // resident kernel, the march's last tile when its length is not a multiple of R: the fast body for the rows
+                // that exist (a rolled loop: at most R-1 rows).  Lets the host pick ANY marching length, i.e. the one that
+                // fills the GPU's block slots evenly (1440 x 720: 15-row marches in 288 blocks instead of 16 rows in 270).
+#pragma unroll 1
+                for (int rr = 0; rr < jb - j0; ++rr) {
+                    const StarRows<V2> sr{ring_row(rr - 3), ring_row(rr - 2), ring_row(rr - 1), ring_row(rr + 1)};
+                    do_row(HotTag(), j0 + rr, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true, SSTAR ? sr : no_star);
+                }
             } else {
 #pragma unroll 1
                 for (int rr = 0; rr < R; ++rr)

@@ -807,6 +807,8 @@ def test_resident_kernel_marching_lengths_and_load_paths(monkeypatch):
     for env in ({"SWB_RES_CHUNK": "1", "SWB_KERNEL": "ldg"}, {"SWB_RES_CHUNK": "3", "SWB_KERNEL": "ldg"},
                 {"SWB_RES_CHUNK": "4", "SWB_KERNEL": "tma"}, {"SWB_RES_CHUNK": "12", "SWB_KERNEL": "tma"},
                 {"SWB_RES_CHUNK": "32", "SWB_KERNEL": "tma"},
+                # marches that do not end on a tile: the last, partial tile runs the fast body too
+                {"SWB_RES_CHUNK": "5", "SWB_KERNEL": "tma"}, {"SWB_RES_CHUNK": "7", "SWB_KERNEL": "tma"}, {"SWB_RES_CHUNK": "18", "SWB_KERNEL": "tma"},
                 # long marches: row records scaled straight from the per-context table; three ring stages beyond 96 rows
                 {"SWB_RES_CHUNK": "64", "SWB_KERNEL": "tma"}, {"SWB_RES_CHUNK": "112", "SWB_KERNEL": "tma"}):
         res, tr, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, False, "fast", batches, 1e12, True, monkeypatch, env)
@@ -814,7 +816,8 @@ def test_resident_kernel_marching_lengths_and_load_paths(monkeypatch):
         for name, a, b in zip("huv", res, ref):
             assert _bits(a, b), (env, name, _worst(a, b))
     ref, tr_ref, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, "fast_guarded", batches, 1e12, False, monkeypatch)
-    for env in ({"SWB_RES_CHUNK": "40", "SWB_KERNEL": "tma"}, {"SWB_RES_CHUNK": "128", "SWB_KERNEL": "tma"}):
+    for env in ({"SWB_RES_CHUNK": "40", "SWB_KERNEL": "tma"}, {"SWB_RES_CHUNK": "128", "SWB_KERNEL": "tma"},
+                {"SWB_RES_CHUNK": "15", "SWB_KERNEL": "tma"}, {"SWB_RES_CHUNK": "9", "SWB_KERNEL": "tma"}, {"SWB_RES_CHUNK": "6", "SWB_KERNEL": "tma"}):
         res, tr, _, _ = _run_batches(M, N, ICType.RossbyHaurwitzWave, True, "fast_guarded", batches, 1e12, True, monkeypatch, env)
         assert tr == tr_ref, env
         for name, a, b in zip("huv", res, ref):
