@@ -87,6 +87,7 @@ struct swb_ctx {
     unsigned long long *d_scratch = nullptr;
     swb_status *h_status = nullptr;  // pinned mirror
     int launch = 0;                  // index of the next step launch (mod-3 cycle)
+    long long since_init = 0;        // step launches since swb_cfl_init (its parity: the buffer set an active step reads)
     unsigned long long seq = 1;      // stamp of the next step launch (multi-GPU)
     int64_t launches = 0;
     int sm_count = 148;
@@ -534,7 +535,7 @@ int make_map(CUtensorMap *out, void *base, uint64_t cols, uint64_t rows, uint64_
 // march starts with two extra rows, so: the longest chunk (<= 64 rows: two blocks of records
 // + rings fit one SM) that still fills about one wave of blocks (2 per SM); small grids end
 // up with 2-row marches, large ones with 64 (measured).
-int pick_chunk(int rows, int nstrips, int sm_count)
+int pick_chunk(int rows, int nstrips, int sm_count, bool diffusion)
 {
     // (A wave-quantisation model -- waves x (rows + start-up) -- was tried for grids of several waves and
     // dropped: measured at 7200 x 3600, 56 / 64 / 72 / 76 / 96-row marches take 267.9 / 272.1 / 271.9 / 275.1 /
@@ -542,6 +543,11 @@ int pick_chunk(int rows, int nstrips, int sm_count)
     // better than fuller last waves pay; 64 stays.)
     const long long want_blocks = (long long)sm_count * 2 * 9 / 10;
     const int gx = (nstrips + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    // grids of several waves of blocks: 96-row marches (a march start costs ~5 us of a block slot; the guided tail of
+    // swb_bind_state takes care of the end of the launch) -- with the tail, 64 / 80 / 96 rows: 16384 x 8192 1342 / 1326 / 1315 us,
+    // 7200 x 3600 270.0 / 270.1 / 266.0 us per step
+    // (not with diffusion: 7200 x 3600 423 -> 445 us)
+    if (!diffusion && (long long)gx * ((rows + 63) / 64) >= 3 * (long long)sm_count * 2) return 96;
     int chunk = 64;
     while (chunk > 2 && (long long)gx * ((rows + chunk - 1) / chunk) < want_blocks) chunk >>= 1;
     return chunk;
@@ -663,7 +669,7 @@ static int create_resources(swb_ctx *c)
     p.pole_s = (cfg->j_begin == 0);
     p.pole_n = (cfg->j_begin + cfg->n_local == cfg->N);
     p.nstrips = nstrips_of(p.M, cfg->dtype);
-    p.chunk = pick_chunk(p.jl_last - p.jl_first + 1, p.nstrips, c->sm_count);
+    p.chunk = pick_chunk(p.jl_last - p.jl_first + 1, p.nstrips, c->sm_count, cfg->use_diffusion != 0);
     if (const char *ch = getenv("SWB_CHUNK")) {  // tuning knob: 1 .. 100 (the row records of longer marches do not fit two blocks per SM)
         const int v = atoi(ch);
         if (v >= 1 && v <= 100) p.chunk = v;
@@ -837,7 +843,7 @@ int swb_bind_state(swb_ctx *c, void *h0, void *u0, void *v0, void *h1, void *u1,
         long long tail_rows = 0;
         // (about one wave of long marches: measured at 7200 x 3600, 0 / 192 / 320 / 640 tail rows give 274.1 / 266.4 / 260.3 /
         // 256.3 us per step; at 16384 x 8192, 0 / 128 / 256 rows 1263 / 1247 / 1246 us; 8- or 32-row tails are no better)
-        if (p.chunk == 64 && (long long)gx * ((rows + 63) / 64) >= 3 * slots) tail_rows = 64 * ((2 * slots + gx) / (2 * gx));
+        if (p.chunk >= 32 && (long long)gx * ((rows + 63) / 64) >= 3 * slots) tail_rows = 64LL * ((2 * slots + gx) / (2 * gx));
         if (const char *e = getenv("SWB_TAIL_ROWS")) tail_rows = atoll(e);
         if (const char *e = getenv("SWB_TAIL_CHUNK")) p.chunk_small = atoi(e) > 0 ? atoi(e) : 16;
         // (a second level -- 4-row marches in the very last block rows -- was measured and dropped: 268.6 / 269.7 / 266.8 / 271.9 us
@@ -919,6 +925,7 @@ int swb_cfl_init(swb_ctx *c, void *stream)
     c->launches++;
     CK(cudaGetLastError());
     c->launch = 0;
+    c->since_init = 0;
     if (c->linked) {  // deposit the maxima of slot 0 with the first step's stamp
         p.launch = 2;
         p.stamp = c->seq - 1;
@@ -994,6 +1001,7 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
             c->launches++;
             c->launch = (c->launch + m) % 3000000;
             c->seq += (unsigned long long)m;
+            c->since_init += m;
             left -= m;
         }
         if (c->resident) return 0;
@@ -1002,10 +1010,12 @@ int swb_enqueue_steps(swb_ctx *c, int n, void *stream)
     for (int k = 0; k < n; ++k) {
         c->prm.launch = c->launch;
         c->prm.stamp = c->seq;
+        c->prm.par_guess = (int)(c->since_init & 1);
         int rc = launch_one(c, st);
         if (rc) return rc;
         c->launch = (c->launch + 1) % 3000000;  // stays a multiple-of-3 cycle
         c->seq++;
+        c->since_init++;
     }
     return 0;
 }
@@ -1018,6 +1028,7 @@ int swb_step_fixed_dt(swb_ctx *c, double dt, void *stream)
     c->prm.fixed = 1;
     c->prm.fixed_dt = dt;
     c->prm.launch = 0;
+    c->prm.par_guess = 0;
     int rc = launch_one(c, (cudaStream_t)stream);
     c->prm.fixed = 0;
     return rc;

@@ -68,6 +68,7 @@ march_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps t
     __shared__ int s_flags;
     __shared__ CflFilter s_filter;
     int tbase = 0, par = -1;
+    par = p.par_guess;  // (used by the fp64 TMA kernels only, see march_step)
     pdl_enter();
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) SWB_TLOG(p, 2);
     const int by = (int)blockIdx.y;

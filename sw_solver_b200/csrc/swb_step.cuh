@@ -478,7 +478,11 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     // RES, second step onwards: the parity is known, so the first tile is requested while thread 0
     // works out dt (only the first: the SM's whole share of the state arrives in microseconds anyway,
     // and a deeper prefetch by every warp at once only queues up in front of the first tiles)
-    const bool early = RES && par_io >= 0;
+    // march_kernel (fp64 TMA kernels; round 2): the host passes the buffer parity it expects -- all launches since swb_cfl_init
+    // active; if they were not, this step is inactive too and nothing of it is used -- so the first tile and the first rows
+    // are requested before thread 0 has worked out dt (7200 x 3600: 257.9 -> 254.1 us per step; the 16-byte cp.async of the
+    // first rows needs the fp64 pairs' alignment, hence not fp32)
+    const bool early = (RES || (TMA && sizeof(T) == 8)) && par_io >= 0;
     if (early) {
         bind(par_io);
         if (warp != 0) {  // (warp 0: after the prologue -- its lane 0 is the prologue's thread)
@@ -520,6 +524,12 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             for (int u = 0; u < kEarly && u < nload; ++u) wait_tile(u);
         return false;
     }
+    if (!RES && early && ((flags >> 1) & 1) != par) {  // cannot happen (see above); if it did, the prefetched tile would be the wrong buffer's
+        if (TMA && warp_on && lane == 0)
+            for (int u = 0; u < kEarly && u < nload; ++u) wait_tile(u);
+        if (threadIdx.x == 0) atomicMin(p.err, -2);  // SWB_E_STATE
+        return false;
+    }
     if (!early) bind((flags >> 1) & 1);
     start_ring(early ? kEarly : 0, kFirstIssue);
     if (RES) par_io = par ^ 1;
@@ -532,7 +542,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     T *rowd = rowc + (size_t)(p.chunk + 2) * kRowRec;
     if (STREAM) {
         // nothing here: the records travel with the tiles
-    } else if (RES) {
+    } else if (RES) {  // (march_kernel reading the same table instead of rebuilding stage 1: measured, no gain -- 16384 x 8192 1337 -> 1349 us)
         // stage 1 (everything that does not depend on dt: look-ups, reciprocals of the metric
         // spacings) was computed once per context by prerec_kernel and is kept in shared memory for
         // the launch; stage 2 is one multiplication per slot (STRICT: the reference's own

@@ -102,6 +102,7 @@ struct Params {
                             // marches are dispatched last and shorten the tail of the launch); n_big == 0: every block row `chunk`
     int nstrips;            // warps needed along longitude
     int launch;             // launch index L (mod 3 cycle)
+    int par_guess;          // march_kernel: the buffer set the host expects to hold the current state (launches since swb_cfl_init, mod 2)
     int nsteps;             // resident_kernel: time steps run by this one launch
     int pre_smem;           // resident_kernel: the dt-independent row records are kept in shared memory (short marches)
     long long *dbg;         // SWB_RES_TIMING builds: per block 8 clock64 stamps of one step (dev instrumentation)
