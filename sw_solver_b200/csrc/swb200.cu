@@ -1086,6 +1086,8 @@ int swb_status_peek(swb_ctx *c, swb_status *out)
 
 int swb_get_status(swb_ctx *c, swb_status *out, void *stream)
 {
+    if (!c) return fail(SWB_E_INVALID, "swb_get_status: null context");
+    ON_DEVICE(c);  // (also for the synchronisation: a NULL stream means the CURRENT device's default stream)
     int rc = swb_status_async(c, nullptr, stream);
     if (rc) return rc;
     CK(cudaStreamSynchronize((cudaStream_t)stream));
@@ -1117,6 +1119,7 @@ int swb_max_speed(swb_ctx *c, double *out_host, void *stream)
 {
     if (!c || !out_host) return fail(SWB_E_INVALID, "swb_max_speed: null argument");
     if (!c->state_bound) return fail(SWB_E_STATE, "swb_max_speed: no state bound");
+    ON_DEVICE(c);
     swb_status s;
     int rc = swb_get_status(c, &s, stream);
     if (rc) return rc;
