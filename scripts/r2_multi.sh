@@ -3,6 +3,7 @@
 G=${1:-2}
 set -x
 mkdir -p gpurun_out
+[ -f sw_solver_b200/libswb200_bt.so ] || SWB_NVCC_FLAGS="-DSWB_BAND_TIMING" python -m sw_solver_b200.build --out=$PWD/sw_solver_b200/libswb200_bt.so
 SWB_LIB=$PWD/sw_solver_b200/libswb200_bt.so SWB_BAND_TIMING_FILE=$PWD/gpurun_out/bt$G timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $G --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $G --steps 200 --warmup 10 --no-e2e --no-parity --no-strong --no-sustained > gpurun_out/r2_bt_${G}gpu.json 2> gpurun_out/r2_bt_${G}gpu.err; echo bt rc=$?
 cut -c1-400 gpurun_out/r2_bt_${G}gpu.json; tail -3 gpurun_out/r2_bt_${G}gpu.err
 ls -la gpurun_out/bt$G* | head -20
