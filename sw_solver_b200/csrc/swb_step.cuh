@@ -1007,6 +1007,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                 // and every diffusion grid gets SLOWER -- 7200 x 3600 454 -> 470 us, 1440 x 720 resident 25.9 -> 27.9 us.)
                 // (Unrolling by two instead of four: 234 instead of 248 registers for the headline kernel, and slower --
                 // 16384 x 8192 1333 -> 1356 us, 7200 x 3600 274 -> 281 us, fp32 740 -> 762 us per step.)
+                // (A compiler fence in front of the star's shared-memory loads changes nothing: 255 registers either way.)
 #pragma unroll
                 for (int rr = 0; rr < R; ++rr) {
                     if (SSTAR && rr == R - 1) turn_ring();
