@@ -1,10 +1,12 @@
 // swb_kernels.cuh -- device code of libswb200.so (sm_100a).
 //
 // The hot path is one device function, `march_step`, that replaces the body of the loop at
-// src/sw_solver/numpy.py:496-549 of the reference.  Two kernels call it: `march_kernel` (one
-// launch per time step: any grid, any band decomposition) and `resident_kernel` (grids whose
-// blocks all fit the GPU at once: the whole batch of steps in one cooperative launch, a grid
-// barrier per step).  Per step:
+// src/sw_solver/numpy.py:496-549 of the reference.  Three kernels call it: `march_kernel` (one
+// launch per time step: any grid, any band decomposition; the launches of a step are chained by
+// programmatic dependent launch and the last block rows march fewer latitudes -- the guided tail),
+// `resident_kernel` (grids whose blocks all fit the GPU at once: the whole batch of steps in one
+// cooperative launch, a grid barrier per step) and `stream_kernel` (the resident loop for grids
+// beyond one wave of blocks: several tiles per block per step; opt-in).  Per step:
 //   * prologue: dt from the device-resident CFL maxima + final-time clamp (numpy.py:524-532)
 //   * Lax-Wendroff half-step face values and full-step update      (numpy.py:185-354)
 //   * optional Laplacian diffusion increment on the OLD fields       (numpy.py:541-544, 66-133)
