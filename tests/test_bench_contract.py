@@ -7,6 +7,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def _run(env_extra, *args):
@@ -29,7 +31,16 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"]
+    assert "workload" in d["config"] and "cpu_sample" in d["config"]
+    # the unmodified numpy reference, when its staged copy exists (oracle/_ref, __graft_entry__.build())
+    from oracle import ref_numpy
+
+    nr = d["cpu_baseline"]["numpy_ref"]
+    if ref_numpy.available():
+        assert nr["kind"] == "_ref" and nr["cores"] == 1 and len(nr["runs"]) >= 1
+        assert all(r["value"] > 0 and r["seconds_per_step"] > 0 for r in nr["runs"])
+    else:
+        assert nr is None
 
 
 def test_reference_arm_under_torchrun_runs_on_rank_zero_only():

@@ -50,6 +50,33 @@ def test_ic_bit_exact_with_reference(golden_grid_ic):
                 assert arr.flags.c_contiguous and arr.flags.writeable and arr.dtype == np.float64
 
 
+def test_separable_forms_reproduce_the_reference_zonal_flow(golden_grid_ic):
+    """Williamson case 2 from 1-D tables: the separable Coriolis parameter and the separable state factors (what the
+    kernels and the device-side initial state are fed) give the reference's arrays bit for bit (ic.py:119-154)."""
+    from sw_solver_b200.ic import SeparableCoriolis, separable_zonal_flow, zonal_flow_coriolis
+
+    g = golden_grid_ic
+    for M, N in g["sizes"]:
+        tag = f"{M}x{N}"
+        ll = LatLonGrid(int(M), int(N))
+        ref = {k: g[f"{tag}/ic1/{k}"] for k in "huvf"}
+        sc = zonal_flow_coriolis(ll)
+        assert isinstance(sc, SeparableCoriolis) and sc.matches(ref["f"]) and _bits(sc.array(), ref["f"])
+        assert not sc.matches(ref["f"] + 1e-20 * np.abs(ref["f"]).max()) or np.array_equal(ref["f"] + 1e-20 * np.abs(ref["f"]).max(), ref["f"])
+        assert not sc.matches(ref["f"][:, :-1])
+        s = separable_zonal_flow(ll)
+        rot = (s["ncp"][:, None] * s["ct"][None, :]) * s["sa"] + s["sca"][None, :]
+        assert _bits(s["h0"] - (s["K"] * (rot * rot)) / s["g"], ref["h"])
+        assert _bits(s["u0"] * (s["cca"][None, :] + (s["cp"][:, None] * s["st"][None, :]) * s["sa"]), ref["u"])
+        assert _bits(np.broadcast_to((s["sp_nu0"] * s["sa"])[:, None], ref["v"].shape), ref["v"])
+    # a field that is not the zonal flow's is not mistaken for it
+    ll = LatLonGrid(12, 8)
+    f = get_initial_conditions(ICType.ZonalGeostrophicFlow, ll)[3]
+    f2 = f.copy()
+    f2[3, 4] = np.nextafter(f2[3, 4], np.inf)
+    assert zonal_flow_coriolis(ll).matches(f) and not zonal_flow_coriolis(ll).matches(f2)
+
+
 def test_lazy_views_on_large_grids_match_small_grid_semantics():
     """Above the materialisation limit 2-D attributes are zero-copy broadcast views with the
     same values the oracle's dense arrays hold."""
