@@ -434,25 +434,32 @@ def run_ours(args, M, N):
         host = [torch.from_numpy(q).pin_memory() for q in rossby_haurwitz_window(ll, j_begin, n_local)]
         out = [torch.empty_like(q).pin_memory() for q in host]
         state_bytes = 3 * (M + 3) * n_local * 8
-        barrier()
-        t0 = time.perf_counter()
-        st2 = Stepper(ll, cg, host[0], host[1], host[2], f_lat, None, band=band, world=world, **kw)  # H2D of h, u, v
-        torch.cuda.synchronize(dev)
-        t1 = time.perf_counter()
-        if world > 1:
-            bands.link_distributed(st2)
-        st2.enqueue(args.steps)
-        cur = st2.status().current                                                  # blocks until done
-        t2 = time.perf_counter()
-        st2.download(cur, out)                                                      # K4 + D2H of h, u, v
-        t3 = time.perf_counter()
-        el = max_over_ranks(t3 - t0)
-        st2.close()
+        # Two identical calls, the second one timed: the first is the warm-up the contract asks for -- it leaves the
+        # device allocations of a call (6.4 GB of state, 2 x 1.07 GB of staging) in torch's caching allocator, as in
+        # any process that steps more than one state (a cold call pays ~60 ms of cudaMalloc: scripts/probe_e2e.py).
+        for timed_pass in (False, True):
+            barrier()
+            t0 = time.perf_counter()
+            st2 = Stepper(ll, cg, host[0], host[1], host[2], f_lat, None, band=band, world=world, **kw)  # H2D of h, u, v
+            torch.cuda.synchronize(dev)
+            t1 = time.perf_counter()
+            if world > 1:
+                bands.link_distributed(st2)
+            st2.enqueue(args.steps)
+            cur = st2.status().current                                                  # blocks until done
+            t2 = time.perf_counter()
+            st2.download(cur, out)                                                      # K4 + D2H of h, u, v
+            t3 = time.perf_counter()
+            el = max_over_ranks(t3 - t0)
+            if not timed_pass:
+                cold = el
+            st2.close()
+            del st2
         e2e = {"value": pts * args.steps / el, "unit": UNIT,
                "h2d_bytes_per_step": world * state_bytes / args.steps, "d2h_bytes_per_step": world * state_bytes / args.steps,
                "call": f"per rank: Stepper(host h,u,v) + enqueue({args.steps}) + download (K4 + D2H of h,u,v); "
-                       f"{state_bytes} B each way per rank per call",
-               "seconds": el,
+                       f"{state_bytes} B each way per rank per call; the second of two identical calls is timed",
+               "seconds": el, "seconds_first_call": cold,
                "phases_rank0": {"h2d_s": t1 - t0, "steps_s": t2 - t1, "d2h_s": t3 - t2,
                                 "h2d_gbs": state_bytes / (t1 - t0) / 1e9, "d2h_gbs": state_bytes / (t3 - t2) / 1e9}}
         del host, out

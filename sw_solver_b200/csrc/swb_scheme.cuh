@@ -313,6 +313,172 @@ __device__ __forceinline__ void update_cell(const Cell<T> &cur, const Face<T> &x
     }
 }
 
+// ------------------------------------------------------------------------------------
+// fp32, packed: a lane's two cells (A in the low half, B in the high half) through Blackwell's two-wide
+// FP32 instructions (FFMA2 / FADD2 / FMUL2: fma / add / sub / mul .rn.f32x2).  They round element for
+// element like the scalar instructions (scripts/probes/f32x2_probe.cu: 0 mismatches in 2 x 12 G results),
+// and the functions below perform EXACTLY the operations of make_cell / x_face / y_face / update_cell with
+// T = float, in the same order -- so a row computed here and a row computed by the scalar boundary body
+// are the same bits (test: SWB_FORCE_RARE=1 against the default).  The fp32 kernel is bound by instruction
+// issue (profiles/r2_fp32_ncu.md): halving its arithmetic instructions is the way up.
+// PTX has no way to negate an operand of fma.rn.f32x2, although the instruction (FFMA2) can: the one route to it is ptxas's
+// contraction of mul.rn.f32x2 + sub.rn.f32x2 into `FFMA2 d, -a, b, c` (CUDA 12.9; micro-test in scripts/probes/f32x2_probe.cu).
+// `pnfma` below spells -a * b + c that way; the row coefficients that enter the scheme negated are STORED negated instead
+// (rec_slot, swb_step.cuh).  The bit-identity test named above pins the contraction: were it ever not applied, the hot rows
+// would differ from the boundary rows by a rounding and the test would fail.
+// ------------------------------------------------------------------------------------
+struct P2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ P2 pk(float lo, float hi)
+{
+    P2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ P2 pk(float2 q) { return pk(q.x, q.y); }
+__device__ __forceinline__ P2 pk(double2) { return P2{0ULL}; }  // (never called: lets the discarded packed branch of the fp64 kernels parse)
+__device__ __forceinline__ P2 pdup(float c) { return pk(c, c); }
+__device__ __forceinline__ float plo(P2 a)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    (void)hi;
+    return lo;
+}
+__device__ __forceinline__ float phi(P2 a)
+{
+    float lo, hi;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+    (void)lo;
+    return hi;
+}
+__device__ __forceinline__ P2 padd(P2 a, P2 b) { P2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ P2 psub(P2 a, P2 b) { P2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ P2 pmul(P2 a, P2 b) { P2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ P2 pfma(P2 a, P2 b, P2 c) { P2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ P2 pnfma(P2 a, P2 b, P2 c) { return psub(c, pmul(a, b)); }  // -a * b + c, ONE rounding (contracted by ptxas, see above)
+__device__ __forceinline__ P2 prcp(P2 x)  // fast_rcp(float) on both halves
+{
+    float r0, r1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(plo(x)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(phi(x)));
+    const P2 rr = pk(r0, r1);
+    return pfma(rr, pnfma(x, rr, pdup(1.0f)), rr);
+}
+// both halves: positive(x) ? v : 0
+__device__ __forceinline__ P2 psel_pos(P2 x, P2 v)
+{
+    return pk(positive(plo(x)) ? plo(v) : 0.0f, positive(phi(x)) ? phi(v) : 0.0f);
+}
+
+struct Cell2 {
+    P2 h, u, v, hu, hv, Ux, Vx, hw, Uy, Vy1, pr;
+};
+struct Face2 {
+    P2 hM, huM, hvM, q, F1, F2, F3, hvc;
+};
+__device__ __forceinline__ Cell2 pack_cells(const Cell<float> &a, const Cell<float> &b)
+{
+    Cell2 q;
+    q.h = pk(a.h, b.h); q.u = pk(a.u, b.u); q.v = pk(a.v, b.v); q.hu = pk(a.hu, b.hu); q.hv = pk(a.hv, b.hv);
+    q.Ux = pk(a.Ux, b.Ux); q.Vx = pk(a.Vx, b.Vx); q.hw = pk(a.hw, b.hw); q.Uy = pk(a.Uy, b.Uy); q.Vy1 = pk(a.Vy1, b.Vy1); q.pr = pk(a.pr, b.pr);
+    return q;
+}
+__device__ __forceinline__ void unpack_cells(const Cell2 &q, Cell<float> &a, Cell<float> &b)
+{
+    a.h = plo(q.h); b.h = phi(q.h); a.u = plo(q.u); b.u = phi(q.u); a.v = plo(q.v); b.v = phi(q.v);
+    a.hu = plo(q.hu); b.hu = phi(q.hu); a.hv = plo(q.hv); b.hv = phi(q.hv); a.Ux = plo(q.Ux); b.Ux = phi(q.Ux);
+    a.Vx = plo(q.Vx); b.Vx = phi(q.Vx); a.hw = plo(q.hw); b.hw = phi(q.hw); a.Uy = plo(q.Uy); b.Uy = phi(q.Uy);
+    a.Vy1 = plo(q.Vy1); b.Vy1 = phi(q.Vy1); a.pr = plo(q.pr); b.pr = phi(q.pr);
+    a.f = 0.0f; b.f = 0.0f;
+}
+__device__ __forceinline__ Face2 pack_faces(const Face<float> &a, const Face<float> &b)
+{
+    Face2 F;
+    F.hM = pk(a.hM, b.hM); F.huM = pk(a.huM, b.huM); F.hvM = pk(a.hvM, b.hvM); F.q = pk(a.q, b.q);
+    F.F1 = pk(a.F1, b.F1); F.F2 = pk(a.F2, b.F2); F.F3 = pk(a.F3, b.F3); F.hvc = pk(a.hvc, b.hvc);
+    return F;
+}
+__device__ __forceinline__ void unpack_faces(const Face2 &F, Face<float> &a, Face<float> &b)
+{
+    a.hM = plo(F.hM); b.hM = phi(F.hM); a.huM = plo(F.huM); b.huM = phi(F.huM); a.hvM = plo(F.hvM); b.hvM = phi(F.hvM);
+    a.q = plo(F.q); b.q = phi(F.q); a.F1 = plo(F.F1); b.F1 = phi(F.F1); a.F2 = plo(F.F2); b.F2 = phi(F.F2);
+    a.F3 = plo(F.F3); b.F3 = phi(F.F3); a.hvc = plo(F.hvc); b.hvc = phi(F.hvc);
+}
+
+// make_cell<false, float> for both cells of the lane (c, hg: the row's cos(theta) and g/2, in both halves)
+__device__ __forceinline__ Cell2 make_cell2(P2 h, P2 u, P2 v, P2 c, P2 hg)
+{
+    Cell2 q;
+    q.h = h; q.u = u; q.v = v;
+    q.hu = pmul(h, u);
+    q.hv = pmul(h, v);
+    q.pr = pmul(pmul(hg, h), h);
+    q.Ux = pfma(q.hu, u, q.pr);
+    q.Vx = pmul(q.hu, v);
+    const P2 w = pmul(v, c);
+    q.hw = pmul(h, w);
+    q.Uy = pmul(q.hu, w);
+    q.Vy1 = pmul(q.hv, w);
+    return q;
+}
+// x_face<false, GUARD, float>: the faces right of `a`'s cells (ncdx = -dt/dx_j; hg = g/4)
+template <bool GUARD>
+__device__ __forceinline__ Face2 x_face2(const Cell2 &a, const Cell2 &b, P2 ncdx, P2 kt, P2 fK, P2 hg)
+{
+    Face2 F;
+    const P2 K = pfma(padd(b.u, a.u), kt, fK);
+    const P2 shu = padd(b.hu, a.hu), shv = padd(b.hv, a.hv);
+    F.hM = pfma(ncdx, psub(b.hu, a.hu), padd(b.h, a.h));
+    F.huM = pfma(K, shv, pfma(ncdx, psub(b.Ux, a.Ux), shu));
+    F.hvM = pnfma(K, shu, pfma(ncdx, psub(b.Vx, a.Vx), shv));
+    const P2 r = prcp(F.hM);
+    F.q = pmul(F.huM, r);
+    const P2 pres = pmul(pmul(hg, F.hM), F.hM);
+    const P2 qg = GUARD ? psel_pos(F.hM, F.q) : F.q;
+    F.F1 = pfma(F.huM, qg, pres);
+    F.F2 = pmul(F.hvM, qg);
+    F.F3 = pdup(0.0f);
+    F.hvc = pdup(0.0f);
+    return F;
+}
+// y_face<false, GUARD, float>: the faces above `a`'s cells (nc1 = -dt/dy1_j, nc2 = -dt/dy_j)
+template <bool GUARD>
+__device__ __forceinline__ Face2 y_face2(const Cell2 &a, const Cell2 &b, P2 nc1, P2 nc2, P2 kt, P2 fK, P2 cm, P2 hg)
+{
+    Face2 F;
+    const P2 K = pfma(padd(b.u, a.u), kt, fK);
+    const P2 shu = padd(b.hu, a.hu), shv = padd(b.hv, a.hv);
+    F.hM = pfma(nc1, psub(b.hw, a.hw), padd(b.h, a.h));
+    F.huM = pfma(K, shv, pfma(nc1, psub(b.Uy, a.Uy), shu));
+    F.hvM = pnfma(K, shu, pfma(nc2, psub(b.pr, a.pr), pfma(nc1, psub(b.Vy1, a.Vy1), shv)));
+    const P2 r = prcp(F.hM);
+    F.q = pmul(F.huM, r);
+    F.hvc = pmul(F.hvM, cm);
+    const P2 t = pmul(F.hvM, r);
+    F.F1 = pmul(F.hvc, GUARD ? psel_pos(F.hM, F.q) : F.q);
+    F.F2 = pmul(F.hvc, GUARD ? psel_pos(F.hM, t) : t);
+    F.F3 = pmul(pmul(hg, F.hM), F.hM);
+    return F;
+}
+// update_cell<false, false, float> (the increment form): ncx = -0.5 dt/dx_j, ncy1u, ncyu likewise negated
+__device__ __forceinline__ void update_cell2(const Cell2 &cur, const Face2 &x0, const Face2 &x1, const Face2 &y0, const Face2 &y1, P2 ncx, P2 ncy1u,
+                                             P2 ncyu, P2 kc, P2 fc, P2 &hn, P2 &un, P2 &vn)
+{
+    const P2 dh = pfma(ncy1u, psub(y1.hvc, y0.hvc), pmul(ncx, psub(x1.huM, x0.huM)));
+    hn = padd(cur.h, dh);
+    const P2 qs = padd(padd(x0.q, x1.q), padd(y0.q, y1.q));
+    const P2 D = pfma(qs, kc, fc);
+    const P2 shv = padd(padd(x0.hvM, x1.hvM), padd(y0.hvM, y1.hvM));
+    const P2 shu = padd(padd(x0.huM, x1.huM), padd(y0.huM, y1.huM));
+    const P2 dhu = pfma(D, shv, pfma(ncy1u, psub(y1.F1, y0.F1), pmul(ncx, psub(x1.F1, x0.F1))));
+    const P2 dhv = pnfma(D, shu, pfma(ncyu, psub(y1.F3, y0.F3), pfma(ncy1u, psub(y1.F2, y0.F2), pmul(ncx, psub(x1.F2, x0.F2)))));
+    const P2 r = prcp(hn);
+    un = pfma(pnfma(cur.u, dh, dhu), r, cur.u);
+    vn = pfma(pnfma(cur.v, dh, dhv), r, cur.v);
+}
+
 // 3-point first-derivative weights on spacings d0 (minus side), d1 (plus side):
 // numpy.py:32-34, 37-39, 42-44.
 __device__ __forceinline__ void weights_strict(double d0, double d1, double &A, double &B, double &C)

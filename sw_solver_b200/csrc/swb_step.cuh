@@ -236,6 +236,27 @@ __host__ __device__ constexpr int rec_bytes(int chunk, bool diff)
 }
 
 
+// fp32 kernels built with -DSWB_F32_PACKED=1 run their hot rows through Blackwell's two-wide FP32 instructions (PK; P2 in
+// swb_scheme.cuh).  OFF by default: measured on the headline grid the packed kernel executes 25 % fewer instructions (issue slots
+// busy 80 % -> 60 %) but is no faster -- 0.685 against 0.690 ms per step -- because FFMA2 / FADD2 / FMUL2 issue at half the rate of
+// the scalar instructions (scripts/probes/ffma2_rate.cu: 0.48 against 0.95 warp-instructions per cycle and sub-partition: the
+// FP32 pipe delivers the same flops either way) and the pairs cost ptxas ~30 register moves per latitude and 40 more registers
+// (three blocks per SM instead of four); profiles/r2_fp32_ncu.md.  Kept for A/B:
+//   SWB_NVCC_FLAGS=-DSWB_F32_PACKED=1 python -m sw_solver_b200.build --out=sw_solver_b200/libswb200_pk.so
+//   SWB_LIB=sw_solver_b200/libswb200_pk.so SWB_TEST_F32_PACKED=1 pytest tests/test_gpu_parity.py -k packed
+// A packed kernel keeps the coefficients that enter the scheme negated (-dt/dx, -dt/dy ...: PTX cannot negate an operand of a
+// two-wide instruction) with their sign flipped in the row record; slot k of such a record, as the scalar code wants it:
+#ifndef SWB_F32_PACKED
+#define SWB_F32_PACKED 0
+#endif
+constexpr unsigned kRecNegated = (1u << RC_CDX) | (1u << RC_CXU) | (1u << RC_CY1F) | (1u << RC_CYF) | (1u << RC_CY1U) | (1u << RC_CYU);
+template <bool PK, typename T>
+__device__ __forceinline__ T rec_slot(const T *rec, int k)
+{
+    const T v = rec[k];
+    return (PK && ((kRecNegated >> k) & 1u)) ? -v : v;
+}
+
 // Store a lane's pair of values without branching: both (one 16-byte store), or only the
 // first / only the second (the strip's edge lanes and the right end of the grid).
 __device__ __forceinline__ void st_pair(double *addr, double a, double b, int both, int only_a, int only_b)
@@ -387,6 +408,9 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     using V2 = vec2_t<T>;
     constexpr int kValid = sizeof(T) == 8 ? kStripValid : kStripValidF32;
     constexpr bool kGuard = STRICT || GUARD;
+    // PK: the fp32 kernels carry a lane's two cells as one packed pair through two-wide instructions (hot rows)
+    constexpr bool PK = SWB_F32_PACKED && sizeof(T) == 4 && !STRICT && FM == 0 && !HS;
+    static_assert(!PK || !RES, "packed fp32 arithmetic: launch-per-step kernels");
     constexpr int kLdStar = RES ? LD_CA : LD_PLAIN;                   // diffusion star
     constexpr int kLdRow = RES ? (DIFF ? LD_CA : LD_CG) : LD_PLAIN;   // the march's own rows
 
@@ -572,7 +596,10 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             double pre[kRowRec];
             build_row_pre<STRICT>(p, ja - 1 + r, pre);
 #pragma unroll
-            for (int k = 0; k < kRowRec; ++k) rowc[(size_t)r * kRowRec + k] = (T)scale_row_slot<STRICT>(k, pre[k], s_dt);
+            for (int k = 0; k < kRowRec; ++k) {
+                const T val = (T)scale_row_slot<STRICT>(k, pre[k], s_dt);
+                rowc[(size_t)r * kRowRec + k] = (PK && ((kRecNegated >> k) & 1u)) ? -val : val;
+            }
             if (DIFF && !STRICT) {
                 double rd[kRowDiff];
                 build_diff_pre(p, ja - 1 + r, rd);
@@ -635,7 +662,7 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     const T *rec_tile = rowc;
     int rec_j0 = ja - 1;
     constexpr int kRecStep = STREAM ? kRecStride : kRowRec;  // elements between the records of consecutive latitudes
-    auto rec_of = [&](int jl) { return STREAM ? rec_tile + (jl - rec_j0) * kRecStep : rowc + (size_t)(jl - (ja - 1)) * kRowRec; };
+    auto rec_of = [&](int jl) { return STREAM ? rec_tile + (jl - rec_j0) * kRecStep : rowc + (size_t)(jl - (ja - 1)) * kRecStep; };
     auto set_rec_tile = [&](int u) {
         rec_tile = reinterpret_cast<const T *>(wbase + (size_t)stage_of(u) * LY::kStage + 3 * LY::kField);
         rec_j0 = ja - 1 + (u - kLead) * R;
@@ -687,16 +714,24 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
     {
         const V2 f0 = load_f(ja - 1), f1 = load_f(ja);
         const T *r0 = rec_of(ja - 1), *r1 = rec_of(ja);
-        const Cell<T> pA = make_cell<STRICT>(h0.x, u0.x, v0.x, r0[RC_C], hgCell, f0.x);
-        const Cell<T> pB = make_cell<STRICT>(h0.y, u0.y, v0.y, r0[RC_C], hgCell, f0.y);
-        curA = make_cell<STRICT>(h1.x, u1.x, v1.x, r1[RC_C], hgCell, f1.x);
-        curB = make_cell<STRICT>(h1.y, u1.y, v1.y, r1[RC_C], hgCell, f1.y);
+        auto rs0 = [&](int k) { return rec_slot<PK>(r0, k); };
+        const Cell<T> pA = make_cell<STRICT>(h0.x, u0.x, v0.x, rs0(RC_C), hgCell, f0.x);
+        const Cell<T> pB = make_cell<STRICT>(h0.y, u0.y, v0.y, rs0(RC_C), hgCell, f0.y);
+        curA = make_cell<STRICT>(h1.x, u1.x, v1.x, rec_slot<PK>(r1, RC_C), hgCell, f1.x);
+        curB = make_cell<STRICT>(h1.y, u1.y, v1.y, rec_slot<PK>(r1, RC_C), hgCell, f1.y);
         auto fy = [&](const Cell<T> &a, const Cell<T> &b) -> T {
-            if (!F2D) return r0[RC_FKY];
+            if (!F2D) return rs0(RC_FKY);
             return STRICT ? O::mul(T(0.5), O::add(b.f, a.f)) : hdt * T(0.5) * (b.f + a.f);
         };
-        y0A = y_face<STRICT, kGuard>(pA, curA, r0[RC_CY1F], r0[RC_CYF], r0[RC_KY], fy(pA, curA), r0[RC_CM], hdt, hgK, raK);
-        y0B = y_face<STRICT, kGuard>(pB, curB, r0[RC_CY1F], r0[RC_CYF], r0[RC_KY], fy(pB, curB), r0[RC_CM], hdt, hgK, raK);
+        y0A = y_face<STRICT, kGuard>(pA, curA, rs0(RC_CY1F), rs0(RC_CYF), rs0(RC_KY), fy(pA, curA), rs0(RC_CM), hdt, hgK, raK);
+        y0B = y_face<STRICT, kGuard>(pB, curB, rs0(RC_CY1F), rs0(RC_CYF), rs0(RC_KY), fy(pB, curB), rs0(RC_CM), hdt, hgK, raK);
+    }
+    // PK: between rows the lane's cells and their lower y-faces are carried packed
+    Cell2 cur2;
+    Face2 y02;
+    if constexpr (PK) {
+        cur2 = pack_cells(curA, curB);
+        y02 = pack_faces(y0A, y0B);
     }
 
     // rows at which a cell owes more than its own store: zero-gradient pole rows
@@ -754,14 +789,59 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         constexpr bool HOT = decltype(hot_tag)::value;
         // resident kernel: ghost columns and pole rows are served inside the fast (unrolled) body
         constexpr bool EXTRA = RES && HOT && !STREAM;  // (the streaming kernel deals many tiles per block: its few seam strips take the boundary body)
-        const V2 *rc2 = reinterpret_cast<const V2 *>(rec_of(jl));
+        T hnA, unA, vnA, hnB, unB, vnB;
+        Cell<T> nxtA, nxtB;
+        Face<T> y1A, y1B, xAB, xBN;  // (of the x-faces the tail below reads the half-step depths only)
+        V2 r_c_ac;
+        if constexpr (PK && HOT) {
+            // ---- fp32, hot rows: both cells of the lane through two-wide instructions (swb_scheme.cuh, P2) -------------
+            // the record: four slots per 16-byte read; one register feeds both halves of a packed instruction
+            const T *rec = rec_of(jl);
+            const float4 *r4 = reinterpret_cast<const float4 *>(rec);
+            const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2], q3 = r4[3];
+            static_assert(RC_KX == 2 && RC_CDX == 4 && RC_KY == 6 && RC_CM == 8 && RC_CYF == 10 && RC_CYU == 12 && RC_FD == 14, "record layout");
+            const P2 kx = pdup(q0.z), fkx = pdup(q0.w), ncdx = pdup(q1.x), ncxu = pdup(q1.y), ky = pdup(q1.z), fky = pdup(q1.w);
+            const P2 cm = pdup(q2.x), ncy1f = pdup(q2.y), ncyf = pdup(q2.z), ncy1u = pdup(q2.w), ncyu = pdup(q3.x), kc = pdup(q3.y), fd = pdup(q3.z);
+            const P2 cn = pdup(rec[kRecStep + RC_C]);
+            const P2 hgC2 = pdup(hgCell), hgK2 = pdup(hgK);
+            const Cell2 nxt2 = make_cell2(pk(h2), pk(u2), pk(v2), cn, hgC2);
+            const Face2 y12 = y_face2<kGuard>(cur2, nxt2, ncy1f, ncyf, ky, fky, cm, hgK2);
+            // x-faces of this latitude: (A | B) in the low half, (B | next lane's A) in the high half
+            Cell2 b2;
+            b2.h = pk(phi(cur2.h), shfl_down1(plo(cur2.h)));    b2.u = pk(phi(cur2.u), shfl_down1(plo(cur2.u)));
+            b2.hu = pk(phi(cur2.hu), shfl_down1(plo(cur2.hu))); b2.hv = pk(phi(cur2.hv), shfl_down1(plo(cur2.hv)));
+            b2.Ux = pk(phi(cur2.Ux), shfl_down1(plo(cur2.Ux))); b2.Vx = pk(phi(cur2.Vx), shfl_down1(plo(cur2.Vx)));
+            const Face2 xf = x_face2<kGuard>(cur2, b2, ncdx, kx, fkx, hgK2);
+            Face2 x0;  // (previous lane's B | A) and (A | B)
+            x0.huM = pk(shfl_up1(phi(xf.huM)), plo(xf.huM)); x0.hvM = pk(shfl_up1(phi(xf.hvM)), plo(xf.hvM));
+            x0.q = pk(shfl_up1(phi(xf.q)), plo(xf.q));
+            x0.F1 = pk(shfl_up1(phi(xf.F1)), plo(xf.F1));    x0.F2 = pk(shfl_up1(phi(xf.F2)), plo(xf.F2));
+            P2 hn2, un2, vn2;
+            update_cell2(cur2, x0, xf, y02, y12, ncxu, ncy1u, ncyu, kc, fd, hn2, un2, vn2);
+            hnA = plo(hn2); hnB = phi(hn2); unA = plo(un2); unB = phi(un2); vnA = plo(vn2); vnB = phi(vn2);
+            xAB.hM = plo(xf.hM); xBN.hM = phi(xf.hM); y1A.hM = plo(y12.hM); y1B.hM = phi(y12.hM);
+            if (DIFF) {  // the star's centre values
+                curA.h = plo(cur2.h); curB.h = phi(cur2.h); curA.u = plo(cur2.u); curB.u = phi(cur2.u); curA.v = plo(cur2.v); curB.v = phi(cur2.v);
+            }
+            cur2 = nxt2;
+            y02 = y12;
+        } else {
+        if constexpr (PK) {  // a boundary row of a packed kernel: the scalar body on the unpacked state
+            unpack_cells(cur2, curA, curB);
+            unpack_faces(y02, y0A, y0B);
+        }
         // the row record, read as 16-byte pairs (broadcast LDS.128)
-        const V2 r_c_ac = rc2[RC_C / 2], r_kx_fkx = rc2[RC_KX / 2], r_cdx_cxu = rc2[RC_CDX / 2], r_ky_fky = rc2[RC_KY / 2];
-        const V2 r_cm_cy1f = rc2[RC_CM / 2], r_cyf_cy1u = rc2[RC_CYF / 2], r_cyu_kc = rc2[RC_CYU / 2], r_fd_dy1s = rc2[RC_FD / 2];
-        const T cn = rec_of(jl)[kRecStep + RC_C];
+        auto rec_pair = [&](int k) -> V2 {
+            if constexpr (PK) return mk2(rec_slot<true>(rec_of(jl), k), rec_slot<true>(rec_of(jl), k + 1));
+            else return reinterpret_cast<const V2 *>(rec_of(jl))[k / 2];
+        };
+        r_c_ac = rec_pair(RC_C);
+        const V2 r_kx_fkx = rec_pair(RC_KX), r_cdx_cxu = rec_pair(RC_CDX), r_ky_fky = rec_pair(RC_KY);
+        const V2 r_cm_cy1f = rec_pair(RC_CM), r_cyf_cy1u = rec_pair(RC_CYF), r_cyu_kc = rec_pair(RC_CYU), r_fd_dy1s = rec_pair(RC_FD);
+        const T cn = rec_slot<PK>(rec_of(jl) + kRecStep, RC_C);
         const V2 f2 = load_f(jl + 1);
-        const Cell<T> nxtA = make_cell<STRICT>(h2.x, u2.x, v2.x, cn, hgCell, f2.x);
-        const Cell<T> nxtB = make_cell<STRICT>(h2.y, u2.y, v2.y, cn, hgCell, f2.y);
+        nxtA = make_cell<STRICT>(h2.x, u2.x, v2.x, cn, hgCell, f2.x);
+        nxtB = make_cell<STRICT>(h2.y, u2.y, v2.y, cn, hgCell, f2.y);
 
         // y-faces (jl | jl+1)
         T fyA = r_ky_fky.y, fyB = fyA;
@@ -769,8 +849,8 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             fyA = STRICT ? O::mul(T(0.5), O::add(nxtA.f, curA.f)) : hdt * T(0.5) * (nxtA.f + curA.f);
             fyB = STRICT ? O::mul(T(0.5), O::add(nxtB.f, curB.f)) : hdt * T(0.5) * (nxtB.f + curB.f);
         }
-        const Face<T> y1A = y_face<STRICT, kGuard>(curA, nxtA, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyA, r_cm_cy1f.x, hdt, hgK, raK);
-        const Face<T> y1B = y_face<STRICT, kGuard>(curB, nxtB, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyB, r_cm_cy1f.x, hdt, hgK, raK);
+        y1A = y_face<STRICT, kGuard>(curA, nxtA, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyA, r_cm_cy1f.x, hdt, hgK, raK);
+        y1B = y_face<STRICT, kGuard>(curB, nxtB, r_cm_cy1f.y, r_cyf_cy1u.x, r_ky_fky.x, fyB, r_cm_cy1f.x, hdt, hgK, raK);
 
         // x-faces of this latitude: (A | B) and (B | next lane's A)
         Cell<T> nA;
@@ -799,8 +879,8 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             fxAB = STRICT ? O::mul(T(0.5), O::add(curB.f, curA.f)) : hdt * T(0.5) * (curB.f + curA.f);
             fxBN = STRICT ? O::mul(T(0.5), O::add(nA.f, curB.f)) : hdt * T(0.5) * (nA.f + curB.f);
         }
-        const Face<T> xAB = x_face<STRICT, kGuard>(curA, curB, cdxAB, r_kx_fkx.x, fxAB, hdt, hgK, raK);
-        const Face<T> xBN = x_face<STRICT, kGuard>(curB, nA, cdxBN, r_kx_fkx.x, fxBN, hdt, hgK, raK);
+        xAB = x_face<STRICT, kGuard>(curA, curB, cdxAB, r_kx_fkx.x, fxAB, hdt, hgK, raK);
+        xBN = x_face<STRICT, kGuard>(curB, nA, cdxBN, r_kx_fkx.x, fxBN, hdt, hgK, raK);
         Face<T> xL;  // (previous lane's B | A)
         xL.huM = shfl_up1(xBN.huM); xL.hvM = shfl_up1(xBN.hvM); xL.q = shfl_up1(xBN.q);
         xL.F1 = shfl_up1(xBN.F1);   xL.F2 = shfl_up1(xBN.F2);
@@ -819,13 +899,13 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             hsyB = O::sub(hu_[1], hd_[1]);
         }
 
-        T hnA, unA, vnA, hnB, unB, vnB;
         const T fcA = F2D ? (STRICT ? curA.f : dt * T(0.125) * curA.f) : r_fd_dy1s.x;
         const T fcB = F2D ? (STRICT ? curB.f : dt * T(0.125) * curB.f) : r_fd_dy1s.x;
         update_cell<STRICT, HS>(curA, xL, xAB, y0A, y1A, cxA, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcA, dt, g_, raK, hsxA, hsyA,
                                 dxsA, r_fd_dy1s.y, hnA, unA, vnA);
         update_cell<STRICT, HS>(curB, xAB, xBN, y0B, y1B, cxB, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcB, dt, g_, raK, hsxB, hsyB,
                                 dxsB, r_fd_dy1s.y, hnB, unB, vnB);
+        }  // (scalar body)
 
         if (DIFF) {  // numpy.py:541-544: Laplacian of the OLD fields; u, v (not hu, hv)
             const int iA = min(max(colA, 1), p.M + 1), iB = min(max(colA + 1, 1), p.M + 1);  // keep invalid lanes in bounds
@@ -959,8 +1039,15 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
             }
         }
         krow += P;
-        curA = nxtA; curB = nxtB;
-        y0A = y1A;   y0B = y1B;
+        if constexpr (PK) {
+            if constexpr (!HOT) {
+                cur2 = pack_cells(nxtA, nxtB);
+                y02 = pack_faces(y1A, y1B);
+            }
+        } else {
+            curA = nxtA; curB = nxtB;
+            y0A = y1A;   y0B = y1B;
+        }
     };
     using HotTag = std::integral_constant<bool, true>;
     using RareTag = std::integral_constant<bool, false>;

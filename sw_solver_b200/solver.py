@@ -245,6 +245,12 @@ class Stepper:
         cfg.g, cfg.a, cfg.nu = EARTH_CONSTANTS.g, EARTH_CONSTANTS.a, EARTH_CONSTANTS.nu
         cfg.dphi = float(latlon_grid.dphi)
         self.cfg = cfg
+        # host arrays: the copy of the first field is under way while the context is created (tables, tensor maps ...)
+        self._copy_stream: Optional[torch.cuda.Stream] = None
+        self._stage_pair: List[Optional[torch.Tensor]] = [None, None]
+        self._prefetched: Optional[Tuple[torch.Tensor, torch.cuda.Event]] = None
+        if layout == "reference":
+            self._prefetch(h)
         self._ctx = ctypes.c_void_p()
         check(self.lib.swb_create(ctypes.byref(self._ctx), ctypes.byref(cfg)))
 
@@ -256,8 +262,6 @@ class Stepper:
         check(self.lib.swb_set_tables(self._ctx, ctypes.byref(ct)))
 
         # set 0 receives the initial state (H2D copies and K4 transposes pipelined over two streams)
-        self._copy_stream: Optional[torch.cuda.Stream] = None
-        self._stage_pair: List[Optional[torch.Tensor]] = [None, None]
         self._upload((h, u, v), [self._raw[0, k] for k in range(3)])
         self._f2d = self._upload((f,), [None])[0] if (f_lat is None and f_sep is None) else None
         self._hs = None if hs_flat else self._upload((hs,), [None])[0]
@@ -273,6 +277,31 @@ class Stepper:
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(self.device)
         return self._copy_stream
+
+    def _host_window(self, q) -> torch.Tensor:
+        """A field given in the reference layout as the (M+3, n_local) float64 tensor this stepper owns (validated)."""
+        M, nl = self.M, self.n_local
+        t = q if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64))
+        if t.dtype != torch.float64 or t.ndim != 2 or t.shape[0] != M + 3 or t.shape[1] not in (self.N, nl):
+            raise ValueError(f"expected a float64 array of shape {(M + 3, self.N)} (or the band window {(M + 3, nl)}), "
+                             f"got {tuple(t.shape)} {t.dtype}")
+        if t.shape[1] != nl:  # the full grid was given: take this band's rows
+            t = t[:, self.j_begin:self.j_begin + nl]
+        return t
+
+    def _prefetch(self, q) -> None:
+        """Start the H2D copy of a PINNED host field into the first staging buffer (copy stream); `_upload` picks it up."""
+        if not (isinstance(q, torch.Tensor) and not q.is_cuda and q.is_pinned()):
+            return
+        t = self._host_window(q)
+        main, side = torch.cuda.current_stream(self.device), self._side_stream()
+        self._stage_pair[0] = torch.empty((self.M + 3, self.n_local), dtype=torch.float64, device=self.device)
+        side.wait_stream(main)  # the allocation is ordered on the current stream
+        with torch.cuda.stream(side):
+            self._stage_pair[0].copy_(t, non_blocking=True)
+            landed = torch.cuda.Event()
+            landed.record(side)
+        self._prefetched = (t, landed)
 
     def _upload(self, fields, dsts: List[Optional[torch.Tensor]]) -> List[torch.Tensor]:
         """Bring fields into the device layout (``dsts[k]`` or a fresh (n_local, pitch) array each).
@@ -296,12 +325,7 @@ class Stepper:
                     raise ValueError(f"layout='device' expects float64 CUDA tensors of shape {(nl, M + 3)}")
                 dst[:, : M + 3].copy_(q)  # rounds to the state type in the fp32 mode
                 continue
-            t = q if isinstance(q, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(q, dtype=np.float64))
-            if t.dtype != torch.float64 or t.ndim != 2 or t.shape[0] != M + 3 or t.shape[1] not in (self.N, nl):
-                raise ValueError(f"expected a float64 array of shape {(M + 3, self.N)} (or the band window {(M + 3, nl)}), "
-                                 f"got {tuple(t.shape)} {t.dtype}")
-            if t.shape[1] != nl:  # the full grid was given: take this band's rows
-                t = t[:, self.j_begin:self.j_begin + nl]
+            t = self._host_window(q)
             if t.is_cuda:
                 src = t if t.stride(1) == 1 else t.contiguous()
                 check(self.lib.swb_to_device_layout(self._ctx, ctypes.c_void_p(src.data_ptr()), int(src.stride(0)),
@@ -310,15 +334,21 @@ class Stepper:
             k = nhost & 1
             nhost += 1
             side = self._side_stream()
-            if staging[k] is None:
-                staging[k] = torch.empty((M + 3, nl), dtype=torch.float64, device=self.device)
-                side.wait_stream(main)  # the allocation is ordered on the current stream
-            if freed[k] is not None:
-                side.wait_event(freed[k])
-            with torch.cuda.stream(side):
-                staging[k].copy_(t, non_blocking=True)  # H2D: plumbing
-                landed = torch.cuda.Event()
-                landed.record(side)
+            pre, self._prefetched = self._prefetched, None
+            if pre is not None and k == 0 and pre[0].data_ptr() == t.data_ptr() and pre[0].shape == t.shape and pre[0].stride() == t.stride():
+                landed = pre[1]  # this field's copy into staging[0] was started by `_prefetch`
+            else:
+                if pre is not None:
+                    side.wait_event(pre[1])  # (a prefetched field that is not the one asked for: its staging buffer is reused)
+                if staging[k] is None:
+                    staging[k] = torch.empty((M + 3, nl), dtype=torch.float64, device=self.device)
+                    side.wait_stream(main)  # the allocation is ordered on the current stream
+                if freed[k] is not None:
+                    side.wait_event(freed[k])
+                with torch.cuda.stream(side):
+                    staging[k].copy_(t, non_blocking=True)  # H2D: plumbing
+                    landed = torch.cuda.Event()
+                    landed.record(side)
             main.wait_event(landed)
             check(self.lib.swb_to_device_layout(self._ctx, ctypes.c_void_p(staging[k].data_ptr()), int(staging[k].stride(0)),
                                                 ctypes.c_void_p(dst.data_ptr()), _stream(self.device)))
@@ -469,6 +499,7 @@ class Stepper:
         """Replace the state of buffer set 0 (and a 2-D ``f`` / ``hs`` of a context created with them) by
         new arrays of the same kind -- the operator-level entry points reuse one context per grid."""
         self._upload((h, u, v), [self._raw[0, k] for k in range(3)])
+        self._cfl_ready = False  # the next `enqueue` restarts the loop (time 0) from the CFL maxima of this state
         if self._f2d is not None and f is not None:
             self._upload((f,), [self._f2d])
         if self._hs is not None and hs is not None:

@@ -639,6 +639,70 @@ def test_fp32_mode_against_oracle(M, N, diff, nsteps):
         assert np.array_equal(q[:, 0], q[:, 1]) and np.array_equal(q[:, -1], q[:, -2])
 
 
+def test_pinned_host_state_upload_and_download():
+    """`Stepper(pinned host tensors)` starts the copy of the first field before the context exists (`_prefetch`) and pipelines
+    the rest with the K4 transposes; `download` returns through the same staging buffers.  Same bits as the plain numpy path,
+    also for a band window and after `reload`."""
+    M, N = 333, 97
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    h, u, v, f = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+    kw = dict(courant=0.5, final_time=1e12, use_diffusion=True, mode="fast")
+    ref = Stepper(ll, cg, h, u, v, f, None, **kw)
+    ref.enqueue(7)
+    want = ref.to_numpy()
+    cur_ref = ref.status().current
+    ref.close()
+    pinned = [torch.from_numpy(np.ascontiguousarray(q)).pin_memory() for q in (h, u, v)]
+    st = Stepper(ll, cg, pinned[0], pinned[1], pinned[2], f, None, **kw)
+    assert st._prefetched is None  # consumed by the upload
+    for rep in range(2):
+        st.enqueue(7)
+        s = st.status()
+        assert s.error == 0
+        out = [torch.empty((M + 3, ll.N), dtype=torch.float64).pin_memory() for _ in range(3)]
+        st.download(s.current, out)
+        for name, a, b in zip("huv", out, want):
+            assert _bits(a.numpy(), b), (rep, name, _worst(a.numpy(), b))
+        if rep == 0:  # the same state again through `reload` (buffer set 0) in a fresh context
+            st.close()
+            st = Stepper(ll, cg, pinned[2], pinned[0], pinned[1], f, None, **kw)  # (another field first: the prefetched one is h's slot)
+            st.reload(pinned[0], pinned[1], pinned[2])
+    st.close()
+    assert cur_ref in (0, 1)
+
+
+@pytest.mark.parametrize("M,N,diff,mode,kernel", [
+    (360, 180, False, "fast", "tma"), (360, 180, False, "fast_guarded", "tma"), (1440, 720, False, "fast", "tma"),
+    (333, 97, True, "fast", "tma"), (333, 97, True, "fast_guarded", "ldg"), (360, 180, False, "fast", "ldg"), (61, 33, False, "fast", "tma"),
+])
+def test_fp32_packed_rows_are_the_scalar_rows(M, N, diff, mode, kernel, monkeypatch):
+    """A library built with -DSWB_F32_PACKED=1 (an experiment kept for A/B, see swb_step.cuh; SWB_LIB points at it and
+    SWB_TEST_F32_PACKED=1 says so) runs the hot rows of the fp32 kernels through Blackwell's two-wide FP32 instructions (a
+    lane's two cells as one packed pair: `make_cell2 / x_face2 / y_face2 / update_cell2`, swb_scheme.cuh) and the boundary
+    rows through the scalar templates.  Both must be the same arithmetic, bit for bit -- SWB_FORCE_RARE=1 sends every row
+    through the scalar body.  (This also pins ptxas's contraction of mul.rn.f32x2 + sub.rn.f32x2 into FFMA2 with a negated
+    operand, which `pnfma` relies on: without it the packed rows would differ by a rounding.)  With the default library the
+    two runs are the same scalar arithmetic in the hot and the boundary body -- the property holds there as well."""
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    h, u, v, f = get_initial_conditions(ICType.RossbyHaurwitzWave, ll)
+    monkeypatch.setenv("SWB_KERNEL", kernel)
+    out = {}
+    for rare in ("0", "1"):
+        monkeypatch.setenv("SWB_FORCE_RARE", rare)
+        st = Stepper(ll, cg, h, u, v, f, None, courant=0.5, final_time=1e12, use_diffusion=diff, mode=mode, dtype="float32", log_capacity=64)
+        st.enqueue(25)
+        s = st.status()
+        assert s.steps == 25 and s.error == 0
+        out[rare] = (st.to_numpy(), s.time, st.read_log(25))
+        st.close()
+    assert out["0"][1] == out["1"][1]
+    assert _bits(out["0"][2][0], out["1"][2][0])
+    for name, a, b in zip("huv", out["0"][0], out["1"][0]):
+        assert _bits(a, b), (name, _worst(a, b), int((np.asarray(a) != np.asarray(b)).sum()))
+
+
 def test_fp32_mode_driver_and_limits(golden_ref10):
     sd = {"interval": 392}
     solve(10, 10, ICType.RossbyHaurwitzWave, 2, 0.5, True, save_data=sd, dtype="float32")
