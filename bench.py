@@ -138,6 +138,27 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference loop body on a bounded sample
 # --------------------------------------------------------------------------------------
+def workload_config(M, N, world, strong, dtype, diffusion, mode):
+    """The `config` object of the JSON line -- the SAME for both arms (`--impl ours` / `--impl reference`), so that the driver
+    compares like with like: the workload, and the bounded sample of it the CPU arm steps (`cpu_sample`)."""
+    n_glob = N if (strong or world == 1) else N * world
+    rows_rank = (n_glob - 2) / world if world > 1 else n_glob - 2
+    bpu = BYTES_PER_UPDATE_F64 if dtype == "f64" else BYTES_PER_UPDATE_F64 / 2
+    per_gpu = f"{M}x{n_glob}"
+    if world > 1:
+        per_gpu = (f"{M}x{n_glob} globe split into {world} latitude bands" if strong
+                   else f"{M}x{N} per GPU, {M}x{n_glob} globe in {world} latitude bands")
+    touched = bpu * (M + 1) * rows_rank
+    ns = cpu_sample_rows(M)
+    return {"workload": f"Rossby-Haurwitz {per_gpu} {'fp64' if dtype == 'f64' else 'fp32'}, CFL 0.5, diffusion {'on' if diffusion else 'off'}",
+            "mode": mode,
+            "l2": (f"state ({touched / 1e9:.2f} GB touched per GPU per step) is larger than the 126 MB L2; no flush needed"
+                   if touched > 4 * 126e6 else
+                   "state fits the L2: this grid is L2-resident by nature (no flush; the roofline fraction is not an HBM figure)"),
+            "pts_per_step": (M + 1) * (n_glob - 2), "parallelism": f"lat-bands x{world}",
+            "cpu_sample": f"{M}x{ns} latitude band ({(M + 1) * (ns - 2)} updates per step): what the CPU arm (--impl reference, cpu_baseline) steps"}
+
+
 def cpu_reference_run(M, N_sample, diffusion, steps, warmup):
     """Time `steps` loop bodies (numpy.py:503-549) of the oracle port on an M x N_sample
     latitude-band grid (same longitudes as the workload, fewer latitudes)."""
@@ -187,10 +208,12 @@ def numpy_reference_leg(M, budget_s=25.0):
         return {"kind": "_ref", "error": f"{type(e).__name__}: {e}"[:300]}
 
 
-def run_reference_arm(args, M, N):
+def run_reference_arm(args, M, N_per_gpu):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = max(1, args.gpus)
+    N = N_per_gpu if (args.strong or world == 1) else N_per_gpu * world
     # torchrun pins OMP_NUM_THREADS=1 for its workers; this arm is one CPU job on rank 0 and takes
     # every host thread (set before the oracle's OpenMP runtime is loaded)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 or "TORCHELASTIC_RUN_ID" in os.environ:
@@ -203,12 +226,11 @@ def run_reference_arm(args, M, N):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / r["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"Rossby-Haurwitz {M}x{N} fp64, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
-                   "cpu_sample": f"{M}x{r['N_sample']} latitude band ({r['pts_per_step']} updates per step)",
-                   "reference_kind": "value = the C/OpenMP port of the reference loop body (oracle, pinned bit-exact to the reference) on all "
-                                     "host threads -- the FASTER of the two CPU baselines, so ratios against it are conservative; "
-                                     "numpy_ref = the unmodified numpy reference itself on one core"},
-        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample},
+        "config": workload_config(M, N_per_gpu, world, args.strong, "f64", args.diffusion, args.mode),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample,
+                         "reference_kind": "value = the C/OpenMP port of the reference loop body (oracle, pinned bit-exact to the reference) on all "
+                                           "host threads -- the FASTER of the two CPU baselines, so ratios against it are conservative; "
+                                           "numpy_ref = the unmodified numpy reference itself on one core"},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -519,13 +541,11 @@ def run_ours(args, M, N):
             pass
 
     cpu = None
-    cpu_sample = None
     if not args.no_cpu_baseline and world == 1:
         ns = cpu_sample_rows(M)
         probe = cpu_reference_run(M, ns, args.diffusion, 1, 1)
         nsteps = int(max(2, min(200, 12.0 / max(probe["seconds"], 1e-3))))
         r = cpu_reference_run(M, ns, args.diffusion, nsteps, 1)
-        cpu_sample = f"{M}x{r['N_sample']} latitude band ({r['pts_per_step']} updates per step)"
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                "sample": f"oracle port of numpy.py:503-549 (C, OpenMP) on a {M}x{r['N_sample']} latitude band of the "
                          f"workload, {nsteps} steps, {r['seconds']:.1f} s",
@@ -541,20 +561,11 @@ def run_ours(args, M, N):
     if dist is not None:
         dist.barrier()
     if rank == 0:
-        per_gpu = f"{M}x{ll.N}"
-        if world > 1:
-            per_gpu = (f"{M}x{ll.N} globe split into {world} latitude bands" if args.strong
-                       else f"{M}x{N} per GPU, {M}x{ll.N} globe in {world} latitude bands")
         line = {
             "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"Rossby-Haurwitz {per_gpu} {'fp64' if args.dtype == 'f64' else 'fp32'}, CFL 0.5, diffusion {'on' if args.diffusion else 'off'}",
-                       "mode": args.mode,
-                       "l2": (f"state ({2 * bytes_per_update / 2 * pts_rank / 1e9:.2f} GB touched per GPU per step) is larger than the 126 MB L2; no flush needed"
-                              if bytes_per_update * pts_rank > 4 * 126e6 else
-                              "state fits the L2: this grid is L2-resident by nature (no flush; the roofline fraction is not an HBM figure)"),
-                       "pts_per_step": pts, "parallelism": f"lat-bands x{world}", "cpu_sample": cpu_sample},
+            "config": workload_config(M, N, world, args.strong, args.dtype, args.diffusion, args.mode),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
             "clocks": clocks, "fp32": fp32, "band_parity": band_parity, "strong_7200x3600": strong, "l2_resident_configs": small,
         }
@@ -572,7 +583,7 @@ def main():
     args = parse_args()
     M, N = (int(x) for x in args.grid.lower().split("x"))
     if args.impl == "reference":
-        run_reference_arm(args, M, N * max(1, args.gpus))
+        run_reference_arm(args, M, N)
     else:
         run_ours(args, M, N)
 

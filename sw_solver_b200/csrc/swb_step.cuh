@@ -905,6 +905,9 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                                 dxsA, r_fd_dy1s.y, hnA, unA, vnA);
         update_cell<STRICT, HS>(curB, xAB, xBN, y0B, y1B, cxB, r_cyf_cy1u.y, r_cyu_kc.x, r_cyu_kc.y, fcB, dt, g_, raK, hsxB, hsyB,
                                 dxsB, r_fd_dy1s.y, hnB, unB, vnB);
+#ifdef SWB_COPY_ONLY  // dev probe (scripts/r3_copy_probe.sh): the kernel's memory traffic without its arithmetic -- the row above is stored as the result
+        hnA = h2.x; hnB = h2.y; unA = u2.x; unB = u2.y; vnA = v2.x; vnB = v2.y;
+#endif
         }  // (scalar body)
 
         if (DIFF) {  // numpy.py:541-544: Laplacian of the OLD fields; u, v (not hu, hv)
