@@ -302,6 +302,44 @@ def small_configs(dev):
     return out
 
 
+def config3_one_gpu(dev, peak):
+    """BASELINE.json config 3's grid (7200 x 3600) on ONE GPU, without and with diffusion: step time of `march_kernel` and its
+    fraction of the measured HBM bandwidth at 48 algorithmic bytes per update (state 1.24 GB per step: far beyond the L2).
+    Informational sub-record of the N = 1 line."""
+    import torch
+
+    from sw_solver_b200 import bands
+    from sw_solver_b200.grid import CartesianGrid, LatLonGrid
+    from sw_solver_b200.solver import Stepper
+
+    M, N, steps = 7200, 3600, 200
+    ll = LatLonGrid(M, N)
+    cg = CartesianGrid(ll)
+    out = []
+    for diff in (False, True):
+        hd, ud, vd, f_lat = bands.rossby_haurwitz_band(ll, 0, ll.N, dev)
+        st = Stepper(ll, cg, hd, ud, vd, f_lat, None, courant=0.5, final_time=1e12, use_diffusion=diff, mode="fast", device=dev, layout="device")
+        del hd, ud, vd
+        st.enqueue(20)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st.enqueue(steps)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        s = st.status()
+        assert s.steps == 20 + steps and s.error == 0
+        pts = (M + 1) * (ll.N - 2)
+        out.append({"workload": f"Rossby-Haurwitz {M}x{ll.N} fp64, diffusion {'on' if diff else 'off'}", "steps": steps, "us_per_step": 1e3 * ms,
+                    "value": pts / (ms * 1e-3), "unit": UNIT, "kernel": "swb::resident_kernel" if st.resident else "swb::march_kernel",
+                    "frac_of_hbm": BYTES_PER_UPDATE_F64 * pts / (ms * 1e-3) / 1e9 / peak})
+        st.close()
+        del st
+    torch.cuda.empty_cache()
+    return out
+
+
 def _timed(st, steps, barrier, local_rank, torch):
     """`steps` loop iterations timed with CUDA events on the launch stream between two barriers."""
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -486,16 +524,15 @@ def run_ours(args, M, N):
                                 "h2d_gbs": state_bytes / (t1 - t0) / 1e9, "d2h_gbs": state_bytes / (t3 - t2) / 1e9}}
         del host, out
 
-    # --- N > 1: strong scaling of BASELINE config 4 (7200 x 3600 split into N bands) ---------------
-    strong = None
-    if world > 1 and not args.strong and not args.no_strong:
+    # --- N > 1: strong scaling of BASELINE config 4 (7200 x 3600 split into N bands) and, on two GPUs, of config 2
+    # (1440 x 720 with diffusion): the same globe on N GPUs and on one GPU of the same box -----------------------
+    def strong_leg(sM, sN, diff, ssteps):
         try:
-            sM, sN, ssteps = 7200, 3600, 400
             sll = LatLonGrid(sM, sN)
             scg = CartesianGrid(sll)
             sf = coriolis_latitude(sll)
-            skw = dict(courant=0.5, final_time=1e12, use_diffusion=False, mode="fast", device=dev, layout="device")
-            sband = band_layout(sll.N, world, 1)[rank]
+            skw = dict(courant=0.5, final_time=1e12, use_diffusion=diff, mode="fast", device=dev, layout="device")
+            sband = band_layout(sll.N, world, 2 if diff else 1)[rank]
             hd, ud, vd, _ = bands.rossby_haurwitz_band(sll, sband["j_begin"], sband["n_local"], dev)
             sst = Stepper(sll, scg, hd, ud, vd, sf, None, band=sband, world=world, **skw)
             del hd, ud, vd
@@ -506,7 +543,7 @@ def run_ours(args, M, N):
             kern = "swb::resident_kernel" if sst.resident else "swb::march_kernel"
             assert sst.status().error == 0
             sst.close()
-            ms_1 = None
+            ms_1 = kern1 = None
             if rank == 0:  # the same globe on ONE GPU, same steps
                 hd, ud, vd, _ = bands.rossby_haurwitz_band(sll, 0, sll.N, dev)
                 one = Stepper(sll, scg, hd, ud, vd, sf, None, **skw)
@@ -516,14 +553,21 @@ def run_ours(args, M, N):
                 kern1 = "swb::resident_kernel" if one.resident else "swb::march_kernel"
                 one.close()
             dist.barrier()
-            if rank == 0:
-                spts = (sM + 1) * (sll.N - 2)
-                strong = {"workload": f"Rossby-Haurwitz {sM}x{sll.N} fp64 globe split into {world} latitude bands, diffusion off", "steps": ssteps,
-                          "us_per_step": 1e3 * ms_b / ssteps, "value": spts * ssteps / (ms_b * 1e-3), "unit": UNIT, "kernel": kern,
-                          "one_gpu_us_per_step": 1e3 * ms_1 / ssteps, "one_gpu_kernel": kern1, "speedup": ms_1 / ms_b,
-                          "one_gpu_frac_of_hbm": 48.0 * spts / (ms_1 / ssteps * 1e-3) / 1e9 / peak}
+            if rank != 0:
+                return None
+            spts = (sM + 1) * (sll.N - 2)
+            return {"workload": f"Rossby-Haurwitz {sM}x{sll.N} fp64 globe split into {world} latitude bands, diffusion {'on' if diff else 'off'}",
+                    "steps": ssteps, "us_per_step": 1e3 * ms_b / ssteps, "value": spts * ssteps / (ms_b * 1e-3), "unit": UNIT, "kernel": kern,
+                    "one_gpu_us_per_step": 1e3 * ms_1 / ssteps, "one_gpu_kernel": kern1, "speedup": ms_1 / ms_b,
+                    "one_gpu_frac_of_hbm": 48.0 * spts / (ms_1 / ssteps * 1e-3) / 1e9 / peak}
         except Exception as e:  # noqa: BLE001  (informational leg)
-            strong = {"error": f"{type(e).__name__}: {e}"[:300]}
+            return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    strong = strong_small = None
+    if world > 1 and not args.strong and not args.no_strong:
+        strong = strong_leg(7200, 3600, False, 400)
+        if world == 2:
+            strong_small = strong_leg(1440, 720, True, 2000)
 
     achieved = bytes_per_update * pts_rank / (kernel_ms * 1e-3) / 1e9  # per GPU
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -551,12 +595,16 @@ def run_ours(args, M, N):
                          f"workload, {nsteps} steps, {r['seconds']:.1f} s",
                "numpy_ref": numpy_reference_leg(M)}
 
-    small = None
+    small = config3 = None
     if world == 1 and not args.no_small:
-        try:  # informational leg: never at the expense of the headline line
+        try:  # informational legs: never at the expense of the headline line
             small = small_configs(dev)
         except Exception as e:  # noqa: BLE001
             small = [{"error": f"{type(e).__name__}: {e}"[:300]}]
+        try:
+            config3 = config3_one_gpu(dev, peak)
+        except Exception as e:  # noqa: BLE001
+            config3 = [{"error": f"{type(e).__name__}: {e}"[:300]}]
 
     if dist is not None:
         dist.barrier()
@@ -567,7 +615,8 @@ def run_ours(args, M, N):
             "dtype": args.dtype, "data": "synthetic",
             "config": workload_config(M, N, world, args.strong, args.dtype, args.diffusion, args.mode),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches) * world,
-            "clocks": clocks, "fp32": fp32, "band_parity": band_parity, "strong_7200x3600": strong, "l2_resident_configs": small,
+            "clocks": clocks, "fp32": fp32, "band_parity": band_parity, "strong_7200x3600": strong, "strong_1440x720_diffusion": strong_small,
+            "l2_resident_configs": small, "config3_7200x3600_one_gpu": config3,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -8,6 +8,9 @@
 #ifndef PROBE_DIFF
 #define PROBE_DIFF false
 #endif
+#ifndef PROBE_R
+#define PROBE_R 4
+#endif
 #ifndef PROBE_S
 #define PROBE_S 3
 #endif
@@ -16,6 +19,6 @@
 template __global__ void swb::march_kernel<double, false, PROBE_DIFF, 0, false, true, 4, (PROBE_DIFF ? 3 : 4), false, 2, 4, !PROBE_DIFF>(
     const __grid_constant__ swb::Params, const __grid_constant__ swb::TmaMaps);
 #else
-template __global__ void swb::march_kernel<float, false, PROBE_DIFF, 0, false, true, 4, PROBE_S, false, PROBE_MINB, 4, false>(
+template __global__ void swb::march_kernel<float, false, PROBE_DIFF, 0, false, true, PROBE_R, PROBE_S, false, PROBE_MINB, 4, false>(
     const __grid_constant__ swb::Params, const __grid_constant__ swb::TmaMaps);
 #endif

@@ -656,6 +656,10 @@ def test_pinned_host_state_upload_and_download():
     pinned = [torch.from_numpy(np.ascontiguousarray(q)).pin_memory() for q in (h, u, v)]
     st = Stepper(ll, cg, pinned[0], pinned[1], pinned[2], f, None, **kw)
     assert st._prefetched is None  # consumed by the upload
+    back = [torch.empty((M + 3, ll.N), dtype=torch.float64).pin_memory() for _ in range(3)]
+    st.download(0, back)  # round trip without a step: H2D + K4 there, K4 + D2H back -- the caller's arrays, bit for bit
+    for name, a, b in zip("huv", back, (h, u, v)):
+        assert _bits(a.numpy(), b), name
     for rep in range(2):
         st.enqueue(7)
         s = st.status()
