@@ -961,11 +961,17 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
         if (CFLF && HOT) {
             // estimate only; tiles in which an estimate reaches the trigger threshold are
             // re-evaluated exactly after their last row (see CflFilter)
+            // (Round 2: the estimate costs 4.9 % of the headline step -- a build without it, -DSWB_NO_CFL_EST, scripts/r3_cflest_probe.sh.
+            // Moving it to fp32 -- three cvt.rz.f32.f64, two FMUL, MUFU.RSQ, two FADD per cell instead of two DMUL, MUFU.RSQ64H, two
+            // DADD; exact all the same, 240 instead of 254 registers -- was measured 0.5 % SLOWER on the same box (1.169 against
+            // 1.163 ms): the conversions run on the XU pipe at one per eight cycles, next to the MUFU seeds of the reciprocals.)
+#ifndef SWB_NO_CFL_EST
             const T xA = g_ * fabs(hnA), xB = g_ * fabs(hnB);
             const T cA = xA * (T)rsqrt_seed((double)xA), cB = xB * (T)rsqrt_seed((double)xB);
             // (bitwise | on purpose: no short-circuit branches inside the hot tile)
             trig = trig | ((hi_word(fabs(unA) + cA) & 0x7fffffff) >= trig_x) | ((hi_word(fabs(vnA) + cA) & 0x7fffffff) >= trig_y) |
                    ((hi_word(fabs(unB) + cB) & 0x7fffffff) >= trig_x) | ((hi_word(fabs(vnB) + cB) & 0x7fffffff) >= trig_y);
+#endif
         } else if (HOT || live) {
             bits_t<T> kxA, kyA, kxB, kyB;
             if (STRICT) {
