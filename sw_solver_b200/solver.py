@@ -307,6 +307,7 @@ class Stepper:
         t = self._host_window(q)
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
         self._stage_pair[0] = torch.empty((self.M + 3, self.n_local), dtype=torch.float64, device=self.device)
+        self._stage_pair[0].record_stream(side)  # (used on the copy stream: the allocator must not hand it out again before that work is done)
         side.wait_stream(main)  # the allocation is ordered on the current stream
         with torch.cuda.stream(side):
             self._stage_pair[0].copy_(t, non_blocking=True)
@@ -353,6 +354,7 @@ class Stepper:
                     side.wait_event(pre[1])  # (a prefetched field that is not the one asked for: its staging buffer is reused)
                 if staging[k] is None:
                     staging[k] = torch.empty((M + 3, nl), dtype=torch.float64, device=self.device)
+                    staging[k].record_stream(side)
                     side.wait_stream(main)  # the allocation is ordered on the current stream
                 if freed[k] is not None:
                     side.wait_event(freed[k])
@@ -389,6 +391,7 @@ class Stepper:
             b = k & 1
             if self._stage_pair[b] is None:
                 self._stage_pair[b] = torch.empty((M + 3, nl), dtype=torch.float64, device=self.device)
+                self._stage_pair[b].record_stream(side)
             if copied[b] is not None:
                 main.wait_event(copied[b])  # the copy out of this buffer has finished
             self.export(self._raw[current, k], self._stage_pair[b])
