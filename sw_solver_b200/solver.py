@@ -263,7 +263,12 @@ class Stepper:
         if layout == "reference":
             self._prefetch(h)
         self._ctx = ctypes.c_void_p()
-        check(self.lib.swb_create(ctypes.byref(self._ctx), ctypes.byref(cfg)))
+        try:
+            check(self.lib.swb_create(ctypes.byref(self._ctx), ctypes.byref(cfg)))
+        except Exception:
+            if self._copy_stream is not None:  # the prefetched copy must not outlive its staging buffer
+                self._copy_stream.synchronize()
+            raise
 
         tabs = latitude_tables(latlon_grid, cart_grid, f_lat, self.use_diffusion, self.j_begin, self.n_local, f_sep)
         ct = SwbTables()
@@ -307,7 +312,6 @@ class Stepper:
         t = self._host_window(q)
         main, side = torch.cuda.current_stream(self.device), self._side_stream()
         self._stage_pair[0] = torch.empty((self.M + 3, self.n_local), dtype=torch.float64, device=self.device)
-        self._stage_pair[0].record_stream(side)  # (used on the copy stream: the allocator must not hand it out again before that work is done)
         side.wait_stream(main)  # the allocation is ordered on the current stream
         with torch.cuda.stream(side):
             self._stage_pair[0].copy_(t, non_blocking=True)
@@ -354,7 +358,6 @@ class Stepper:
                     side.wait_event(pre[1])  # (a prefetched field that is not the one asked for: its staging buffer is reused)
                 if staging[k] is None:
                     staging[k] = torch.empty((M + 3, nl), dtype=torch.float64, device=self.device)
-                    staging[k].record_stream(side)
                     side.wait_stream(main)  # the allocation is ordered on the current stream
                 if freed[k] is not None:
                     side.wait_event(freed[k])
@@ -391,7 +394,6 @@ class Stepper:
             b = k & 1
             if self._stage_pair[b] is None:
                 self._stage_pair[b] = torch.empty((M + 3, nl), dtype=torch.float64, device=self.device)
-                self._stage_pair[b].record_stream(side)
             if copied[b] is not None:
                 main.wait_event(copied[b])  # the copy out of this buffer has finished
             self.export(self._raw[current, k], self._stage_pair[b])
