@@ -674,6 +674,16 @@ def test_pinned_host_state_upload_and_download():
             st.reload(pinned[0], pinned[1], pinned[2])
     st.close()
     assert cur_ref in (0, 1)
+    # a latitude band cut out of the caller's full pinned arrays (a strided window): the same device state as from numpy
+    from sw_solver_b200.solver import band_layout
+
+    band = band_layout(ll.N, 2, 2)[1]
+    a = Stepper(ll, cg, h, u, v, f, None, band=band, world=2, **kw)
+    b = Stepper(ll, cg, pinned[0], pinned[1], pinned[2], f, None, band=band, world=2, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(a._raw[0], b._raw[0])
+    a.close()
+    b.close()
 
 
 @pytest.mark.parametrize("M,N,diff,mode,kernel", [
