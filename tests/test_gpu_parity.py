@@ -10,6 +10,8 @@ stay within 1e-12 normwise (max|diff| / max|ref| per field) -- BASELINE.json's n
 tolerance -- and in practice stays below 1e-13 on these runs, which the tests also pin.
 """
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -637,6 +639,25 @@ def test_fp32_mode_against_oracle(M, N, diff, nsteps):
     for q in (hg, ug, vg):
         assert np.array_equal(q[0, 1:-1], q[M, 1:-1]) and np.array_equal(q[M + 2, 1:-1], q[2, 1:-1])
         assert np.array_equal(q[:, 0], q[:, 1]) and np.array_equal(q[:, -1], q[:, -2])
+
+
+def test_example_scripts_run_like_reference_user_code(tmp_path):
+    """The caller side of the path: the two scripts under examples/ -- a reference user script with its import line changed, and
+    the reference's known-answer case regenerated on the B200 path and compared with the reference's own .npy arrays."""
+    import subprocess
+    import sys as _sys
+
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    r = subprocess.run([_sys.executable, os.path.join(root, "examples", "rossby_wave_b200.py"), "--days", "1", "--check"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Time =" in r.stdout and "save_data['h']" in r.stdout and "against strict" in r.stdout
+    for mode in ("strict", "fast"):
+        r = subprocess.run([_sys.executable, os.path.join(root, "examples", "regenerate_known_answers.py"), "--out", str(tmp_path), "--mode", mode],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "matches the reference's known answers" in r.stdout
+    assert sorted(os.listdir(tmp_path)) == sorted(f"swes-b200-ref-10-{k}.npy" for k in ("h", "u", "v", "t", "phi", "theta"))
 
 
 def test_pinned_host_state_upload_and_download():
