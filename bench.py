@@ -80,7 +80,7 @@ class ClockSampler:
 
     def __init__(self, index=0, period=0.02):
         self.index, self.period = index, period
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.power = [], set(), []
         self.max_mhz = None
         self._stop = threading.Event()
         self._thread = None
@@ -107,6 +107,10 @@ class ClockSampler:
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)  # board power, W
+                except Exception:
+                    pass
+                try:
                     mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
                 except Exception:
                     mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
@@ -131,8 +135,11 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        out = {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        if self.power:
+            out["power_w"] = float(np.median(self.power))
+        return out
 
 
 # --------------------------------------------------------------------------------------
