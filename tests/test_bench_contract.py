@@ -32,6 +32,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"] and "cpu_sample" in d["config"]
+    # both arms print the SAME config object (the driver compares the two lines): the function our arm calls, same arguments
+    import bench
+
+    assert d["config"] == bench.workload_config(360, 180, 1, False, "f64", False, "fast")
     # the unmodified numpy reference, when its staged copy exists (oracle/_ref, __graft_entry__.build())
     from oracle import ref_numpy
 
@@ -53,3 +57,7 @@ def test_reference_arm_under_torchrun_runs_on_rank_zero_only():
     assert r1.stdout.strip() == ""
     d = json.loads(r0.stdout.strip().splitlines()[-1])
     assert d["n_gpus"] == 2 and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    import bench
+
+    assert d["config"] == bench.workload_config(360, 180, 2, False, "f64", False, "fast")
+    assert "360x360 globe in 2 latitude bands" in d["config"]["workload"]
