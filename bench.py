@@ -340,11 +340,20 @@ def config3_one_gpu(dev, peak):
         pts = (M + 1) * (ll.N - 2)
         out.append({"workload": f"Rossby-Haurwitz {M}x{ll.N} fp64, diffusion {'on' if diff else 'off'}", "steps": steps, "us_per_step": 1e3 * ms,
                     "value": pts / (ms * 1e-3), "unit": UNIT, "kernel": "swb::resident_kernel" if st.resident else "swb::march_kernel",
-                    "frac_of_hbm": BYTES_PER_UPDATE_F64 * pts / (ms * 1e-3) / 1e9 / peak})
+                    "frac_of_hbm": BYTES_PER_UPDATE_F64 * pts / (ms * 1e-3) / 1e9 / peak, "bytes_per_launch": BYTES_PER_UPDATE_F64 * pts,
+                    "traffic": _traffic(f"{M}x{ll.N}:fast" + (":diffusion" if diff else ""))})
         st.close()
         del st
     torch.cuda.empty_cache()
     return out
+
+
+def _traffic(key):
+    """DRAM bytes per launch of the captured kernel `key` (profiles/traffic.json, from the ncu --set full captures), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key)
+    except Exception:
+        return None
 
 
 def _timed(st, steps, barrier, local_rank, torch):
@@ -470,7 +479,7 @@ def run_ours(args, M, N):
             err = [float((q32[k].double() - q64[k]).abs().max()) / float(q64[k].abs().max()) for k in range(3)]
             a32 = 0.5 * BYTES_PER_UPDATE_F64 * pts / (ms32 / args.steps * 1e-3) / 1e9
             fp32 = {"ms_per_step": ms32 / args.steps, "value": pts * args.steps / (ms32 * 1e-3), "unit": UNIT, "bytes_per_update": 24,
-                    "roofline": {"bound": "hbm", "achieved": a32, "peak": peak, "unit": "GB/s", "frac": a32 / peak},
+                    "roofline": {"bound": "hbm", "achieved": a32, "peak": peak, "unit": "GB/s", "frac": a32 / peak, "traffic": _traffic(f"{M}x{N}:{args.mode}:f32")},
                     "normwise_error_vs_fp64": {"h": err[0], "u": err[1], "v": err[2], "after_steps": int(s.steps), "tolerance": 1e-5},
                     "clocks": clk32}
             st32.close()
@@ -584,12 +593,7 @@ def run_ours(args, M, N):
                          if resident else
                          "per GPU; one march_kernel launch per step (kernel_ms = step time, CUDA events on the launch stream)"),
                 "sustained": sustained}
-    prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
-        try:
-            roofline["traffic"] = json.load(open(prof)).get(f"{M}x{N}:{args.mode}" + ("" if args.dtype == "f64" else ":f32"))
-        except Exception:
-            pass
+    roofline["traffic"] = _traffic(f"{M}x{N}:{args.mode}" + ("" if args.dtype == "f64" else ":f32") + (":diffusion" if args.diffusion else ""))
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

@@ -82,6 +82,15 @@ def step_kernel():
     open(os.path.join(PROF, f"r{ROUND}_step_kernel_ncu.md"), "w").write("\n".join(out + body) + "\n")
     tj = {"16384x8192:fast": traffic,
           "source": f"profiles/r{ROUND}_step_kernel_ncu.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch)"}
+    # the other captured kernels, when their raw pages are there (fp32: scripts/gpu_prof_f32.sh; diffusion: scripts/r3_prof_diff.sh)
+    for key, raw in (("16384x8192:fast:f32", "r2_prof_f32_raw.csv"), ("7200x3600:fast:diffusion", "r3_prof_diff_raw.csv")):
+        path = os.path.join(OUT, raw)
+        if os.path.exists(path):
+            rows = list(csv.reader(open(path)))
+            d = dict(zip(rows[0], rows[2]))
+            u = dict(zip(rows[0], rows[1]))
+            scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            tj[key] = sum(float(d[m]) * scale[u[m]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     json.dump(tj, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
 
 
