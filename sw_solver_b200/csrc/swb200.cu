@@ -302,17 +302,20 @@ constexpr int kResFourStageChunk = 96;  // no diffusion: four ring stages up to 
 constexpr int res_max_chunk(bool tma, bool /*diff*/) { return !tma ? kResPreSmemChunk : 128; }
 
 struct ResKernel { const void *fn; int smem; };
-template <bool STRICT, bool DIFF, bool TMA, bool GUARD, int S = (DIFF ? 3 : 4), bool BANDS = false, int FM = 0>  // (with diffusion: three stages of wider boxes, as in march_kernel)
+constexpr int kResMixChunk = 24;  // diffusion, one band, marches up to this long: resident_kernel<..., MIX> (mixed pole tiles, see march_step)
+template <bool STRICT, bool DIFF, bool TMA, bool GUARD, int S = (DIFF ? 3 : 4), bool BANDS = false, int FM = 0, bool MIX = false>  // (with diffusion: three stages of wider boxes, as in march_kernel)
 ResKernel res_kernel_inst(int chunk)
 {
     using LY = TmaLayout<4, S, double, box_cols<double, DIFF, TMA>()>;
-    auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? S : 1), GUARD, 2, BANDS, kWarpsPerBlock, FM>;
+    auto fn = resident_kernel<double, STRICT, DIFF, TMA, (TMA ? 4 : 1), (TMA ? S : 1), GUARD, 2, BANDS, kWarpsPerBlock, FM, MIX>;
     return ResKernel{(const void *)fn, (chunk <= kResPreSmemChunk ? 2 : 1) * rec_bytes(chunk, DIFF) +
                                            (TMA ? kWarpsPerBlock * LY::kWarpBytes : kWarpsPerBlock * kFirstRowsBytes)};
 }
 template <bool BANDS>
 ResKernel res_kernel_sel(int mode, bool diff, bool tma, int chunk)
 {
+    if (tma && diff && !BANDS && chunk <= kResMixChunk)
+        return mode == SWB_FAST ? res_kernel_inst<false, true, true, false, 3, false, 0, true>(chunk) : res_kernel_inst<false, true, true, true, 3, false, 0, true>(chunk);
     if (tma && diff)
         return mode == SWB_FAST ? res_kernel_inst<false, true, true, false, 3, BANDS>(chunk) : res_kernel_inst<false, true, true, true, 3, BANDS>(chunk);
     if (tma && chunk > kResFourStageChunk)
@@ -491,6 +494,12 @@ int setup_resident(swb_ctx *c)
     }
     if (chunk <= 0) return 0;
     const ResKernel rk = res_kernel_of(cfg.mode, cfg.use_diffusion, tma, chunk, cfg.world > 1, sep);
+    CK(cudaFuncSetAttribute(rk.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, rk.smem));  // (it may be none of the kernels probed above)
+    {
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rk.fn, kWarpsPerBlock * 32, (size_t)rk.smem));
+        if ((long long)nb * c->sm_count < (long long)gx * ((rows + chunk - 1) / chunk)) return 0;  // does not fit after all: launch per step
+    }
     c->res_fn = rk.fn;
     c->res_smem = rk.smem;
     c->res_grid = dim3((unsigned)gx, (unsigned)((rows + chunk - 1) / chunk));

@@ -172,7 +172,8 @@ __device__ __forceinline__ bool band_gather(const Params &p, int launch, unsigne
 // acquire at gpu scope), behind which the next step reads the CFL maxima -- accumulated by
 // the same atomics as in march_kernel -- and its neighbours' new rows and columns straight
 // from the L2.  Same step body, same arithmetic: bit-identical to a launch per step.
-template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, bool BANDS = false, int W = kWarpsPerBlock, int FM = 0>
+template <typename T, bool STRICT, bool DIFF, bool TMA, int R, int S, bool GUARD, int MINB, bool BANDS = false, int W = kWarpsPerBlock, int FM = 0,
+          bool MIX = false>
 __global__ void __launch_bounds__(W * 32, MINB)
 resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMaps tm)
 {
@@ -222,7 +223,7 @@ resident_kernel(const __grid_constant__ Params p, const __grid_constant__ TmaMap
         }
         const int ja = p.jl_first + blockIdx.y * p.chunk;
         const Tile tl{(int)blockIdx.x * W, ja, min(ja + p.chunk, p.jl_last + 1), blockIdx.x == 0 && blockIdx.y == 0, true};
-        const bool active = march_step<T, STRICT, DIFF, FM, false, TMA, R, S, GUARD, W, false, true, BANDS>(p, tm, p.launch + s, s == 0, tbase, par, smem_raw,
+        const bool active = march_step<T, STRICT, DIFF, FM, false, TMA, R, S, GUARD, W, false, true, BANDS, false, MIX>(p, tm, p.launch + s, s == 0, tbase, par, smem_raw,
                                                                                                          s_dt, s_flags, s_filter, s_max, tl);
         if (!active) break;
         // Grid barrier: all stores and atomics of step s happen before any load of step s+1.

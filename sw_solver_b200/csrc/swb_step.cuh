@@ -382,8 +382,10 @@ __device__ __forceinline__ unsigned swb_smid() { unsigned r; asm volatile("mov.u
 // and are scaled by dt in place once the tile has landed.
 // FM: how the Coriolis parameter reaches a cell -- 0 latitude-only (folded into the row records), 1 a 2-D array, 2 separable
 // (rebuilt per cell from a longitude and two latitude tables in the reference's operation order, see Params::fa).
+// RESMIX (resident kernel with diffusion, short marches): a tile that holds a pole row / a neighbour band's halo row runs only THAT
+// row through the boundary body and its other rows through the fast one (see the tile loop).
 template <typename T, bool STRICT, bool DIFF, int FM, bool HS, bool TMA, int R, int S, bool GUARD, int W, bool CFLF, bool RES, bool RESBANDS = false,
-          bool STREAM = false>
+          bool STREAM = false, bool RESMIX = false>
 __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, const int launch, const bool first, int &tbase,
                                            int &par_io, unsigned char *smem_raw, double &s_dt, int &s_flags, CflFilter &s_filter,
                                            unsigned long long *s_max, const Tile tl)
@@ -1125,6 +1127,23 @@ __device__ __forceinline__ bool march_step(const Params &p, const TmaMaps &tm, c
                         }
                     }
                     trig = false;
+                }
+            } else if (RES && !STREAM && RESMIX) {
+                // A tile that is not fast as a whole -- the march's last, partial tile, or one that holds a pole row or a halo row of
+                // a neighbour band: the rows that exist, each through the body it needs (a rolled loop).  The blocks that own the
+                // pole rows are the ones every step of a small grid waits for: with whole tiles through the boundary body their
+                // march is 20 % longer than the mean (profiles/r1_small_grids.md).  1440 x 720 with diffusion (15-row marches)
+                // 26.3 -> 24.7 us per step; NOT for longer marches and not without diffusion, where the extra loop costs the
+                // kernel's other paths more than it saves (2000 x 1000 + diffusion, 32 rows: 47.2 -> 48.4 us; 1440 x 720: 16.3 -> 18.4).
+#pragma unroll 1
+                for (int rr = 0; rr < min(R, jb - j0); ++rr) {
+                    const int jl = j0 + rr;
+                    if (jl >= res_lo && jl <= res_hi) {
+                        const StarRows<V2> sr{ring_row(rr - 3), ring_row(rr - 2), ring_row(rr - 1), ring_row(rr + 1)};
+                        do_row(HotTag(), jl, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true, SSTAR ? sr : no_star);
+                    } else {
+                        do_row(RareTag(), jl, tile[rr * kRowV], tile[kFieldV + rr * kRowV], tile[2 * kFieldV + rr * kRowV], true, no_star);
+                    }
                 }
             } else if (RES && !STREAM && j0 + R > jb && j0 >= res_lo && jb - 1 <= res_hi) {
                 // resident kernel, the march's last tile when its length is not a multiple of R: the fast body for the rows
